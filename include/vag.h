@@ -1,0 +1,181 @@
+/*
+ * vag.h -- C ABI of the B200-native VegasAfterglow model-evaluation path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no
+ * torch / pybind / xtensor types.  Every entry point names the reference interface it
+ * replaces (paths relative to the reference repository root).
+ *
+ * Units at this boundary are the reference's *Python-facing* units (pybind/pymodel.cpp:498-514,
+ * pybind/pymodel.h:246): seconds, Hz, cm, erg, cm^-3 in; erg cm^-2 s^-1 Hz^-1 out.
+ *
+ * All compute entry points run on the GPU (sm_100a kernels).  There is no CPU fallback: when no
+ * CUDA device is usable they return VAG_ERR_CUDA and vag_last_error() says why.
+ */
+#ifndef VAG_H_
+#define VAG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------- */
+/* status codes                                                                                 */
+/* ------------------------------------------------------------------------------------------- */
+enum {
+    VAG_OK = 0,
+    VAG_ERR_INVALID = 1, /* argument validation failed: mirrors AFTERGLOW_REQUIRE -> ValueError
+                            (pybind/error_handling.h:31-69) */
+    VAG_ERR_CUDA = 2,    /* CUDA runtime error / no device                                       */
+    VAG_ERR_UNSUPPORTED = 3, /* a switch of the reference that this path does not implement yet
+                                (jet spreading, Ejecta/Medium callbacks, k_m != 2)               */
+    VAG_ERR_CAPACITY = 4     /* a per-model grid exceeded the compiled capacity                  */
+};
+
+/* jet / medium enumerations: the typed variants of JetVariant / MediumVariant
+ * (src/environment/jet.h:272, src/environment/medium.h:144). */
+enum { VAG_JET_TOPHAT = 0, VAG_JET_GAUSSIAN = 1, VAG_JET_POWERLAW = 2 };
+enum { VAG_MEDIUM_ISM = 0, VAG_MEDIUM_WIND = 1 };
+
+/* per-model status bits written by the kernels (the reference prints a
+ * warning on stderr and leaves the row at its initial values; we mirror that and set a bit). */
+enum {
+    VAG_ST_ODE_STEP_CAP = 1,  /* forward-shock.tpp:196-200 / reverse-shock.tpp:555-559           */
+    VAG_ST_ODE_STALLED = 2,   /* reverse-shock.tpp:560-566                                       */
+    VAG_ST_ODE_FAIL500 = 4,   /* boost max_step_checker.hpp:99-106 (reference throws)            */
+    VAG_ST_GRID_NONFINITE = 8, /* grid-refinement.h:633-635                                      */
+    VAG_ST_CAPACITY = 16      /* grid larger than compiled capacity; model output is NaN         */
+};
+
+/* Radiation(eps_e, eps_B, p, xi_e=1, ssc=False, kn=False): pybind/pymodel.h:303-313 */
+typedef struct vag_radiation {
+    double eps_e, eps_B, p, xi_e;
+    int32_t ssc, kn;
+} vag_radiation;
+
+/* One parameter set = everything Model.__init__ receives (pybind/pybind.cpp:384-422,
+ * pybind/pymodel.h:613-649) for the typed jet/medium variants. */
+typedef struct vag_params {
+    /* jet: TophatJet/GaussianJet/PowerLawJet(theta_c, E_iso, Gamma0[, k_e, k_g], spreading,
+     * duration)  pybind/pymodel.cpp:47-95 */
+    int32_t jet_type;
+    int32_t spreading; /* must be 0 (VAG_ERR_UNSUPPORTED otherwise) */
+    double theta_c, E_iso, Gamma0, k_e, k_g, duration;
+    /* medium: ISM(n_ism) / Wind(A_star, n_ism=0, n0=inf, k_m=2)  pybind/pymodel.cpp:148-186 */
+    int32_t medium_type;
+    int32_t pad0_;
+    double n_ism, A_star, n0;
+    /* Observer(lumi_dist[cm], z, theta_obs, phi_obs=0)  pybind/pymodel.h:190-204 */
+    double lumi_dist, z, theta_obs, phi_obs;
+    /* radiation */
+    vag_radiation fwd;
+    vag_radiation rvs;
+    int32_t has_rvs;
+    int32_t axisymmetric;       /* default 1 */
+    int32_t radiative_fireball; /* default 1 */
+    int32_t pad1_;
+    /* resolutions=(phi, theta, t); a value <= 0 selects the reference default
+     * (0.06,0.15,6) forward-only or (0.06,0.2,10) with a reverse shock
+     * (src/config/simulation-defaults.h:71-83, pybind/pymodel.h:633-640) */
+    double phi_resol, theta_resol, t_resol;
+    double rtol; /* <= 0 selects defaults::solver::dynamics_rtol = 1e-6 */
+} vag_params;
+
+/* Fill *p with the reference defaults (Tophat/ISM values are NOT set, only the switches). */
+void vag_params_default(vag_params* p);
+
+/* Validate one parameter set exactly like the reference constructors do
+ * (pybind/pymodel.cpp:47-186, pybind/pymodel.h:190-204,303-313,613-649).
+ * Returns VAG_OK or VAG_ERR_INVALID / VAG_ERR_UNSUPPORTED; message via vag_last_error(). */
+int vag_params_validate(const vag_params* p);
+
+/* ------------------------------------------------------------------------------------------- */
+/* context                                                                                      */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct vag_context vag_context;
+
+/* Create a context bound to CUDA device `device` (owns a stream and growable workspaces). */
+int vag_create(int device, vag_context** out);
+void vag_destroy(vag_context* ctx);
+const char* vag_last_error(void);
+const char* vag_version(void);
+
+/* Output component order of every flux entry point: PyFlux (pybind/pymodel.h:394-400). */
+enum { VAG_C_TOTAL = 0, VAG_C_FWD_SYNC = 1, VAG_C_FWD_SSC = 2, VAG_C_RVS_SYNC = 3, VAG_C_RVS_SSC = 4, VAG_NCOMP = 5 };
+
+/* ------------------------------------------------------------------------------------------- */
+/* batched model evaluation, HOST buffers (copies inside)                                       */
+/* ------------------------------------------------------------------------------------------- */
+
+/* Replaces PyModel::flux_density_grid (pybind/pymodel.cpp:498-514) for n_models parameter sets
+ * sharing one (t, nu) request.  t ascending [s], nu [Hz].
+ * out[n_models][VAG_NCOMP][n_nu][n_t]  (components a model does not have are 0; total = sum,
+ * pybind/pymodel.cpp:350-364).  status[n_models] receives VAG_ST_* bits (may be NULL). */
+int vag_flux_density_grid(vag_context* ctx, const vag_params* params, size_t n_models, const double* t, size_t n_t,
+                          const double* nu, size_t n_nu, double* out, int32_t* status);
+
+/* Replaces PyModel::flux_density (pybind/pymodel.cpp:373-389): series of (t[i], nu[i]) points,
+ * t ascending.  out[n_models][VAG_NCOMP][n]. */
+int vag_flux_density_series(vag_context* ctx, const vag_params* params, size_t n_models, const double* t,
+                            const double* nu, size_t n, double* out, int32_t* status);
+
+/* Replaces Fitter._evaluate + _chi2_sum for point data (VegasAfterglow/fitting/fitter.py:497-522):
+ * chi2[m] = sum_i w[i] * ((lnF_obs[i] - ln max(F_model[i], 1e-300)) / sigma_ln[i])^2
+ * over the series (t[i], nu[i]); non-finite chi2 is returned as +inf (samplers.py:63-70 maps it
+ * to logL = -inf).  t ascending. */
+int vag_chi2_series(vag_context* ctx, const vag_params* params, size_t n_models, const double* t, const double* nu,
+                    const double* lnF_obs, const double* sigma_ln, const double* w, size_t n, double* chi2,
+                    int32_t* status);
+
+/* ------------------------------------------------------------------------------------------- */
+/* batched model evaluation, DEVICE buffers (no copies; asynchronous on `stream`)               */
+/* ------------------------------------------------------------------------------------------- */
+/* Same contracts as above; every pointer is a device pointer on ctx's device; `stream` is a
+ * cudaStream_t passed as void* (NULL = the context's own stream).  The call only enqueues work. */
+int vag_flux_density_grid_dev(vag_context* ctx, const vag_params* d_params, size_t n_models, const double* d_t,
+                              size_t n_t, const double* d_nu, size_t n_nu, double* d_out, int32_t* d_status,
+                              void* stream);
+int vag_flux_density_series_dev(vag_context* ctx, const vag_params* d_params, size_t n_models, const double* d_t,
+                                const double* d_nu, size_t n, double* d_out, int32_t* d_status, void* stream);
+int vag_chi2_series_dev(vag_context* ctx, const vag_params* d_params, size_t n_models, const double* d_t,
+                        const double* d_nu, const double* d_lnF_obs, const double* d_sigma_ln, const double* d_w,
+                        size_t n, double* d_chi2, int32_t* d_status, void* stream);
+int vag_synchronize(vag_context* ctx);
+
+/* ------------------------------------------------------------------------------------------- */
+/* introspection (tests, profiling): stage tables of ONE model, the analogue of                 */
+/* PyModel::details (pybind/pymodel.cpp:315-348)                                                */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct vag_grid_info {
+    int32_t n_phi, n_theta, n_t;   /* Coord shape (src/core/mesh.h:55-83)                        */
+    int32_t n_reps;                /* coord.theta_reps.size()                                    */
+    int32_t symmetry;              /* Symmetry enum value (src/core/mesh.h:49-54)                */
+    int32_t phi_mirrored;
+    int32_t n_phi_eff;             /* Observer::eff_phi_grid (src/core/observer.cpp:218-222)     */
+    int32_t status;
+} vag_grid_info;
+
+/* Runs grid + dynamics (+radiation) for one model and the observation window [t_min, t_max] s.
+ * Any output pointer may be NULL.  Sizes: theta[n_theta], phi[n_phi], reps[n_reps],
+ * t_rows[n_reps][n_t] (engine-frame lattice of each representative row, code units),
+ * fwd_shock / rvs_shock [7][n_reps][n_t] in the order t_comv, r, theta, Gamma, Gamma_th, B, N_p
+ * (code units, src/dynamics/shock.h:33-39), inj_idx[n_reps] (reverse shock injection_idx).
+ * Call once with all NULL to get *info, then allocate. */
+int vag_details(vag_context* ctx, const vag_params* p, double t_min, double t_max, vag_grid_info* info,
+                double* theta, double* phi, int32_t* reps, double* t_rows, double* fwd_shock, double* rvs_shock,
+                int32_t* inj_idx);
+
+/* per-stage device time of the most recent batched call on this context, milliseconds:
+ * [0]=grid (K0) [1]=dynamics (K1) [2]=radiation (K2) [3]=EATS flux (K3) [4]=likelihood (K4)
+ * Only filled when vag_set_profiling(ctx, 1) was called (adds event records + one sync). */
+int vag_set_profiling(vag_context* ctx, int enable);
+int vag_last_stage_ms(vag_context* ctx, float ms[8]);
+/* number of kernel launches issued by the most recent batched call */
+int vag_last_launch_count(vag_context* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAG_H_ */
