@@ -133,7 +133,10 @@ int vag_chi2_series(vag_context* ctx, const vag_params* params, size_t n_models,
 /* batched model evaluation, DEVICE buffers (no copies; asynchronous on `stream`)               */
 /* ------------------------------------------------------------------------------------------- */
 /* Same contracts as above; every pointer is a device pointer on ctx's device; `stream` is a
- * cudaStream_t passed as void* (NULL = the context's own stream).  The call only enqueues work. */
+ * cudaStream_t passed as void* (NULL = the context's own stream).  The calls are stream-ordered;
+ * they synchronise the stream once internally (to size the ragged workspace after the grid
+ * kernel) and return with the remaining kernels enqueued: call vag_synchronize / sync the stream
+ * before reading the outputs.  t must be ascending (not checked on the device path). */
 int vag_flux_density_grid_dev(vag_context* ctx, const vag_params* d_params, size_t n_models, const double* d_t,
                               size_t n_t, const double* d_nu, size_t n_nu, double* d_out, int32_t* d_status,
                               void* stream);
@@ -143,6 +146,11 @@ int vag_chi2_series_dev(vag_context* ctx, const vag_params* d_params, size_t n_m
                         const double* d_nu, const double* d_lnF_obs, const double* d_sigma_ln, const double* d_w,
                         size_t n, double* d_chi2, int32_t* d_status, void* stream);
 int vag_synchronize(vag_context* ctx);
+/* The *_dev entry points cannot see the parameters on the host, so they use the context's grid
+ * capacities (theta nodes / phi nodes per model; defaults 384 / 128).  The host-buffer entry
+ * points derive tight capacities from the parameters themselves.  A model that needs more nodes
+ * than the capacity gets VAG_ST_CAPACITY and NaN output. */
+int vag_set_capacity(vag_context* ctx, int cap_theta, int cap_phi);
 
 /* ------------------------------------------------------------------------------------------- */
 /* introspection (tests, profiling): stage tables of ONE model, the analogue of                 */

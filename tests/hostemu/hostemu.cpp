@@ -1,0 +1,223 @@
+// TEST INFRASTRUCTURE ONLY: sequential host execution of the *same* kernel bodies that
+// vegasafterglow_b200/csrc/vag_kernels.cu launches on the GPU (every body is an HD function of the
+// thread index; barriers become loop boundaries).  Lets the CPU-only test tier compare the
+// device algorithm against the reference stage by stage.  It is never built into, linked with or
+// called by the product library (libvag_b200.so).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../vegasafterglow_b200/csrc/vag_pipeline.cuh"
+
+using namespace vag;
+
+namespace {
+
+struct HostBatch {
+    BatchWs w{};
+    std::vector<void*> allocs;
+    template <class T>
+    T* alloc(size_t n) {
+        T* p = static_cast<T*>(std::calloc(std::max<size_t>(n, 1), sizeof(T)));
+        allocs.push_back(p);
+        return p;
+    }
+    ~HostBatch() {
+        for (void* p : allocs) std::free(p);
+    }
+};
+
+void caps_for(const vag_params* p, size_t n, int& cap_theta, int& cap_phi);
+
+void run_front(HostBatch& hb, const vag_params* params, size_t n, double t_min, double t_max) {
+    BatchWs& w = hb.w;
+    w.n_models = (int)n;
+    caps_for(params, n, w.cap_theta, w.cap_phi);
+    w.work_per_model = grid_work_doubles(w.cap_theta, w.cap_phi);
+    w.params = params;
+    w.cfg = hb.alloc<ModelCfg>(n);
+    w.hdr = hb.alloc<GridHeader>(n);
+    w.theta = hb.alloc<double>(n * w.cap_theta);
+    w.phi = hb.alloc<double>(n * w.cap_phi);
+    w.t_dec = hb.alloc<double>(n * w.cap_theta);
+    w.work = hb.alloc<double>(n * w.work_per_model);
+    w.reps = hb.alloc<int>(n * w.cap_theta);
+    w.rep_of = hb.alloc<int>(n * w.cap_theta);
+    w.row_off = hb.alloc<int>(n + 1);
+    w.cell_off = hb.alloc<long long>(n + 1);
+    w.totals = hb.alloc<int>(TOT_N);
+    w.status = hb.alloc<int>(n);
+    for (size_t i = 0; i < n; ++i) k0_grid_body(w, (int)i, t_min, t_max);
+    k0b_scan_body(w);
+    const int rows = w.totals[TOT_ROWS];
+    const long long cells = w.cell_off[n];
+    w.n_cells = cells;
+    w.row_model = hb.alloc<int>(rows);
+    w.row_rep = hb.alloc<int>(rows);
+    w.inj_idx = hb.alloc<int>(rows);
+    w.t_rows = hb.alloc<double>(cells);
+    for (int a = 0; a < 6; ++a) {
+        w.fwd[a] = hb.alloc<double>(cells);
+        w.rvs[a] = hb.alloc<double>(cells);
+    }
+    w.coef_fwd = hb.alloc<double>((size_t)cells * PH_NCOEF);
+    w.coef_rvs = hb.alloc<double>((size_t)cells * PH_NCOEF);
+    for (size_t i = 0; i < n; ++i) k0c_rowmap_body(w, (int)i);
+    for (int r = 0; r < rows; ++r) k1_dynamics_body(w, r);
+    for (int r = 0; r < rows; ++r) {
+        const GridHeader& h = w.hdr[w.row_model[r]];
+        const bool rvs = w.cfg[w.row_model[r]].has_rvs;
+        for (int k = 0; k < h.n_t; ++k) {
+            k2_radiation_cell(w, r, k, 0);
+            if (rvs) k2_radiation_cell(w, r, k, 1);
+        }
+    }
+}
+
+// mirrors the host-side capacity planning of vag_api.cu (kept in sync by tests)
+void caps_for(const vag_params* p, size_t n, int& cap_theta, int& cap_phi) {
+    cap_theta = 64;
+    cap_phi = 8;
+    for (size_t i = 0; i < n; ++i) {
+        const bool r = p[i].has_rvs != 0;
+        const double th_res = p[i].theta_resol > 0 ? p[i].theta_resol : (r ? 0.2 : 0.15);
+        const double ph_res = p[i].phi_resol > 0 ? p[i].phi_resol : 0.06;
+        const double lg = std::log10(std::max(1.0, p[i].Gamma0 * 1.5708));
+        const int ct = 36 + (int)(90 * th_res) + (int)(std::max(0.0, lg - 1) * th_res * 55) + (int)(lg * th_res * 25) + 40;
+        const int cp = std::max((int)(360 * ph_res), 1) * 5 + 8;
+        cap_theta = std::max(cap_theta, ct);
+        cap_phi = std::max(cap_phi, cp);
+    }
+}
+
+// sequential emulation of the K3 CTA (vag_kernels.cu: k_eats) for one (model, shock)
+void eats_emulate(const BatchWs& w, int mi, int which, const EatsRequest& rq0, double* out /*[n_nu][n_t] or [n]*/) {
+    const int NTHR = 128;
+    EatsModel M = make_eats_model(w, mi, which);
+    const GridHeader& h = *M.h;
+    const int n_t = h.n_t;
+    const int erows = h.n_theta * h.n_phi_eff;
+    const bool series = rq0.series != 0;
+    std::vector<double> smem(eats_shared_doubles(n_t, series, EATS_ROW_CHUNK) + 8);
+    std::vector<double> acc(EATS_NU_TILE * EATS_T_BLOCK);
+    EatsShared sh = eats_carve(smem.data(), n_t, series, EATS_ROW_CHUNK);
+    EatsRequest rq = rq0;
+    const int n_nu_tiles = series ? 1 : (rq.n_nu + EATS_NU_TILE - 1) / EATS_NU_TILE;
+    for (int tile = 0; tile < n_nu_tiles; ++tile) {
+        const int l0 = tile * EATS_NU_TILE;
+        const int nl = series ? 1 : std::min(EATS_NU_TILE, rq.n_nu - l0);
+        for (int i0 = 0; i0 < rq.n_t_obs; i0 += EATS_T_BLOCK) {
+            rq.i0 = i0;
+            rq.ni = std::min(EATS_T_BLOCK, rq.n_t_obs - i0);
+            std::fill(acc.begin(), acc.end(), 0.0);
+            for (int q0 = 0; q0 < erows; q0 += EATS_ROW_CHUNK) {
+                const int nrows = std::min(EATS_ROW_CHUNK, erows - q0);
+                for (int tid = 0; tid < NTHR; ++tid) eats_phase0(M, sh, q0, nrows, tid, NTHR);
+                for (int tid = 0; tid < NTHR; ++tid) eats_phase1(M, rq, sh, nrows, l0, nl, tid, NTHR);
+                for (int tid = 0; tid < NTHR; ++tid) {
+                    if (series)
+                        eats_phase2_series(M, rq, sh, nrows, acc.data(), tid, NTHR);
+                    else
+                        eats_phase2_grid(M, rq, sh, nrows, nl, acc.data(), tid, NTHR);
+                }
+            }
+            if (series) {
+                for (int ii = 0; ii < rq.ni; ++ii) out[i0 + ii] = flux_scale(M, acc[ii]);
+            } else {
+                for (int l = 0; l < nl; ++l)
+                    for (int ii = 0; ii < rq.ni; ++ii)
+                        out[(size_t)(l0 + l) * rq.n_t_obs + i0 + ii] = flux_scale(M, acc[l * EATS_T_BLOCK + ii]);
+            }
+        }
+    }
+}
+
+int run_flux(const vag_params* params, size_t n, const double* t, size_t n_t, const double* nu, size_t n_nu,
+             bool series, double* out, int32_t* status) {
+    HostBatch hb;
+    const double t_min = *std::min_element(t, t + n_t), t_max = *std::max_element(t, t + n_t);
+    run_front(hb, params, n, t_min, t_max);
+    std::vector<double> lg2t(n_t), tl(n_t), lg2nu(n_nu);
+    for (size_t i = 0; i < n_t; ++i) {
+        tl[i] = t[i] * unit::sec;
+        lg2t[i] = std::log2(tl[i]);
+    }
+    for (size_t i = 0; i < n_nu; ++i) lg2nu[i] = std::log2(nu[i] * unit::Hz);
+    EatsRequest rq{};
+    rq.series = series ? 1 : 0;
+    rq.n_t_obs = (int)n_t;
+    rq.n_nu = (int)n_nu;
+    rq.lg2_t_obs = lg2t.data();
+    rq.lg2_nu_obs = lg2nu.data();
+    rq.t_obs_lin = tl.data();
+    const size_t comp = series ? n_t : n_nu * n_t;
+    for (size_t mi = 0; mi < n; ++mi) {
+        double* o = out + mi * VAG_NCOMP * comp;
+        std::memset(o, 0, sizeof(double) * VAG_NCOMP * comp);
+        if (hb.w.hdr[mi].status & VAG_ST_CAPACITY) continue;
+        eats_emulate(hb.w, (int)mi, 0, rq, o + VAG_C_FWD_SYNC * comp);
+        if (params[mi].has_rvs) eats_emulate(hb.w, (int)mi, 1, rq, o + VAG_C_RVS_SYNC * comp);
+        for (size_t i = 0; i < comp; ++i)
+            o[i] = o[VAG_C_FWD_SYNC * comp + i] + o[VAG_C_FWD_SSC * comp + i] + o[VAG_C_RVS_SYNC * comp + i] +
+                   o[VAG_C_RVS_SSC * comp + i];
+        if (status) status[mi] = hb.w.status[mi];
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vagemu_flux_density_grid(const vag_params* params, size_t n, const double* t, size_t n_t, const double* nu,
+                             size_t n_nu, double* out, int32_t* status) {
+    return run_flux(params, n, t, n_t, nu, n_nu, false, out, status);
+}
+
+int vagemu_flux_density_series(const vag_params* params, size_t n, const double* t, const double* nu, size_t npts,
+                               double* out, int32_t* status) {
+    return run_flux(params, n, t, npts, nu, npts, true, out, status);
+}
+
+// same contract as vag_details (include/vag.h) + photon coefficient planes
+int vagemu_details(const vag_params* p, double t_min, double t_max, vag_grid_info* info, double* theta, double* phi,
+                   int32_t* reps, double* t_rows, double* fwd_shock, double* rvs_shock, int32_t* inj_idx,
+                   double* coef_fwd, double* coef_rvs) {
+    HostBatch hb;
+    run_front(hb, p, 1, t_min, t_max);
+    const BatchWs& w = hb.w;
+    const GridHeader& h = w.hdr[0];
+    if (info) {
+        info->n_phi = h.n_phi;
+        info->n_theta = h.n_theta;
+        info->n_t = h.n_t;
+        info->n_reps = h.n_reps;
+        info->symmetry = h.symmetry;
+        info->phi_mirrored = h.phi_mirrored;
+        info->n_phi_eff = h.n_phi_eff;
+        info->status = w.status[0];
+    }
+    const size_t cells = (size_t)h.n_reps * h.n_t;
+    if (theta) std::memcpy(theta, w.theta, sizeof(double) * h.n_theta);
+    if (phi) std::memcpy(phi, w.phi, sizeof(double) * h.n_phi);
+    if (reps) std::memcpy(reps, w.reps, sizeof(int) * h.n_reps);
+    if (t_rows) std::memcpy(t_rows, w.t_rows, sizeof(double) * cells);
+    auto dump = [&](double* const* pl, double* o) {
+        // order t_comv, r, theta, Gamma, Gamma_th, B, N_p
+        const int map[7] = {0, 1, -1, 2, 3, 4, 5};
+        for (int a = 0; a < 7; ++a)
+            for (int r = 0; r < h.n_reps; ++r)
+                for (int k = 0; k < h.n_t; ++k)
+                    o[((size_t)a * h.n_reps + r) * h.n_t + k] =
+                        map[a] < 0 ? w.theta[w.reps[r]] : pl[map[a]][(size_t)r * h.n_t + k];
+    };
+    if (fwd_shock) dump(w.fwd, fwd_shock);
+    if (rvs_shock && p->has_rvs) dump(w.rvs, rvs_shock);
+    if (inj_idx) std::memcpy(inj_idx, w.inj_idx, sizeof(int) * h.n_reps);
+    if (coef_fwd) std::memcpy(coef_fwd, w.coef_fwd, sizeof(double) * cells * PH_NCOEF);
+    if (coef_rvs && p->has_rvs) std::memcpy(coef_rvs, w.coef_rvs, sizeof(double) * cells * PH_NCOEF);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,752 @@
+// vag_b200.cu -- sm_100a kernels and the C ABI (include/vag.h) of the B200-native
+// VegasAfterglow model-evaluation path.  Kernel bodies live in vag_pipeline.cuh / vag_observer.cuh.
+//
+// Launch geometry (B200: 148 SMs, FP64 path, no tensor cores -- nothing here is a contraction):
+//   k_grid / k_dynamics : one thread per model / unique row, 32-thread CTAs so that a 4096-row
+//                         batch spreads over all SMs (the ODE is dependent-latency bound; the
+//                         state lives in registers).
+//   k_radiation         : one 64-thread CTA per unique row, threads stride over the time lattice,
+//                         SoA plane stores are coalesced along k.
+//   k_eats              : one 128-thread CTA per (model, row-split, shock); cell tables and
+//                         per-node log2-luminosities staged in dynamic shared memory.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/vag.h"
+#include "vag_pipeline.cuh"
+
+using namespace vag;
+
+static_assert(sizeof(vag_params) == 248, "vag_params layout must match vegasafterglow_b200/abi.py");
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_grid(BatchWs w, const double* __restrict__ t_obs, int n_t_obs) {
+    const int mi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mi >= w.n_models) return;
+    k0_grid_body(w, mi, t_obs[0], t_obs[n_t_obs - 1]);
+}
+
+__global__ void k_scan(BatchWs w) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) k0b_scan_body(w);
+}
+
+__global__ void k_rowmap(BatchWs w) {
+    const int mi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mi >= w.n_models) return;
+    k0c_rowmap_body(w, mi);
+}
+
+__global__ void __launch_bounds__(32) k_dynamics(BatchWs w, int n_rows) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    k1_dynamics_body(w, row);
+}
+
+__global__ void __launch_bounds__(64) k_radiation(BatchWs w) {
+    const int row = blockIdx.x;
+    const int which = blockIdx.y;
+    const int mi = w.row_model[row];
+    if (which && !w.cfg[mi].has_rvs) return;
+    const int n_t = w.hdr[mi].n_t;
+    for (int k = threadIdx.x; k < n_t; k += blockDim.x) k2_radiation_cell(w, row, k, which);
+}
+
+// observation request pre-pass: log2 of the (unit-scaled) times and frequencies
+__global__ void k_prep_obs(const double* __restrict__ t, int n_t, const double* __restrict__ nu, int n_nu,
+                           double* lg2_t, double* t_lin, double* lg2_nu) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_t) {
+        const double tl = t[i] * unit::sec;
+        t_lin[i] = tl;
+        lg2_t[i] = log2(tl);
+    }
+    if (i < n_nu) lg2_nu[i] = log2(nu[i] * unit::Hz);
+}
+
+// K3.  grid = (model, split, shock).  out[model][comp][n_nu][n_t] (grid) or [model][comp][n] (series)
+__global__ void __launch_bounds__(128) k_eats(BatchWs w, EatsRequest rq0, double* __restrict__ out, int n_split,
+                                              int row_chunk, int max_n_t) {
+    extern __shared__ double smem[];
+    const int mi = blockIdx.x;
+    const int split = blockIdx.y;
+    const int which = blockIdx.z;
+    if (which && !w.cfg[mi].has_rvs) return;
+    if (w.hdr[mi].status & VAG_ST_CAPACITY) return;
+    const EatsModel M = make_eats_model(w, mi, which);
+    const int n_t = M.h->n_t;
+    const int erows = M.h->n_theta * M.h->n_phi_eff;
+    const bool series = rq0.series != 0;
+    double* acc = smem;  // [EATS_NU_TILE][EATS_T_BLOCK]
+    const EatsShared sh = eats_carve(smem + EATS_NU_TILE * EATS_T_BLOCK, max_n_t, series, row_chunk);
+    EatsRequest rq = rq0;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int comp = which ? VAG_C_RVS_SYNC : VAG_C_FWD_SYNC;
+    const size_t comp_sz = series ? (size_t)rq.n_t_obs : (size_t)rq.n_nu * rq.n_t_obs;
+    double* dst = out + ((size_t)mi * VAG_NCOMP + comp) * comp_sz;
+    const int n_nu_tiles = series ? 1 : (rq.n_nu + EATS_NU_TILE - 1) / EATS_NU_TILE;
+    for (int tile = 0; tile < n_nu_tiles; ++tile) {
+        const int l0 = tile * EATS_NU_TILE;
+        const int nl = series ? 1 : imin(EATS_NU_TILE, rq.n_nu - l0);
+        for (int i0 = 0; i0 < rq.n_t_obs; i0 += EATS_T_BLOCK) {
+            rq.i0 = i0;
+            rq.ni = imin(EATS_T_BLOCK, rq.n_t_obs - i0);
+            for (int a = tid; a < EATS_NU_TILE * EATS_T_BLOCK; a += nthr) acc[a] = 0.0;
+            for (int q0 = split * row_chunk; q0 < erows; q0 += n_split * row_chunk) {
+                const int nrows = imin(row_chunk, erows - q0);
+                __syncthreads();  // previous pass finished reading the staged rows
+                eats_phase0(M, sh, q0, nrows, tid, nthr);
+                __syncthreads();
+                eats_phase1(M, rq, sh, nrows, l0, nl, tid, nthr);
+                __syncthreads();
+                if (series)
+                    eats_phase2_series(M, rq, sh, nrows, acc, tid, nthr);
+                else
+                    eats_phase2_grid(M, rq, sh, nrows, nl, acc, tid, nthr);
+            }
+            // accumulator columns are thread-owned (ii == tid mod nthr): no barrier needed here
+            for (int ii = tid; ii < rq.ni; ii += nthr) {
+                for (int l = 0; l < nl; ++l) {
+                    const double v = flux_scale(M, acc[l * EATS_T_BLOCK + ii]);
+                    double* p = series ? (dst + i0 + ii) : (dst + (size_t)(l0 + l) * rq.n_t_obs + i0 + ii);
+                    if (n_split == 1)
+                        *p = v;
+                    else
+                        atomicAdd(p, v);
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// total = sum of the present components (PyFlux::calc_total, pybind/pymodel.cpp:350-364)
+__global__ void k_total(double* out, size_t n_models, size_t comp_sz) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_models * comp_sz) return;
+    const size_t mi = i / comp_sz, e = i - mi * comp_sz;
+    double* o = out + mi * VAG_NCOMP * comp_sz;
+    o[e] = o[VAG_C_FWD_SYNC * comp_sz + e] + o[VAG_C_FWD_SSC * comp_sz + e] + o[VAG_C_RVS_SYNC * comp_sz + e] +
+           o[VAG_C_RVS_SSC * comp_sz + e];
+}
+
+// K4: one warp per model; chi2 over the series total (fitter.py:497-501)
+__global__ void k_chi2(const double* __restrict__ flux, size_t n_models, int n, const double* __restrict__ lnF,
+                       const double* __restrict__ sigma_ln, const double* __restrict__ wgt, double* chi2) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= (int)n_models) return;
+    const double* F = flux + (size_t)warp * VAG_NCOMP * n;  // total
+    double s = 0;
+    for (int i = lane; i < n; i += 32) s += chi2_term(lnF[i], F[i], sigma_ln[i], wgt[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) chi2[warp] = isfinite(s) ? s : kInf;
+}
+
+__global__ void k_nan_capacity(BatchWs w, double* out, size_t comp_sz_total) {
+    // models whose grid exceeded the compiled capacity produce NaN, never a silent partial result
+    const int mi = blockIdx.x;
+    if (!(w.hdr[mi].status & VAG_ST_CAPACITY)) return;
+    for (size_t i = threadIdx.x; i < comp_sz_total; i += blockDim.x) out[(size_t)mi * comp_sz_total + i] = NAN;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(VAG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct vag_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf model_buf, row_buf, cell_buf, obs_buf, io_params, io_t, io_nu, io_out, io_status, io_aux;
+    int* h_totals = nullptr;        // pinned
+    long long* h_cells = nullptr;   // pinned
+    int cap_theta = 384, cap_phi = 128;
+    bool profiling = false;
+    cudaEvent_t ev[8] = {};
+    float stage_ms[8] = {};
+    int launches = 0;
+    int sm_count = 148;
+};
+
+namespace {
+
+template <class T>
+T* carve(char*& p, size_t n) {
+    T* r = reinterpret_cast<T*>(p);
+    p += ((n * sizeof(T) + 255) / 256) * 256;
+    return r;
+}
+template <class T>
+size_t carve_sz(size_t n) {
+    return ((n * sizeof(T) + 255) / 256) * 256;
+}
+
+// capacity planning from host-side parameters (upper bounds of auto_grid's node counts,
+// src/core/grid-refinement.h:246-262,655,664-677)
+void caps_for(const vag_params* p, size_t n, int& cap_theta, int& cap_phi) {
+    cap_theta = 64;
+    cap_phi = 8;
+    for (size_t i = 0; i < n; ++i) {
+        const bool r = p[i].has_rvs != 0;
+        const double th_res = p[i].theta_resol > 0 ? p[i].theta_resol : (r ? 0.2 : 0.15);
+        const double ph_res = p[i].phi_resol > 0 ? p[i].phi_resol : 0.06;
+        const double lg = std::log10(std::max(1.0, p[i].Gamma0 * 1.5708));
+        const int ct = 36 + (int)(90 * th_res) + (int)(std::max(0.0, lg - 1) * th_res * 55) + (int)(lg * th_res * 25) + 40;
+        const int cp = std::max((int)(360 * ph_res), 1) * 5 + 8;
+        cap_theta = std::max(cap_theta, ct);
+        cap_phi = std::max(cap_phi, cp);
+    }
+}
+
+struct Request {
+    bool series;
+    const double* d_t;
+    const double* d_nu;
+    size_t n_t, n_nu;
+};
+
+int setup_models(vag_context* ctx, BatchWs& w, const vag_params* d_params, size_t n) {
+    w = BatchWs{};
+    w.n_models = (int)n;
+    w.cap_theta = ctx->cap_theta;
+    w.cap_phi = ctx->cap_phi;
+    w.work_per_model = grid_work_doubles(w.cap_theta, w.cap_phi);
+    w.params = d_params;
+    size_t bytes = carve_sz<ModelCfg>(n) + carve_sz<GridHeader>(n) + carve_sz<double>(n * w.cap_theta) * 2 +
+                   carve_sz<double>(n * w.cap_phi) + carve_sz<double>(n * w.work_per_model) +
+                   carve_sz<int>(n * w.cap_theta) * 2 + carve_sz<int>(n + 1) + carve_sz<long long>(n + 1) +
+                   carve_sz<int>(TOT_N) + carve_sz<int>(n);
+    CK(ctx->model_buf.ensure(bytes));
+    char* p = static_cast<char*>(ctx->model_buf.p);
+    w.cfg = carve<ModelCfg>(p, n);
+    w.hdr = carve<GridHeader>(p, n);
+    w.theta = carve<double>(p, n * w.cap_theta);
+    w.t_dec = carve<double>(p, n * w.cap_theta);
+    w.phi = carve<double>(p, n * w.cap_phi);
+    w.work = carve<double>(p, n * w.work_per_model);
+    w.reps = carve<int>(p, n * w.cap_theta);
+    w.rep_of = carve<int>(p, n * w.cap_theta);
+    w.row_off = carve<int>(p, n + 1);
+    w.cell_off = carve<long long>(p, n + 1);
+    w.totals = carve<int>(p, TOT_N);
+    w.status = carve<int>(p, n);
+    return VAG_OK;
+}
+
+int setup_rows(vag_context* ctx, BatchWs& w, int rows, long long cells) {
+    w.n_cells = cells;
+    CK(ctx->row_buf.ensure(carve_sz<int>(rows) * 3));
+    char* p = static_cast<char*>(ctx->row_buf.p);
+    w.row_model = carve<int>(p, rows);
+    w.row_rep = carve<int>(p, rows);
+    w.inj_idx = carve<int>(p, rows);
+    const size_t plane = carve_sz<double>((size_t)cells);
+    CK(ctx->cell_buf.ensure(plane * (1 + 12) + carve_sz<double>((size_t)cells * PH_NCOEF) * 2));
+    p = static_cast<char*>(ctx->cell_buf.p);
+    w.t_rows = carve<double>(p, (size_t)cells);
+    for (int a = 0; a < 6; ++a) w.fwd[a] = carve<double>(p, (size_t)cells);
+    for (int a = 0; a < 6; ++a) w.rvs[a] = carve<double>(p, (size_t)cells);
+    w.coef_fwd = carve<double>(p, (size_t)cells * PH_NCOEF);
+    w.coef_rvs = carve<double>(p, (size_t)cells * PH_NCOEF);
+    return VAG_OK;
+}
+
+void mark(vag_context* ctx, int i, cudaStream_t s) {
+    if (ctx->profiling) cudaEventRecord(ctx->ev[i], s);
+}
+
+// grid + dynamics + radiation for a batch; fills w and the totals
+int run_front(vag_context* ctx, BatchWs& w, const vag_params* d_params, size_t n, const double* d_t, size_t n_t,
+              cudaStream_t s, int* totals_out, long long* cells_out) {
+    int rc = setup_models(ctx, w, d_params, n);
+    if (rc) return rc;
+    mark(ctx, 0, s);
+    k_grid<<<(unsigned)((n + 31) / 32), 32, 0, s>>>(w, d_t, (int)n_t);
+    k_scan<<<1, 32, 0, s>>>(w);
+    ctx->launches += 2;
+    CK(cudaMemcpyAsync(ctx->h_totals, w.totals, sizeof(int) * TOT_N, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->h_cells, w.cell_off + n, sizeof(long long), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const int rows = ctx->h_totals[TOT_ROWS];
+    const long long cells = *ctx->h_cells;
+    std::memcpy(totals_out, ctx->h_totals, sizeof(int) * TOT_N);
+    *cells_out = cells;
+    rc = setup_rows(ctx, w, std::max(rows, 1), std::max<long long>(cells, 1));
+    if (rc) return rc;
+    if (rows > 0) {
+        k_rowmap<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(w);
+        mark(ctx, 1, s);
+        k_dynamics<<<(unsigned)((rows + 31) / 32), 32, 0, s>>>(w, rows);
+        mark(ctx, 2, s);
+        k_radiation<<<dim3((unsigned)rows, 2), 64, 0, s>>>(w);
+        ctx->launches += 3;
+    } else {
+        mark(ctx, 1, s);
+        mark(ctx, 2, s);
+    }
+    mark(ctx, 3, s);
+    CK(cudaGetLastError());
+    return VAG_OK;
+}
+
+int run_flux(vag_context* ctx, const vag_params* d_params, size_t n, const Request& rq_in, double* d_out,
+             int32_t* d_status, const double* d_lnF, const double* d_sig, const double* d_w, double* d_chi2,
+             cudaStream_t s) {
+    if (n == 0) return VAG_OK;
+    ctx->launches = 0;
+    const size_t n_t = rq_in.n_t, n_nu = rq_in.n_nu;
+    // observation arrays
+    CK(ctx->obs_buf.ensure(sizeof(double) * (2 * n_t + n_nu + 8)));
+    double* lg2_t = static_cast<double*>(ctx->obs_buf.p);
+    double* t_lin = lg2_t + n_t;
+    double* lg2_nu = t_lin + n_t;
+    {
+        const size_t m = std::max(n_t, n_nu);
+        k_prep_obs<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(rq_in.d_t, (int)n_t, rq_in.d_nu, (int)n_nu, lg2_t, t_lin,
+                                                              lg2_nu);
+        ctx->launches++;
+    }
+    BatchWs w;
+    int totals[TOT_N];
+    long long cells = 0;
+    int rc = run_front(ctx, w, d_params, n, rq_in.d_t, n_t, s, totals, &cells);
+    if (rc) return rc;
+
+    const size_t comp_sz = rq_in.series ? n_t : n_nu * n_t;
+    CK(cudaMemsetAsync(d_out, 0, sizeof(double) * n * VAG_NCOMP * comp_sz, s));
+    const int max_n_t = std::max(totals[TOT_MAX_NT], 2);
+    const int max_erows = std::max(totals[TOT_MAX_EROWS], 1);
+    if (totals[TOT_ROWS] > 0) {
+        // shared-memory budget -> rows staged per pass
+        const size_t budget = 200 * 1024;
+        int row_chunk = EATS_ROW_CHUNK;
+        auto smem_bytes = [&](int rc_) {
+            return sizeof(double) * (EATS_NU_TILE * EATS_T_BLOCK + eats_shared_doubles(max_n_t, rq_in.series, rc_));
+        };
+        while (row_chunk > 1 && smem_bytes(row_chunk) > budget) --row_chunk;
+        if (smem_bytes(row_chunk) > budget)
+            return fail(VAG_ERR_CAPACITY, "time lattice too long for the EATS shared-memory stage");
+        // row-split so that small batches still fill the 148 SMs
+        const int chunks = (max_erows + row_chunk - 1) / row_chunk;
+        int n_split = 1;
+        const size_t target_ctas = (size_t)ctx->sm_count * 2;
+        if (n * 2 < target_ctas) n_split = (int)std::min<size_t>(chunks, (target_ctas + n * 2 - 1) / (n * 2));
+        n_split = std::max(n_split, 1);
+        const size_t sb = smem_bytes(row_chunk);
+        CK(cudaFuncSetAttribute(k_eats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
+        EatsRequest rq{};
+        rq.series = rq_in.series ? 1 : 0;
+        rq.n_t_obs = (int)n_t;
+        rq.n_nu = (int)n_nu;
+        rq.lg2_t_obs = lg2_t;
+        rq.lg2_nu_obs = lg2_nu;
+        rq.t_obs_lin = t_lin;
+        k_eats<<<dim3((unsigned)n, (unsigned)n_split, 2), 128, sb, s>>>(w, rq, d_out, n_split, row_chunk, max_n_t);
+        ctx->launches++;
+    }
+    mark(ctx, 4, s);
+    {
+        const size_t tot = n * comp_sz;
+        k_total<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_out, n, comp_sz);
+        ctx->launches++;
+        if (totals[TOT_STATUS_OR] & VAG_ST_CAPACITY) {
+            k_nan_capacity<<<(unsigned)n, 128, 0, s>>>(w, d_out, VAG_NCOMP * comp_sz);
+            ctx->launches++;
+        }
+    }
+    if (d_chi2) {
+        k_chi2<<<(unsigned)((n * 32 + 127) / 128), 128, 0, s>>>(d_out, n, (int)n_t, d_lnF, d_sig, d_w, d_chi2);
+        ctx->launches++;
+    }
+    mark(ctx, 5, s);
+    if (d_status) CK(cudaMemcpyAsync(d_status, w.status, sizeof(int) * n, cudaMemcpyDeviceToDevice, s));
+    CK(cudaGetLastError());
+    if (ctx->profiling) {
+        CK(cudaStreamSynchronize(s));
+        for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
+    }
+    return VAG_OK;
+}
+
+int check_ascending(const double* t, size_t n) {  // is_ascending, pybind/pybind.h:28
+    for (size_t i = 1; i < n; ++i)
+        if (!(t[i - 1] <= t[i])) return 0;
+    return 1;
+}
+
+bool finite_pos(double x) { return std::isfinite(x) && x > 0; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* vag_last_error(void) { return g_err.c_str(); }
+const char* vag_version(void) { return "vegasafterglow_b200 0.1 (sm_100a)"; }
+
+void vag_params_default(vag_params* p) {
+    std::memset(p, 0, sizeof(*p));
+    p->k_e = p->k_g = 2.0;
+    p->duration = 1.0;
+    p->n0 = INFINITY;
+    p->fwd = vag_radiation{0.1, 0.01, 2.3, 1.0, 0, 0};
+    p->rvs = vag_radiation{0.1, 0.01, 2.3, 1.0, 0, 0};
+    p->axisymmetric = 1;
+    p->radiative_fireball = 1;
+}
+
+int vag_params_validate(const vag_params* p) {
+    auto bad = [&](const std::string& m) { return fail(VAG_ERR_INVALID, m); };
+    auto rng_oi = [](double v, double lo, double hi) { return std::isfinite(v) && v > lo && v <= hi; };
+    if (p->jet_type < 0 || p->jet_type > 2) return bad("jet_type must be 0 (tophat), 1 (gaussian) or 2 (powerlaw)");
+    if (p->medium_type < 0 || p->medium_type > 1) return bad("medium_type must be 0 (ISM) or 1 (wind)");
+    // PyTophatJet / PyGaussianJet / PyPowerLawJet: pybind/pymodel.cpp:47-95
+    if (!rng_oi(p->theta_c, 0.0, con::pi / 2)) return bad("theta_c must be in (0, pi/2]");
+    if (!finite_pos(p->E_iso)) return bad("E_iso must be finite and > 0");
+    if (!(std::isfinite(p->Gamma0) && p->Gamma0 > 1.0)) return bad("Gamma0 must be > 1");
+    if (!finite_pos(p->duration)) return bad("duration must be finite and > 0");
+    if (p->jet_type == VAG_JET_POWERLAW && (!finite_pos(p->k_e) || !finite_pos(p->k_g)))
+        return bad("k_e and k_g must be finite and > 0");
+    // PyISM / PyWind: pybind/pymodel.cpp:148-186
+    if (p->medium_type == VAG_MEDIUM_ISM) {
+        if (!(std::isfinite(p->n_ism) && p->n_ism >= 0)) return bad("n_ism must be finite and >= 0");
+    } else {
+        if (!finite_pos(p->A_star)) return bad("A_star must be finite and > 0");
+        if (!(std::isfinite(p->n_ism) && p->n_ism >= 0)) return bad("n_ism must be finite and >= 0");
+        if (!(p->n0 > 0)) return bad("n0 must be > 0 (or +inf for no floor)");
+    }
+    // PyObserver: pybind/pymodel.h:190-204
+    if (!finite_pos(p->lumi_dist)) return bad("lumi_dist must be finite and > 0");
+    if (!(std::isfinite(p->z) && p->z >= 0)) return bad("z must be finite and >= 0");
+    if (!(std::isfinite(p->theta_obs) && p->theta_obs >= 0 && p->theta_obs <= con::pi))
+        return bad("theta_obs must be in [0, pi]");
+    if (!std::isfinite(p->phi_obs)) return bad("phi_obs must be finite");
+    // PyRadiation: pybind/pymodel.h:303-313
+    auto chk_rad = [&](const vag_radiation& r, const char* who) -> int {
+        if (!rng_oi(r.eps_e, 0.0, 1.0)) return bad(std::string(who) + ".eps_e must be in (0, 1]");
+        if (!rng_oi(r.eps_B, 0.0, 1.0)) return bad(std::string(who) + ".eps_B must be in (0, 1]");
+        if (!rng_oi(r.xi_e, 0.0, 1.0)) return bad(std::string(who) + ".xi_e must be in (0, 1]");
+        if (!(std::isfinite(r.p) && r.p > 1.0)) return bad(std::string(who) + ".p must be > 1");
+        if (r.ssc || r.kn)
+            return fail(VAG_ERR_UNSUPPORTED, std::string(who) + ": ssc/kn (inverse Compton) is not implemented on the GPU path yet");
+        return VAG_OK;
+    };
+    if (int rc = chk_rad(p->fwd, "fwd_rad")) return rc;
+    if (p->has_rvs)
+        if (int rc = chk_rad(p->rvs, "rvs_rad")) return rc;
+    // PyModel ctor: pybind/pymodel.h:642-647 (a non-positive value selects the default)
+    if (p->rtol > 0 && !(p->rtol < 1)) return bad("rtol must be in (0, 1)");
+    if (!std::isfinite(p->rtol) || !std::isfinite(p->phi_resol) || !std::isfinite(p->theta_resol) ||
+        !std::isfinite(p->t_resol))
+        return bad("resolutions and rtol must be finite");
+    if (p->spreading) return fail(VAG_ERR_UNSUPPORTED, "jet spreading is not implemented on the GPU path yet");
+    if (!p->axisymmetric) return fail(VAG_ERR_UNSUPPORTED, "axisymmetric=False is not implemented on the GPU path yet");
+    return VAG_OK;
+}
+
+int vag_create(int device, vag_context** out) {
+    if (!out) return fail(VAG_ERR_INVALID, "out is NULL");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(VAG_ERR_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0"));
+    if (device < 0 || device >= count) return fail(VAG_ERR_INVALID, "device index out of range");
+    CK(cudaSetDevice(device));
+    vag_context* c = new vag_context();
+    c->device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaMallocHost(&c->h_totals, sizeof(int) * TOT_N));
+    CK(cudaMallocHost(&c->h_cells, sizeof(long long)));
+    for (auto& ev : c->ev) CK(cudaEventCreate(&ev));
+    // the dynamics kernel keeps the dopri5 state in registers and spills the rest: prefer L1
+    cudaFuncSetCacheConfig(k_dynamics, cudaFuncCachePreferL1);
+    cudaFuncSetCacheConfig(k_grid, cudaFuncCachePreferL1);
+    *out = c;
+    return VAG_OK;
+}
+
+void vag_destroy(vag_context* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (DevBuf* b : {&c->model_buf, &c->row_buf, &c->cell_buf, &c->obs_buf, &c->io_params, &c->io_t, &c->io_nu,
+                      &c->io_out, &c->io_status, &c->io_aux})
+        b->release();
+    if (c->h_totals) cudaFreeHost(c->h_totals);
+    if (c->h_cells) cudaFreeHost(c->h_cells);
+    for (auto& ev : c->ev)
+        if (ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int vag_set_profiling(vag_context* ctx, int enable) {
+    ctx->profiling = enable != 0;
+    return VAG_OK;
+}
+int vag_last_stage_ms(vag_context* ctx, float ms[8]) {
+    for (int i = 0; i < 8; ++i) ms[i] = ctx->stage_ms[i];
+    return VAG_OK;
+}
+int vag_last_launch_count(vag_context* ctx) { return ctx->launches; }
+int vag_synchronize(vag_context* ctx) {
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VAG_OK;
+}
+int vag_set_capacity(vag_context* ctx, int cap_theta, int cap_phi) {
+    if (cap_theta < 40 || cap_phi < 2) return fail(VAG_ERR_INVALID, "capacity too small");
+    ctx->cap_theta = cap_theta;
+    ctx->cap_phi = cap_phi;
+    return VAG_OK;
+}
+
+// ---- device-buffer entry points ----------------------------------------------------------------
+int vag_flux_density_grid_dev(vag_context* ctx, const vag_params* d_params, size_t n_models, const double* d_t,
+                              size_t n_t, const double* d_nu, size_t n_nu, double* d_out, int32_t* d_status,
+                              void* stream) {
+    if (!ctx) return fail(VAG_ERR_INVALID, "ctx is NULL");
+    if (n_t == 0) return fail(VAG_ERR_INVALID, "time array must be non-empty");
+    if (n_nu == 0) return fail(VAG_ERR_INVALID, "frequency array must be non-empty");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    Request rq{false, d_t, d_nu, n_t, n_nu};
+    return run_flux(ctx, d_params, n_models, rq, d_out, d_status, nullptr, nullptr, nullptr, nullptr, s);
+}
+
+int vag_flux_density_series_dev(vag_context* ctx, const vag_params* d_params, size_t n_models, const double* d_t,
+                                const double* d_nu, size_t n, double* d_out, int32_t* d_status, void* stream) {
+    if (!ctx) return fail(VAG_ERR_INVALID, "ctx is NULL");
+    if (n == 0) return fail(VAG_ERR_INVALID, "time array must be non-empty");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    Request rq{true, d_t, d_nu, n, n};
+    return run_flux(ctx, d_params, n_models, rq, d_out, d_status, nullptr, nullptr, nullptr, nullptr, s);
+}
+
+int vag_chi2_series_dev(vag_context* ctx, const vag_params* d_params, size_t n_models, const double* d_t,
+                        const double* d_nu, const double* d_lnF_obs, const double* d_sigma_ln, const double* d_w,
+                        size_t n, double* d_chi2, int32_t* d_status, void* stream) {
+    if (!ctx) return fail(VAG_ERR_INVALID, "ctx is NULL");
+    if (n == 0) return fail(VAG_ERR_INVALID, "time array must be non-empty");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    CK(ctx->io_out.ensure(sizeof(double) * n_models * VAG_NCOMP * n));
+    Request rq{true, d_t, d_nu, n, n};
+    return run_flux(ctx, d_params, n_models, rq, static_cast<double*>(ctx->io_out.p), d_status, d_lnF_obs, d_sigma_ln,
+                    d_w, d_chi2, s);
+}
+
+// ---- host-buffer entry points --------------------------------------------------------------------
+static int host_prepare(vag_context* ctx, const vag_params* params, size_t n_models, const double* t, size_t n_t,
+                        const double* nu, size_t n_nu, bool series) {
+    if (!ctx) return fail(VAG_ERR_INVALID, "ctx is NULL");
+    if (!params && n_models) return fail(VAG_ERR_INVALID, "params is NULL");
+    if (n_t == 0 || !t) return fail(VAG_ERR_INVALID, "time array must be non-empty");
+    if (n_nu == 0 || !nu) return fail(VAG_ERR_INVALID, "frequency array must be non-empty");
+    if (series && n_t != n_nu)
+        return fail(VAG_ERR_INVALID,
+                    "time and frequency arrays must have the same size\nIf you intend to get grid-like output, use "
+                    "the generic `flux_density_grid` instead");
+    if (!check_ascending(t, n_t)) return fail(VAG_ERR_INVALID, "time array must be in ascending order");
+    for (size_t i = 0; i < n_models; ++i)
+        if (int rc = vag_params_validate(&params[i])) return rc;
+    CK(cudaSetDevice(ctx->device));
+    int ct, cp;
+    caps_for(params, n_models, ct, cp);
+    ctx->cap_theta = ct;
+    ctx->cap_phi = cp;
+    CK(ctx->io_params.ensure(sizeof(vag_params) * std::max<size_t>(n_models, 1)));
+    CK(ctx->io_t.ensure(sizeof(double) * n_t));
+    CK(ctx->io_nu.ensure(sizeof(double) * n_nu));
+    CK(ctx->io_status.ensure(sizeof(int32_t) * std::max<size_t>(n_models, 1)));
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->io_params.p, params, sizeof(vag_params) * n_models, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->io_t.p, t, sizeof(double) * n_t, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->io_nu.p, nu, sizeof(double) * n_nu, cudaMemcpyHostToDevice, s));
+    return VAG_OK;
+}
+
+int vag_flux_density_grid(vag_context* ctx, const vag_params* params, size_t n_models, const double* t, size_t n_t,
+                          const double* nu, size_t n_nu, double* out, int32_t* status) {
+    if (int rc = host_prepare(ctx, params, n_models, t, n_t, nu, n_nu, false)) return rc;
+    if (n_models == 0) return VAG_OK;
+    const size_t out_bytes = sizeof(double) * n_models * VAG_NCOMP * n_nu * n_t;
+    CK(ctx->io_out.ensure(out_bytes));
+    cudaStream_t s = ctx->stream;
+    Request rq{false, static_cast<double*>(ctx->io_t.p), static_cast<double*>(ctx->io_nu.p), n_t, n_nu};
+    if (int rc = run_flux(ctx, static_cast<vag_params*>(ctx->io_params.p), n_models, rq,
+                          static_cast<double*>(ctx->io_out.p), static_cast<int32_t*>(ctx->io_status.p), nullptr, nullptr,
+                          nullptr, nullptr, s))
+        return rc;
+    CK(cudaMemcpyAsync(out, ctx->io_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+    if (status) CK(cudaMemcpyAsync(status, ctx->io_status.p, sizeof(int32_t) * n_models, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return VAG_OK;
+}
+
+int vag_flux_density_series(vag_context* ctx, const vag_params* params, size_t n_models, const double* t,
+                            const double* nu, size_t n, double* out, int32_t* status) {
+    if (int rc = host_prepare(ctx, params, n_models, t, n, nu, n, true)) return rc;
+    if (n_models == 0) return VAG_OK;
+    const size_t out_bytes = sizeof(double) * n_models * VAG_NCOMP * n;
+    CK(ctx->io_out.ensure(out_bytes));
+    cudaStream_t s = ctx->stream;
+    Request rq{true, static_cast<double*>(ctx->io_t.p), static_cast<double*>(ctx->io_nu.p), n, n};
+    if (int rc = run_flux(ctx, static_cast<vag_params*>(ctx->io_params.p), n_models, rq,
+                          static_cast<double*>(ctx->io_out.p), static_cast<int32_t*>(ctx->io_status.p), nullptr, nullptr,
+                          nullptr, nullptr, s))
+        return rc;
+    CK(cudaMemcpyAsync(out, ctx->io_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+    if (status) CK(cudaMemcpyAsync(status, ctx->io_status.p, sizeof(int32_t) * n_models, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return VAG_OK;
+}
+
+int vag_chi2_series(vag_context* ctx, const vag_params* params, size_t n_models, const double* t, const double* nu,
+                    const double* lnF_obs, const double* sigma_ln, const double* w, size_t n, double* chi2,
+                    int32_t* status) {
+    if (!lnF_obs || !sigma_ln || !w || !chi2) return fail(VAG_ERR_INVALID, "data arrays must not be NULL");
+    if (int rc = host_prepare(ctx, params, n_models, t, n, nu, n, true)) return rc;
+    if (n_models == 0) return VAG_OK;
+    cudaStream_t s = ctx->stream;
+    CK(ctx->io_out.ensure(sizeof(double) * n_models * VAG_NCOMP * n));
+    CK(ctx->io_aux.ensure(sizeof(double) * (3 * n + n_models)));
+    double* d_lnF = static_cast<double*>(ctx->io_aux.p);
+    double* d_sig = d_lnF + n;
+    double* d_w = d_sig + n;
+    double* d_chi2 = d_w + n;
+    CK(cudaMemcpyAsync(d_lnF, lnF_obs, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_sig, sigma_ln, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_w, w, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+    Request rq{true, static_cast<double*>(ctx->io_t.p), static_cast<double*>(ctx->io_nu.p), n, n};
+    if (int rc = run_flux(ctx, static_cast<vag_params*>(ctx->io_params.p), n_models, rq,
+                          static_cast<double*>(ctx->io_out.p), static_cast<int32_t*>(ctx->io_status.p), d_lnF, d_sig,
+                          d_w, d_chi2, s))
+        return rc;
+    CK(cudaMemcpyAsync(chi2, d_chi2, sizeof(double) * n_models, cudaMemcpyDeviceToHost, s));
+    if (status) CK(cudaMemcpyAsync(status, ctx->io_status.p, sizeof(int32_t) * n_models, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return VAG_OK;
+}
+
+// ---- introspection ---------------------------------------------------------------------------------
+int vag_details(vag_context* ctx, const vag_params* p, double t_min, double t_max, vag_grid_info* info, double* theta,
+                double* phi, int32_t* reps, double* t_rows, double* fwd_shock, double* rvs_shock, int32_t* inj_idx) {
+    if (!ctx || !p) return fail(VAG_ERR_INVALID, "NULL argument");
+    if (int rc = vag_params_validate(p)) return rc;
+    CK(cudaSetDevice(ctx->device));
+    int ct, cp;
+    caps_for(p, 1, ct, cp);
+    ctx->cap_theta = ct;
+    ctx->cap_phi = cp;
+    cudaStream_t s = ctx->stream;
+    CK(ctx->io_params.ensure(sizeof(vag_params)));
+    CK(ctx->io_t.ensure(sizeof(double) * 2));
+    const double tt[2] = {t_min, t_max};
+    CK(cudaMemcpyAsync(ctx->io_params.p, p, sizeof(vag_params), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->io_t.p, tt, sizeof(tt), cudaMemcpyHostToDevice, s));
+    BatchWs w;
+    int totals[TOT_N];
+    long long cells = 0;
+    ctx->launches = 0;
+    if (int rc = run_front(ctx, w, static_cast<vag_params*>(ctx->io_params.p), 1, static_cast<double*>(ctx->io_t.p), 2,
+                           s, totals, &cells))
+        return rc;
+    GridHeader h;
+    int st = 0;
+    CK(cudaMemcpyAsync(&h, w.hdr, sizeof(h), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&st, w.status, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (info) {
+        info->n_phi = h.n_phi;
+        info->n_theta = h.n_theta;
+        info->n_t = h.n_t;
+        info->n_reps = h.n_reps;
+        info->symmetry = h.symmetry;
+        info->phi_mirrored = h.phi_mirrored;
+        info->n_phi_eff = h.n_phi_eff;
+        info->status = st;
+    }
+    const size_t nc = (size_t)h.n_reps * h.n_t;
+    if (theta) CK(cudaMemcpyAsync(theta, w.theta, sizeof(double) * h.n_theta, cudaMemcpyDeviceToHost, s));
+    if (phi) CK(cudaMemcpyAsync(phi, w.phi, sizeof(double) * h.n_phi, cudaMemcpyDeviceToHost, s));
+    if (reps) CK(cudaMemcpyAsync(reps, w.reps, sizeof(int) * h.n_reps, cudaMemcpyDeviceToHost, s));
+    if (t_rows) CK(cudaMemcpyAsync(t_rows, w.t_rows, sizeof(double) * nc, cudaMemcpyDeviceToHost, s));
+    if (inj_idx) CK(cudaMemcpyAsync(inj_idx, w.inj_idx, sizeof(int) * h.n_reps, cudaMemcpyDeviceToHost, s));
+    std::vector<double> th_host(h.n_theta);
+    std::vector<int> reps_host(h.n_reps);
+    CK(cudaMemcpyAsync(th_host.data(), w.theta, sizeof(double) * h.n_theta, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(reps_host.data(), w.reps, sizeof(int) * h.n_reps, cudaMemcpyDeviceToHost, s));
+    auto dump = [&](double* const* pl, double* o) -> int {
+        const int map[7] = {0, 1, -1, 2, 3, 4, 5};
+        for (int a = 0; a < 7; ++a)
+            if (map[a] >= 0) CK(cudaMemcpyAsync(o + (size_t)a * nc, pl[map[a]], sizeof(double) * nc, cudaMemcpyDeviceToHost, s));
+        return VAG_OK;
+    };
+    if (fwd_shock)
+        if (int rc = dump(w.fwd, fwd_shock)) return rc;
+    if (rvs_shock && p->has_rvs)
+        if (int rc = dump(w.rvs, rvs_shock)) return rc;
+    CK(cudaStreamSynchronize(s));
+    auto fill_theta = [&](double* o) {
+        for (int r = 0; r < h.n_reps; ++r)
+            for (int k = 0; k < h.n_t; ++k) o[(2 * (size_t)h.n_reps + r) * h.n_t + k] = th_host[reps_host[r]];
+    };
+    if (fwd_shock) fill_theta(fwd_shock);
+    if (rvs_shock && p->has_rvs) fill_theta(rvs_shock);
+    return VAG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,109 @@
+// vag_common.cuh -- shared scalar definitions of the B200 model-evaluation path.
+//
+// Everything here is FP64 (the reference computes in `using Real = double`, src/util/macros.h:24).
+// The code-unit system and physical constants restate src/util/macros.h:43-107 with the same
+// expression order so the compile-time values are bit-identical to the reference's.
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define VAG_HD __host__ __device__ __forceinline__
+#define VAG_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define VAG_HD inline
+#define VAG_HD_NOINLINE inline
+#endif
+
+namespace vag {
+
+using std::isfinite;
+using std::isinf;
+using std::isnan;
+
+// ---- unit system: src/util/macros.h:43-77 ---------------------------------------------------
+namespace unit {
+constexpr double len = 1.5e13;
+constexpr double cm = 1 / len;
+constexpr double sec = 3e10 / len;
+constexpr double cm2 = cm * cm;
+constexpr double cm3 = cm * cm * cm;
+constexpr double g = 1 / 2e33;
+constexpr double Hz = 1 / sec;
+constexpr double erg = g * cm * cm / sec / sec;
+constexpr double flux_cgs = erg / cm2 / sec;
+constexpr double flux_den_cgs = erg / cm2 / sec / Hz;
+}  // namespace unit
+
+// ---- constants: src/util/macros.h:86-107 ----------------------------------------------------
+namespace con {
+constexpr double c = 1;
+constexpr double c2 = c * c;
+constexpr double mp = 1.67e-24 * unit::g;
+constexpr double me = mp / 1836;
+constexpr double e = 4.8e-10 / 4.472136e16 / 5.809475e19 / unit::sec;
+constexpr double e2 = e * e;
+constexpr double e3 = e2 * e;
+constexpr double pi = 3.14159265358979323846;
+constexpr double sigmaT = 6.65e-25 * unit::cm * unit::cm;
+constexpr double Gamma_cut = 1.0 + 1e-6;        // src/config/simulation-defaults.h:41
+constexpr double gamma_therm_cut = 1.0 + 1e-6;  // :47
+constexpr double sigma_cut = 1e-6;              // :45
+constexpr double sqrt3 = 1.732050807568877293527446341505872367;
+constexpr double ln2 = 0.693147180559945309417232121458176568;
+constexpr double log2e = 1.442695040888963407359924681001892137;
+}  // namespace con
+
+// ---- numeric defaults: src/config/simulation-defaults.h ------------------------------------
+namespace dflt {
+constexpr double phi_resolution = 0.06;
+constexpr double theta_resolution = 0.15;
+constexpr double time_resolution = 6.0;
+constexpr double rvs_theta_resolution = 0.2;
+constexpr double rvs_time_resolution = 10.0;
+constexpr int min_theta_points = 36;
+constexpr double theta_min = 1e-6;
+constexpr double ode_rtol = 1e-6;
+constexpr double dynamics_rtol = 1e-6;
+constexpr double magnetized_rtol_factor = 0.1;
+constexpr double binary_search_eps = 1e-9;
+constexpr int max_ode_steps = 100000;
+constexpr int theta_samples = 200;
+}  // namespace dflt
+
+constexpr double kInf = __builtin_huge_val();
+
+// std::min / std::max / std::clamp semantics (NaN behaviour included: the first argument wins
+// when the comparison is false).
+VAG_HD double vmin(double a, double b) { return (b < a) ? b : a; }
+VAG_HD double vmax(double a, double b) { return (a < b) ? b : a; }
+VAG_HD double vclamp(double v, double lo, double hi) { return (v < lo) ? lo : ((hi < v) ? hi : v); }
+VAG_HD int imin(int a, int b) { return a < b ? a : b; }
+VAG_HD int imax(int a, int b) { return a > b ? a : b; }
+
+// src/util/fast-math.h with AFTERGLOW_FAST_MATH off (the default build, CMakeLists.txt:39):
+// fast_log2/exp2/exp/log are libm calls and fast_pow(a,b) = exp2(b*log2(a)) (fast-math.h:147-149).
+VAG_HD double fast_log2(double x) { return log2(x); }
+VAG_HD double fast_exp2(double x) { return exp2(x); }
+VAG_HD double fast_exp(double x) { return exp(x); }
+VAG_HD double fast_pow(double a, double b) { return exp2(b * log2(a)); }
+
+// src/util/fast-math.h:179-185
+VAG_HD double log2_softplus(double x) {
+    if (x > 20.0) return x;
+    if (x < -20.0) return 0.0;
+    return log2(1.0 + exp2(x));
+}
+// src/util/fast-math.h:199-202
+VAG_HD double log2_broken_power_ratio(double log2_x, double log2_x_break, double s_delta_beta, double s) {
+    return -log2_softplus(s_delta_beta * (log2_x - log2_x_break)) / s;
+}
+
+// src/core/physics.h:36-40, :59-61
+VAG_HD double gamma_to_beta(double gamma) { return sqrt((gamma - 1) * (gamma + 1)) / gamma; }
+VAG_HD double adiabatic_idx(double gamma) { return 4.0 / 3.0 + 1 / (3 * gamma); }
+
+VAG_HD bool vfinite(double x) { return isfinite(x); }
+
+}  // namespace vag

@@ -1,0 +1,155 @@
+// vag_dopri5.cuh -- register-resident Dormand-Prince 5(4) with FSAL, dense output and the step
+// controller of Boost.odeint 1.82 (the integrator the reference instantiates as
+// make_dense_output(rtol, rtol, runge_kutta_dopri5<State>()), src/dynamics/forward-shock.tpp:191,
+// src/dynamics/reverse-shock.tpp:539, src/core/grid-refinement.h:147).
+//
+// Semantics restated from the published algorithm as vendored by the reference:
+//   tableau / stages        external/boost/numeric/odeint/stepper/runge_kutta_dopri5.hpp:92-158
+//   error coefficients      :163-198
+//   dense output            :229-275 (Hairer-Norsett-Wanner I, p.191)
+//   error norm              external/boost/numeric/odeint/stepper/controlled_runge_kutta.hpp:64-90,
+//                           algebra/default_operations.hpp:431-444 (inf-norm, a_x = a_dxdt = 1)
+//   step decrease/increase  controlled_runge_kutta.hpp:114-153 (order 5, error order 4)
+//   do_step retry loop      stepper/dense_output_runge_kutta.hpp:324-345, 500-failure cap from
+//                           integrate/max_step_checker.hpp:84-107
+//
+// Layout: all N-vectors are fixed-size arrays indexed with compile-time-unrolled loops so they
+// live in registers (N = 1 grid CDF, 5 forward shock, 11 forward+reverse shock pair).
+#pragma once
+
+#include "vag_common.cuh"
+
+namespace vag {
+
+template <int N>
+struct Dopri5 {
+    double x[N];     // current state
+    double k1[N];    // derivative at current state (FSAL)
+    double xo[N];    // state at the start of the last accepted step
+    double ko[N];    // derivative at the start of the last accepted step
+    double k3[N], k4[N], k5[N], k6[N];  // stages of the last attempted step
+    double t, t_old, dt;
+    double eps;      // eps_abs = eps_rel
+    bool deriv_ready;
+
+    VAG_HD void initialize(const double* x0, double t0, double dt0, double tol) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = x0[i];
+        t = t0;
+        t_old = t0;
+        dt = dt0;
+        eps = tol;
+        deriv_ready = false;
+    }
+
+    // One accepted step (retrying with smaller dt on rejection).  Returns false when 500
+    // consecutive attempts were rejected (Boost throws std::runtime_error there).
+    template <class Sys>
+    VAG_HD bool do_step(Sys& sys) {
+        if (!deriv_ready) {
+            sys(x, k1, t);
+            deriv_ready = true;
+        }
+        t_old = t;
+        constexpr double a2 = 1.0 / 5, a3 = 3.0 / 10, a4 = 4.0 / 5, a5 = 8.0 / 9;
+        constexpr double b21 = 1.0 / 5;
+        constexpr double b31 = 3.0 / 40, b32 = 9.0 / 40;
+        constexpr double b41 = 44.0 / 45, b42 = -56.0 / 15, b43 = 32.0 / 9;
+        constexpr double b51 = 19372.0 / 6561, b52 = -25360.0 / 2187, b53 = 64448.0 / 6561, b54 = -212.0 / 729;
+        constexpr double b61 = 9017.0 / 3168, b62 = -355.0 / 33, b63 = 46732.0 / 5247, b64 = 49.0 / 176,
+                         b65 = -5103.0 / 18656;
+        constexpr double c1 = 35.0 / 384, c3 = 500.0 / 1113, c4 = 125.0 / 192, c5 = -2187.0 / 6784, c6 = 11.0 / 84;
+        constexpr double dc1 = c1 - 5179.0 / 57600, dc3 = c3 - 7571.0 / 16695, dc4 = c4 - 393.0 / 640,
+                         dc5 = c5 - (-92097.0 / 339200), dc6 = c6 - 187.0 / 2100, dc7 = -1.0 / 40;
+
+        for (int fails = 0;; ) {
+            double xt[N], k2[N], k7[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) xt[i] = 1.0 * x[i] + (dt * b21) * k1[i];
+            sys(xt, k2, t + dt * a2);
+#pragma unroll
+            for (int i = 0; i < N; ++i) xt[i] = 1.0 * x[i] + (dt * b31) * k1[i] + (dt * b32) * k2[i];
+            sys(xt, k3, t + dt * a3);
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+                xt[i] = 1.0 * x[i] + (dt * b41) * k1[i] + (dt * b42) * k2[i] + (dt * b43) * k3[i];
+            sys(xt, k4, t + dt * a4);
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+                xt[i] = 1.0 * x[i] + (dt * b51) * k1[i] + (dt * b52) * k2[i] + (dt * b53) * k3[i] + (dt * b54) * k4[i];
+            sys(xt, k5, t + dt * a5);
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+                xt[i] = 1.0 * x[i] + (dt * b61) * k1[i] + (dt * b62) * k2[i] + (dt * b63) * k3[i] +
+                        (dt * b64) * k4[i] + (dt * b65) * k5[i];
+            sys(xt, k6, t + dt);
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+                xt[i] = 1.0 * x[i] + (dt * c1) * k1[i] + (dt * c3) * k3[i] + (dt * c4) * k4[i] + (dt * c5) * k5[i] +
+                        (dt * c6) * k6[i];
+            sys(xt, k7, t + dt);
+
+            // error estimate and inf-norm of err_i / (eps + eps * (|x_i| + |dt| |k1_i|))
+            double err = 0;
+            const double adt = fabs(dt);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const double e = (dt * dc1) * k1[i] + (dt * dc3) * k3[i] + (dt * dc4) * k4[i] + (dt * dc5) * k5[i] +
+                                 (dt * dc6) * k6[i] + (dt * dc7) * k7[i];
+                const double r = fabs(e) / (eps + eps * (1.0 * fabs(x[i]) + adt * fabs(k1[i])));
+                // boost norm_inf: max over |r| starting from 0 with std::max(init, |r|)
+                err = vmax(err, fabs(r));
+            }
+
+            if (err > 1.0) {
+                dt *= vmax(0.9 * pow(err, -1.0 / 3.0), 0.2);
+                if (++fails >= 500) return false;
+                continue;
+            }
+            // accept
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                xo[i] = x[i];
+                ko[i] = k1[i];
+                x[i] = xt[i];
+                k1[i] = k7[i];
+            }
+            t += dt;
+            if (err < 0.5) {
+                err = vmax(pow(5.0, -5.0), err);
+                dt *= 0.9 * pow(err, -1.0 / 5.0);
+            }
+            return true;
+        }
+    }
+
+    // Dense output at time tq inside the last accepted step [t_old, t].
+    VAG_HD void calc_state(double tq, double* out) const {
+        constexpr double b1 = 35.0 / 384, b3 = 500.0 / 1113, b4 = 125.0 / 192, b5 = -2187.0 / 6784, b6 = 11.0 / 84;
+        const double h = t - t_old;
+        const double th = (tq - t_old) / h;
+        const double X1 = 5.0 * (2558722523.0 - 31403016.0 * th) / 11282082432.0;
+        const double X3 = 100.0 * (882725551.0 - 15701508.0 * th) / 32700410799.0;
+        const double X4 = 25.0 * (443332067.0 - 31403016.0 * th) / 1880347072.0;
+        const double X5 = 32805.0 * (23143187.0 - 3489224.0 * th) / 199316789632.0;
+        const double X6 = 55.0 * (29972135.0 - 7076736.0 * th) / 822651844.0;
+        const double X7 = 10.0 * (7414447.0 - 829305.0 * th) / 29380423.0;
+        const double thm1 = th - 1.0;
+        const double thsq = th * th;
+        const double A = thsq * (3.0 - 2.0 * th);
+        const double B = thsq * thm1;
+        const double C = thsq * thm1 * thm1;
+        const double D = th * thm1 * thm1;
+        const double w1 = h * (A * b1 - C * X1 + D);
+        const double w3 = h * (A * b3 + C * X3);
+        const double w4 = h * (A * b4 - C * X4);
+        const double w5 = h * (A * b5 + C * X5);
+        const double w6 = h * (A * b6 - C * X6);
+        const double w7 = h * (B + C * X7);
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            out[i] = 1.0 * xo[i] + w1 * ko[i] + w3 * k3[i] + w4 * k4[i] + w5 * k5[i] + w6 * k6[i] + w7 * k1[i];
+    }
+};
+
+}  // namespace vag

@@ -1,0 +1,609 @@
+// vag_grid.cuh -- K0: per-parameter-set adaptive (phi, theta, t) grid.
+//
+// Restates auto_grid and its callees (src/core/grid-refinement.h:40-706,
+// src/core/grid-refinement.cpp:140-197, Coord::detect_symmetry src/core/mesh.h:120-185) for the
+// typed jets / isotropic media, i.e. symmetry >= phi_symmetric and no spreading.  One device
+// thread builds one model's grid; all arrays live in a per-model slab of global memory.
+#pragma once
+
+#include "vag_dopri5.cuh"
+#include "vag_model.cuh"
+
+namespace vag {
+
+enum Symmetry : int { SYM_STRUCTURED = 0, SYM_PHI_SYMMETRIC = 1, SYM_PIECEWISE = 2, SYM_ISOTROPIC = 3 };
+
+// Per-model grid header (device resident).
+struct GridHeader {
+    int n_theta, n_phi, n_phi_eff, n_t;
+    int n_reps, symmetry, phi_mirrored, status;
+    int t_num_tot, t_num_base, has_early, is_rvs;
+    double t_end, min_t_start, min_t_early;
+};
+
+// Slab of per-model arrays (capacities fixed per batch by the host).
+struct GridSlab {
+    double* theta;   // [cap_theta]
+    double* phi;     // [cap_phi]
+    int* reps;       // [cap_theta]
+    double* t_dec;   // [cap_theta]  t_dec of each representative row
+    double* work;    // scratch: >= 6*cap_theta + 4*theta_samples + cap_phi
+    int cap_theta, cap_phi;
+};
+
+VAG_HD double structure_weight(double Gamma) {  // grid-refinement.h:11-13
+    return Gamma * sqrt(vmax((Gamma - 1) * Gamma, 0.0));
+}
+
+// xt::linspace(a, b, n)[i] (external/xtensor/generators/xbuilder.hpp:199-222,460-468):
+// a + step*i with the last element forced to b.
+VAG_HD double linspace_at(double a, double b, int n, int i) {
+    const double step = (b - a) / fmax(1.0, (double)(n - 1));
+    if (n > 1 && i == n - 1) return b;
+    return a + step * (double)i;
+}
+
+// ---- find_jet_jumps: grid-refinement.h:40-86 -------------------------------------------------
+VAG_HD int find_jet_jumps(const ModelCfg& m, double gamma_cut, double* jumps, int cap) {
+    constexpr int n_scan = 512;
+    constexpr double eps = dflt::binary_search_eps;
+    const double theta_lo = dflt::theta_min;
+    const double theta_hi = con::pi / 2;
+    const double dtheta = (theta_hi - theta_lo) / (n_scan - 1);
+    if (jet_Gamma0(m, theta_hi) >= gamma_cut) {
+        jumps[0] = theta_hi;
+        return 1;
+    }
+    int n = 0;
+    double prev_th = theta_lo;
+    double prev_G = jet_Gamma0(m, theta_lo);
+    for (int j = 1; j < n_scan; ++j) {
+        const double cur_th = theta_lo + dtheta * (double)j;
+        const double cur_G = jet_Gamma0(m, cur_th);
+        if (prev_G >= gamma_cut || cur_G >= gamma_cut) {
+            const double dG = fabs(cur_G - prev_G);
+            const double scale = vmax(prev_G - 1, cur_G - 1);
+            if (scale > 0 && dG > 0.5 * scale) {
+                double lo = prev_th, hi = cur_th;
+                while (hi - lo > eps) {
+                    const double mid = 0.5 * (lo + hi);
+                    const double G_mid = jet_Gamma0(m, mid);
+                    if (fabs(G_mid - prev_G) < fabs(G_mid - cur_G)) {
+                        lo = mid;
+                    } else {
+                        hi = mid;
+                    }
+                }
+                if (n < cap) jumps[n++] = prev_G > cur_G ? lo : hi;
+            }
+        }
+        prev_th = cur_th;
+        prev_G = cur_G;
+    }
+    return n;
+}
+
+// ---- find_theta_range: grid-refinement.h:88-111 ----------------------------------------------
+VAG_HD void find_theta_range(const ModelCfg& m, double gamma_cut, double& theta_min, double& theta_max) {
+    constexpr int n_scan = 512;
+    const double theta_lo = dflt::theta_min;
+    const double theta_hi = con::pi / 2;
+    theta_max = theta_hi;
+    theta_min = theta_lo;
+    const double step = (theta_hi - theta_lo) / n_scan;
+    for (double th = theta_hi; th >= theta_lo; th -= step) {
+        if (jet_Gamma0(m, th) >= gamma_cut) {
+            theta_max = th;
+            break;
+        }
+    }
+    for (double th = theta_lo; th <= theta_hi; th += step) {
+        if (jet_Gamma0(m, th) >= gamma_cut) {
+            theta_min = th;
+            break;
+        }
+    }
+}
+
+// ---- inverse_CFD_sampling: grid-refinement.h:137-189 -----------------------------------------
+// pdf(x) functor; writes num nodes to x_out.  x_i / cdf_i are scratch of n_samp doubles each.
+template <class Pdf>
+VAG_HD void inverse_cdf_sampling(Pdf& pdf, double lo, double hi, int num, bool log_sample, bool midpoint, double* x_out,
+                                 double* x_i, double* cdf_i) {
+    constexpr int n_samp = dflt::theta_samples;
+    constexpr double rtol = dflt::ode_rtol;
+    if (log_sample) {
+        const double a = log10(lo), b = log10(hi);
+        for (int i = 0; i < n_samp; ++i) x_i[i] = pow(10.0, linspace_at(a, b, n_samp, i));
+    } else {
+        for (int i = 0; i < n_samp; ++i) x_i[i] = linspace_at(lo, hi, n_samp, i);
+    }
+    for (int i = 0; i < n_samp; ++i) cdf_i[i] = 0;
+
+    struct Sys {
+        Pdf& pdf;
+        VAG_HD void operator()(const double* /*x*/, double* dxdt, double t) { dxdt[0] = pdf(t); }
+    } sys{pdf};
+
+    Dopri5<1> st;
+    const double x0 = 0;
+    st.initialize(&x0, lo, (hi - lo) / 1e3, rtol);
+    int k = 1;
+    for (int steps = 0; st.t <= hi;) {
+        if (!st.do_step(sys)) break;
+        if (++steps > dflt::max_ode_steps) break;
+        while (k < n_samp && st.t > x_i[k]) {
+            st.calc_state(x_i[k], &cdf_i[k]);
+            ++k;
+        }
+    }
+    const double c0 = cdf_i[0], c1 = cdf_i[n_samp - 1];
+    int j = 0;
+    for (int q = 0; q < num; ++q) {
+        const double target = midpoint ? (c0 + (c1 - c0) * ((double)q + 0.5) / (double)num) : linspace_at(c0, c1, num, q);
+        // first j with target <= cdf_i[j]; the reference restarts from 0 for every q, which for a
+        // non-decreasing target sequence is equivalent to resuming from the previous hit.
+        while (j < n_samp && !(target <= cdf_i[j])) ++j;
+        double xo = 0;
+        if (j < n_samp) {
+            if (j == 0) {
+                xo = x_i[0];
+            } else {
+                const double denom = cdf_i[j] - cdf_i[j - 1];
+                if (denom > 0) {
+                    const double slope = (x_i[j] - x_i[j - 1]) / denom;
+                    xo = x_i[j - 1] + slope * (target - cdf_i[j - 1]);
+                } else {
+                    xo = x_i[j - 1];
+                }
+            }
+        }
+        x_out[q] = xo;
+    }
+}
+
+// ---- adaptive_theta_grid: grid-refinement.h:199-291 ------------------------------------------
+struct ThetaPdf {
+    const ModelCfg& m;
+    double theta_v, core_weight, view_weight, Gamma_peak_sq, Gamma_v_sq, doppler_alpha, floor_weight;
+    VAG_HD double operator()(double theta) const {
+        const double Gamma = jet_Gamma0(m, theta);
+        const double beta = gamma_to_beta(Gamma);
+        const double doppler = (1 - beta) / (1 - beta * cos(theta - theta_v));
+        const double structure = structure_weight(Gamma);
+        const double dtheta = theta - theta_v;
+        return core_weight * Gamma_peak_sq * theta / (1.0 + Gamma_peak_sq * theta * theta) +
+               view_weight * Gamma_v_sq * fabs(dtheta) / (1.0 + Gamma_v_sq * dtheta * dtheta) +
+               (1 + doppler_alpha * doppler) * structure + floor_weight;
+    }
+};
+
+VAG_HD int adaptive_theta_grid(const ModelCfg& m, double theta_min, double theta_max, int base_pts, double theta_v,
+                               double theta_resol, double* out, int cap, double* scratch) {
+    constexpr double core_beam_coeff = 55.0, view_beam_coeff = 25.0, doppler_alpha0 = 12.0, floor_fraction = 0.25;
+    constexpr int scan_pts = 100;
+    const double theta_extent = theta_max - theta_min;
+    double peak_weight = 0, Gamma_peak = 1.0, struct_sum = 0, Gamma_v = 1.0;
+    int last_bright = 0;
+    for (int i = 0; i <= scan_pts; ++i) {
+        const double theta = theta_min + theta_extent * i / scan_pts;
+        const double Gamma = jet_Gamma0(m, theta);
+        const double w = structure_weight(Gamma);
+        struct_sum += w;
+        if (w > peak_weight) {
+            peak_weight = w;
+            Gamma_peak = Gamma;
+            last_bright = i;
+        } else if (w > 0.01 * peak_weight) {
+            last_bright = i;
+        }
+        const double dth = theta - theta_v;
+        Gamma_v = vmax(Gamma_v, Gamma / sqrt(1.0 + Gamma * Gamma * dth * dth));
+    }
+    const double floor_weight = floor_fraction * peak_weight;
+    const double CDF_est = (struct_sum / scan_pts + floor_weight) * theta_extent;
+    const double theta_bright = theta_min + theta_extent * last_bright / scan_pts;
+
+    Gamma_peak = vmax(Gamma_peak, Gamma_v);
+    const double doppler_alpha = doppler_alpha0 * sqrt(peak_weight / vmax(structure_weight(Gamma_v), 1.0));
+
+    const double Gamma_peak_sq = Gamma_peak * Gamma_peak;
+    const double Gamma_v_sq = Gamma_v * Gamma_v;
+    // compute_beam_pts(log_decades, coeff, offset) = size_t(max(0, log_decades - offset) * resol * coeff)
+    const long long core_beam_pts = (long long)(vmax(0.0, log10(vmax(1.0, Gamma_peak * (theta_bright - theta_min))) - 1.0) *
+                                                theta_resol * core_beam_coeff);
+    const long long view_beam_pts =
+        (theta_v * Gamma_peak > 3.0)
+            ? (long long)(vmax(0.0, log10(vmax(1.0, Gamma_v * vmax(theta_v - theta_min, theta_max - theta_v))) - 0.0) *
+                          theta_resol * view_beam_coeff)
+            : 0;
+    const long long total_pts = base_pts + core_beam_pts + view_beam_pts;
+    if (total_pts > cap) return -(int)total_pts;
+
+    auto calibrate = [&](long long n_pts, double beam_cdf) -> double {
+        return (n_pts > 0 && beam_cdf > 0) ? (double)n_pts / base_pts * CDF_est / beam_cdf : 0.0;
+    };
+    const double core_weight = calibrate(core_beam_pts, 0.5 * log((1.0 + Gamma_peak_sq * theta_max * theta_max) /
+                                                                  (1.0 + Gamma_peak_sq * theta_min * theta_min)));
+    const double theta_v_left = theta_v - theta_min;
+    const double theta_v_right = theta_max - theta_v;
+    const double view_weight = calibrate(view_beam_pts, 0.5 * (log(1.0 + Gamma_v_sq * theta_v_left * theta_v_left) +
+                                                              log(1.0 + Gamma_v_sq * theta_v_right * theta_v_right)));
+
+    ThetaPdf pdf{m, theta_v, core_weight, view_weight, Gamma_peak_sq, Gamma_v_sq, doppler_alpha, floor_weight};
+    inverse_cdf_sampling(pdf, theta_min, theta_max, (int)total_pts, /*log=*/true, /*midpoint=*/false, out, scratch,
+                         scratch + dflt::theta_samples);
+    return (int)total_pts;
+}
+
+// ---- jump_refinement_grid (grid-refinement.cpp:140-164) + merge_grids (grid-refinement.h:362-393)
+VAG_HD int jump_refinement_grid(const double* jumps, int n_jumps, double theta_min, double theta_max,
+                                double avg_spacing, double* pts) {
+    int n = 0;
+    const double tight = avg_spacing / 8;
+    for (int idx = 0; idx < n_jumps; ++idx) {
+        const double jt = jumps[idx];
+        if (jt >= con::pi / 2 - 0.01) continue;
+        if (jt - tight >= theta_min) pts[n++] = jt - tight;
+        if (jt + tight <= theta_max) pts[n++] = jt + tight;
+        if (jt >= theta_min && jt <= theta_max) pts[n++] = jt;
+    }
+    // sort + unique (tiny n: insertion sort)
+    for (int i = 1; i < n; ++i) {
+        const double v = pts[i];
+        int j = i - 1;
+        while (j >= 0 && pts[j] > v) {
+            pts[j + 1] = pts[j];
+            --j;
+        }
+        pts[j + 1] = v;
+    }
+    int u = 0;
+    for (int i = 0; i < n; ++i)
+        if (u == 0 || pts[u - 1] != pts[i]) pts[u++] = pts[i];
+    return u;
+}
+
+VAG_HD int merge_grids(const double* a, int na, const double* b, int nb, double* out, int cap) {
+    int n = 0, i = 0, j = 0;
+    double last = 0;
+    auto add_unique = [&](double v) {
+        if (n == 0 || last != v) {
+            if (n < cap) out[n] = v;
+            last = v;
+            ++n;
+        }
+    };
+    while (i < na && j < nb) {
+        if (a[i] <= b[j]) {
+            add_unique(a[i++]);
+            if (a[i - 1] == b[j]) j++;
+        } else {
+            add_unique(b[j++]);
+        }
+    }
+    while (i < na) add_unique(a[i++]);
+    while (j < nb) add_unique(b[j++]);
+    return n;
+}
+
+// ---- adaptive_phi_grid: grid-refinement.h:295-360 --------------------------------------------
+// Per-theta invariants (beta, structure weight, cos/sin theta, dcos) are hoisted out of the
+// pdf: every typed jet is phi-independent, so the hoisted values are the ones the reference
+// recomputes inside phi_weight on every call.
+VAG_HD int adaptive_phi_grid(const ModelCfg& m, int phi_num, double theta_v, const double* theta, int n_theta,
+                             bool is_axisymmetric, double phi_max, double self_boost_cap, double* out, int cap,
+                             double* scratch) {
+    if (theta_v == 0 && is_axisymmetric) {
+        if (phi_num > cap) return -phi_num;
+        for (int i = 0; i < phi_num; ++i) out[i] = linspace_at(0., 2 * con::pi, phi_num, i);
+        return phi_num;
+    }
+    const bool half_range = phi_max < 2 * con::pi;
+    double* beta = scratch;
+    double* sw = beta + n_theta;
+    double* ct = sw + n_theta;
+    double* st = ct + n_theta;
+    double* dcos_arr = st + n_theta;
+    double* samp = dcos_arr + n_theta;  // 2 * theta_samples
+    for (int it = 0; it < n_theta; ++it) {
+        const double left = (it == 0) ? 0.0 : 0.5 * (theta[it - 1] + theta[it]);
+        const double right = (it == n_theta - 1) ? theta[it] : 0.5 * (theta[it] + theta[it + 1]);
+        dcos_arr[it] = fabs(cos(left) - cos(right));
+        const double Gamma = jet_Gamma0(m, theta[it]);
+        beta[it] = gamma_to_beta(Gamma);
+        sw[it] = structure_weight(Gamma);
+        ct[it] = cos(theta[it]);
+        st[it] = sin(theta[it]);
+    }
+
+    struct Pdf2 {
+        const double *beta, *sw, *dcos, *ct, *st;
+        int n_theta;
+        double cos_tv, sin_tv, floor_weight;
+        VAG_HD double weight(double phi) const {
+            const double cos_phi = cos(phi);
+            double w = 0;
+            for (int it = 0; it < n_theta; ++it) {
+                const double cos_alpha = ct[it] * cos_tv + st[it] * sin_tv * cos_phi;
+                const double a = (1 - beta[it]) / (1 - beta[it] * cos_alpha);
+                w += a * sw[it] * dcos[it];
+            }
+            return w;
+        }
+        VAG_HD double operator()(double phi) const { return weight(phi) + floor_weight; }
+    } pdf{beta, sw, dcos_arr, ct, st, n_theta, cos(theta_v), sin(theta_v), 0.0};
+
+    constexpr int scan_pts = 100;
+    double peak_weight = 0, sum_weight = 0;
+    for (int s = 0; s <= scan_pts; ++s) {
+        const double phi = phi_max * (double)s / scan_pts;
+        const double w = pdf.weight(phi);
+        peak_weight = vmax(peak_weight, w);
+        sum_weight += w;
+    }
+    const double floor_weight = 0.05 * peak_weight;
+    if (self_boost_cap > 0 && peak_weight > 0) {
+        const double mean_pdf = sum_weight / (scan_pts + 1) + floor_weight;
+        const double concentration = (peak_weight + floor_weight) / mean_pdf;
+        const double boost = vclamp(concentration / 5, 1.0, self_boost_cap);
+        phi_num = (int)(long long)((double)phi_num * boost);
+    }
+    if (phi_num > cap) return -phi_num;
+    pdf.floor_weight = floor_weight;
+    inverse_cdf_sampling(pdf, 0, phi_max, phi_num, /*log=*/false, /*midpoint=*/half_range, out, samp,
+                         samp + dflt::theta_samples);
+    return phi_num;
+}
+
+// ---- estimate_t_dec: grid-refinement.h:401-453 -----------------------------------------------
+VAG_HD double estimate_t_dec(const ModelCfg& m, double theta) {
+    const double gamma = jet_Gamma0(m, theta);
+    const double beta = gamma_to_beta(gamma);
+    const double m_jet = jet_eps_k(m, theta) / (gamma * con::c2);
+    const double target = m_jet / gamma;
+    constexpr double r_min = 1e-3;
+    const double r_max = r_min * pow(10.0, 40.0);
+    if (target <= 0) return r_min * (1 - beta) / (beta * con::c);
+
+    if (m.medium_type == VAG_MEDIUM_ISM) {
+        const double rho = m.rho_ism;
+        if (rho > 0) {
+            const double r3_dec = r_min * r_min * r_min + 3 * target / rho;
+            const double r_dec = cbrt(vmax(r3_dec, 0.0));
+            return vmin(r_dec, r_max) * (1 - beta) / (beta * con::c);
+        }
+        return r_max * (1 - beta) / (beta * con::c);
+    }
+    constexpr int N = 256;
+    const double u_min = log(1e-3);
+    const double u_max = u_min + 40 * log(10.0);
+    const double du = (u_max - u_min) / N;
+    double mass = 0;
+    double r_prev = exp(u_min);
+    double f_prev = medium_rho(m, r_prev) * r_prev * r_prev;
+    for (int i = 1; i <= N; ++i) {
+        const double r_i = exp(u_min + i * du);
+        const double f_i = medium_rho(m, r_i) * r_i * r_i;
+        const double dr = r_i - r_prev;
+        mass += 0.5 * (f_prev + f_i) * dr;
+        if (mass >= target) {
+            const double r_dec = r_prev + (target - (mass - 0.5 * (f_prev + f_i) * dr)) / f_i;
+            return r_dec * (1 - beta) / (beta * con::c);
+        }
+        f_prev = f_i;
+        r_prev = r_i;
+    }
+    return exp(u_max) * (1 - beta) / (beta * con::c);
+}
+
+// ---- time lattice: grid-refinement.h:516-581, grid-refinement.cpp:166-197 ---------------------
+VAG_HD double logspace_at(double la, double lb, int n, int i) { return pow(10.0, linspace_at(la, lb, n, i)); }
+
+// logspace_with_band_refinement(ts, t_end, b_lo, b_hi, n, factor) -> grid[n]
+VAG_HD void logspace_with_band_refinement(double ts, double t_end, double b_lo, double b_hi, int n, double factor,
+                                          double* grid) {
+    b_lo = vmax(b_lo, ts);
+    b_hi = vmin(b_hi, t_end);
+    if (!(b_hi > b_lo) || n < 8) {
+        const double la = log10(ts), lb = log10(t_end);
+        for (int i = 0; i < n; ++i) grid[i] = logspace_at(la, lb, n, i);
+        return;
+    }
+    const double l0 = log10(ts), l1 = log10(b_lo), l2 = log10(b_hi), l3 = log10(t_end);
+    const double w1 = l1 - l0, w2 = factor * (l2 - l1), w3 = l3 - l2;
+    const long long segs = n - 1;
+    long long n1 = (long long)round((double)segs * w1 / (w1 + w2 + w3));
+    long long n3 = (long long)round((double)segs * w3 / (w1 + w2 + w3));
+    n1 = n1 < segs - 2 ? n1 : segs - 2;
+    n3 = n3 < segs - 1 - n1 - 1 ? n3 : segs - 1 - n1 - 1;
+    const long long n2 = segs - n1 - n3;
+    int idx = 0;
+    for (long long k = 0; k < n1; ++k) grid[idx++] = pow(10.0, l0 + (l1 - l0) * (double)k / (double)n1);
+    for (long long k = 0; k < n2; ++k) grid[idx++] = pow(10.0, l1 + (l2 - l1) * (double)k / (double)n2);
+    for (long long k = 0; k <= n3; ++k)
+        grid[idx++] = pow(10.0, (n3 > 0) ? l2 + (l3 - l2) * (double)k / (double)n3 : l3);
+}
+
+// logspace_with_cross_refinement(t_start, t_end, t_refine, t_num, base_t_num) -> grid[t_num]
+VAG_HD void logspace_with_cross_refinement(double t_start, double t_end, double t_refine, int t_num, int base_t_num,
+                                           double* grid) {
+    t_refine = vclamp(t_refine, t_start, t_end);
+    if (t_refine <= t_start || t_refine >= t_end) {
+        const double la = log10(t_start), lb = log10(t_end);
+        for (int i = 0; i < t_num; ++i) grid[i] = logspace_at(la, lb, t_num, i);
+        return;
+    }
+    const double log_total = log10(t_end / t_start);
+    const double log_after = log10(t_end / t_refine);
+    long long n_post = (long long)((double)base_t_num * log_after / log_total);
+    if (n_post < 2) n_post = 2;
+    if (n_post >= t_num) n_post = t_num / 2;
+    const long long n_pre = t_num + 1 - n_post;
+    for (int i = 0; i < t_num; ++i) grid[i] = 0;
+    int idx = 0;
+    {
+        const double la = log10(t_start), lb = log10(t_refine);
+        for (long long k = 0; k < n_pre; ++k) grid[idx++] = logspace_at(la, lb, (int)n_pre, (int)k);
+    }
+    {
+        const double la = log10(t_refine), lb = log10(t_end);
+        for (long long k = 1; k < n_post && idx < t_num; ++k) grid[idx++] = logspace_at(la, lb, (int)n_post, (int)k);
+    }
+}
+
+// Lattice of one representative row: make_time_grid + store_time_grid (grid-refinement.h:571-591)
+VAG_HD void build_row_lattice(const GridHeader& h, double t_dec, double T0, double* t_row) {
+    double* grid = t_row + (h.has_early ? 1 : 0);
+    if (h.is_rvs) {
+        const double t_cross_limit = vmax(t_dec, T0);
+        logspace_with_cross_refinement(h.min_t_start, h.t_end, 10 * t_cross_limit, h.t_num_tot, h.t_num_base, grid);
+    } else {
+        logspace_with_band_refinement(h.min_t_start, h.t_end, t_dec / 3, 3 * t_dec, h.t_num_tot, 3.0, grid);
+    }
+    if (h.has_early) t_row[0] = h.min_t_early;
+}
+
+// ---- auto_grid: grid-refinement.h:638-706 (axisymmetric, typed jets) --------------------------
+VAG_HD void build_grid(const ModelCfg& m, double t_obs_min, double t_obs_max, GridHeader& h, GridSlab& s) {
+    h.status = 0;
+    h.is_rvs = m.has_rvs ? 1 : 0;
+    const double theta_view = m.theta_v;
+    const double theta_cut = con::pi / 2;
+
+    double jumps[8];
+    const int n_jumps = find_jet_jumps(m, con::Gamma_cut, jumps, 8);
+    double inner_edge, outer_edge;
+    find_theta_range(m, con::Gamma_cut, inner_edge, outer_edge);
+    for (int i = 0; i < n_jumps; ++i) outer_edge = vmax(outer_edge, jumps[i]);
+    const double theta_min = vmax(dflt::theta_min, inner_edge);
+    const double theta_max = vmin(outer_edge, theta_cut);
+
+    const int theta_num =
+        dflt::min_theta_points + (int)(long long)((theta_max - theta_min) * 180 / con::pi * m.theta_resol);
+
+    double* base_theta = s.work;                      // cap_theta
+    double* scratch = s.work + s.cap_theta;           // >= 5*cap_theta + 4*samples
+    const int n_base = adaptive_theta_grid(m, theta_min, theta_max, theta_num, theta_view, m.theta_resol, base_theta,
+                                           s.cap_theta, scratch);
+    if (n_base < 0) {
+        h.status |= VAG_ST_CAPACITY;
+        h.n_theta = h.n_phi = h.n_phi_eff = h.n_t = h.n_reps = 0;
+        return;
+    }
+    const double avg_spacing = (theta_max - theta_min) / n_base;
+    double feat[24];
+    const int n_feat = jump_refinement_grid(jumps, n_jumps, theta_min, theta_max, avg_spacing, feat);
+    const int n_theta = merge_grids(base_theta, n_base, feat, n_feat, s.theta, s.cap_theta);
+    if (n_theta > s.cap_theta) {
+        h.status |= VAG_ST_CAPACITY;
+        h.n_theta = h.n_phi = h.n_phi_eff = h.n_t = h.n_reps = 0;
+        return;
+    }
+    h.n_theta = n_theta;
+
+    // phi grid (grid-refinement.h:664-693); is_axisymmetric = true on this path
+    const long long phi_base_ll = (long long)(360 * m.phi_resol);
+    const int phi_base = (int)(phi_base_ll > 1 ? phi_base_ll : 1);
+    const bool mirror_phi = theta_view != 0 && phi_base > 4;
+    int n_phi;
+    if (mirror_phi) {
+        const int n_half = (phi_base + 1) / 2;
+        n_phi = adaptive_phi_grid(m, n_half, theta_view, s.theta, n_theta, true, con::pi, 5.0, s.phi, s.cap_phi, scratch);
+        h.phi_mirrored = 1;
+    } else {
+        const double doppler_sharpness = jet_Gamma0(m, theta_view) * sin(theta_view);
+        const double phi_boost = sqrt(vmax(doppler_sharpness / (2 * con::pi), 1.0));
+        long long phi_num = (long long)(phi_base * phi_boost);
+        if (phi_num < 1) phi_num = 1;
+        if (phi_num > (long long)phi_base * 5) phi_num = (long long)phi_base * 5;
+        if (phi_num <= 2) {
+            n_phi = (int)phi_num;
+            if (n_phi <= s.cap_phi)
+                for (int i = 0; i < n_phi; ++i) s.phi[i] = linspace_at(0., 2 * con::pi, n_phi, i);
+            else
+                n_phi = -n_phi;
+        } else {
+            n_phi = adaptive_phi_grid(m, (int)phi_num, theta_view, s.theta, n_theta, true, 2 * con::pi, 0.0, s.phi,
+                                      s.cap_phi, scratch);
+        }
+        if (n_phi >= 2) {
+            const double shift = 0.5 * (s.phi[1] - s.phi[0]);
+            for (int i = 0; i < n_phi; ++i) s.phi[i] += shift;
+        }
+        h.phi_mirrored = 0;
+    }
+    if (n_phi < 0) {
+        h.status |= VAG_ST_CAPACITY;
+        h.n_theta = h.n_phi = h.n_phi_eff = h.n_t = h.n_reps = 0;
+        return;
+    }
+    h.n_phi = n_phi;
+    // Observer::build_time_grid (src/core/observer.cpp:211-222): axisymmetric shock tables have
+    // phi extent 1 (jet_3d = 0), so an on-axis observer needs a single phi sample.
+    h.n_phi_eff = (theta_view == 0) ? 1 : n_phi;
+
+    // detect_symmetry (mesh.h:120-185): non-spreading jet in an isotropic medium
+    int n_reps = 0;
+    s.reps[n_reps++] = 0;
+    {
+        double e_prev = jet_eps_k(m, s.theta[0]);
+        double g_prev = jet_Gamma0(m, s.theta[0]);
+        for (int j = 1; j < n_theta; ++j) {
+            const double e_cur = jet_eps_k(m, s.theta[j]);
+            const double g_cur = jet_Gamma0(m, s.theta[j]);
+            if (e_prev != e_cur || g_prev != g_cur) s.reps[n_reps++] = j;
+            e_prev = e_cur;
+            g_prev = g_cur;
+        }
+    }
+    h.n_reps = n_reps;
+    h.symmetry = (n_reps == 1) ? SYM_ISOTROPIC : (n_reps < n_theta ? SYM_PIECEWISE : SYM_PHI_SYMMETRIC);
+
+    // build_time_grid (grid-refinement.h:593-636) with phi_size = 1
+    const double t_end = 1.01 * t_obs_max / (1 + m.z);
+    const double cos_tv = cos(theta_view), sin_tv = sin(theta_view);
+    const double cos_phi0 = cos(s.phi[0]);
+    double min_raw = t_end, min_guarded = t_end, min_cut = t_end, max_ref = 0;
+    {
+        // scan_time_bounds (grid-refinement.h:471-514); t_dec only depends on (eps_k, Gamma0), so
+        // it is evaluated once per representative group and reused inside the group.
+        int r = 0;
+        double td = 0;
+        for (int j = 0; j < n_theta; ++j) {
+            const double th = s.theta[j];
+            const double b = gamma_to_beta(jet_Gamma0(m, th));
+            const double cos_a = cos(th) * cos_tv + sin(th) * sin_tv * cos_phi0;
+            const double ts = 0.99 * t_obs_min * (1 - b) / (1 - cos_a * b) / (1 + m.z);
+            if (r < n_reps && s.reps[r] == j) {
+                td = estimate_t_dec(m, th);
+                s.t_dec[r] = td;
+                ++r;
+            }
+            double cut = vmin(0.01 * td, 1e-2 * unit::sec);
+            if (h.is_rvs) {
+                cut = vmin(cut, 0.01 * m.T0);
+                max_ref = vmax(max_ref, 10.0 * vmax(td, m.T0));
+            }
+            min_raw = vmin(min_raw, ts);
+            min_guarded = vmin(min_guarded, vmax(ts, cut));
+            min_cut = vmin(min_cut, cut);
+        }
+    }
+    h.min_t_early = min_raw;
+    h.min_t_start = min_guarded;
+    h.has_early = (min_raw < min_cut) ? 1 : 0;
+    h.t_end = t_end;
+    // compute_time_grid_size (grid-refinement.h:516-528)
+    const long long t_num_base = (long long)(vmax(log10(t_end / min_guarded), 1.0) * m.t_resol);
+    long long extra = 0;
+    if (h.is_rvs && max_ref > min_guarded) {
+        const double log_pre_span = log10(vmin(max_ref, t_end) / min_guarded);
+        extra = (long long)((2.0 - 1.0) * log_pre_span * m.t_resol);
+    }
+    h.t_num_base = (int)t_num_base;
+    h.t_num_tot = (int)(t_num_base + extra);
+    h.n_t = h.t_num_tot + h.has_early;
+}
+
+}  // namespace vag

@@ -1,0 +1,130 @@
+// vag_model.cuh -- one parameter set in code units + the typed jet / medium profiles.
+//
+// Restates (from scratch) the unit conversions of the reference's Python-facing factories
+// (pybind/pymodel.cpp:47-186, pybind/pymodel.h:190-204,613-649) and the inline profile classes
+// TophatJet / GaussianJet / PowerLawJet (src/environment/jet.h:84-257) and ISM / Wind
+// (src/environment/medium.h:50-140) as one POD evaluated by enumerated type on the device.
+#pragma once
+
+#include "../../include/vag.h"
+#include "vag_common.cuh"
+
+namespace vag {
+
+struct RadCfg {
+    double eps_e, eps_B, p, xi_e;
+    int ssc, kn;
+    int radiative;
+    // RadiativeEfficiency precomputed coefficients (src/dynamics/shock-physics.h:251-261)
+    double gamma_m_coeff, gamma_c_coeff, eps_e_rad;
+};
+
+struct ModelCfg {
+    // jet
+    int jet_type;
+    double theta_c, eps_k0, Gamma0, k_e, k_g, gauss_norm, T0;
+    // medium
+    int medium_type;
+    double rho_ism, wind_A, wind_r02;
+    // observer
+    double lumi_dist, z, theta_v;
+    // radiation
+    RadCfg fwd, rvs;
+    int has_rvs;
+    // numerics
+    double phi_resol, theta_resol, t_resol, rtol;
+};
+
+VAG_HD RadCfg make_rad(const vag_radiation& r, int radiative) {
+    RadCfg c;
+    c.eps_e = r.eps_e;
+    c.eps_B = r.eps_B;
+    c.p = r.p;
+    c.xi_e = r.xi_e;
+    c.ssc = r.ssc;
+    c.kn = r.kn;
+    c.radiative = radiative;
+    c.gamma_m_coeff = (r.p - 2) / (r.p - 1) * r.eps_e * con::mp / con::me / r.xi_e;
+    c.gamma_c_coeff = 6 * con::pi * con::me * con::c / con::sigmaT / (8 * con::pi * r.eps_B);
+    c.eps_e_rad = radiative ? r.eps_e : 0;
+    return c;
+}
+
+VAG_HD ModelCfg make_cfg(const vag_params& p) {
+    ModelCfg m;
+    m.jet_type = p.jet_type;
+    m.theta_c = p.theta_c;
+    m.eps_k0 = (p.E_iso * unit::erg) / (4 * con::pi);  // jet.h:97,142,205
+    m.Gamma0 = p.Gamma0;
+    m.k_e = p.k_e;
+    m.k_g = p.k_g;
+    m.gauss_norm = -1 / (2 * p.theta_c * p.theta_c);  // jet.h:141
+    m.T0 = p.duration * unit::sec;
+    m.medium_type = p.medium_type;
+    const double n_ism = p.n_ism / unit::cm3;
+    m.rho_ism = n_ism * con::mp;  // medium.h:52,98
+    m.wind_A = 0;
+    m.wind_r02 = 0;
+    if (p.medium_type == VAG_MEDIUM_WIND) {
+        m.wind_A = p.A_star * 5e11 * unit::g / unit::cm;           // medium.h:98
+        m.wind_r02 = m.wind_A / ((p.n0 / unit::cm3) * 1.3 * con::mp);  // 0 when n0 = inf
+    }
+    m.lumi_dist = p.lumi_dist * unit::cm;
+    m.z = p.z;
+    m.theta_v = p.theta_obs;
+    m.fwd = make_rad(p.fwd, p.radiative_fireball);
+    m.rvs = make_rad(p.rvs, p.radiative_fireball);
+    m.has_rvs = p.has_rvs;
+    const bool r = p.has_rvs != 0;
+    m.phi_resol = p.phi_resol > 0 ? p.phi_resol : dflt::phi_resolution;
+    m.theta_resol = p.theta_resol > 0 ? p.theta_resol : (r ? dflt::rvs_theta_resolution : dflt::theta_resolution);
+    m.t_resol = p.t_resol > 0 ? p.t_resol : (r ? dflt::rvs_time_resolution : dflt::time_resolution);
+    m.rtol = p.rtol > 0 ? p.rtol : dflt::dynamics_rtol;
+    return m;
+}
+
+// ---- jet profiles (phi-independent for every typed variant) --------------------------------
+VAG_HD double jet_Gamma0(const ModelCfg& m, double theta) {
+    switch (m.jet_type) {
+        case VAG_JET_TOPHAT:
+            return theta < m.theta_c ? m.Gamma0 : 1;  // jet.h:116
+        case VAG_JET_GAUSSIAN:
+            return (m.Gamma0 - 1) * fast_exp(theta * theta * m.gauss_norm) + 1;  // jet.h:175-177
+        default:
+            return (m.Gamma0 - 1) / (1 + fast_pow(theta / m.theta_c, m.k_g)) + 1;  // jet.h:243-245
+    }
+}
+
+VAG_HD double jet_eps_k(const ModelCfg& m, double theta) {
+    switch (m.jet_type) {
+        case VAG_JET_TOPHAT:
+            return theta < m.theta_c ? m.eps_k0 : 0;  // jet.h:107
+        case VAG_JET_GAUSSIAN:
+            return m.eps_k0 * fast_exp(theta * theta * m.gauss_norm);  // jet.h:164-166
+        default:
+            return m.eps_k0 / (1 + fast_pow(theta / m.theta_c, m.k_e));  // jet.h:232-234
+    }
+}
+
+// ---- medium profiles (isotropic) ------------------------------------------------------------
+VAG_HD double medium_rho(const ModelCfg& m, double r) {
+    if (m.medium_type == VAG_MEDIUM_ISM) return m.rho_ism;  // medium.h:58
+    return m.wind_A / (m.wind_r02 + r * r) + m.rho_ism;     // medium.h:107-109
+}
+
+// analytic enclosed mass per solid angle: ISM medium.h:61, Wind medium.h:115-127
+VAG_HD double medium_mass(const ModelCfg& m, double r) {
+    if (m.medium_type == VAG_MEDIUM_ISM) return m.rho_ism * r * r * r / 3.0;
+    double mass = m.rho_ism * r * r * r / 3.0;
+    if (m.wind_A != 0) {
+        if (m.wind_r02 > 0) {
+            const double a = sqrt(m.wind_r02);
+            mass += m.wind_A * (r - a * atan(r / a));
+        } else {
+            mass += m.wind_A * r;
+        }
+    }
+    return mass;
+}
+
+}  // namespace vag

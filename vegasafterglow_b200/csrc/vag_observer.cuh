@@ -1,0 +1,281 @@
+// vag_observer.cuh -- K3: equal-arrival-time-surface flux integration for one model.
+//
+// Restates Observer::observe for non-spreading axisymmetric jets (calc_eat_non_spreading +
+// finalize_log_grids, src/core/observer.cpp:143-205,439-454; compute_dphi :17-37) fused with
+// Observer::specific_flux (src/core/observer.h:355-445, grid form) and specific_flux_series
+// (:447-538, series form).  The reference materialises lg2_t / lg2_doppler / lg2_geom_factor for
+// every (phi,theta,t) cell and a broadcast photon object per cell; here the EAT geometry is
+// recomputed on the fly per row from the UNIQUE shock rows, staged in shared memory together with
+// the per-node log2-luminosities, and never written to HBM.
+//
+// The work of one CTA is expressed as barrier-separated phases, each an HD function of the
+// thread index, so the same code runs as a CUDA block (vag_kernels.cu) and as a sequential
+// host emulation in the CPU test-suite (tests/hostemu).
+#pragma once
+
+#include "vag_grid.cuh"
+#include "vag_radiation.cuh"
+
+namespace vag {
+
+constexpr int EATS_NU_TILE = 8;     // frequencies handled per pass in grid mode
+constexpr int EATS_ROW_CHUNK = 8;   // max (phi,theta) rows staged per pass
+
+// Everything the EATS stage needs about one model (device pointers into the batch workspace).
+struct EatsModel {
+    const GridHeader* h;
+    const double* theta;     // [n_theta]
+    const double* phi;       // [n_phi]
+    const int* rep_of;       // [n_theta] -> index of the representative row of theta_j
+    const double* t_rows;    // [n_reps][n_t] engine-frame lattice
+    const double* r;         // [n_reps][n_t]
+    const double* Gamma;     // [n_reps][n_t]
+    const double* coef;      // [PH_NCOEF][n_reps][n_t]  photon coefficients (SoA)
+    long coef_stride;        // distance between coefficient planes (= total cells of the batch)
+    double smooth_thick, log2_x_far;
+    double one_plus_z, lumi_dist, theta_v;
+};
+
+// compute_dphi: src/core/observer.cpp:17-37
+VAG_HD double compute_dphi(const GridHeader& h, const double* phi, int i) {
+    const int n = h.n_phi_eff;
+    if (n == 1) return 2 * con::pi;
+    const int last = n - 1;
+    if (h.phi_mirrored) {
+        const double left = (i > 0) ? 0.5 * (phi[i - 1] + phi[i]) : 0.0;
+        const double right = (i < last) ? 0.5 * (phi[i] + phi[i + 1]) : con::pi;
+        return 2 * (right - left);
+    }
+    return 0.5 * (phi[imin(i + 1, last)] - phi[i > 0 ? i - 1 : 0]);
+}
+
+// Row constants of calc_eat_non_spreading (observer.cpp:167-192): t_coeff and log2(dOmega)
+struct RowGeom {
+    double cos_v, t_coeff, lg2_dOmega;
+    int rep;  // representative row index
+};
+
+VAG_HD RowGeom row_geometry(const EatsModel& M, int i, int j) {
+    const GridHeader& h = *M.h;
+    const double cos_obs = cos(M.theta_v), sin_obs = sin(M.theta_v);
+    const double cos_phi = cos(M.phi[i] - 0.0);  // coord.phi_view is never set by auto_grid: 0
+    const double th = M.theta[j];
+    const double ct = cos(th), st = sin(th);
+    RowGeom g;
+    g.cos_v = st * cos_phi * sin_obs + ct * cos_obs;
+    g.t_coeff = (1 - g.cos_v) / con::c * M.one_plus_z;
+    const int last = h.n_theta - 1;
+    const double cos_th_lo = (j == 0) ? ct : cos(0.5 * (M.theta[j - 1] + th));
+    const double cos_th_hi = (j == last) ? ct : cos(0.5 * (th + M.theta[j + 1]));
+    const double dOmega = fabs((cos_th_hi - cos_th_lo) * compute_dphi(h, M.phi, i));
+    g.lg2_dOmega = log2(dOmega);
+    g.rep = M.rep_of[j];
+    return g;
+}
+
+// Linear observer time of node k of a row (observer.cpp:201)
+VAG_HD double node_time(const EatsModel& M, const RowGeom& g, int n_t, int k) {
+    const long o = (long)g.rep * n_t + k;
+    return M.t_rows[o] * M.one_plus_z + g.t_coeff * M.r[o];
+}
+
+// log2 grids of one node: finalize_log_grids (observer.cpp:439-454) on the pre-logged geometry path
+VAG_HD void node_logs(const EatsModel& M, const RowGeom& g, int n_t, int k, double& lg2_t, double& lg2_dop,
+                      double& lg2_geom) {
+    const long o = (long)g.rep * n_t + k;
+    const double gamma_ = M.Gamma[o];
+    const double r = M.r[o];
+    const double dop_lin = gamma_ - sqrt((gamma_ - 1) * (gamma_ + 1)) * g.cos_v;
+    const double time = M.t_rows[o] * M.one_plus_z + g.t_coeff * r;
+    lg2_dop = -log2(dop_lin);
+    lg2_t = log2(time);
+    lg2_geom = (g.lg2_dOmega + 2.0 * log2(r)) + 3.0 * lg2_dop;
+}
+
+VAG_HD double cell_log2_I_nu(const EatsModel& M, int rep, int n_t, int k, double log2_nu) {
+    const double* base = M.coef + (long)rep * n_t + k;
+    const long stride = M.coef_stride;
+    return photon_log2_I_nu([&](int c) { return base[c * stride]; }, M.smooth_thick, M.log2_x_far, log2_nu);
+}
+
+// Interval lookup on a row's log2 observer-time lattice.
+//   grid form   (iterate_to,      observer.h:309-313,405-433): t_row[k] <= x <  t_row[k+1]
+//   series form (iterate_through, observer.h:316-320,494):     t_row[k] <  x <= t_row[k+1], x == t_row[0] -> k = 0
+// Returns -1 when the row does not contribute to x.
+VAG_HD int find_interval(const double* t_row, int n_t, double x, bool series) {
+    if (!(x >= t_row[0])) return -1;
+    int lo = 0, hi = n_t;  // count nodes (strictly) below / not above x
+    if (series) {
+        while (lo < hi) {  // cnt = #nodes < x
+            const int mid = (lo + hi) >> 1;
+            if (t_row[mid] < x)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        const int k = lo > 0 ? lo - 1 : 0;
+        return (k <= n_t - 2) ? k : -1;
+    }
+    while (lo < hi) {  // cnt = #nodes <= x
+        const int mid = (lo + hi) >> 1;
+        if (t_row[mid] <= x)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    const int k = lo - 1;
+    return (k >= 0 && k <= n_t - 2) ? k : -1;
+}
+
+// log-log interpolation inside interval k (observer.h:417-433 / :515-520); returns the linear
+// contribution exp2(...) or 0 when the slope is not finite.
+VAG_HD double interp_contrib(double lo, double hi, double t_lo, double t_hi, double x) {
+    const double inv_dt = 1.0 / (t_hi - t_lo);
+    const double s = (hi - lo) * inv_dt;
+    if (!isfinite(s)) return 0.0;
+    return exp2(lo + (x - t_lo) * s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA work description.  Shared memory layout (doubles):
+//   rowg   [ROW_CHUNK] RowGeom
+//   lg2t   [ROW_CHUNK][n_t]
+//   lg2dop [ROW_CHUNK][n_t]          (series mode only)
+//   lg2geo [ROW_CHUNK][n_t]          (series mode only)
+//   bv     [ROW_CHUNK][n_t][nu_tile] (grid mode only)
+// ---------------------------------------------------------------------------------------------
+struct EatsShared {
+    RowGeom* rowg;
+    double* lg2t;
+    double* lg2dop;
+    double* lg2geo;
+    double* bv;
+};
+
+struct EatsRequest {
+    int series;            // 0: grid (t x nu), 1: series (t[i], nu[i])
+    int n_t_obs, n_nu;     // series: n_nu == n_t_obs (per-point frequencies)
+    const double* lg2_t_obs;   // [n_t_obs]  log2(t * unit::sec)
+    const double* lg2_nu_obs;  // [n_nu]     log2(nu * unit::Hz)   (without the 1+z shift)
+    const double* t_obs_lin;   // [n_t_obs]  t * unit::sec
+    int i0, ni;                // block of observation points handled by the current pass
+};
+
+constexpr int EATS_T_BLOCK = 256;   // observation points accumulated per pass
+
+// row_chunk <= EATS_ROW_CHUNK rows are staged per pass (the host lowers it when n_t is large)
+VAG_HD size_t eats_shared_doubles(int n_t, bool series, int row_chunk) {
+    size_t n = (sizeof(RowGeom) * EATS_ROW_CHUNK + 7) / 8;
+    n += (size_t)row_chunk * n_t;
+    if (series)
+        n += 2 * (size_t)row_chunk * n_t;
+    else
+        n += (size_t)row_chunk * n_t * EATS_NU_TILE;
+    return n;
+}
+
+VAG_HD EatsShared eats_carve(double* base, int n_t, bool series, int row_chunk) {
+    EatsShared s;
+    s.rowg = reinterpret_cast<RowGeom*>(base);
+    double* p = base + (sizeof(RowGeom) * EATS_ROW_CHUNK + 7) / 8;
+    s.lg2t = p;
+    p += (size_t)row_chunk * n_t;
+    if (series) {
+        s.lg2dop = p;
+        p += (size_t)row_chunk * n_t;
+        s.lg2geo = p;
+        s.bv = nullptr;
+    } else {
+        s.lg2dop = s.lg2geo = nullptr;
+        s.bv = p;
+    }
+    return s;
+}
+
+// phase 0: row constants of the chunk [q0, q0+nrows)
+VAG_HD void eats_phase0(const EatsModel& M, const EatsShared& sh, int q0, int nrows, int tid, int nthr) {
+    const int n_theta = M.h->n_theta;
+    for (int r = tid; r < nrows; r += nthr) {
+        const int q = q0 + r;
+        sh.rowg[r] = row_geometry(M, q / n_theta, q % n_theta);
+    }
+}
+
+// phase 1: node logs (+ boundary luminosities for the frequency tile [l0, l0+nl) in grid mode)
+VAG_HD void eats_phase1(const EatsModel& M, const EatsRequest& rq, const EatsShared& sh, int nrows, int l0, int nl,
+                        int tid, int nthr) {
+    const int n_t = M.h->n_t;
+    const double lg2_1pz = fast_log2(M.one_plus_z);
+    const double w_lo = rq.t_obs_lin[rq.i0], w_hi = rq.t_obs_lin[rq.i0 + rq.ni - 1];
+    for (int it = tid; it < nrows * n_t; it += nthr) {
+        const int r = it / n_t, k = it - r * n_t;
+        const RowGeom g = sh.rowg[r];
+        double lt, ld, lg;
+        node_logs(M, g, n_t, k, lt, ld, lg);
+        sh.lg2t[it] = lt;
+        if (rq.series) {
+            sh.lg2dop[it] = ld;
+            sh.lg2geo[it] = lg;
+        } else {
+            // observed_window (observer.h:324-338) skips nodes no observation interval touches;
+            // here a node is evaluated when one of its two adjacent intervals can hold a point.
+            const bool need = (k + 1 >= n_t || node_time(M, g, n_t, k + 1) >= w_lo) &&
+                              (k == 0 || node_time(M, g, n_t, k - 1) <= w_hi);
+            double* bv = sh.bv + (size_t)it * EATS_NU_TILE;
+            if (need) {
+                for (int l = 0; l < nl; ++l) {
+                    const double lg2_nu_src = rq.lg2_nu_obs[l0 + l] + lg2_1pz;
+                    bv[l] = cell_log2_I_nu(M, g.rep, n_t, k, lg2_nu_src - ld) + lg;
+                }
+            }
+        }
+    }
+}
+
+// phase 2 (grid): thread <-> observation time; accumulates the chunk's rows into acc[l][idx]
+// acc layout: [EATS_NU_TILE][EATS_T_BLOCK] (thread-owned columns, no atomics)
+VAG_HD void eats_phase2_grid(const EatsModel& M, const EatsRequest& rq, const EatsShared& sh, int nrows, int nl,
+                             double* acc, int tid, int nthr) {
+    const int n_t = M.h->n_t;
+    for (int ii = tid; ii < rq.ni; ii += nthr) {
+        const double x = rq.lg2_t_obs[rq.i0 + ii];
+        double sum[EATS_NU_TILE];
+        for (int l = 0; l < EATS_NU_TILE; ++l) sum[l] = 0;
+        for (int r = 0; r < nrows; ++r) {
+            const double* t_row = sh.lg2t + (size_t)r * n_t;
+            const int k = find_interval(t_row, n_t, x, false);
+            if (k < 0) continue;
+            const double* b_lo = sh.bv + ((size_t)r * n_t + k) * EATS_NU_TILE;
+            const double* b_hi = b_lo + EATS_NU_TILE;
+            const double t_lo = t_row[k], t_hi = t_row[k + 1];
+            for (int l = 0; l < nl; ++l) sum[l] += interp_contrib(b_lo[l], b_hi[l], t_lo, t_hi, x);
+        }
+        for (int l = 0; l < nl; ++l) acc[l * EATS_T_BLOCK + ii] += sum[l];
+    }
+}
+
+// phase 2 (series): thread <-> data point (t_s, nu_s); acc[EATS_T_BLOCK]
+VAG_HD void eats_phase2_series(const EatsModel& M, const EatsRequest& rq, const EatsShared& sh, int nrows, double* acc,
+                               int tid, int nthr) {
+    const int n_t = M.h->n_t;
+    const double lg2_1pz = fast_log2(M.one_plus_z);
+    for (int ii = tid; ii < rq.ni; ii += nthr) {
+        const int s = rq.i0 + ii;
+        const double x = rq.lg2_t_obs[s];
+        const double lg2_nu = rq.lg2_nu_obs[s] + lg2_1pz;
+        double sum = 0;
+        for (int r = 0; r < nrows; ++r) {
+            const size_t ro = (size_t)r * n_t;
+            const double* t_row = sh.lg2t + ro;
+            const int k = find_interval(t_row, n_t, x, true);
+            if (k < 0) continue;
+            const int rep = sh.rowg[r].rep;
+            const double lo = cell_log2_I_nu(M, rep, n_t, k, lg2_nu - sh.lg2dop[ro + k]) + sh.lg2geo[ro + k];
+            const double hi = cell_log2_I_nu(M, rep, n_t, k + 1, lg2_nu - sh.lg2dop[ro + k + 1]) + sh.lg2geo[ro + k + 1];
+            sum += interp_contrib(lo, hi, t_row[k], t_row[k + 1], x);
+        }
+        acc[ii] += sum;
+    }
+}
+
+}  // namespace vag

@@ -1,0 +1,670 @@
+// vag_shock.cuh -- K1: blast-wave dynamics of one (phi,theta) row.
+//
+// Restates, for non-spreading typed jets without energy/mass injection:
+//   jump conditions / helpers   src/dynamics/shock-physics.h:40-371, src/dynamics/shock.cpp:90-138
+//   forward shock ODE           src/dynamics/forward-shock.tpp:27-208
+//   forward+reverse shock ODE   src/dynamics/reverse-shock.tpp:17-591
+// State vectors drop the constant theta component (d theta/dt = 0 without spreading: its error
+// term is identically zero, so the step controller is unaffected).
+#pragma once
+
+#include "vag_dopri5.cuh"
+#include "vag_grid.cuh"
+#include "vag_model.cuh"
+
+namespace vag {
+
+// Per-row view of the SoA shock table: 6 arrays of n_t doubles (theta is the row's constant).
+struct ShockRow {
+    double* t_comv;
+    double* r;
+    double* Gamma;
+    double* Gamma_th;
+    double* B;
+    double* N_p;
+};
+
+// ---------------------------------------------------------------------------------------------
+// shock-physics.h helpers
+// ---------------------------------------------------------------------------------------------
+// compute_downstr_4vel: src/dynamics/shock.cpp:90-138
+VAG_HD double compute_downstr_4vel(double gamma_rel, double sigma) {
+    const double ad_idx = adiabatic_idx(gamma_rel);
+    const double gamma_m_1 = gamma_rel - 1;
+    const double ad_idx_m_2 = ad_idx - 2;
+    const double ad_idx_m_1 = ad_idx - 1;
+    if (sigma <= con::sigma_cut) {
+        return sqrt(vmax(gamma_m_1 * ad_idx_m_1 * ad_idx_m_1 / (-ad_idx * ad_idx_m_2 * gamma_m_1 + 2), 0.0));
+    }
+    const double gamma_sq = gamma_rel * gamma_rel;
+    const double gamma_p_1 = gamma_rel + 1;
+    const double term1 = -ad_idx * ad_idx_m_2;
+    const double term2 = gamma_sq - 1;
+    const double A = term1 * gamma_m_1 + 2;
+    const double B = -gamma_p_1 * (-ad_idx_m_2 * (ad_idx * gamma_sq + 1) + ad_idx * ad_idx_m_1 * gamma_rel) * sigma -
+                     gamma_m_1 * (term1 * (gamma_sq - 2) + 2 * gamma_rel + 3);
+    const double C = gamma_p_1 * (ad_idx * (1 - ad_idx / 4) * term2 + 1) * sigma * sigma +
+                     term2 * (2 * gamma_rel + ad_idx_m_2 * (ad_idx * gamma_rel - 1)) * sigma +
+                     gamma_p_1 * gamma_m_1 * gamma_m_1 * ad_idx_m_1 * ad_idx_m_1;
+    const double D = -gamma_m_1 * gamma_p_1 * gamma_p_1 * ad_idx_m_2 * ad_idx_m_2 * sigma * sigma / 4;
+    const double b = B / A;
+    const double c = C / A;
+    const double d = D / A;
+    const double P = c - b * b / 3;
+    const double Q = 2 * b * b * b / 27 - b * c / 3 + d;
+    const double u = sqrt(vmax(-P, 0.0) / 3);
+    const double denom = 2 * P * u;
+    const double v = (denom != 0) ? vclamp(3 * Q / denom, -1.0, 1.0) : 0.0;
+    const double x_max = 2 * u * cos(acos(v) / 3) - b / 3;
+    if (x_max <= 0) return 0;
+    const double prod = -d / x_max;
+    const double sum = (c - prod) / x_max;
+    const double uds = (sum + sqrt(vmax(sum * sum - 4 * prod, 0.0))) / 2;
+    return sqrt(vmax(uds, 0.0));
+}
+
+// shock-physics.h:40-66
+VAG_HD double compute_upstr_4vel(double u_down, double gamma_rel) {
+    return sqrt((1 + u_down * u_down) * vmax((gamma_rel - 1) * (gamma_rel + 1), 0.0)) + u_down * gamma_rel;
+}
+VAG_HD double compute_4vel_jump(double gamma_rel, double sigma_upstr) {
+    const double u_down_s = compute_downstr_4vel(gamma_rel, sigma_upstr);
+    const double u_up_s = compute_upstr_4vel(u_down_s, gamma_rel);
+    double ratio_u = u_up_s / u_down_s;
+    if (u_down_s == 0.) ratio_u = 4 * gamma_rel;
+    return ratio_u;
+}
+// shock-physics.h:75-78
+VAG_HD double compute_sound_speed(double Gamma_rel) {
+    const double ad_idx = adiabatic_idx(Gamma_rel);
+    return sqrt(vmax(ad_idx * (ad_idx - 1) * (Gamma_rel - 1) / (1 + (Gamma_rel - 1) * ad_idx), 0.0)) * con::c;
+}
+// shock-physics.h:88-102
+VAG_HD double compute_effective_Gamma(double adx, double Gamma) { return (adx * Gamma * Gamma - adx + 1) / Gamma; }
+VAG_HD double compute_effective_Gamma_dGamma(double adx, double Gamma) {
+    const double Gamma2 = Gamma * Gamma;
+    return (adx * Gamma2 + adx - 1) / Gamma2;
+}
+// shock-physics.h:179-181
+VAG_HD double compute_upstr_B(double rho_up, double sigma) { return sqrt((4 * con::pi * con::c2) * sigma * rho_up); }
+// shock-physics.h:192-204
+VAG_HD double compute_rel_Gamma(double gamma1, double gamma2) {
+    const double u1u2 = sqrt(vmax((gamma1 - 1) * (gamma1 + 1) * (gamma2 - 1) * (gamma2 + 1), 0.0));
+    const double d = gamma1 - gamma2;
+    const double denom = gamma1 * gamma2 - 1 + u1u2;
+    if (denom <= 0) return 1;
+    return 1 + d * d / denom;
+}
+// shock-physics.h:223-229
+VAG_HD double compute_adiabatic_cooling_rate2(double ad_idx, double r, double x, double u, double drdt, double dxdt) {
+    double dlnvdt = 2 * drdt / r;
+    if (x > 0) dlnvdt += dxdt / x;
+    return -(ad_idx - 1) * dlnvdt * u;
+}
+// shock-physics.h:247-288
+VAG_HD double radiative_efficiency(const RadCfg& rad, double t_comv, double Gamma_th, double e_th) {
+    if (rad.eps_e_rad == 0) return 0;
+    const double gamma_m = rad.gamma_m_coeff * (Gamma_th - 1) + 1;
+    const double gamma_bar = rad.gamma_c_coeff / (e_th * t_comv);
+    const double gamma_c = 0.5 * (gamma_bar + sqrt(gamma_bar * gamma_bar + 4));
+    const double ratio = gamma_m / gamma_c;
+    if (ratio < 1 && rad.p > 2) return rad.eps_e_rad * fast_pow(ratio, rad.p - 2);
+    return rad.eps_e_rad;
+}
+// shock-physics.h:300-312
+VAG_HD double compute_Gamma_therm(double U_th, double mass, bool limiter = false) {
+    if (mass == 0) return 1;
+    const double Gamma_th = U_th / (mass * con::c2) + 1;
+    if (limiter && Gamma_th < con::gamma_therm_cut) return 1;
+    return Gamma_th;
+}
+// shock-physics.h:352-371
+VAG_HD double compute_compression(double Gamma_upstr, double Gamma_downstr, double sigma_upstr) {
+    return compute_4vel_jump(compute_rel_Gamma(Gamma_upstr, Gamma_downstr), sigma_upstr);
+}
+VAG_HD double compute_downstr_B(double eps_B, double rho_upstr, double B_upstr, double Gamma_th, double comp_ratio) {
+    const double rho_downstr = rho_upstr * comp_ratio;
+    const double e_th = (Gamma_th - 1) * rho_downstr * con::c2;
+    return sqrt(8 * con::pi * eps_B * e_th) + B_upstr * comp_ratio;
+}
+
+// simpson_logspace / enclosed_mass / enclosed_thermal_energy: shock-physics.h:401-450
+template <class F>
+VAG_HD double simpson_logspace(const F& f, double r) {
+    constexpr int N = 32;
+    const double u_max = log(r);
+    const double u_min = u_max - 18;
+    const double h = (u_max - u_min) / N;
+    double sum = f(u_min) + f(u_max);
+    for (int i = 1; i < N; i += 2) sum += 4 * f(u_min + i * h);
+    for (int i = 2; i < N; i += 2) sum += 2 * f(u_min + i * h);
+    return sum * h / 3;
+}
+VAG_HD double enclosed_mass_numeric(const ModelCfg& m, double r) {
+    return simpson_logspace(
+        [&](double u) {
+            const double ri = exp(u);
+            return medium_rho(m, ri) * ri * ri * ri;
+        },
+        r);
+}
+VAG_HD double enclosed_thermal_energy_numeric(const ModelCfg& m, double r, double Gamma, double ad_idx, double eps_e) {
+    const double cooling_exp = 3 * (ad_idx - 1);
+    return (1 - eps_e) * (Gamma - 1) * con::c2 *
+           simpson_logspace(
+               [&](double u) {
+                   const double ri = exp(u);
+                   return medium_rho(m, ri) * ri * ri * ri * pow(ri / r, cooling_exp);
+               },
+               r);
+}
+// enclosed_thermal_energy_medium: shock-physics.h:452-469 (ISM closed form, otherwise Simpson)
+VAG_HD double enclosed_thermal_energy_medium(const ModelCfg& m, double r, double Gamma, double ad_idx, double eps_e) {
+    if (m.medium_type == VAG_MEDIUM_ISM) {
+        const double rho = m.rho_ism;
+        const double cooling_exp = 3 * (ad_idx - 1);
+        const double pow_exp = 3 + cooling_exp;
+        const double x0 = exp(-18.0);
+        const double attenuation = 1 - pow(x0, pow_exp);
+        const double integral = rho * r * r * r * attenuation / pow_exp;
+        return (1 - eps_e) * (Gamma - 1) * con::c2 * integral;
+    }
+    return enclosed_thermal_energy_numeric(m, r, Gamma, ad_idx, eps_e);
+}
+
+// Default table values of an untouched row (Shock ctor, src/dynamics/shock.cpp:12-25).
+VAG_HD void fill_default_row(const ShockRow& s, int k0, int n_t) {
+    for (int k = k0; k < n_t; ++k) {
+        s.t_comv[k] = 0;
+        s.r[k] = 0;
+        s.Gamma[k] = 1;
+        s.Gamma_th[k] = 1;
+        s.B[k] = 0;
+        s.N_p[k] = 0;
+    }
+}
+// set_stopping_shock: shock-physics.h:388-397
+VAG_HD void set_stopping_row(const ShockRow& s, int n_t, double t_comv, double r) {
+    for (int k = 0; k < n_t; ++k) {
+        s.t_comv[k] = t_comv;
+        s.r[k] = r;
+        s.Gamma[k] = 1;
+        s.Gamma_th[k] = 1;
+        s.B[k] = 0;
+        s.N_p[k] = 0;
+    }
+}
+
+// save_fwd_shock_state: forward-shock.tpp:151-173 (+ write_shock_state shock-physics.h:329-338)
+VAG_HD void save_fwd_state(const ModelCfg& m, double eps_B, const ShockRow& s, int k, double Gamma, double m2,
+                           double U2_th, double r, double t_comv) {
+    const double comp_ratio = compute_compression(1, Gamma, 0);
+    const double rho = medium_rho(m, r);
+    const double Gamma_th = compute_Gamma_therm(U2_th, m2);
+    const double B = compute_downstr_B(eps_B, rho, 0, Gamma_th, comp_ratio);
+    s.t_comv[k] = t_comv;
+    s.r[k] = r;
+    s.Gamma[k] = Gamma;
+    s.Gamma_th[k] = Gamma_th;
+    s.B[k] = B;
+    s.N_p[k] = m2 / con::mp;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward shock: state = [Gamma, m2, U2_th, r, t_comv]
+// ---------------------------------------------------------------------------------------------
+struct FwdEqn {
+    const ModelCfg& m;
+    double m_jet0;
+    enum { iG = 0, iM2 = 1, iU = 2, iR = 3, iT = 4, N = 5 };
+
+    VAG_HD FwdEqn(const ModelCfg& m_, double theta) : m(m_) {
+        m_jet0 = jet_eps_k(m, theta) / jet_Gamma0(m, theta) / con::c2;  // forward-shock.tpp:20
+    }
+
+    // ForwardShockEqn::operator(): forward-shock.tpp:27-118
+    VAG_HD void operator()(const double* x, double* d, double /*t*/) const {
+        const double Gamma = x[iG];
+        const double u2 = (Gamma - 1) * (Gamma + 1);
+        const double u = sqrt(u2);
+        d[iR] = u * (Gamma + u) * con::c;
+        d[iT] = Gamma + u;
+        const double rho = medium_rho(m, x[iR]);
+        d[iM2] = x[iR] * x[iR] * rho * d[iR];
+        const double e_th = (Gamma - 1) * 4 * Gamma * rho * con::c2;
+        const double eps_rad = radiative_efficiency(m.fwd, x[iT], Gamma, e_th);
+        const double ad_idx = adiabatic_idx(Gamma);
+        // compute_dGamma_dt
+        {
+            const double Gamma2 = Gamma * Gamma;
+            const double Gamma_eff = (ad_idx * (Gamma2 - 1) + 1) / Gamma;
+            const double dGamma_eff = (ad_idx * (Gamma2 + 1) - 1) / Gamma2;
+            const double dlnVdt = 3 / x[iR] * d[iR];
+            const double U = x[iU];
+            const double a1 = -(Gamma - 1) * (Gamma_eff + 1) * con::c2 * d[iM2];
+            const double a2 = (ad_idx - 1) * Gamma_eff * U * dlnVdt;
+            const double b1 = (m_jet0 + x[iM2]) * con::c2;
+            const double b2 = (dGamma_eff + Gamma_eff * (ad_idx - 1) / Gamma) * U;
+            d[iG] = (a1 + a2) / (b1 + b2);
+        }
+        // compute_dU_dt
+        {
+            const double dlnVdt = 3 / x[iR] * d[iR] - d[iG] / Gamma;
+            d[iU] = (1 - eps_rad) * (Gamma - 1) * con::c2 * d[iM2] - (ad_idx - 1) * dlnVdt * x[iU];
+        }
+    }
+
+    // set_init_state: forward-shock.tpp:120-149
+    VAG_HD void set_init_state(double* x, double theta, double t0) const {
+        const double Gamma4 = jet_Gamma0(m, theta);
+        const double beta4 = gamma_to_beta(Gamma4);
+        x[iR] = beta4 * con::c * t0 * Gamma4 * Gamma4 * (1 + beta4);
+        x[iT] = x[iR] / sqrt((Gamma4 - 1) * (Gamma4 + 1)) / con::c;
+        x[iM2] = medium_mass(m, x[iR]);
+        x[iG] = Gamma4;
+        const double ad_idx = adiabatic_idx(Gamma4);
+        x[iU] = enclosed_thermal_energy_medium(m, x[iR], Gamma4, ad_idx, m.fwd.radiative ? m.fwd.eps_e : 0.0);
+    }
+};
+
+// grid_solve_fwd_shock: forward-shock.tpp:175-208.  Returns VAG_ST_* bits.
+VAG_HD int solve_fwd_row(const ModelCfg& m, double theta, double t_dec, const double* t, int n_t, const ShockRow& s) {
+    FwdEqn eqn(m, theta);
+    double x[FwdEqn::N];
+    const double t0 = vmin(t[0], vmin(0.1 * unit::sec, 0.1 * t_dec));
+    eqn.set_init_state(x, theta, t0);
+    if (x[FwdEqn::iG] <= con::Gamma_cut) {
+        set_stopping_row(s, n_t, x[FwdEqn::iT], x[FwdEqn::iR]);
+        return 0;
+    }
+    Dopri5<FwdEqn::N> st;
+    st.initialize(x, t0, 0.01 * t0, m.rtol);
+    const double t_back = t[n_t - 1];
+    int k = 0, status = 0;
+    for (int steps = 0; st.t <= t_back;) {
+        if (!st.do_step(eqn)) {
+            status |= VAG_ST_ODE_FAIL500;
+            break;
+        }
+        if (++steps > dflt::max_ode_steps) {
+            status |= VAG_ST_ODE_STEP_CAP;
+            break;
+        }
+        while (k < n_t && st.t > t[k]) {
+            st.calc_state(t[k], x);
+            save_fwd_state(m, m.fwd.eps_B, s, k, x[FwdEqn::iG], x[FwdEqn::iM2], x[FwdEqn::iU], x[FwdEqn::iR],
+                           x[FwdEqn::iT]);
+            ++k;
+        }
+    }
+    fill_default_row(s, k, n_t);
+    return status;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward + reverse shock pair: reverse-shock.hpp:29-45 without theta
+// state = [Gamma, x4, x3, m2, m3, U2_th, U3_th, r, t_comv, eps4, m4]
+// ---------------------------------------------------------------------------------------------
+VAG_HD double smoothstep(double edge0, double edge1, double x) {  // reverse-shock.tpp:11-20
+    double t = (x - edge0) / (edge1 - edge0);
+    if (t < 0.0)
+        t = 0.0;
+    else if (t > 1.0)
+        t = 1.0;
+    return t * t * (3.0 - 2.0 * t);
+}
+
+struct FRState {
+    double Gamma, x4, x3, m2, m3, U2_th, U3_th, r, t_comv, eps4, m4;
+};
+
+struct FREqn {
+    const ModelCfg& m;
+    double Gamma4, deps0_dt, dm0_dt, u4;
+    // crossing state: reverse-shock.hpp:66-70
+    double u_x, r_x, B3_ordered_x, V3_comv_x, rho3_x;
+    enum { iG = 0, iX4, iX3, iM2, iM3, iU2, iU3, iR, iT, iE4, iM4, N };
+
+    // FRShockEqn ctor: reverse-shock.tpp:22-40
+    VAG_HD FREqn(const ModelCfg& m_, double theta) : m(m_) {
+        Gamma4 = jet_Gamma0(m, theta);
+        deps0_dt = jet_eps_k(m, theta) / m.T0;
+        dm0_dt = deps0_dt / (Gamma4 * con::c2);
+        u4 = sqrt(Gamma4 * Gamma4 - 1) * con::c;
+        u_x = r_x = B3_ordered_x = V3_comv_x = rho3_x = 0;
+    }
+
+    VAG_HD double injection_efficiency(double dm4) const {  // reverse-shock.tpp:42-47
+        if (dm0_dt > 0 && dm4 > 0) return vmin(dm4 / dm0_dt, 1.0);
+        return 0.0;
+    }
+    VAG_HD double shell_sigma(double eps4, double m4) const {  // reverse-shock.tpp:359-363
+        const double sigma = eps4 / (Gamma4 * m4 * con::c2) - 1;
+        return (sigma > con::sigma_cut) ? sigma : 0;
+    }
+    VAG_HD bool crossing_complete(const double* x, double t) const {  // reverse-shock.tpp:49-60
+        if (x[iM3] < 0.999 * x[iM4]) return false;
+        if (smoothstep(m.T0 * 1.5, m.T0 * 0.5, t) > 1e-6) return false;
+        return true;
+    }
+
+    // FRShockEqn::operator(): reverse-shock.tpp:252-294 (+ the rate terms :62-250)
+    VAG_HD void operator()(const double* xr, double* d, double t) const {
+        // projection onto the physical domain
+        const double Gamma = vclamp(xr[iG], 1.0, Gamma4);
+        const double m4 = xr[iM4];
+        const double m3 = vclamp(xr[iM3], 0.0, vmax(m4, 0.0));
+        const double x3 = vmax(xr[iX3], 0.0);
+        const double U3 = vmax(xr[iU3], 0.0);
+        const double x4 = xr[iX4], m2 = xr[iM2], U2 = xr[iU2], r = xr[iR], t_comv = xr[iT], eps4 = xr[iE4];
+
+        const double u3 = sqrt((Gamma - 1) * (Gamma + 1));
+        const double dr = u3 * (Gamma + u3) * con::c;
+        const double dtc = Gamma + u3;
+        d[iR] = dr;
+        d[iT] = dtc;
+        const double rho = medium_rho(m, r);
+        const double dm2 = r * r * rho * dr;  // compute_dm2_dt :215-218
+        d[iM2] = dm2;
+
+        // compute_deps4_dt / compute_dm4_dt :220-250
+        const double inject_w = smoothstep(m.T0 * 1.5, m.T0 * 0.5, t);
+        double deps4 = 0, dm4 = 0;
+        if (inject_w > 1e-6) {
+            deps4 = inject_w * deps0_dt;
+            dm4 = inject_w * dm0_dt;
+        }
+        d[iE4] = deps4;
+        d[iM4] = dm4;
+
+        const double Gamma34 = compute_rel_Gamma(Gamma4, Gamma);
+        const double sigma = shell_sigma(eps4, m4);
+        const double comp_ratio = compute_4vel_jump(Gamma34, sigma);
+
+        const double f = injection_efficiency(dm4);
+        // compute_dx4_dt :205-213
+        double dx4;
+        {
+            const double sound_expansion = compute_sound_speed(Gamma4) * dtc;
+            dx4 = (f > 1e-6) ? f * u4 + (1 - f) * sound_expansion : sound_expansion;
+        }
+        d[iX4] = dx4;
+
+        // compute_dx3_dt :124-179
+        double dx3;
+        {
+            const double sound_expansion = compute_sound_speed(Gamma34) * dtc;
+            dx3 = sound_expansion;
+            if (!(m4 <= 0)) {
+                const double remaining = vmax(m4 - m3, 0.0);
+                const double crossing_w = f + (1.0 - f) * remaining / m4;
+                if (!(crossing_w < 1e-6)) {
+                    const double penetration = Gamma * comp_ratio / Gamma4 - 1;
+                    if (!(penetration <= 0)) {
+                        const double beta3 = gamma_to_beta(Gamma);
+                        const double beta4 = gamma_to_beta(Gamma4);
+                        const double dx3dt = (Gamma4 - Gamma) * (Gamma4 + Gamma) * (1 + beta3) * con::c /
+                                             (Gamma4 * Gamma4 * (beta3 + beta4) * penetration);
+                        double crossing = fabs(dx3dt * Gamma);
+                        if (penetration < 1) {
+                            const double cs = compute_sound_speed(Gamma34);
+                            const double va2 = sigma / (1 + sigma);
+                            const double cs2 = cs * cs / (con::c * con::c);
+                            const double v_ms = sqrt(va2 + cs2 * (1 - va2)) * con::c;
+                            crossing = vmin(crossing, v_ms * dtc);
+                        }
+                        dx3 = crossing_w * crossing + (1.0 - crossing_w) * sound_expansion;
+                    }
+                }
+            }
+        }
+        d[iX3] = dx3;
+
+        // compute_dm3_dt :181-203
+        double dm3;
+        {
+            dm3 = 0.;
+            if (!(m4 <= 0)) {
+                const double remaining = vmax(m4 - m3, 0.0);
+                if (!(remaining <= 0 && f < 1e-6)) {
+                    const double eff_mass = f * m4 + (1.0 - f) * remaining;
+                    const double column_den3 = eff_mass * comp_ratio / x4;
+                    const double dm3dt = column_den3 * dx3;
+                    if (f > 1e-6) {
+                        const double ratio = m3 / m4;
+                        const double cap_w = smoothstep(0, 1.0, ratio);
+                        const double capped_rate = vmin(dm3dt, dm4);
+                        dm3 = (1.0 - cap_w) * dm3dt + cap_w * capped_rate;
+                    } else {
+                        dm3 = dm3dt;
+                    }
+                }
+            }
+        }
+        d[iM3] = dm3;
+
+        // compute_dU2_dt :96-110
+        double dU2;
+        {
+            const double e_th = (Gamma - 1) * 4 * Gamma * rho * con::c2;
+            const double eps_rad = radiative_efficiency(m.fwd, t_comv, Gamma, e_th);
+            const double ad_idx = adiabatic_idx(Gamma);
+            const double shock_heating = dm2 * (Gamma - 1) * con::c2;
+            const double adiabatic_cooling = compute_adiabatic_cooling_rate2(ad_idx, r, x4, U2, dr, dx4);
+            dU2 = (1 - eps_rad) * shock_heating + adiabatic_cooling;
+        }
+        d[iU2] = dU2;
+        // compute_dU3_dt :112-122
+        double dU3;
+        {
+            const double ad_idx = adiabatic_idx(Gamma34);
+            const double adiabatic_cooling = compute_adiabatic_cooling_rate2(ad_idx, r, x3, U3, dr, dx3);
+            const double shock_heating = dm3 * (Gamma34 - 1) * con::c2;
+            dU3 = shock_heating + adiabatic_cooling;
+        }
+        d[iU3] = dU3;
+
+        // compute_dGamma_dt :62-94
+        {
+            const double ad_idx2 = adiabatic_idx(Gamma);
+            const double ad_idx3 = adiabatic_idx(Gamma34);
+            const double Gamma_eff2 = compute_effective_Gamma(ad_idx2, Gamma);
+            const double Gamma_eff3 = compute_effective_Gamma(ad_idx3, Gamma);
+            const double dGamma_eff2 = compute_effective_Gamma_dGamma(ad_idx2, Gamma);
+            const double dGamma_eff3 = compute_effective_Gamma_dGamma(ad_idx3, Gamma);
+            const double deps_dt = 0;
+            const double a = (Gamma - 1) * con::c2 * dm2 + (Gamma - Gamma4) * con::c2 * dm3 + Gamma_eff2 * dU2 +
+                             Gamma_eff3 * dU3 - deps_dt;
+            const double b = (m2 + m3) * con::c2 + dGamma_eff2 * U2 + dGamma_eff3 * U3;
+            const double q = -a / b;
+            d[iG] = (b == 0 || isnan(q) || isinf(q)) ? 0 : q;
+        }
+    }
+
+    // set_init_state: reverse-shock.tpp:314-357 (+ compute_init_comv_shell_width :381-390)
+    VAG_HD void set_init_state(double* x, double t0) const {
+        const double beta4 = gamma_to_beta(Gamma4);
+        x[iR] = beta4 * con::c * t0 * Gamma4 * Gamma4 * (1 + beta4);
+        x[iT] = x[iR] / sqrt((Gamma4 - 1) * (Gamma4 + 1)) / con::c;
+        const double dt = vmin(t0, m.T0);
+        x[iE4] = deps0_dt * dt;
+        x[iM4] = dm0_dt * dt;
+        if (t0 < m.T0) {
+            x[iX4] = Gamma4 * t0 * beta4 * con::c;
+        } else {
+            const double cs = compute_sound_speed(Gamma4);
+            x[iX4] = Gamma4 * m.T0 * beta4 * con::c + cs * (t0 - m.T0) * Gamma4;
+        }
+        x[iM2] = enclosed_mass_numeric(m, x[iR]);
+        const double m_jet_total = dm0_dt * m.T0;
+        if (m_jet_total > 0 && x[iM2] > 0) {
+            x[iG] = Gamma4 / (1 + x[iM2] / m_jet_total);
+        } else {
+            x[iG] = Gamma4;
+        }
+        const double ad_idx = adiabatic_idx(x[iG]);
+        x[iU2] = enclosed_thermal_energy_numeric(m, x[iR], x[iG], ad_idx, m.fwd.radiative ? m.fwd.eps_e : 0.0);
+        const double Gamma34 = compute_rel_Gamma(Gamma4, x[iG]);
+        if (Gamma34 > 1 && x[iM4] > 0 && x[iX4] > 0) {
+            constexpr double seed_frac = 1e-8;
+            const double sigma = shell_sigma(x[iE4], x[iM4]);
+            const double comp_ratio = compute_4vel_jump(Gamma34, sigma);
+            x[iX3] = x[iX4] * seed_frac;
+            x[iM3] = x[iM4] * comp_ratio * x[iX3] / x[iX4];
+            x[iU3] = (Gamma34 - 1) * x[iM3] * con::c2;
+        } else {
+            x[iM3] = 0;
+            x[iU3] = 0;
+            x[iX3] = 0;
+        }
+    }
+
+    // save_cross_state: reverse-shock.tpp:298-312
+    VAG_HD void save_cross_state(const double* x) {
+        r_x = x[iR];
+        u_x = sqrt((x[iG] - 1) * (x[iG] + 1));
+        V3_comv_x = r_x * r_x * x[iX3];
+        const double sigma4 = shell_sigma(x[iE4], x[iM4]);
+        const double comp_ratio34 = compute_compression(Gamma4, x[iG], sigma4);
+        const double rho4 = x[iM4] / (x[iR] * x[iR] * x[iX4]);
+        rho3_x = rho4 * comp_ratio34;
+        const double B4 = compute_upstr_B(rho4, sigma4);
+        B3_ordered_x = B4 * comp_ratio34;
+    }
+
+    // save_rvs_shock_state: reverse-shock.tpp:403-426
+    VAG_HD void save_rvs_state(double eps_B, const ShockRow& s, int k, int injection_idx, const double* x) const {
+        double Gamma3_th, B3;
+        if (k <= injection_idx) {
+            const double sigma4 = shell_sigma(x[iE4], x[iM4]);
+            const double comp_ratio34 = compute_compression(Gamma4, x[iG], sigma4);
+            const double rho4 = x[iM4] / (x[iR] * x[iR] * x[iX4]);
+            Gamma3_th = compute_Gamma_therm(x[iU3], x[iM3], true);
+            const double B4 = compute_upstr_B(rho4, sigma4);
+            B3 = compute_downstr_B(eps_B, rho4, B4, Gamma3_th, comp_ratio34);
+        } else {
+            const double V3_comv = x[iR] * x[iR] * x[iX3];
+            const double comp_ratio = V3_comv_x / V3_comv;
+            Gamma3_th = compute_Gamma_therm(x[iU3], x[iM3]);
+            B3 = compute_downstr_B(eps_B, rho3_x, B3_ordered_x, Gamma3_th, comp_ratio);
+        }
+        s.t_comv[k] = x[iT];
+        s.r[k] = x[iR];
+        s.Gamma[k] = x[iG];
+        s.Gamma_th[k] = Gamma3_th;
+        s.B[k] = B3;
+        s.N_p[k] = x[iM3] / con::mp;
+    }
+};
+
+// reverse_shock_early_extrap: reverse-shock.tpp:428-467
+VAG_HD void reverse_shock_early_extrap(const ShockRow& s, int n_t, int injection_idx) {
+    int idx_cut = 0;
+    for (; idx_cut < n_t; ++idx_cut)
+        if (s.Gamma_th[idx_cut] > con::gamma_therm_cut) break;
+    constexpr int offset = 2;
+    if (idx_cut == 0 || idx_cut >= n_t - offset || idx_cut >= injection_idx) return;
+    const double log2_r = fast_log2(s.r[idx_cut]);
+    const double log2_Gamma_th = fast_log2(s.Gamma_th[idx_cut] - 1);
+    const double log2_B = fast_log2(s.B[idx_cut]);
+    const double log2_N_p = fast_log2(s.N_p[idx_cut]);
+    const double dl = fast_log2(s.r[idx_cut + offset]) - log2_r;
+    const double gamma_slope = (fast_log2(s.Gamma_th[idx_cut + offset] - 1) - log2_Gamma_th) / dl;
+    const double B_slope = (fast_log2(s.B[idx_cut + offset]) - log2_B) / dl;
+    const double N_p_slope = (fast_log2(s.N_p[idx_cut + offset]) - log2_N_p) / dl;
+    for (int k = 0; k < idx_cut; k++) {
+        const double dlog2_r = fast_log2(s.r[k]) - log2_r;
+        s.Gamma_th[k] = 1 + fast_exp2(log2_Gamma_th + gamma_slope * dlog2_r);
+        s.B[k] = fast_exp2(log2_B + B_slope * dlog2_r);
+        s.N_p[k] = fast_exp2(log2_N_p + N_p_slope * dlog2_r);
+    }
+}
+
+// grid_solve_shock_pair: reverse-shock.tpp:511-591.  Returns VAG_ST_* bits; *inj_idx_out receives
+// the row's injection_idx (n_t when the crossing never completes inside the lattice).
+VAG_HD int solve_pair_row(const ModelCfg& m, double theta, double t_dec, const double* t, int n_t, const ShockRow& sf,
+                          const ShockRow& sr, int* inj_idx_out) {
+    FREqn eqn(m, theta);
+    double x[FREqn::N];
+    const double t0 = vmin(t[0], vmin(0.01 * unit::sec, 0.1 * t_dec));
+    eqn.set_init_state(x, t0);
+    int injection_idx = n_t;
+    *inj_idx_out = injection_idx;
+
+    constexpr double RS_Gamma_limit = 1.03;
+    if (x[FREqn::iG] <= RS_Gamma_limit) {
+        set_stopping_row(sf, n_t, x[FREqn::iT], x[FREqn::iR]);
+        set_stopping_row(sr, n_t, x[FREqn::iT], x[FREqn::iR]);
+        return 0;
+    }
+    double rtol = m.rtol;
+    if (eqn.shell_sigma(x[FREqn::iE4], x[FREqn::iM4]) > 0) rtol *= dflt::magnetized_rtol_factor;
+
+    Dopri5<FREqn::N> st;
+    st.initialize(x, t0, 1e-9 * t0, rtol);
+
+    int k = 0;
+    for (; k < n_t && t[k] < t0; k++) {
+        eqn.set_init_state(x, t[k]);
+        save_fwd_state(m, m.fwd.eps_B, sf, k, x[FREqn::iG], x[FREqn::iM2], x[FREqn::iU2], x[FREqn::iR], x[FREqn::iT]);
+        eqn.save_rvs_state(m.rvs.eps_B, sr, k, injection_idx, x);
+    }
+
+    bool reverse_shock_crossing = true;
+    bool injection_idx_pending = false;
+    double t_cross = 0;
+    double t_step_start = t0;
+    const double t_back = t[n_t - 1];
+    int status = 0;
+    for (int steps = 0; st.t <= t_back;) {
+        if (!st.do_step(eqn)) {
+            status |= VAG_ST_ODE_FAIL500;
+            break;
+        }
+        if (++steps > dflt::max_ode_steps) {
+            status |= VAG_ST_ODE_STEP_CAP;
+            break;
+        }
+        if (st.t + st.dt == st.t) {
+            status |= VAG_ST_ODE_STALLED;
+            break;
+        }
+        if (reverse_shock_crossing && eqn.crossing_complete(st.x, st.t)) {
+            // locate_crossing_time: reverse-shock.tpp:482-495
+            double t_lo = t_step_start, t_hi = st.t;
+            for (int iter = 0; iter < 100 && (t_hi - t_lo) > 1e-12 * t_hi; ++iter) {
+                const double t_mid = 0.5 * (t_lo + t_hi);
+                st.calc_state(t_mid, x);
+                if (eqn.crossing_complete(x, t_mid)) {
+                    t_hi = t_mid;
+                } else {
+                    t_lo = t_mid;
+                }
+            }
+            st.calc_state(t_hi, x);
+            t_cross = t_hi;
+            eqn.save_cross_state(x);
+            reverse_shock_crossing = false;
+            injection_idx_pending = true;
+        }
+        t_step_start = st.t;
+        while (k < n_t && st.t > t[k]) {
+            st.calc_state(t[k], x);
+            if (injection_idx_pending && t[k] >= t_cross) {
+                injection_idx = k > 0 ? k : 1;
+                injection_idx_pending = false;
+            }
+            save_fwd_state(m, m.fwd.eps_B, sf, k, x[FREqn::iG], x[FREqn::iM2], x[FREqn::iU2], x[FREqn::iR],
+                           x[FREqn::iT]);
+            eqn.save_rvs_state(m.rvs.eps_B, sr, k, injection_idx, x);
+            ++k;
+        }
+    }
+    fill_default_row(sf, k, n_t);
+    fill_default_row(sr, k, n_t);
+    *inj_idx_out = injection_idx;
+    reverse_shock_early_extrap(sr, n_t, injection_idx);
+    return status;
+}
+
+}  // namespace vag

@@ -1,0 +1,130 @@
+"""Batched model evaluation on one GPU through the C ABI (include/vag.h).
+
+``Engine`` owns one ``vag_context`` (a CUDA stream + growable HBM workspaces).  Host-array
+methods copy inputs/outputs inside the call; ``*_dev`` methods take raw device pointers (e.g.
+``torch.Tensor.data_ptr()``) and only enqueue work.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, abi
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self._lib.vag_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.vag_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- host buffers -------------------------------------------------------------------------
+    @staticmethod
+    def _params(params):
+        p = np.ascontiguousarray(params, dtype=abi.PARAMS_DTYPE).reshape(-1)
+        return p
+
+    def flux_density_grid(self, params, t, nu, return_status=False):
+        """Batched ``Model.flux_density_grid`` -> float64[n_models, 5, n_nu, n_t]
+        (component order ``abi.COMPONENTS``)."""
+        p, t, nu = self._params(params), _f64(t).reshape(-1), _f64(nu).reshape(-1)
+        out = np.empty((p.size, abi.NCOMP, nu.size, t.size))
+        st = np.zeros(p.size, dtype=np.int32)
+        _lib.check(self._lib.vag_flux_density_grid(self._h, p.ctypes.data, p.size, t.ctypes.data, t.size,
+                                                   nu.ctypes.data, nu.size, out.ctypes.data, st.ctypes.data))
+        return (out, st) if return_status else out
+
+    def flux_density_series(self, params, t, nu, return_status=False):
+        """Batched ``Model.flux_density`` -> float64[n_models, 5, n]."""
+        p, t, nu = self._params(params), _f64(t).reshape(-1), _f64(nu).reshape(-1)
+        out = np.empty((p.size, abi.NCOMP, t.size))
+        st = np.zeros(p.size, dtype=np.int32)
+        _lib.check(self._lib.vag_flux_density_series(self._h, p.ctypes.data, p.size, t.ctypes.data, nu.ctypes.data,
+                                                     t.size, out.ctypes.data, st.ctypes.data))
+        return (out, st) if return_status else out
+
+    def chi2_series(self, params, t, nu, lnF_obs, sigma_ln, w, return_status=False):
+        """Batched ``Fitter._evaluate`` for point data -> chi2[n_models] (+inf where non-finite)."""
+        p = self._params(params)
+        t, nu, lnF_obs, sigma_ln, w = (_f64(a).reshape(-1) for a in (t, nu, lnF_obs, sigma_ln, w))
+        if not (t.size == nu.size == lnF_obs.size == sigma_ln.size == w.size):
+            raise ValueError("t, nu, lnF_obs, sigma_ln and w must have the same size")
+        chi2 = np.empty(p.size)
+        st = np.zeros(p.size, dtype=np.int32)
+        _lib.check(self._lib.vag_chi2_series(self._h, p.ctypes.data, p.size, t.ctypes.data, nu.ctypes.data,
+                                             lnF_obs.ctypes.data, sigma_ln.ctypes.data, w.ctypes.data, t.size,
+                                             chi2.ctypes.data, st.ctypes.data))
+        return (chi2, st) if return_status else chi2
+
+    # ---- device buffers (raw pointers) ---------------------------------------------------------
+    def flux_density_grid_dev(self, d_params, n_models, d_t, n_t, d_nu, n_nu, d_out, d_status=0, stream=0):
+        _lib.check(self._lib.vag_flux_density_grid_dev(self._h, d_params, n_models, d_t, n_t, d_nu, n_nu, d_out,
+                                                       d_status or None, stream or None))
+
+    def flux_density_series_dev(self, d_params, n_models, d_t, d_nu, n, d_out, d_status=0, stream=0):
+        _lib.check(self._lib.vag_flux_density_series_dev(self._h, d_params, n_models, d_t, d_nu, n, d_out,
+                                                         d_status or None, stream or None))
+
+    def chi2_series_dev(self, d_params, n_models, d_t, d_nu, d_lnF, d_sig, d_w, n, d_chi2, d_status=0, stream=0):
+        _lib.check(self._lib.vag_chi2_series_dev(self._h, d_params, n_models, d_t, d_nu, d_lnF, d_sig, d_w, n, d_chi2,
+                                                 d_status or None, stream or None))
+
+    def synchronize(self):
+        _lib.check(self._lib.vag_synchronize(self._h))
+
+    def set_capacity(self, cap_theta, cap_phi):
+        _lib.check(self._lib.vag_set_capacity(self._h, int(cap_theta), int(cap_phi)))
+
+    def set_profiling(self, on=True):
+        _lib.check(self._lib.vag_set_profiling(self._h, 1 if on else 0))
+
+    def last_stage_ms(self):
+        ms = (C.c_float * 8)()
+        self._lib.vag_last_stage_ms(self._h, ms)
+        names = ("grid", "rowmap", "dynamics", "radiation", "eats", "finish")
+        return {k: float(ms[i]) for i, k in enumerate(names)}
+
+    def last_launch_count(self):
+        return int(self._lib.vag_last_launch_count(self._h))
+
+    def details(self, param, t_min, t_max):
+        """Stage tables of one model (code units) -- the analogue of ``Model.details``."""
+        p = self._params(param)
+        assert p.size == 1
+        info = np.zeros(1, dtype=abi.GRID_INFO_DTYPE)
+        f = self._lib.vag_details
+        _lib.check(f(self._h, p.ctypes.data, t_min, t_max, info.ctypes.data, *([None] * 7)))
+        i = info[0]
+        n_phi, n_theta, n_t, n_reps = (int(i[k]) for k in ("n_phi", "n_theta", "n_t", "n_reps"))
+        d = {
+            "info": i,
+            "theta": np.zeros(n_theta),
+            "phi": np.zeros(n_phi),
+            "reps": np.zeros(n_reps, dtype=np.int32),
+            "t_rows": np.zeros((n_reps, n_t)),
+            "fwd_shock": np.zeros((7, n_reps, n_t)),
+            "rvs_shock": np.zeros((7, n_reps, n_t)),
+            "inj_idx": np.zeros(n_reps, dtype=np.int32),
+        }
+        _lib.check(f(self._h, p.ctypes.data, t_min, t_max, info.ctypes.data, d["theta"].ctypes.data,
+                     d["phi"].ctypes.data, d["reps"].ctypes.data, d["t_rows"].ctypes.data,
+                     d["fwd_shock"].ctypes.data, d["rvs_shock"].ctypes.data, d["inj_idx"].ctypes.data))
+        return d
