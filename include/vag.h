@@ -182,6 +182,8 @@ int vag_set_profiling(vag_context* ctx, int enable);
 int vag_last_stage_ms(vag_context* ctx, float ms[8]);
 /* number of kernel launches issued by the most recent batched call */
 int vag_last_launch_count(vag_context* ctx);
+/* dependent-free DFMA throughput of the device in TFLOP/s (FP64 roofline denominator) */
+int vag_measure_fp64_peak(vag_context* ctx, double* tflops);
 
 #ifdef __cplusplus
 }

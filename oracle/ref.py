@@ -17,22 +17,42 @@ from vegasafterglow_b200 import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _REF_DIR = os.path.join(_HERE, "_ref")
-_lib = None
+_libs = {}
+_variant = "main"  # "main": reference flags (x86-64-v3, FMA, xsimd); "alt": -O2, no FMA, no xsimd
 
 
-def available() -> bool:
-    return os.path.exists(os.path.join(_REF_DIR, "libvagref.so"))
+def _path(variant):
+    return os.path.join(_REF_DIR, "libvagref.so" if variant == "main" else "libvagref_alt.so")
+
+
+def available(variant="main") -> bool:
+    return os.path.exists(_path(variant))
+
+
+class use_variant:
+    """Context manager selecting which build of the unmodified reference the calls below use."""
+
+    def __init__(self, variant):
+        self.variant = variant
+
+    def __enter__(self):
+        global _variant
+        self._old, _variant = _variant, self.variant
+
+    def __exit__(self, *a):
+        global _variant
+        _variant = self._old
 
 
 def lib():
-    global _lib
-    if _lib is None:
-        path = os.path.join(_REF_DIR, "libvagref.so")
+    if _variant not in _libs:
+        path = _path(_variant)
         if not os.path.exists(path):
             raise RuntimeError(f"{path} missing: run `make -C oracle` where /root/reference exists")
-        _lib = C.CDLL(path)
-        _lib.vagref_hardware_threads.restype = C.c_int
-    return _lib
+        l = C.CDLL(path)
+        l.vagref_hardware_threads.restype = C.c_int
+        _libs[_variant] = l
+    return _libs[_variant]
 
 
 def pymodule():

@@ -1,0 +1,109 @@
+"""Generate the committed golden fixtures from the UNMODIFIED reference (oracle/_ref, built by
+oracle/Makefile from /root/reference) -- run in the CPU container where /root/reference exists:
+
+    python tests/golden/make_golden.py
+
+Writes tests/golden/*.npz (inputs + reference outputs) and tests/golden/PINNING.json, which
+records how closely the locally built reference reproduces the reference's OWN committed golden
+vectors (/root/reference/tests/python/golden/*.npz) for the in-scope configurations.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref  # noqa: E402
+from vegasafterglow_b200 import abi, configs  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+REF_GOLDEN = "/root/reference/tests/python/golden"
+
+
+def save(name, params, t, nu, series=False, **extra):
+    fn = ref.flux_density_series if series else ref.flux_density_grid
+    f = fn(params, t, nu, n_threads=8)
+    # the same unmodified reference built with different code generation (oracle/Makefile,
+    # libvagref_alt.so): |flux - flux_alt| is the reference's own reproducibility floor
+    with ref.use_variant("alt"):
+        f_alt = fn(params, t, nu, n_threads=8)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), params=params, t=t, nu=nu, flux=f, flux_alt=f_alt,
+                        series=series, **extra)
+    return f
+
+
+def main():
+    pin = {}
+    # 1. the reference's own golden configurations that are in scope (typed jets, no SSC)
+    for name in configs.GOLDEN:
+        p = configs.golden(name)
+        f = save("golden_" + name, p, configs.GOLDEN_T, configs.GOLDEN_NU)
+        path = os.path.join(REF_GOLDEN, name + ".npz")
+        if os.path.exists(path):
+            g = np.load(path)
+            dev = {}
+            for ci, cname in enumerate(abi.COMPONENTS):
+                b = np.asarray(g[cname])
+                if b.ndim != 2 or not b.any():
+                    continue
+                a = f[0, ci]
+                m = b > 1e-2 * b.max()
+                dev[cname] = float(np.max(np.abs(a[m] - b[m]) / b[m]))
+            pin[name] = dev
+    # 2. BASELINE.json configs C1-C3 (+ dense C2)
+    for name, (p, t, nu) in {"C1": configs.C1(), "C2": configs.C2(), "C2_dense": configs.C2(dense=True),
+                             "C3": configs.C3()}.items():
+        save("config_" + name, p, t, nu)
+    # 3. stage tables of C1, C2, C3 (Coord + Shock + observer grids)
+    for name, (p, t, nu) in {"C1": configs.C1(), "C2": configs.C2(), "C3": configs.C3()}.items():
+        d = ref.details(p, t[0], t[-1])
+        np.savez_compressed(os.path.join(OUT, "stages_" + name + ".npz"), params=p, t_min=t[0], t_max=t[-1],
+                            info=np.array(tuple(d["info"].tolist())), **{k: v for k, v in d.items() if k != "info"})
+    # 4. seeded random batches (SURVEY.md section 8d draw), grid and series (config C5 data layout)
+    t, nu = configs.C1()[1:]
+    save("batch_fs_tophat_ism", configs.random_draw(48, seed=11), t, nu)
+    save("batch_rs_tophat_ism", configs.random_draw(48, seed=12, rvs=True), t, nu)
+    save("batch_fs_gauss_offaxis", configs.random_draw(12, seed=13, jet="gaussian", theta_obs_max=0.4), t, nu)
+    save("batch_fs_powerlaw_wind", configs.random_draw(12, seed=14, jet="powerlaw", medium="wind", theta_obs_max=0.3), t, nu)
+    save("batch_rs_tophat_wind", configs.random_draw(24, seed=15, rvs=True, medium="wind"), t, nu)
+    ts = np.sort(np.tile(np.logspace(2.5, 6.5, 20), 5))
+    nus = np.tile([1e9, 5e9, 4.84e14, 1e17, 1e18], 20)
+    save("series_rs_tophat_ism", configs.random_draw(48, seed=16, rvs=True), ts, nus, series=True)
+    save("series_rs_gauss", configs.random_draw(8, seed=17, rvs=True, jet="gaussian", theta_obs_max=0.4), ts, nus, series=True)
+    # 5. edge cases the reference tests exercise (tests/python/test_parameter_corners.py,
+    #    test_pybind_validation.py): single point, repeated times, extreme early/late windows,
+    #    unsorted frequencies, p < 2, tiny / huge Gamma0, off-axis beyond the jet edge
+    pe = configs.make()
+    save("edge_single_point", pe, np.array([1e4]), np.array([1e14]))
+    save("edge_repeated_times", pe, np.array([1e3, 1e3, 1e4, 1e4, 1e5]), np.array([1e17, 1e9]))
+    save("edge_tiny_times", pe, np.array([1e-9, 1e-8]), np.array([1e9, 1e14, 1e17]))
+    save("edge_late_times", pe, np.logspace(8, 11, 12), np.array([1e9, 1e14]))
+    corners = np.concatenate([
+        configs.make(fwd=(0.1, 1e-3, 1.8)),                       # 1 < p < 2
+        configs.make(fwd=(0.1, 1e-3, 3.4)),                       # p > 3: cyclotron correction branch
+        configs.make(Gamma0=2.0),                                 # barely relativistic
+        configs.make(Gamma0=2000.0, E_iso=1e54),                  # ultra-relativistic
+        configs.make(theta_obs=0.5),                              # tophat far off-axis
+        configs.make(theta_c=1.5, theta_obs=0.0),                 # nearly spherical
+        configs.make(n_ism=1e-5),                                 # tenuous medium
+        configs.make(n_ism=1e4, fwd=(0.3, 0.1, 2.2)),             # dense, strongly self-absorbed
+        configs.make(medium="wind", A_star=1.0, n0=1e3),          # wind with inner density floor
+        configs.make(medium="wind_ism", A_star=0.01, n_ism=0.1),  # wind + ISM floor
+        configs.make(radiative_fireball=False, rvs=(0.1, 0.01, 2.3), duration=100.0),
+        configs.make(xi_e=0.1, rvs=(0.05, 0.001, 2.6), rvs_xi_e=0.3),
+        configs.make(jet="powerlaw", k_e=4.0, k_g=1.0, theta_obs=0.05),
+        configs.make(jet="gaussian", theta_c=0.05, theta_obs=0.0, resolutions=(0.1, 0.3, 5.0)),
+        configs.make(z=3.0, lumi_dist=8e28, rtol=1e-8),
+    ])
+    save("edge_parameter_corners", corners, np.logspace(1, 8, 30), np.array([1e8, 1e11, 1e14, 1e18, 1e22]))
+    with open(os.path.join(OUT, "PINNING.json"), "w") as fh:
+        json.dump({"what": "max relative deviation (bins > 1% of peak) of oracle/_ref (reference built here, "
+                           "x86-64-v3, g++ 13) from the reference's own committed golden .npz",
+                   "deviation": pin}, fh, indent=1)
+    print(json.dumps(pin, indent=1))
+
+
+if __name__ == "__main__":
+    main()

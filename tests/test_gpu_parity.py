@@ -1,0 +1,183 @@
+"""GPU tier (-m gpu): the sm_100a kernels, called through the C ABI (libvag_b200.so), against
+(1) the committed reference fixtures, (2) the unmodified reference itself (oracle/_ref travels to
+the GPU box) on fresh seeded draws, and (3) size-independent invariants at BASELINE.json's full
+batch size."""
+import numpy as np
+import pytest
+
+from tests.helpers import assert_parity, golden_names, load_golden, model_errors
+from vegasafterglow_b200 import abi, configs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if n != "golden_gauss_ism_rs"])
+def test_fixture_parity(engine, name):
+    g = load_golden(name)
+    fn = engine.flux_density_series if bool(g["series"]) else engine.flux_density_grid
+    f, st = fn(g["params"], g["t"], g["nu"], return_status=True)
+    assert (st == 0).all()
+    errs = assert_parity(f, g, name)
+    print(f"{name}: median rel err {np.median(errs):.2e}, max {errs.max():.2e}")
+
+
+def test_structured_reverse_shock_within_reference_floor(engine):
+    # gauss_ism_rs: the reference documents the wing-row reverse-shock solves as chaotic
+    # (tests/python/test_golden.py:95); its own cross-build deviation from its committed golden is
+    # 2.4e-4 (fwd) / 1.2e-3 (rvs) (tests/golden/PINNING.json).  Accept the reference's own
+    # acceptance contract here: |a-b| <= 2e-3*|b| + 1e-2*peak (regenerate.py:29-30).
+    g = load_golden("golden_gauss_ism_rs")
+    f = engine.flux_density_grid(g["params"], g["t"], g["nu"])
+    for comp in (0, 1, 3):
+        a, b = f[0, comp], g["flux"][0, comp]
+        assert np.all(np.abs(a - b) <= 2e-3 * np.abs(b) + 1e-2 * b.max())
+
+
+@pytest.mark.parametrize("kw,n", [(dict(), 192), (dict(rvs=True), 192), (dict(medium="wind"), 64),
+                                  (dict(jet="gaussian", theta_obs_max=0.4), 24),
+                                  (dict(jet="powerlaw", medium="wind", theta_obs_max=0.3), 16)])
+def test_fresh_draws_against_reference(engine, kw, n):
+    from oracle import ref
+
+    if not ref.available() or not ref.available("alt"):
+        pytest.skip("oracle/_ref not present")
+    P = configs.random_draw(n, seed=101, **kw)
+    t, nu = configs.C1()[1:]
+    g = {"flux": ref.flux_density_grid(P, t, nu, n_threads=ref.hardware_threads())}
+    with ref.use_variant("alt"):
+        g["flux_alt"] = ref.flux_density_grid(P, t, nu, n_threads=ref.hardware_threads())
+    f, st = engine.flux_density_grid(P, t, nu, return_status=True)
+    assert (st == 0).all()
+    errs = assert_parity(f, g, str(kw))
+    print(f"{kw}: median {np.median(errs):.2e} max {errs.max():.2e}; reference self-spread median "
+          f"{np.median(model_errors(g['flux_alt'], g['flux'])):.2e}")
+
+
+def test_series_equals_grid(engine):
+    p, t, nu = configs.C3()
+    fg = engine.flux_density_grid(p, t, nu)
+    ts, nus = np.repeat(t, nu.size), np.tile(nu, t.size)
+    fs = engine.flux_density_series(p, ts, nus)
+    for c in (0, 1, 3):
+        np.testing.assert_allclose(fs[0, c].reshape(t.size, nu.size).T, fg[0, c], rtol=1e-12)
+
+
+def test_exact_invariants(engine):
+    # tests/python/test_physics_invariants.py:37-105
+    p, t, nu = configs.C3()
+    f1 = engine.flux_density_grid(p, t, nu)
+    q = p.copy()
+    q["lumi_dist"] *= 3.0
+    f2 = engine.flux_density_grid(q, t, nu)
+    np.testing.assert_allclose(f2[0, 0] * 9.0, f1[0, 0], rtol=1e-9)
+    np.testing.assert_allclose(f1[0, 0], f1[0, 1] + f1[0, 3], rtol=1e-12)
+    assert np.all(f1[0, 2] == 0) and np.all(f1[0, 4] == 0)  # no SSC components
+
+
+def test_batch_is_independent_of_order_and_size(engine):
+    # every model of a batch is an independent evaluation: permuting / splitting the batch must
+    # give bit-identical rows (no cross-model term anywhere, fitter.py:503-533)
+    t, nu = configs.C1()[1:]
+    P = configs.random_draw(300, seed=7, rvs=True)
+    f = engine.flux_density_grid(P, t, nu)
+    perm = np.random.default_rng(0).permutation(P.size)
+    fp = engine.flux_density_grid(P[perm], t, nu)
+    np.testing.assert_array_equal(fp, f[perm])
+    f1 = engine.flux_density_grid(P[17:18], t, nu)   # single model takes the row-split (atomic) path
+    np.testing.assert_allclose(f1[0], f[17], rtol=1e-13)
+
+
+def test_chi2_matches_manual_formula(engine):
+    g = load_golden("series_rs_tophat_ism")
+    P, t, nu = g["params"], g["t"], g["nu"]
+    rng = np.random.default_rng(42)
+    obs = g["flux"][0, 0] * (1 + 0.05 * rng.standard_normal(t.size))
+    sig = np.full(t.size, 0.1)
+    w = rng.uniform(0.5, 1.5, t.size)
+    chi2 = engine.chi2_series(P, t, nu, np.log(obs), sig, w)
+    f = engine.flux_density_series(P, t, nu)
+    manual = np.array([np.sum(w * ((np.log(obs) - np.log(np.maximum(f[i, 0], 1e-300))) / sig) ** 2) for i in range(P.size)])
+    np.testing.assert_allclose(chi2, manual, rtol=1e-12)
+    # and against the reference's flux
+    ref_chi2 = np.array([np.sum(w * ((np.log(obs) - np.log(np.maximum(g["flux"][i, 0], 1e-300))) / sig) ** 2) for i in range(P.size)])
+    np.testing.assert_allclose(chi2, ref_chi2, rtol=1e-4, atol=1e-6)
+
+
+def test_full_size_batch_properties(engine):
+    # BASELINE.json config 5 size: 4096 walkers, forward+reverse shock, 100-point 5-band series
+    n = 4096
+    P = configs.random_draw(n, seed=5, rvs=True)
+    ts = np.sort(np.tile(np.logspace(2.5, 6.5, 20), 5))
+    nus = np.tile([1e9, 5e9, 4.84e14, 1e17, 1e18], 20)
+    f, st = engine.flux_density_series(P, ts, nus, return_status=True)
+    assert (st == 0).all()
+    assert np.isfinite(f).all() and (f[:, 0] > 0).all()
+    np.testing.assert_allclose(f[:, 0], f[:, 1] + f[:, 3], rtol=1e-12)
+    # a strided sample of the batch equals the same models evaluated on their own
+    idx = np.arange(0, n, 257)
+    fs = engine.flux_density_series(P[idx], ts, nus)
+    np.testing.assert_array_equal(fs, f[idx])
+    # and matches the reference where it is available
+    from oracle import ref
+
+    if ref.available() and ref.available("alt"):
+        g = {"flux": ref.flux_density_series(P[idx], ts, nus, n_threads=ref.hardware_threads())}
+        with ref.use_variant("alt"):
+            g["flux_alt"] = ref.flux_density_series(P[idx], ts, nus, n_threads=ref.hardware_threads())
+        assert_parity(fs, g, "4096-walker sample")
+
+
+def test_error_conventions(engine):
+    p, t, nu = configs.C1()
+    with pytest.raises(ValueError, match="ascending"):
+        engine.flux_density_grid(p, t[::-1], nu)
+    with pytest.raises(ValueError, match="non-empty"):
+        engine.flux_density_grid(p, np.array([]), nu)
+    with pytest.raises(ValueError, match="same size"):
+        engine.flux_density_series(p, t, nu)
+    q = p.copy()
+    q["fwd"]["eps_e"] = 2.0
+    with pytest.raises(ValueError, match="eps_e"):
+        engine.flux_density_grid(q, t, nu)
+    q = p.copy()
+    q["fwd"]["ssc"] = 1
+    with pytest.raises(NotImplementedError):
+        engine.flux_density_grid(q, t, nu)
+    assert engine.flux_density_grid(p[:0], t, nu).shape == (0, abi.NCOMP, nu.size, t.size)
+
+
+def test_stage_tables_on_device(engine):
+    for name in ("C1", "C2", "C3"):
+        g = load_golden("stages_" + name)
+        d = engine.details(g["params"], float(g["t_min"]), float(g["t_max"]))
+        i = d["info"]
+        assert (i["n_phi"], i["n_theta"], i["n_t"], i["n_reps"], i["symmetry"]) == tuple(g["info"][:5])
+        np.testing.assert_array_equal(d["reps"], g["reps"])
+        rel = lambda a, b: float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+        assert rel(d["theta"], g["theta"]) < 5e-6
+        assert rel(d["t_rows"], g["t_rows"]) < 1e-12
+        for a in (0, 1, 3, 4, 5, 6):
+            assert rel(d["fwd_shock"][a], g["fwd_shock"][a]) < 5e-6
+        if g["params"]["has_rvs"][0]:
+            np.testing.assert_array_equal(d["inj_idx"], g["inj_idx"])
+            for a in (0, 1, 3, 4, 5, 6):
+                assert rel(d["rvs_shock"][a], g["rvs_shock"][a]) < 5e-6
+
+
+def test_device_pointer_api_matches_host_api(engine):
+    import torch
+
+    P = configs.random_draw(64, seed=9, rvs=True)
+    t, nu = configs.C1()[1:]
+    host = engine.flux_density_grid(P, t, nu)
+    dev = torch.device("cuda:0")
+    d_p = torch.from_numpy(P.view(np.uint8).copy()).to(dev)
+    d_t, d_nu = torch.from_numpy(t).to(dev), torch.from_numpy(nu).to(dev)
+    d_out = torch.empty((P.size, abi.NCOMP, nu.size, t.size), dtype=torch.float64, device=dev)
+    d_st = torch.zeros(P.size, dtype=torch.int32, device=dev)
+    engine.set_capacity(384, 128)
+    engine.flux_density_grid_dev(d_p.data_ptr(), P.size, d_t.data_ptr(), t.size, d_nu.data_ptr(), nu.size,
+                                 d_out.data_ptr(), d_st.data_ptr())
+    engine.synchronize()
+    np.testing.assert_array_equal(d_out.cpu().numpy(), host)
+    assert int(d_st.abs().sum()) == 0

@@ -159,6 +159,18 @@ __global__ void k_nan_capacity(BatchWs w, double* out, size_t comp_sz_total) {
     for (size_t i = threadIdx.x; i < comp_sz_total; i += blockDim.x) out[(size_t)mi * comp_sz_total + i] = NAN;
 }
 
+// FP64 FMA throughput probe (roofline denominator for the ODE / radiation / EATS kernels, which are
+// FP64-pipe or dependent-latency bound; MEASURED_PEAKS.json has no FP64 entry)
+__global__ void __launch_bounds__(256) k_fp64_peak(double* sink, int iters) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678) sink[0] = a0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -549,6 +561,30 @@ int vag_set_capacity(vag_context* ctx, int cap_theta, int cap_phi) {
     if (cap_theta < 40 || cap_phi < 2) return fail(VAG_ERR_INVALID, "capacity too small");
     ctx->cap_theta = cap_theta;
     ctx->cap_phi = cap_phi;
+    return VAG_OK;
+}
+
+int vag_measure_fp64_peak(vag_context* ctx, double* tflops) {
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->io_aux.ensure(64));
+    const int iters = 1 << 16, blocks = ctx->sm_count * 8, threads = 256;
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(a, ctx->stream));
+        k_fp64_peak<<<blocks, threads, 0, ctx->stream>>>(static_cast<double*>(ctx->io_aux.p), iters);
+        CK(cudaEventRecord(b, ctx->stream));
+        CK(cudaEventSynchronize(b));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        const double fl = 2.0 * 8 * (double)iters * blocks * threads;
+        best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *tflops = best;
     return VAG_OK;
 }
 

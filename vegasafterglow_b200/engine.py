@@ -99,8 +99,13 @@ class Engine:
     def last_stage_ms(self):
         ms = (C.c_float * 8)()
         self._lib.vag_last_stage_ms(self._h, ms)
-        names = ("grid", "rowmap", "dynamics", "radiation", "eats", "finish")
+        names = ("grid", "dynamics", "radiation", "eats", "finish")
         return {k: float(ms[i]) for i, k in enumerate(names)}
+
+    def measure_fp64_peak(self):
+        v = C.c_double()
+        _lib.check(self._lib.vag_measure_fp64_peak(self._h, C.byref(v)))
+        return float(v.value)
 
     def last_launch_count(self):
         return int(self._lib.vag_last_launch_count(self._h))
