@@ -48,7 +48,7 @@ void run_front(HostBatch& hb, const vag_params* params, size_t n, double t_min, 
     w.cell_off = hb.alloc<long long>(n + 1);
     w.totals = hb.alloc<int>(TOT_N);
     w.status = hb.alloc<int>(n);
-    for (size_t i = 0; i < n; ++i) k0_grid_body(w, (int)i, t_min, t_max);
+    for (size_t i = 0; i < n; ++i) k0_grid_body(SeqPar{}, w, (int)i, t_min, t_max);
     k0b_scan_body(w);
     const int rows = w.totals[TOT_ROWS];
     const long long cells = w.cell_off[n];

@@ -29,14 +29,90 @@ static_assert(sizeof(vag_params) == 248, "vag_params layout must match vegasafte
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) k_grid(BatchWs w, const double* __restrict__ t_obs, int n_t_obs) {
-    const int mi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (mi >= w.n_models) return;
-    k0_grid_body(w, mi, t_obs[0], t_obs[n_t_obs - 1]);
+// K0: one warp per model (vag_grid.cuh), 4 warps per CTA
+__global__ void __launch_bounds__(128) k_grid(BatchWs w, const double* __restrict__ t_obs, int n_t_obs) {
+    const int mi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (mi >= w.n_models) return;  // whole warps exit together
+    const WarpPar par{(int)(threadIdx.x & 31)};
+    k0_grid_body(par, w, mi, t_obs[0], t_obs[n_t_obs - 1]);
 }
 
-__global__ void k_scan(BatchWs w) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) k0b_scan_body(w);
+// K0b: exclusive scan of the ragged row / cell counts over the models of the batch + totals.
+// One CTA of 1024 threads; thread i owns a contiguous slice of models (k0b_scan_body is the
+// sequential statement of the same result).
+__global__ void __launch_bounds__(1024) k_scan(BatchWs w) {
+    __shared__ int s_rows[1024];
+    __shared__ long long s_cells[1024];
+    __shared__ int s_max[3][32];
+    __shared__ int s_or[32];
+    const int tid = threadIdx.x, n = w.n_models;
+    const int per = (n + 1023) / 1024;
+    const int m0 = min(tid * per, n), m1 = min(m0 + per, n);
+    int rows = 0, max_nt = 0, max_nth = 0, max_er = 0, st = 0;
+    long long cells = 0;
+    for (int mi = m0; mi < m1; ++mi) {
+        const GridHeader& h = w.hdr[mi];
+        rows += h.n_reps;
+        cells += (long long)h.n_reps * h.n_t;
+        max_nt = max(max_nt, h.n_t);
+        max_nth = max(max_nth, h.n_theta);
+        max_er = max(max_er, h.n_theta * h.n_phi_eff);
+        st |= h.status;
+    }
+    s_rows[tid] = rows;
+    s_cells[tid] = cells;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over the 1024 slice totals
+    for (int off = 1; off < 1024; off <<= 1) {
+        int r = 0;
+        long long c = 0;
+        if (tid >= off) {
+            r = s_rows[tid - off];
+            c = s_cells[tid - off];
+        }
+        __syncthreads();
+        s_rows[tid] += r;
+        s_cells[tid] += c;
+        __syncthreads();
+    }
+    int row0 = s_rows[tid] - rows;
+    long long cell0 = s_cells[tid] - cells;
+    for (int mi = m0; mi < m1; ++mi) {
+        const GridHeader& h = w.hdr[mi];
+        w.row_off[mi] = row0;
+        w.cell_off[mi] = cell0;
+        row0 += h.n_reps;
+        cell0 += (long long)h.n_reps * h.n_t;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        max_nt = max(max_nt, __shfl_xor_sync(0xffffffffu, max_nt, o));
+        max_nth = max(max_nth, __shfl_xor_sync(0xffffffffu, max_nth, o));
+        max_er = max(max_er, __shfl_xor_sync(0xffffffffu, max_er, o));
+        st |= __shfl_xor_sync(0xffffffffu, st, o);
+    }
+    if ((tid & 31) == 0) {
+        s_max[0][tid >> 5] = max_nt;
+        s_max[1][tid >> 5] = max_nth;
+        s_max[2][tid >> 5] = max_er;
+        s_or[tid >> 5] = st;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int i = 1; i < 32; ++i) {
+            max_nt = max(max_nt, s_max[0][i]);
+            max_nth = max(max_nth, s_max[1][i]);
+            max_er = max(max_er, s_max[2][i]);
+            st |= s_or[i];
+        }
+        w.row_off[n] = s_rows[1023];
+        w.cell_off[n] = s_cells[1023];
+        w.totals[TOT_ROWS] = s_rows[1023];
+        w.totals[TOT_MAX_NT] = max_nt;
+        w.totals[TOT_MAX_NTHETA] = max_nth;
+        w.totals[TOT_MAX_EROWS] = max_er;
+        w.totals[TOT_STATUS_OR] = st;
+    }
 }
 
 __global__ void k_rowmap(BatchWs w) {
@@ -319,8 +395,8 @@ int run_front(vag_context* ctx, BatchWs& w, const vag_params* d_params, size_t n
     int rc = setup_models(ctx, w, d_params, n);
     if (rc) return rc;
     mark(ctx, 0, s);
-    k_grid<<<(unsigned)((n + 31) / 32), 32, 0, s>>>(w, d_t, (int)n_t);
-    k_scan<<<1, 32, 0, s>>>(w);
+    k_grid<<<(unsigned)((n * 32 + 127) / 128), 128, 0, s>>>(w, d_t, (int)n_t);
+    k_scan<<<1, 1024, 0, s>>>(w);
     ctx->launches += 2;
     CK(cudaMemcpyAsync(ctx->h_totals, w.totals, sizeof(int) * TOT_N, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(ctx->h_cells, w.cell_off + n, sizeof(long long), cudaMemcpyDeviceToHost, s));

@@ -46,11 +46,27 @@ struct Dopri5 {
     // consecutive attempts were rejected (Boost throws std::runtime_error there).
     template <class Sys>
     VAG_HD bool do_step(Sys& sys) {
+        begin_step(sys);
+        for (int fails = 0;;) {
+            if (try_step(sys)) return true;
+            if (++fails >= 500) return false;
+        }
+    }
+
+    // First half of dense_output_runge_kutta::do_step: lazily evaluate the FSAL derivative.
+    template <class Sys>
+    VAG_HD void begin_step(Sys& sys) {
         if (!deriv_ready) {
             sys(x, k1, t);
             deriv_ready = true;
         }
         t_old = t;
+    }
+
+    // One attempt with the current dt (controlled_runge_kutta::try_step): true = accepted.
+    // The six stage evaluations are sys(.., t + a_i dt) for a_i = 1/5, 3/10, 4/5, 8/9, 1, 1.
+    template <class Sys>
+    VAG_HD bool try_step(Sys& sys) {
         constexpr double a2 = 1.0 / 5, a3 = 3.0 / 10, a4 = 4.0 / 5, a5 = 8.0 / 9;
         constexpr double b21 = 1.0 / 5;
         constexpr double b31 = 3.0 / 40, b32 = 9.0 / 40;
@@ -62,7 +78,7 @@ struct Dopri5 {
         constexpr double dc1 = c1 - 5179.0 / 57600, dc3 = c3 - 7571.0 / 16695, dc4 = c4 - 393.0 / 640,
                          dc5 = c5 - (-92097.0 / 339200), dc6 = c6 - 187.0 / 2100, dc7 = -1.0 / 40;
 
-        for (int fails = 0;; ) {
+        {
             double xt[N], k2[N], k7[N];
 #pragma unroll
             for (int i = 0; i < N; ++i) xt[i] = 1.0 * x[i] + (dt * b21) * k1[i];
@@ -103,8 +119,7 @@ struct Dopri5 {
 
             if (err > 1.0) {
                 dt *= vmax(0.9 * pow(err, -1.0 / 3.0), 0.2);
-                if (++fails >= 500) return false;
-                continue;
+                return false;
             }
             // accept
 #pragma unroll

@@ -2,8 +2,19 @@
 //
 // Restates auto_grid and its callees (src/core/grid-refinement.h:40-706,
 // src/core/grid-refinement.cpp:140-197, Coord::detect_symmetry src/core/mesh.h:120-185) for the
-// typed jets / isotropic media, i.e. symmetry >= phi_symmetric and no spreading.  One device
-// thread builds one model's grid; all arrays live in a per-model slab of global memory.
+// typed jets / isotropic media, i.e. symmetry >= phi_symmetric and no spreading.
+//
+// Execution model: ONE WARP builds one model's grid.  The algorithm is written as uniform code
+// (every lane executes it redundantly -- the same latency as one lane -- so scalar state stays in
+// registers and needs no broadcast) interleaved with `par.for_each(n, f)` regions whose index
+// space is strided over the 32 lanes and whose results go to a per-model scratch slab:
+//   * the 512-point jet-profile scans, the 101-point pdf pre-scans, the 200 CDF sample abscissae
+//   * the six stage evaluations of every dopri5 attempt of the CDF quadrature (a pure quadrature:
+//     the pdf does not depend on the state, so the stages are independent) and its dense output
+//   * the inverse-CDF look-ups, the per-theta symmetry probes, t_dec and the time-bound scan.
+// Order-dependent reductions (running peaks, sums whose rounding matters, first-hit searches) stay
+// in uniform code over the precomputed values, so results equal the sequential restatement's.
+// On the host (tests/hostemu) `Par` is a plain loop.
 #pragma once
 
 #include "vag_dopri5.cuh"
@@ -27,9 +38,36 @@ struct GridSlab {
     double* phi;     // [cap_phi]
     int* reps;       // [cap_theta]
     double* t_dec;   // [cap_theta]  t_dec of each representative row
-    double* work;    // scratch: >= 6*cap_theta + 4*theta_samples + cap_phi
+    double* work;    // scratch: grid_work_doubles(cap_theta, cap_phi)
     int cap_theta, cap_phi;
 };
+
+// sequential executor (host emulation, single-thread fallback inside tests)
+struct SeqPar {
+    template <class F>
+    VAG_HD void for_each(int n, F f) const {
+        for (int i = 0; i < n; ++i) f(i);
+    }
+};
+#if defined(__CUDACC__)
+// one warp: index space strided over the lanes, warp barrier (with memory ordering) afterwards
+struct WarpPar {
+    int lane;
+    template <class F>
+    __device__ __forceinline__ void for_each(int n, F f) const {
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) f(i);
+        __syncwarp();
+    }
+};
+#endif
+
+constexpr int GRID_NSCAN = 513;  // longest scan (find_theta_range visits at most 513 nodes)
+
+VAG_HD size_t grid_work_doubles(int cap_theta, int cap_phi) {
+    // base_theta[cap_theta] + 5 per-theta arrays + 2 scan arrays + CDF samples + stage values
+    return (size_t)6 * cap_theta + 2 * (GRID_NSCAN + 7) + 2 * dflt::theta_samples + cap_phi + 32;
+}
 
 VAG_HD double structure_weight(double Gamma) {  // grid-refinement.h:11-13
     return Gamma * sqrt(vmax((Gamma - 1) * Gamma, 0.0));
@@ -44,7 +82,8 @@ VAG_HD double linspace_at(double a, double b, int n, int i) {
 }
 
 // ---- find_jet_jumps: grid-refinement.h:40-86 -------------------------------------------------
-VAG_HD int find_jet_jumps(const ModelCfg& m, double gamma_cut, double* jumps, int cap) {
+template <class Par>
+VAG_HD int find_jet_jumps(const Par& par, const ModelCfg& m, double gamma_cut, double* jumps, int cap, double* G) {
     constexpr int n_scan = 512;
     constexpr double eps = dflt::binary_search_eps;
     const double theta_lo = dflt::theta_min;
@@ -54,12 +93,13 @@ VAG_HD int find_jet_jumps(const ModelCfg& m, double gamma_cut, double* jumps, in
         jumps[0] = theta_hi;
         return 1;
     }
+    par.for_each(n_scan, [&](int j) { G[j] = jet_Gamma0(m, j == 0 ? theta_lo : theta_lo + dtheta * (double)j); });
     int n = 0;
     double prev_th = theta_lo;
-    double prev_G = jet_Gamma0(m, theta_lo);
+    double prev_G = G[0];
     for (int j = 1; j < n_scan; ++j) {
         const double cur_th = theta_lo + dtheta * (double)j;
-        const double cur_G = jet_Gamma0(m, cur_th);
+        const double cur_G = G[j];
         if (prev_G >= gamma_cut || cur_G >= gamma_cut) {
             const double dG = fabs(cur_G - prev_G);
             const double scale = vmax(prev_G - 1, cur_G - 1);
@@ -84,65 +124,97 @@ VAG_HD int find_jet_jumps(const ModelCfg& m, double gamma_cut, double* jumps, in
 }
 
 // ---- find_theta_range: grid-refinement.h:88-111 ----------------------------------------------
-VAG_HD void find_theta_range(const ModelCfg& m, double gamma_cut, double& theta_min, double& theta_max) {
+// The reference walks th -= step / th += step with early exit; the node sequence (a running sum,
+// so not j*step) is generated in uniform code, the profile evaluated at all nodes in parallel,
+// and the first hit taken in walk order.
+template <class Par>
+VAG_HD void find_theta_range(const Par& par, const ModelCfg& m, double gamma_cut, double& theta_min, double& theta_max,
+                             double* TH, double* G) {
     constexpr int n_scan = 512;
     const double theta_lo = dflt::theta_min;
     const double theta_hi = con::pi / 2;
     theta_max = theta_hi;
     theta_min = theta_lo;
     const double step = (theta_hi - theta_lo) / n_scan;
-    for (double th = theta_hi; th >= theta_lo; th -= step) {
-        if (jet_Gamma0(m, th) >= gamma_cut) {
-            theta_max = th;
+    int n = 0;
+    for (double th = theta_hi; th >= theta_lo && n < GRID_NSCAN + 6; th -= step) TH[n++] = th;
+    par.for_each(n, [&](int j) { G[j] = jet_Gamma0(m, TH[j]); });
+    for (int j = 0; j < n; ++j)
+        if (G[j] >= gamma_cut) {
+            theta_max = TH[j];
             break;
         }
-    }
-    for (double th = theta_lo; th <= theta_hi; th += step) {
-        if (jet_Gamma0(m, th) >= gamma_cut) {
-            theta_min = th;
+    n = 0;
+    for (double th = theta_lo; th <= theta_hi && n < GRID_NSCAN + 6; th += step) TH[n++] = th;
+    par.for_each(n, [&](int j) { G[j] = jet_Gamma0(m, TH[j]); });
+    for (int j = 0; j < n; ++j)
+        if (G[j] >= gamma_cut) {
+            theta_min = TH[j];
             break;
         }
-    }
 }
 
 // ---- inverse_CFD_sampling: grid-refinement.h:137-189 -----------------------------------------
-// pdf(x) functor; writes num nodes to x_out.  x_i / cdf_i are scratch of n_samp doubles each.
-template <class Pdf>
-VAG_HD void inverse_cdf_sampling(Pdf& pdf, double lo, double hi, int num, bool log_sample, bool midpoint, double* x_out,
-                                 double* x_i, double* cdf_i) {
+// pdf(x) functor; writes num nodes to x_out.  x_i / cdf_i: n_samp doubles each, kk: 8 doubles.
+template <class Par, class Pdf>
+VAG_HD void inverse_cdf_sampling(const Par& par, const Pdf& pdf, double lo, double hi, int num, bool log_sample,
+                                 bool midpoint, double* x_out, double* x_i, double* cdf_i, double* kk) {
     constexpr int n_samp = dflt::theta_samples;
     constexpr double rtol = dflt::ode_rtol;
-    if (log_sample) {
-        const double a = log10(lo), b = log10(hi);
-        for (int i = 0; i < n_samp; ++i) x_i[i] = pow(10.0, linspace_at(a, b, n_samp, i));
-    } else {
-        for (int i = 0; i < n_samp; ++i) x_i[i] = linspace_at(lo, hi, n_samp, i);
+    {
+        const double a = log_sample ? log10(lo) : lo, b = log_sample ? log10(hi) : hi;
+        par.for_each(n_samp, [&](int i) {
+            const double v = linspace_at(a, b, n_samp, i);
+            x_i[i] = log_sample ? pow(10.0, v) : v;
+            cdf_i[i] = 0;
+        });
     }
-    for (int i = 0; i < n_samp; ++i) cdf_i[i] = 0;
-
+    // Stage values are produced in parallel into kk[0..5] before every attempt; the stepper then
+    // consumes them in call order.  (The pdf ignores the state: dxdt = pdf(t).)
     struct Sys {
-        Pdf& pdf;
-        VAG_HD void operator()(const double* /*x*/, double* dxdt, double t) { dxdt[0] = pdf(t); }
-    } sys{pdf};
+        const double* kk;
+        int next;
+        VAG_HD void operator()(const double* /*x*/, double* dxdt, double /*t*/) { dxdt[0] = kk[next++]; }
+    } sys{kk, 0};
 
     Dopri5<1> st;
     const double x0 = 0;
     st.initialize(&x0, lo, (hi - lo) / 1e3, rtol);
     int k = 1;
     for (int steps = 0; st.t <= hi;) {
-        if (!st.do_step(sys)) break;
+        if (!st.deriv_ready) {
+            kk[0] = pdf(st.t);
+            sys.next = 0;
+        }
+        st.begin_step(sys);
+        bool ok = false;
+        for (int fails = 0; fails < 500; ++fails) {
+            const double t0 = st.t, dt = st.dt;
+            par.for_each(6, [&](int s) {
+                const double a = (s == 0) ? 1.0 / 5 : (s == 1) ? 3.0 / 10 : (s == 2) ? 4.0 / 5 : (s == 3) ? 8.0 / 9 : 1.0;
+                kk[s] = pdf(s < 4 ? t0 + dt * a : t0 + dt);
+            });
+            sys.next = 0;
+            if (st.try_step(sys)) {
+                ok = true;
+                break;
+            }
+        }
+        if (!ok) break;
         if (++steps > dflt::max_ode_steps) break;
-        while (k < n_samp && st.t > x_i[k]) {
-            st.calc_state(x_i[k], &cdf_i[k]);
-            ++k;
+        // dense output for every sample abscissa the accepted step passed
+        int m = 0;
+        while (k + m < n_samp && st.t > x_i[k + m]) ++m;
+        if (m > 0) {
+            const int k0 = k;
+            par.for_each(m, [&](int i) { st.calc_state(x_i[k0 + i], &cdf_i[k0 + i]); });
+            k += m;
         }
     }
     const double c0 = cdf_i[0], c1 = cdf_i[n_samp - 1];
-    int j = 0;
-    for (int q = 0; q < num; ++q) {
+    par.for_each(num, [&](int q) {
         const double target = midpoint ? (c0 + (c1 - c0) * ((double)q + 0.5) / (double)num) : linspace_at(c0, c1, num, q);
-        // first j with target <= cdf_i[j]; the reference restarts from 0 for every q, which for a
-        // non-decreasing target sequence is equivalent to resuming from the previous hit.
+        int j = 0;
         while (j < n_samp && !(target <= cdf_i[j])) ++j;
         double xo = 0;
         if (j < n_samp) {
@@ -159,7 +231,7 @@ VAG_HD void inverse_cdf_sampling(Pdf& pdf, double lo, double hi, int num, bool l
             }
         }
         x_out[q] = xo;
-    }
+    });
 }
 
 // ---- adaptive_theta_grid: grid-refinement.h:199-291 ------------------------------------------
@@ -178,16 +250,25 @@ struct ThetaPdf {
     }
 };
 
-VAG_HD int adaptive_theta_grid(const ModelCfg& m, double theta_min, double theta_max, int base_pts, double theta_v,
-                               double theta_resol, double* out, int cap, double* scratch) {
+// scratch: A[>=101], B[>=101], samples x_i/cdf_i [2*theta_samples], kk[8]
+template <class Par>
+VAG_HD int adaptive_theta_grid(const Par& par, const ModelCfg& m, double theta_min, double theta_max, int base_pts,
+                               double theta_v, double theta_resol, double* out, int cap, double* A, double* B,
+                               double* samp, double* kk) {
     constexpr double core_beam_coeff = 55.0, view_beam_coeff = 25.0, doppler_alpha0 = 12.0, floor_fraction = 0.25;
     constexpr int scan_pts = 100;
     const double theta_extent = theta_max - theta_min;
     double peak_weight = 0, Gamma_peak = 1.0, struct_sum = 0, Gamma_v = 1.0;
     int last_bright = 0;
-    for (int i = 0; i <= scan_pts; ++i) {
+    par.for_each(scan_pts + 1, [&](int i) {
         const double theta = theta_min + theta_extent * i / scan_pts;
         const double Gamma = jet_Gamma0(m, theta);
+        const double dth = theta - theta_v;
+        A[i] = Gamma;
+        B[i] = Gamma / sqrt(1.0 + Gamma * Gamma * dth * dth);
+    });
+    for (int i = 0; i <= scan_pts; ++i) {
+        const double Gamma = A[i];
         const double w = structure_weight(Gamma);
         struct_sum += w;
         if (w > peak_weight) {
@@ -197,8 +278,7 @@ VAG_HD int adaptive_theta_grid(const ModelCfg& m, double theta_min, double theta
         } else if (w > 0.01 * peak_weight) {
             last_bright = i;
         }
-        const double dth = theta - theta_v;
-        Gamma_v = vmax(Gamma_v, Gamma / sqrt(1.0 + Gamma * Gamma * dth * dth));
+        Gamma_v = vmax(Gamma_v, B[i]);
     }
     const double floor_weight = floor_fraction * peak_weight;
     const double CDF_est = (struct_sum / scan_pts + floor_weight) * theta_extent;
@@ -230,9 +310,9 @@ VAG_HD int adaptive_theta_grid(const ModelCfg& m, double theta_min, double theta
     const double view_weight = calibrate(view_beam_pts, 0.5 * (log(1.0 + Gamma_v_sq * theta_v_left * theta_v_left) +
                                                               log(1.0 + Gamma_v_sq * theta_v_right * theta_v_right)));
 
-    ThetaPdf pdf{m, theta_v, core_weight, view_weight, Gamma_peak_sq, Gamma_v_sq, doppler_alpha, floor_weight};
-    inverse_cdf_sampling(pdf, theta_min, theta_max, (int)total_pts, /*log=*/true, /*midpoint=*/false, out, scratch,
-                         scratch + dflt::theta_samples);
+    const ThetaPdf pdf{m, theta_v, core_weight, view_weight, Gamma_peak_sq, Gamma_v_sq, doppler_alpha, floor_weight};
+    inverse_cdf_sampling(par, pdf, theta_min, theta_max, (int)total_pts, /*log=*/true, /*midpoint=*/false, out, samp,
+                         samp + dflt::theta_samples, kk);
     return (int)total_pts;
 }
 
@@ -291,22 +371,40 @@ VAG_HD int merge_grids(const double* a, int na, const double* b, int nb, double*
 // Per-theta invariants (beta, structure weight, cos/sin theta, dcos) are hoisted out of the
 // pdf: every typed jet is phi-independent, so the hoisted values are the ones the reference
 // recomputes inside phi_weight on every call.
-VAG_HD int adaptive_phi_grid(const ModelCfg& m, int phi_num, double theta_v, const double* theta, int n_theta,
-                             bool is_axisymmetric, double phi_max, double self_boost_cap, double* out, int cap,
-                             double* scratch) {
+struct PhiPdf {
+    const double *beta, *sw, *dcos, *ct, *st;
+    int n_theta;
+    double cos_tv, sin_tv, floor_weight;
+    VAG_HD double weight(double phi) const {
+        const double cos_phi = cos(phi);
+        double w = 0;
+        for (int it = 0; it < n_theta; ++it) {
+            const double cos_alpha = ct[it] * cos_tv + st[it] * sin_tv * cos_phi;
+            const double a = (1 - beta[it]) / (1 - beta[it] * cos_alpha);
+            w += a * sw[it] * dcos[it];
+        }
+        return w;
+    }
+    VAG_HD double operator()(double phi) const { return weight(phi) + floor_weight; }
+};
+
+// scratch: per-theta arrays pt[5*n_theta], A[>=101], samples [2*theta_samples], kk[8]
+template <class Par>
+VAG_HD int adaptive_phi_grid(const Par& par, const ModelCfg& m, int phi_num, double theta_v, const double* theta,
+                             int n_theta, bool is_axisymmetric, double phi_max, double self_boost_cap, double* out,
+                             int cap, double* pt, double* A, double* samp, double* kk) {
     if (theta_v == 0 && is_axisymmetric) {
         if (phi_num > cap) return -phi_num;
-        for (int i = 0; i < phi_num; ++i) out[i] = linspace_at(0., 2 * con::pi, phi_num, i);
+        par.for_each(phi_num, [&](int i) { out[i] = linspace_at(0., 2 * con::pi, phi_num, i); });
         return phi_num;
     }
     const bool half_range = phi_max < 2 * con::pi;
-    double* beta = scratch;
+    double* beta = pt;
     double* sw = beta + n_theta;
     double* ct = sw + n_theta;
     double* st = ct + n_theta;
     double* dcos_arr = st + n_theta;
-    double* samp = dcos_arr + n_theta;  // 2 * theta_samples
-    for (int it = 0; it < n_theta; ++it) {
+    par.for_each(n_theta, [&](int it) {
         const double left = (it == 0) ? 0.0 : 0.5 * (theta[it - 1] + theta[it]);
         const double right = (it == n_theta - 1) ? theta[it] : 0.5 * (theta[it] + theta[it + 1]);
         dcos_arr[it] = fabs(cos(left) - cos(right));
@@ -315,32 +413,15 @@ VAG_HD int adaptive_phi_grid(const ModelCfg& m, int phi_num, double theta_v, con
         sw[it] = structure_weight(Gamma);
         ct[it] = cos(theta[it]);
         st[it] = sin(theta[it]);
-    }
-
-    struct Pdf2 {
-        const double *beta, *sw, *dcos, *ct, *st;
-        int n_theta;
-        double cos_tv, sin_tv, floor_weight;
-        VAG_HD double weight(double phi) const {
-            const double cos_phi = cos(phi);
-            double w = 0;
-            for (int it = 0; it < n_theta; ++it) {
-                const double cos_alpha = ct[it] * cos_tv + st[it] * sin_tv * cos_phi;
-                const double a = (1 - beta[it]) / (1 - beta[it] * cos_alpha);
-                w += a * sw[it] * dcos[it];
-            }
-            return w;
-        }
-        VAG_HD double operator()(double phi) const { return weight(phi) + floor_weight; }
-    } pdf{beta, sw, dcos_arr, ct, st, n_theta, cos(theta_v), sin(theta_v), 0.0};
+    });
+    PhiPdf pdf{beta, sw, dcos_arr, ct, st, n_theta, cos(theta_v), sin(theta_v), 0.0};
 
     constexpr int scan_pts = 100;
+    par.for_each(scan_pts + 1, [&](int s) { A[s] = pdf.weight(phi_max * (double)s / scan_pts); });
     double peak_weight = 0, sum_weight = 0;
     for (int s = 0; s <= scan_pts; ++s) {
-        const double phi = phi_max * (double)s / scan_pts;
-        const double w = pdf.weight(phi);
-        peak_weight = vmax(peak_weight, w);
-        sum_weight += w;
+        peak_weight = vmax(peak_weight, A[s]);
+        sum_weight += A[s];
     }
     const double floor_weight = 0.05 * peak_weight;
     if (self_boost_cap > 0 && peak_weight > 0) {
@@ -351,8 +432,8 @@ VAG_HD int adaptive_phi_grid(const ModelCfg& m, int phi_num, double theta_v, con
     }
     if (phi_num > cap) return -phi_num;
     pdf.floor_weight = floor_weight;
-    inverse_cdf_sampling(pdf, 0, phi_max, phi_num, /*log=*/false, /*midpoint=*/half_range, out, samp,
-                         samp + dflt::theta_samples);
+    inverse_cdf_sampling(par, pdf, 0, phi_max, phi_num, /*log=*/false, /*midpoint=*/half_range, out, samp,
+                         samp + dflt::theta_samples, kk);
     return phi_num;
 }
 
@@ -465,16 +546,30 @@ VAG_HD void build_row_lattice(const GridHeader& h, double t_dec, double T0, doub
 }
 
 // ---- auto_grid: grid-refinement.h:638-706 (axisymmetric, typed jets) --------------------------
-VAG_HD void build_grid(const ModelCfg& m, double t_obs_min, double t_obs_max, GridHeader& h, GridSlab& s) {
+template <class Par>
+VAG_HD void build_grid(const Par& par, const ModelCfg& m, double t_obs_min, double t_obs_max, GridHeader& h,
+                       const GridSlab& s) {
     h.status = 0;
     h.is_rvs = m.has_rvs ? 1 : 0;
     const double theta_view = m.theta_v;
     const double theta_cut = con::pi / 2;
+    auto fail_capacity = [&]() {
+        h.status |= VAG_ST_CAPACITY;
+        h.n_theta = h.n_phi = h.n_phi_eff = h.n_t = h.n_reps = 0;
+    };
+
+    // scratch carve-up (grid_work_doubles)
+    double* base_theta = s.work;                       // [cap_theta]
+    double* pt = base_theta + s.cap_theta;             // [5*cap_theta] per-theta arrays
+    double* A = pt + 5 * (size_t)s.cap_theta;          // [GRID_NSCAN+7]
+    double* B = A + (GRID_NSCAN + 7);                  // [GRID_NSCAN+7]
+    double* samp = B + (GRID_NSCAN + 7);               // [2*theta_samples]
+    double* kk = samp + 2 * dflt::theta_samples;       // [8]
 
     double jumps[8];
-    const int n_jumps = find_jet_jumps(m, con::Gamma_cut, jumps, 8);
+    const int n_jumps = find_jet_jumps(par, m, con::Gamma_cut, jumps, 8, A);
     double inner_edge, outer_edge;
-    find_theta_range(m, con::Gamma_cut, inner_edge, outer_edge);
+    find_theta_range(par, m, con::Gamma_cut, inner_edge, outer_edge, A, B);
     for (int i = 0; i < n_jumps; ++i) outer_edge = vmax(outer_edge, jumps[i]);
     const double theta_min = vmax(dflt::theta_min, inner_edge);
     const double theta_max = vmin(outer_edge, theta_cut);
@@ -482,24 +577,14 @@ VAG_HD void build_grid(const ModelCfg& m, double t_obs_min, double t_obs_max, Gr
     const int theta_num =
         dflt::min_theta_points + (int)(long long)((theta_max - theta_min) * 180 / con::pi * m.theta_resol);
 
-    double* base_theta = s.work;                      // cap_theta
-    double* scratch = s.work + s.cap_theta;           // >= 5*cap_theta + 4*samples
-    const int n_base = adaptive_theta_grid(m, theta_min, theta_max, theta_num, theta_view, m.theta_resol, base_theta,
-                                           s.cap_theta, scratch);
-    if (n_base < 0) {
-        h.status |= VAG_ST_CAPACITY;
-        h.n_theta = h.n_phi = h.n_phi_eff = h.n_t = h.n_reps = 0;
-        return;
-    }
+    const int n_base = adaptive_theta_grid(par, m, theta_min, theta_max, theta_num, theta_view, m.theta_resol,
+                                           base_theta, s.cap_theta, A, B, samp, kk);
+    if (n_base < 0) return fail_capacity();
     const double avg_spacing = (theta_max - theta_min) / n_base;
     double feat[24];
     const int n_feat = jump_refinement_grid(jumps, n_jumps, theta_min, theta_max, avg_spacing, feat);
     const int n_theta = merge_grids(base_theta, n_base, feat, n_feat, s.theta, s.cap_theta);
-    if (n_theta > s.cap_theta) {
-        h.status |= VAG_ST_CAPACITY;
-        h.n_theta = h.n_phi = h.n_phi_eff = h.n_t = h.n_reps = 0;
-        return;
-    }
+    if (n_theta > s.cap_theta) return fail_capacity();
     h.n_theta = n_theta;
 
     // phi grid (grid-refinement.h:664-693); is_axisymmetric = true on this path
@@ -509,7 +594,8 @@ VAG_HD void build_grid(const ModelCfg& m, double t_obs_min, double t_obs_max, Gr
     int n_phi;
     if (mirror_phi) {
         const int n_half = (phi_base + 1) / 2;
-        n_phi = adaptive_phi_grid(m, n_half, theta_view, s.theta, n_theta, true, con::pi, 5.0, s.phi, s.cap_phi, scratch);
+        n_phi = adaptive_phi_grid(par, m, n_half, theta_view, s.theta, n_theta, true, con::pi, 5.0, s.phi, s.cap_phi, pt,
+                                  A, samp, kk);
         h.phi_mirrored = 1;
     } else {
         const double doppler_sharpness = jet_Gamma0(m, theta_view) * sin(theta_view);
@@ -524,62 +610,62 @@ VAG_HD void build_grid(const ModelCfg& m, double t_obs_min, double t_obs_max, Gr
             else
                 n_phi = -n_phi;
         } else {
-            n_phi = adaptive_phi_grid(m, (int)phi_num, theta_view, s.theta, n_theta, true, 2 * con::pi, 0.0, s.phi,
-                                      s.cap_phi, scratch);
+            n_phi = adaptive_phi_grid(par, m, (int)phi_num, theta_view, s.theta, n_theta, true, 2 * con::pi, 0.0, s.phi,
+                                      s.cap_phi, pt, A, samp, kk);
         }
         if (n_phi >= 2) {
             const double shift = 0.5 * (s.phi[1] - s.phi[0]);
-            for (int i = 0; i < n_phi; ++i) s.phi[i] += shift;
+            const int np = n_phi;
+            par.for_each(1, [&](int) {
+                for (int i = 0; i < np; ++i) s.phi[i] += shift;
+            });
         }
         h.phi_mirrored = 0;
     }
-    if (n_phi < 0) {
-        h.status |= VAG_ST_CAPACITY;
-        h.n_theta = h.n_phi = h.n_phi_eff = h.n_t = h.n_reps = 0;
-        return;
-    }
+    if (n_phi < 0) return fail_capacity();
     h.n_phi = n_phi;
     // Observer::build_time_grid (src/core/observer.cpp:211-222): axisymmetric shock tables have
     // phi extent 1 (jet_3d = 0), so an on-axis observer needs a single phi sample.
     h.n_phi_eff = (theta_view == 0) ? 1 : n_phi;
 
-    // detect_symmetry (mesh.h:120-185): non-spreading jet in an isotropic medium
-    int n_reps = 0;
-    s.reps[n_reps++] = 0;
-    {
-        double e_prev = jet_eps_k(m, s.theta[0]);
-        double g_prev = jet_Gamma0(m, s.theta[0]);
-        for (int j = 1; j < n_theta; ++j) {
-            const double e_cur = jet_eps_k(m, s.theta[j]);
-            const double g_cur = jet_Gamma0(m, s.theta[j]);
-            if (e_prev != e_cur || g_prev != g_cur) s.reps[n_reps++] = j;
-            e_prev = e_cur;
-            g_prev = g_cur;
-        }
-    }
-    h.n_reps = n_reps;
-    h.symmetry = (n_reps == 1) ? SYM_ISOTROPIC : (n_reps < n_theta ? SYM_PIECEWISE : SYM_PHI_SYMMETRIC);
-
-    // build_time_grid (grid-refinement.h:593-636) with phi_size = 1
+    // detect_symmetry (mesh.h:120-185): non-spreading jet in an isotropic medium.
+    // per-theta probes in parallel: pt[0..n) = eps_k, pt[n..2n) = Gamma0, then an ordered scan.
+    double* e_arr = pt;
+    double* g_arr = pt + n_theta;
+    double* ts_arr = pt + 2 * (size_t)n_theta;
     const double t_end = 1.01 * t_obs_max / (1 + m.z);
     const double cos_tv = cos(theta_view), sin_tv = sin(theta_view);
     const double cos_phi0 = cos(s.phi[0]);
+    par.for_each(n_theta, [&](int j) {
+        const double th = s.theta[j];
+        const double G = jet_Gamma0(m, th);
+        e_arr[j] = jet_eps_k(m, th);
+        g_arr[j] = G;
+        // scan_time_bounds (grid-refinement.h:471-514): raw start time of cell (0, j)
+        const double b = gamma_to_beta(G);
+        const double cos_a = cos(th) * cos_tv + sin(th) * sin_tv * cos_phi0;
+        ts_arr[j] = 0.99 * t_obs_min * (1 - b) / (1 - cos_a * b) / (1 + m.z);
+    });
+    int n_reps = 0;
+    s.reps[n_reps++] = 0;
+    for (int j = 1; j < n_theta; ++j)
+        if (e_arr[j - 1] != e_arr[j] || g_arr[j - 1] != g_arr[j]) s.reps[n_reps++] = j;
+    h.n_reps = n_reps;
+    h.symmetry = (n_reps == 1) ? SYM_ISOTROPIC : (n_reps < n_theta ? SYM_PIECEWISE : SYM_PHI_SYMMETRIC);
+
+    // build_time_grid (grid-refinement.h:593-636) with phi_size = 1.  t_dec only depends on
+    // (eps_k, Gamma0), so it is evaluated once per representative group.
+    {
+        const int nr = n_reps;
+        par.for_each(nr, [&](int r) { s.t_dec[r] = estimate_t_dec(m, s.theta[s.reps[r]]); });
+    }
     double min_raw = t_end, min_guarded = t_end, min_cut = t_end, max_ref = 0;
     {
-        // scan_time_bounds (grid-refinement.h:471-514); t_dec only depends on (eps_k, Gamma0), so
-        // it is evaluated once per representative group and reused inside the group.
-        int r = 0;
+        int r = -1;
         double td = 0;
         for (int j = 0; j < n_theta; ++j) {
-            const double th = s.theta[j];
-            const double b = gamma_to_beta(jet_Gamma0(m, th));
-            const double cos_a = cos(th) * cos_tv + sin(th) * sin_tv * cos_phi0;
-            const double ts = 0.99 * t_obs_min * (1 - b) / (1 - cos_a * b) / (1 + m.z);
-            if (r < n_reps && s.reps[r] == j) {
-                td = estimate_t_dec(m, th);
-                s.t_dec[r] = td;
-                ++r;
-            }
+            if (r + 1 < n_reps && s.reps[r + 1] == j) td = s.t_dec[++r];
+            const double ts = ts_arr[j];
             double cut = vmin(0.01 * td, 1e-2 * unit::sec);
             if (h.is_rvs) {
                 cut = vmin(cut, 0.01 * m.T0);

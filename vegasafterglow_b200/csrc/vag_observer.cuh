@@ -129,11 +129,13 @@ VAG_HD int find_interval(const double* t_row, int n_t, double x, bool series) {
 
 // log-log interpolation inside interval k (observer.h:417-433 / :515-520); returns the linear
 // contribution exp2(...) or 0 when the slope is not finite.
-VAG_HD double interp_contrib(double lo, double hi, double t_lo, double t_hi, double x) {
-    const double inv_dt = 1.0 / (t_hi - t_lo);
+VAG_HD double interp_contrib2(double lo, double hi, double inv_dt, double dx) {
     const double s = (hi - lo) * inv_dt;
     if (!isfinite(s)) return 0.0;
-    return exp2(lo + (x - t_lo) * s);
+    return exp2(lo + dx * s);
+}
+VAG_HD double interp_contrib(double lo, double hi, double t_lo, double t_hi, double x) {
+    return interp_contrib2(lo, hi, 1.0 / (t_hi - t_lo), x - t_lo);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -247,8 +249,8 @@ VAG_HD void eats_phase2_grid(const EatsModel& M, const EatsRequest& rq, const Ea
             if (k < 0) continue;
             const double* b_lo = sh.bv + ((size_t)r * n_t + k) * EATS_NU_TILE;
             const double* b_hi = b_lo + EATS_NU_TILE;
-            const double t_lo = t_row[k], t_hi = t_row[k + 1];
-            for (int l = 0; l < nl; ++l) sum[l] += interp_contrib(b_lo[l], b_hi[l], t_lo, t_hi, x);
+            const double inv_dt = 1.0 / (t_row[k + 1] - t_row[k]), dx = x - t_row[k];
+            for (int l = 0; l < nl; ++l) sum[l] += interp_contrib2(b_lo[l], b_hi[l], inv_dt, dx);
         }
         for (int l = 0; l < nl; ++l) acc[l * EATS_T_BLOCK + ii] += sum[l];
     }

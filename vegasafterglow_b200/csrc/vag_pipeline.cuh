@@ -51,12 +51,9 @@ struct BatchWs {
     double* coef_rvs;
 };
 
-VAG_HD size_t grid_work_doubles(int cap_theta, int cap_phi) {
-    return (size_t)6 * cap_theta + 4 * dflt::theta_samples + cap_phi + 16;
-}
-
 // ---- K0 ---------------------------------------------------------------------------------------
-VAG_HD void k0_grid_body(const BatchWs& w, int mi, double t_obs_min, double t_obs_max) {
+template <class Par>
+VAG_HD void k0_grid_body(const Par& par, const BatchWs& w, int mi, double t_obs_min, double t_obs_max) {
     ModelCfg cfg = make_cfg(w.params[mi]);
     w.cfg[mi] = cfg;
     GridSlab s;
@@ -68,7 +65,7 @@ VAG_HD void k0_grid_body(const BatchWs& w, int mi, double t_obs_min, double t_ob
     s.cap_theta = w.cap_theta;
     s.cap_phi = w.cap_phi;
     GridHeader h;
-    build_grid(cfg, t_obs_min * unit::sec, t_obs_max * unit::sec, h, s);
+    build_grid(par, cfg, t_obs_min * unit::sec, t_obs_max * unit::sec, h, s);
     w.hdr[mi] = h;
     w.status[mi] = h.status;
 }

@@ -55,6 +55,9 @@ class Engine:
     def flux_density_series(self, params, t, nu, return_status=False):
         """Batched ``Model.flux_density`` -> float64[n_models, 5, n]."""
         p, t, nu = self._params(params), _f64(t).reshape(-1), _f64(nu).reshape(-1)
+        if t.size != nu.size:  # pybind/pymodel.cpp:376-379
+            raise ValueError("time and frequency arrays must have the same size\nIf you intend to get grid-like "
+                             "output, use the generic `flux_density_grid` instead")
         out = np.empty((p.size, abi.NCOMP, t.size))
         st = np.zeros(p.size, dtype=np.int32)
         _lib.check(self._lib.vag_flux_density_series(self._h, p.ctypes.data, p.size, t.ctypes.data, nu.ctypes.data,
