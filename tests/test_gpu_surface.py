@@ -1,0 +1,93 @@
+"""GPU tier: the reference-facing surfaces -- the pybind11 `Model` mirror side by side with the
+reference's own pybind11 module (oracle/_ref), and the batched likelihood against the manual
+ln-flux chi-squared of tests/python/test_fit_smoke.py:119-127."""
+import numpy as np
+import pytest
+
+from vegasafterglow_b200 import abi, configs, fitting
+
+pytestmark = pytest.mark.gpu
+
+
+def _both():
+    from oracle import ref
+    from vegasafterglow_b200 import VegasAfterglowC_b200 as ours
+
+    if not ref.available():
+        pytest.skip("oracle/_ref not present")
+    return ours, ref.pymodule()
+
+
+def _build(va, **kw):
+    return va.Model(jet=va.TophatJet(0.1, 1e52, 300), medium=va.ISM(1), observer=va.Observer(1e26, 0.1, 0),
+                    fwd_rad=va.Radiation(0.1, 1e-3, 2.3), **kw)
+
+
+def test_quick_start_side_by_side():
+    # README.md:303-304 of the reference, run through both modules with identical calls
+    ours, theirs = _both()
+    t, nu = np.logspace(2, 8, 100), np.array([1e9, 1e14, 1e17])
+    fo, fr = _build(ours).flux_density_grid(t, nu), _build(theirs).flux_density_grid(t, nu)
+    assert fo.total.shape == np.asarray(fr.total).shape == (3, 100)
+    np.testing.assert_allclose(fo.total, np.asarray(fr.total), rtol=1e-6)
+    np.testing.assert_allclose(fo.fwd.sync, np.asarray(fr.fwd.sync), rtol=1e-6)
+    # absent components are 0-d empty arrays in both (pymodel.h:361-383)
+    for a, b in ((fo.fwd.ssc, fr.fwd.ssc), (fo.rvs.sync, fr.rvs.sync), (fo.rvs.ssc, fr.rvs.ssc)):
+        assert np.asarray(a).size == np.asarray(b).size and np.asarray(a).ndim == np.asarray(b).ndim
+
+
+def test_reverse_shock_wind_series_side_by_side():
+    ours, theirs = _both()
+    def build(va):
+        return va.Model(jet=va.GaussianJet(0.1, 1e52, 300, duration=100), medium=va.Wind(0.1), observer=va.Observer(1e28, 1.0, 0.15),
+                        fwd_rad=va.Radiation(0.1, 0.01, 2.3), rvs_rad=va.Radiation(0.05, 0.02, 2.6, xi_e=0.5),
+                        resolutions=(0.06, 0.2, 8))
+    t = np.sort(np.tile(np.logspace(2, 7, 12), 3))
+    nu = np.tile([1e9, 4.84e14, 1e18], 12)
+    fo, fr = build(ours).flux_density(t, nu), build(theirs).flux_density(t, nu)
+    for a, b in ((fo.total, fr.total), (fo.fwd.sync, fr.fwd.sync), (fo.rvs.sync, fr.rvs.sync)):
+        b = np.asarray(b)
+        m = b > 1e-3 * b.max()
+        # structured-jet reverse shock: reference's own reproducibility floor (tests/helpers.py)
+        np.testing.assert_allclose(np.asarray(a)[m], b[m], rtol=2e-3)
+    np.testing.assert_allclose(fo.total, fo.fwd.sync + fo.rvs.sync, rtol=1e-12)
+
+
+def test_mirror_raises_like_the_reference():
+    ours, theirs = _both()
+    for va in (ours, theirs):
+        m = _build(va)
+        with pytest.raises(ValueError):
+            m.flux_density_grid(np.array([3.0, 2.0, 1.0]), np.array([1e9]))
+        with pytest.raises(ValueError):
+            m.flux_density(np.array([1.0, 2.0]), np.array([1e9]))
+        with pytest.raises(ValueError):
+            _build(va, rtol=1.0)
+
+
+def test_batched_likelihood_matches_manual_chi2(engine):
+    rng = np.random.default_rng(42)
+    truth = configs.make(rvs=(0.1, 0.01, 2.3), lumi_dist=1e27)
+    t = np.tile(np.logspace(2.5, 6.5, 20), 5)
+    nu = np.repeat([1e9, 5e9, 4.84e14, 1e17, 1e18], 20)
+    order = np.argsort(t, kind="stable")
+    f_true = engine.flux_density_series(truth, t[order], nu[order])[0, 0]
+    flux = np.empty_like(f_true)
+    flux[order] = f_true * (1 + 0.05 * rng.standard_normal(t.size))
+    err = 0.1 * flux
+    lk = fitting.BatchedLikelihood(engine, truth, ["E_iso", "Gamma0", "theta_c", "n_ism", "eps_e", "eps_B", "p"],
+                                   [True, True, False, True, True, True, False], t, nu, flux, err,
+                                   lower=[50, 1.5, 0.02, -4, -3, -5, 2.05], upper=[55, 3.2, 0.5, 2, -0.3, -0.5, 2.95])
+    samples = np.column_stack([rng.uniform(51, 54, 64), rng.uniform(1.7, 3, 64), rng.uniform(0.03, 0.4, 64),
+                               rng.uniform(-3, 1, 64), rng.uniform(-2, -0.5, 64), rng.uniform(-4, -1, 64),
+                               rng.uniform(2.1, 2.8, 64)])
+    samples[5, 0] = 60.0  # out of bounds -> -inf without evaluation (samplers.py:73-74)
+    logp = lk(samples)
+    assert logp[5] == -np.inf and np.isfinite(np.delete(logp, 5)).all()
+    P = lk.to_params(samples)
+    f = engine.flux_density_series(P, lk.t, lk.nu)[:, 0]
+    manual = -0.5 * np.sum(lk.w * ((lk.lnF - np.log(np.maximum(f, 1e-300))) / lk.sig) ** 2, axis=1)
+    np.testing.assert_allclose(np.delete(logp, 5), np.delete(manual, 5), rtol=1e-12)
+    # the truth parameters are (close to) the best of the sample
+    best = lk(np.array([[52.0, np.log10(300.0), 0.1, 0.0, -1.0, -3.0, 2.3]]))[0]
+    assert best > np.max(np.delete(logp, 5))
