@@ -121,6 +121,12 @@ int vag_flux_density_grid(vag_context* ctx, const vag_params* params, size_t n_m
 int vag_flux_density_series(vag_context* ctx, const vag_params* params, size_t n_models, const double* t,
                             const double* nu, size_t n, double* out, int32_t* status);
 
+/* Replaces PyModel::flux (pybind/pymodel.cpp:391-410) = Observer::flux (src/core/observer.h:555-567):
+ * flux integrated over [nu_min, nu_max] Hz with Boole weights on num_nu log-spaced frequencies
+ * (src/core/quadrature.h:138-191).  out[n_models][VAG_NCOMP][n_t] in erg cm^-2 s^-1. */
+int vag_flux_band(vag_context* ctx, const vag_params* params, size_t n_models, const double* t, size_t n_t,
+                  double nu_min, double nu_max, size_t num_nu, double* out, int32_t* status);
+
 /* Replaces Fitter._evaluate + _chi2_sum for point data (VegasAfterglow/fitting/fitter.py:497-522):
  * chi2[m] = sum_i w[i] * ((lnF_obs[i] - ln max(F_model[i], 1e-300)) / sigma_ln[i])^2
  * over the series (t[i], nu[i]); non-finite chi2 is returned as +inf (samplers.py:63-70 maps it

@@ -98,6 +98,25 @@ def main():
         configs.make(z=3.0, lumi_dist=8e28, rtol=1e-8),
     ])
     save("edge_parameter_corners", corners, np.logspace(1, 8, 30), np.array([1e8, 1e11, 1e14, 1e18, 1e22]))
+    # 6. Model.flux (band integration) and Model.flux_density_exposures through the reference's own
+    #    pybind11 module (oracle/_ref/VegasAfterglowC*.so)
+    va = ref.pymodule()
+    mdl = va.Model(jet=va.TophatJet(0.1, 1e52, 300, duration=1e3), medium=va.ISM(1), observer=va.Observer(1e27, 0.5, 0),
+                   fwd_rad=va.Radiation(0.1, 1e-3, 2.3), rvs_rad=va.Radiation(0.1, 1e-2, 2.5))
+    pb = configs.make(duration=1e3, lumi_dist=1e27, z=0.5, rvs=(0.1, 1e-2, 2.5))
+    tb = np.logspace(2, 7, 25)
+    band = {}
+    for num in (2, 4, 5, 7, 12, 21):
+        fb = mdl.flux(tb, 2.4e17 * 0.3, 2.4e17 * 10, num)
+        band[str(num)] = np.stack([np.asarray(fb.total), np.asarray(fb.fwd.sync), np.asarray(fb.rvs.sync)])
+    np.savez_compressed(os.path.join(OUT, "method_flux_band.npz"), params=pb, t=tb, nu_min=2.4e17 * 0.3, nu_max=2.4e17 * 10,
+                        **{"num_" + k: v for k, v in band.items()})
+    te = np.array([1e3, 1e3, 5e3, 2e4, 2e4, 1e5, 1e6])
+    nue = np.array([1e9, 1e17, 4.84e14, 1e9, 1e17, 4.84e14, 1e17])
+    ex = np.array([100.0, 500.0, 1e3, 2e4, 1e3, 5e4, 1e5])
+    fe = mdl.flux_density_exposures(te, nue, ex, 10)
+    np.savez_compressed(os.path.join(OUT, "method_exposures.npz"), params=pb, t=te, nu=nue, expo=ex, num_points=10,
+                        flux=np.stack([np.asarray(fe.total), np.asarray(fe.fwd.sync), np.asarray(fe.rvs.sync)]))
     with open(os.path.join(OUT, "PINNING.json"), "w") as fh:
         json.dump({"what": "max relative deviation (bins > 1% of peak) of oracle/_ref (reference built here, "
                            "x86-64-v3, g++ 13) from the reference's own committed golden .npz",

@@ -14,7 +14,7 @@ def load_golden(name):
 
 def golden_names(prefix=""):
     return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f.startswith(prefix)
-                  and not f.startswith("stages_"))
+                  and not f.startswith(("stages_", "method_")))
 
 
 def model_errors(a, b, comp=0, floor=1e-2):

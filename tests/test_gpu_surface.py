@@ -91,3 +91,43 @@ def test_batched_likelihood_matches_manual_chi2(engine):
     # the truth parameters are (close to) the best of the sample
     best = lk(np.array([[52.0, np.log10(300.0), 0.1, 0.0, -1.0, -3.0, 2.3]]))[0]
     assert best > np.max(np.delete(logp, 5))
+
+
+def test_band_flux_matches_reference_fixture(engine):
+    # Model.flux: Boole-rule band integration (observer.h:555-567, quadrature.h:138-191), every
+    # leftover branch of the rule (num_nu = 2, 4, 5, 7, 12, 21)
+    from tests.helpers import load_golden
+
+    g = load_golden("method_flux_band")
+    for key in [k for k in g if k.startswith("num_")]:
+        num = int(key.split("_")[1])
+        f = engine.flux_band(g["params"], g["t"], float(g["nu_min"]), float(g["nu_max"]), num)
+        for ours, theirs in zip((f[0, 0], f[0, 1], f[0, 3]), g[key]):
+            np.testing.assert_allclose(ours, theirs, rtol=1e-6)
+    from vegasafterglow_b200 import VegasAfterglowC_b200 as va
+
+    m = va.Model(jet=va.TophatJet(0.1, 1e52, 300, duration=1e3), medium=va.ISM(1), observer=va.Observer(1e27, 0.5, 0),
+                 fwd_rad=va.Radiation(0.1, 1e-3, 2.3), rvs_rad=va.Radiation(0.1, 1e-2, 2.5))
+    fb = m.flux(g["t"], float(g["nu_min"]), float(g["nu_max"]), 12)
+    np.testing.assert_allclose(fb.total, g["num_12"][0], rtol=1e-6)
+    with pytest.raises(ValueError):
+        m.flux(g["t"], 1e17, 1e16, 5)
+    with pytest.raises(ValueError):
+        m.flux(g["t"], 1e16, 1e17, 1)
+
+
+def test_exposure_averaging_matches_reference_fixture(engine):
+    from tests.helpers import load_golden
+
+    g = load_golden("method_exposures")
+    f = engine.flux_density_exposures(g["params"], g["t"], g["nu"], g["expo"], int(g["num_points"]))
+    for ours, theirs in zip((f[0, 0], f[0, 1], f[0, 3]), g["flux"]):
+        np.testing.assert_allclose(ours, theirs, rtol=1e-6)
+    from vegasafterglow_b200 import VegasAfterglowC_b200 as va
+
+    m = va.Model(jet=va.TophatJet(0.1, 1e52, 300, duration=1e3), medium=va.ISM(1), observer=va.Observer(1e27, 0.5, 0),
+                 fwd_rad=va.Radiation(0.1, 1e-3, 2.3), rvs_rad=va.Radiation(0.1, 1e-2, 2.5))
+    fe = m.flux_density_exposures(g["t"], g["nu"], g["expo"], 10)
+    np.testing.assert_allclose(fe.total, g["flux"][0], rtol=1e-6)
+    with pytest.raises(ValueError):
+        m.flux_density_exposures(g["t"], g["nu"], -g["expo"], 10)

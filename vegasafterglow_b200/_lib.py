@@ -37,6 +37,7 @@ def load():
     lib.vag_params_default.argtypes = [vp]
     lib.vag_flux_density_grid.argtypes = [vp, vp, sz, dp, sz, dp, sz, dp, ip]
     lib.vag_flux_density_series.argtypes = [vp, vp, sz, dp, dp, sz, dp, ip]
+    lib.vag_flux_band.argtypes = [vp, vp, sz, dp, sz, C.c_double, C.c_double, sz, dp, ip]
     lib.vag_chi2_series.argtypes = [vp, vp, sz, dp, dp, dp, dp, dp, sz, dp, ip]
     lib.vag_flux_density_grid_dev.argtypes = [vp, vp, sz, dp, sz, dp, sz, dp, ip, vp]
     lib.vag_flux_density_series_dev.argtypes = [vp, vp, sz, dp, dp, sz, dp, ip, vp]
@@ -54,7 +55,7 @@ def load():
 
 EXPORTS = [
     "vag_params_default", "vag_params_validate", "vag_create", "vag_destroy", "vag_last_error", "vag_version",
-    "vag_flux_density_grid", "vag_flux_density_series", "vag_chi2_series", "vag_flux_density_grid_dev",
+    "vag_flux_density_grid", "vag_flux_density_series", "vag_flux_band", "vag_chi2_series", "vag_flux_density_grid_dev",
     "vag_flux_density_series_dev", "vag_chi2_series_dev", "vag_synchronize", "vag_set_capacity", "vag_details",
     "vag_set_profiling", "vag_last_stage_ms", "vag_last_launch_count", "vag_measure_fp64_peak",
 ]

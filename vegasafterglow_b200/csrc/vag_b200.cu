@@ -138,14 +138,27 @@ __global__ void __launch_bounds__(64) k_radiation(BatchWs w) {
 
 // observation request pre-pass: log2 of the (unit-scaled) times and frequencies
 __global__ void k_prep_obs(const double* __restrict__ t, int n_t, const double* __restrict__ nu, int n_nu,
-                           double* lg2_t, double* t_lin, double* lg2_nu) {
+                           double* lg2_t, double* t_lin, double* lg2_nu, int nu_in_code_units) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_t) {
         const double tl = t[i] * unit::sec;
         t_lin[i] = tl;
         lg2_t[i] = log2(tl);
     }
-    if (i < n_nu) lg2_nu[i] = log2(nu[i] * unit::Hz);
+    if (i < n_nu) lg2_nu[i] = log2(nu_in_code_units ? nu[i] : nu[i] * unit::Hz);
+}
+
+// Observer::flux (src/core/observer.h:555-567): band[m][c][j] = sum_i F[m][c][i][j] * w[i]
+__global__ void k_band_reduce(const double* __restrict__ F, const double* __restrict__ wgt, double* __restrict__ out,
+                              size_t n_mc, int n_nu, int n_t) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_mc * n_t) return;
+    const size_t mc = e / n_t;
+    const int j = (int)(e - mc * n_t);
+    const double* f = F + mc * (size_t)n_nu * n_t + j;
+    double s = 0;
+    for (int i = 0; i < n_nu; ++i) s += f[(size_t)i * n_t] * wgt[i];
+    out[e] = s;
 }
 
 // K3.  grid = (model, split, shock).  out[model][comp][n_nu][n_t] (grid) or [model][comp][n] (series)
@@ -337,6 +350,7 @@ struct Request {
     const double* d_t;
     const double* d_nu;
     size_t n_t, n_nu;
+    bool nu_code_units = false;
 };
 
 int setup_models(vag_context* ctx, BatchWs& w, const vag_params* d_params, size_t n) {
@@ -437,7 +451,7 @@ int run_flux(vag_context* ctx, const vag_params* d_params, size_t n, const Reque
     {
         const size_t m = std::max(n_t, n_nu);
         k_prep_obs<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(rq_in.d_t, (int)n_t, rq_in.d_nu, (int)n_nu, lg2_t, t_lin,
-                                                              lg2_nu);
+                                                              lg2_nu, rq_in.nu_code_units ? 1 : 0);
         ctx->launches++;
     }
     BatchWs w;
@@ -761,6 +775,71 @@ int vag_flux_density_series(vag_context* ctx, const vag_params* params, size_t n
                           nullptr, nullptr, s))
         return rc;
     CK(cudaMemcpyAsync(out, ctx->io_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+    if (status) CK(cudaMemcpyAsync(status, ctx->io_status.p, sizeof(int32_t) * n_models, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return VAG_OK;
+}
+
+// Replaces PyModel::flux (pybind/pymodel.cpp:391-410): band-integrated flux over [nu_min, nu_max]
+int vag_flux_band(vag_context* ctx, const vag_params* params, size_t n_models, const double* t, size_t n_t,
+                  double nu_min, double nu_max, size_t num_nu, double* out, int32_t* status) {
+    if (!(nu_min > 0)) return fail(VAG_ERR_INVALID, "nu_min must be positive");
+    if (!(nu_max > nu_min)) return fail(VAG_ERR_INVALID, "nu_max must be greater than nu_min");
+    if (num_nu < 2) return fail(VAG_ERR_INVALID, "num_nu must be at least 2");
+    // frequency grid in code units exactly as the reference builds it (xt::logspace of the
+    // unit-scaled bounds) and its Boole weights (src/core/quadrature.h:138-191)
+    std::vector<double> nu(num_nu), wgt(num_nu, 0.0);
+    {
+        const double a = std::log10(nu_min * unit::Hz), b = std::log10(nu_max * unit::Hz);
+        for (size_t i = 0; i < num_nu; ++i) nu[i] = std::pow(10.0, linspace_at(a, b, (int)num_nu, (int)i));
+        const double h = std::log(nu[1] / nu[0]);
+        const double cb = 2.0 * h / 45.0;
+        size_t j = 0;
+        for (; j + 4 < num_nu; j += 4) {
+            wgt[j] += cb * 7;
+            wgt[j + 1] += cb * 32;
+            wgt[j + 2] += cb * 12;
+            wgt[j + 3] += cb * 32;
+            wgt[j + 4] += cb * 7;
+        }
+        const size_t remaining = num_nu - 1 - j;
+        if (remaining == 3) {
+            const double c38 = 3.0 * h / 8.0;
+            wgt[j] += c38;
+            wgt[j + 1] += c38 * 3;
+            wgt[j + 2] += c38 * 3;
+            wgt[j + 3] += c38;
+        } else if (remaining == 2) {
+            const double c13 = h / 3.0;
+            wgt[j] += c13;
+            wgt[j + 1] += c13 * 4;
+            wgt[j + 2] += c13;
+        } else if (remaining == 1) {
+            wgt[j] += 0.5 * h;
+            wgt[j + 1] += 0.5 * h;
+        }
+        // Jacobian, and code-unit frequency -> Hz so that sum(F_nu[cgs] * w) is erg cm^-2 s^-1
+        // (the reference divides the code-unit sum by unit::flux_cgs, pymodel.cpp:404)
+        for (size_t i = 0; i < num_nu; ++i) wgt[i] = wgt[i] * nu[i] / unit::Hz;
+    }
+    if (int rc = host_prepare(ctx, params, n_models, t, n_t, nu.data(), num_nu, false)) return rc;
+    if (n_models == 0) return VAG_OK;
+    cudaStream_t s = ctx->stream;
+    const size_t grid_elems = n_models * VAG_NCOMP * num_nu * n_t;
+    CK(ctx->io_out.ensure(sizeof(double) * (grid_elems + n_models * VAG_NCOMP * n_t)));
+    CK(ctx->io_aux.ensure(sizeof(double) * num_nu));
+    double* d_grid = static_cast<double*>(ctx->io_out.p);
+    double* d_band = d_grid + grid_elems;
+    CK(cudaMemcpyAsync(ctx->io_aux.p, wgt.data(), sizeof(double) * num_nu, cudaMemcpyHostToDevice, s));
+    Request rq{false, static_cast<double*>(ctx->io_t.p), static_cast<double*>(ctx->io_nu.p), n_t, num_nu, true};
+    if (int rc = run_flux(ctx, static_cast<vag_params*>(ctx->io_params.p), n_models, rq, d_grid,
+                          static_cast<int32_t*>(ctx->io_status.p), nullptr, nullptr, nullptr, nullptr, s))
+        return rc;
+    const size_t n_mc = n_models * VAG_NCOMP;
+    k_band_reduce<<<(unsigned)((n_mc * n_t + 255) / 256), 256, 0, s>>>(d_grid, static_cast<double*>(ctx->io_aux.p), d_band,
+                                                                     n_mc, (int)num_nu, (int)n_t);
+    ctx->launches++;
+    CK(cudaMemcpyAsync(out, d_band, sizeof(double) * n_mc * n_t, cudaMemcpyDeviceToHost, s));
     if (status) CK(cudaMemcpyAsync(status, ctx->io_status.p, sizeof(int32_t) * n_models, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return VAG_OK;

@@ -64,6 +64,39 @@ class Engine:
                                                      t.size, out.ctypes.data, st.ctypes.data))
         return (out, st) if return_status else out
 
+    def flux_band(self, params, t, nu_min, nu_max, num_nu, return_status=False):
+        """Batched ``Model.flux`` (band-integrated, Boole rule) -> float64[n_models, 5, n_t] [erg cm^-2 s^-1]."""
+        p, t = self._params(params), _f64(t).reshape(-1)
+        out = np.empty((p.size, abi.NCOMP, t.size))
+        st = np.zeros(p.size, dtype=np.int32)
+        _lib.check(self._lib.vag_flux_band(self._h, p.ctypes.data, p.size, t.ctypes.data, t.size, float(nu_min),
+                                           float(nu_max), int(num_nu), out.ctypes.data, st.ctypes.data))
+        return (out, st) if return_status else out
+
+    def flux_density_exposures(self, params, t, nu, expo_time, num_points=10, return_status=False):
+        """Batched ``Model.flux_density_exposures`` (pybind/pymodel.cpp:412-496): each point is the
+        average of ``num_points`` samples spread over its exposure window (host-side sampling and
+        averaging exactly as the reference does; the series itself runs on the GPU)."""
+        t, nu, expo_time = (_f64(a).reshape(-1) for a in (t, nu, expo_time))
+        if not (t.size == nu.size == expo_time.size):
+            raise ValueError("time, frequency, and exposure time arrays must have the same size")
+        if num_points < 2:
+            raise ValueError("num_points must be at least 2 to sample within each exposure time")
+        if not np.all(np.isfinite(expo_time) & (expo_time > 0)):
+            bad = int(np.nonzero(~(np.isfinite(expo_time) & (expo_time > 0)))[0][0])
+            raise ValueError(f"expo_time[{bad}] must be finite and > 0, got {expo_time[bad]}")
+        k = np.arange(num_points, dtype=np.float64)
+        ts = (t[:, None] + k[None, :] * (expo_time / (num_points - 1))[:, None]).reshape(-1)
+        nus = np.repeat(nu, num_points)
+        idx = np.repeat(np.arange(t.size), num_points)
+        order = np.argsort(ts, kind="stable")
+        res = self.flux_density_series(params, ts[order], nus[order], return_status=True)
+        f, st = res
+        out = np.zeros((f.shape[0], abi.NCOMP, t.size))
+        np.add.at(out, (slice(None), slice(None), idx[order]), f)
+        out /= float(num_points)
+        return (out, st) if return_status else out
+
     def chi2_series(self, params, t, nu, lnF_obs, sigma_ln, w, return_status=False):
         """Batched ``Fitter._evaluate`` for point data -> chi2[n_models] (+inf where non-finite)."""
         p = self._params(params)

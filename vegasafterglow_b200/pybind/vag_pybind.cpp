@@ -8,6 +8,7 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <memory>
@@ -190,9 +191,68 @@ class Model {
         return pack(out, {(py::ssize_t)n});
     }
 
-    py::object flux(py::object, double, double, size_t) {
-        PyErr_SetString(PyExc_NotImplementedError, "Model.flux (band integration) is not implemented on the GPU path yet");
-        throw py::error_already_set();
+    // PyModel::flux (pybind/pymodel.cpp:391-410)
+    FluxDict flux(py::array_t<double, py::array::c_style | py::array::forcecast> t, double nu_min, double nu_max,
+                  size_t num_nu) {
+        const size_t n_t = t.size();
+        require(n_t > 0, "time array must be non-empty");
+        require(nu_min > 0, "nu_min must be positive");
+        require(nu_max > nu_min, "nu_max must be greater than nu_min");
+        require(num_nu >= 2, "num_nu must be at least 2");
+        std::vector<double> out(VAG_NCOMP * n_t);
+        {
+            py::gil_scoped_release rel;
+            auto ctx = context(device_);
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            check(vag_flux_band(ctx->h, &p_, 1, t.data(), n_t, nu_min, nu_max, num_nu, out.data(), nullptr));
+        }
+        return pack(out, {(py::ssize_t)n_t});
+    }
+
+    // PyModel::flux_density_exposures (pybind/pymodel.cpp:412-496): host-side sampling of each
+    // exposure window, one series evaluation on the GPU, host-side averaging.
+    FluxDict flux_density_exposures(py::array_t<double, py::array::c_style | py::array::forcecast> t,
+                                    py::array_t<double, py::array::c_style | py::array::forcecast> nu,
+                                    py::array_t<double, py::array::c_style | py::array::forcecast> expo_time,
+                                    size_t num_points) {
+        const size_t n = t.size();
+        require(n == (size_t)nu.size() && n == (size_t)expo_time.size(),
+                "time, frequency, and exposure time arrays must have the same size");
+        require(num_points >= 2, "num_points must be at least 2 to sample within each exposure time");
+        for (size_t i = 0; i < n; ++i)
+            require(std::isfinite(expo_time.data()[i]) && expo_time.data()[i] > 0,
+                    "expo_time[" + std::to_string(i) + "] must be finite and > 0, got " + std::to_string(expo_time.data()[i]));
+        const size_t total = n * num_points;
+        std::vector<double> ts(total), nus(total);
+        std::vector<size_t> idx(total), order(total);
+        for (size_t i = 0, j = 0; i < n; ++i) {
+            const double dt = expo_time.data()[i] / static_cast<double>(num_points - 1);
+            for (size_t k = 0; k < num_points; ++k, ++j) {
+                ts[j] = t.data()[i] + k * dt;
+                nus[j] = nu.data()[i];
+                idx[j] = i;
+                order[j] = j;
+            }
+        }
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return ts[a] < ts[b]; });
+        std::vector<double> ts_s(total), nus_s(total);
+        for (size_t j = 0; j < total; ++j) {
+            ts_s[j] = ts[order[j]];
+            nus_s[j] = nus[order[j]];
+        }
+        std::vector<double> raw(VAG_NCOMP * total);
+        {
+            py::gil_scoped_release rel;
+            auto ctx = context(device_);
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            check(vag_flux_density_series(ctx->h, &p_, 1, ts_s.data(), nus_s.data(), total, raw.data(), nullptr));
+        }
+        std::vector<double> out(VAG_NCOMP * n, 0.0);
+        for (int c = 0; c < VAG_NCOMP; ++c) {
+            for (size_t j = 0; j < total; ++j) out[c * n + idx[order[j]]] += raw[c * total + j];
+            for (size_t i = 0; i < n; ++i) out[c * n + i] /= static_cast<double>(num_points);
+        }
+        return pack(out, {(py::ssize_t)n});
     }
 
     const vag_params& params() const { return p_; }
@@ -328,6 +388,8 @@ PYBIND11_MODULE(VegasAfterglowC_b200, m) {
         .def("flux_density_grid", &Model::flux_density_grid, py::arg("t"), py::arg("nu"))
         .def("flux_density", &Model::flux_density, py::arg("t"), py::arg("nu"))
         .def("flux", &Model::flux, py::arg("t"), py::arg("nu_min"), py::arg("nu_max"), py::arg("num_nu"))
+        .def("flux_density_exposures", &Model::flux_density_exposures, py::arg("t"), py::arg("nu"), py::arg("expo_time"),
+             py::arg("num_points") = 10)
         .def_property_readonly("observer", [](const Model& mdl) { return mdl.obs_; })
         .def_property_readonly("fwd_rad", [](const Model& mdl) { return mdl.fwd_; })
         .def_property_readonly("rvs_rad", [](const Model& mdl) { return mdl.rvs_; })
