@@ -88,18 +88,6 @@ VAG_HD double fast_log2(double x) { return log2(x); }
 VAG_HD double fast_exp2(double x) { return exp2(x); }
 VAG_HD double fast_exp(double x) { return exp(x); }
 VAG_HD double fast_pow(double a, double b) { return exp2(b * log2(a)); }
-
-// src/util/fast-math.h:179-185
-VAG_HD double log2_softplus(double x) {
-    if (x > 20.0) return x;
-    if (x < -20.0) return 0.0;
-    return log2(1.0 + exp2(x));
-}
-// src/util/fast-math.h:199-202
-VAG_HD double log2_broken_power_ratio(double log2_x, double log2_x_break, double s_delta_beta, double s) {
-    return -log2_softplus(s_delta_beta * (log2_x - log2_x_break)) / s;
-}
-
 // src/core/physics.h:36-40, :59-61
 VAG_HD double gamma_to_beta(double gamma) { return sqrt((gamma - 1) * (gamma + 1)) / gamma; }
 VAG_HD double adiabatic_idx(double gamma) { return 4.0 / 3.0 + 1 / (3 * gamma); }

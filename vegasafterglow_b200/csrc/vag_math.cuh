@@ -1,0 +1,108 @@
+// vag_math.cuh -- FP64 exp2 / log2 for the radiation and EATS kernels.
+//
+// The reference calls libm's std::exp2 / std::log2 (fast-math polynomials are compiled OFF,
+// src/util/fast-math.h:40-77).  CUDA's libdevice equivalents materialise every polynomial
+// coefficient with two UMOV/IMAD.MOV instructions per DFMA on sm_100a (ncu: 34 % of k_eats'
+// issued instructions were such moves).  These versions keep the coefficients in __constant__
+// memory (uniform LDCU.128 loads, two coefficients per instruction), use MUFU.RCP64H + Newton for
+// the one division, and fall back to libdevice outside the fast domain.  Accuracy: <= 1 ulp-ish
+// (exp2: |rel| <= 1.2e-16, log2: |abs| <= 2e-16 + 1.2e-16*|result|), far inside the 1e-6 flux bar.
+// Host builds (tests/hostemu) run the same polynomials.
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#include "vag_common.cuh"
+
+namespace vag {
+
+// 2^f on [-0.5, 0.5], degree 12 (Chebyshev-node interpolation, scripts/gen_poly.py: 1.1e-17)
+#define VAG_EXP2_COEF                                                                                          \
+    0x1.0000000000000p+0, 0x1.62e42fefa39efp-1, 0x1.ebfbdff82c58ep-3, 0x1.c6b08d704a0d8p-5, 0x1.3b2ab6fba4eefp-7, \
+        0x1.5d87fe78a143fp-10, 0x1.430912f84f63dp-13, 0x1.ffcbfc78c6f84p-17, 0x1.62c022a64fb88p-20,             \
+        0x1.b524d76e5be40p-24, 0x1.e4cdbf4adcdb1p-28, 0x1.ea0792028e4c7p-32, 0x1.c65f2ac7d2156p-36
+// log2(m) = s * sum_n c_n s^(2n), s = (m-1)/(m+1), c_n = 2 / (ln2 (2n+1)), n = 0..10
+#define VAG_LOG2_COEF                                                                                          \
+    2.8853900817779268147, 0.96179669392597560491, 0.57707801635558536295, 0.41219858311113240211,            \
+        0.32059889797532520164, 0.26230818925253880134, 0.22195308321368667806, 0.19235933878519512098,        \
+        0.16972882833987804793, 0.15186263588304878025, 0.13739952770371080070
+
+#if defined(__CUDACC__)
+__constant__ double c_exp2[13] = {VAG_EXP2_COEF};
+__constant__ double c_log2[11] = {VAG_LOG2_COEF};
+#endif
+static const double h_exp2[13] = {VAG_EXP2_COEF};
+static const double h_log2[11] = {VAG_LOG2_COEF};
+
+#if defined(__CUDA_ARCH__)
+#define VAG_CEXP2 c_exp2
+#define VAG_CLOG2 c_log2
+#else
+#define VAG_CEXP2 h_exp2
+#define VAG_CLOG2 h_log2
+#endif
+
+VAG_HD double bits_to_double(uint64_t u) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)u);
+#else
+    double d;
+    std::memcpy(&d, &u, 8);
+    return d;
+#endif
+}
+VAG_HD uint64_t double_to_bits(double d) {
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(d);
+#else
+    uint64_t u;
+    std::memcpy(&u, &d, 8);
+    return u;
+#endif
+}
+
+VAG_HD double dexp2(double x) {
+    if (!(x > -1021.0 && x < 1023.0)) return exp2(x);  // overflow / subnormal / NaN: libm path
+    // round to nearest integer with the 1.5*2^52 trick
+    const double magic = 6755399441055744.0;
+    const double t = x + magic;
+    const double kf = t - magic;
+    const double f = x - kf;  // [-0.5, 0.5]
+    const int64_t k = (int64_t)(double_to_bits(t) & 0xFFFFFFFFull) | ((double_to_bits(t) & 0x80000000ull) ? ~0xFFFFFFFFll : 0);
+    double p = VAG_CEXP2[12];
+#pragma unroll
+    for (int j = 11; j >= 0; --j) p = fma(p, f, VAG_CEXP2[j]);
+    return bits_to_double(double_to_bits(p) + ((uint64_t)k << 52));
+}
+
+VAG_HD double dlog2(double x) {
+    if (!(x >= 2.2250738585072014e-308 && x < kInf)) return log2(x);  // 0, negative, subnormal, inf, NaN
+    uint64_t u = double_to_bits(x);
+    int e = (int)(u >> 52) - 1023;
+    u = (u & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull;
+    double m = bits_to_double(u);  // [1, 2)
+    if (m > 1.4142135623730951) {
+        m *= 0.5;
+        e += 1;
+    }
+    const double num = m - 1.0, den = m + 1.0;
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+    r = fma(r, fma(-den, r, 1.0), r);
+    r = fma(r, fma(-den, r, 1.0), r);
+    double s = num * r;
+    s = fma(fma(-den, s, num), r, s);
+#else
+    const double s = num / den;
+#endif
+    const double z = s * s;
+    double q = VAG_CLOG2[10];
+#pragma unroll
+    for (int j = 9; j >= 0; --j) q = fma(q, z, VAG_CLOG2[j]);
+    return fma(s, q, (double)e);
+}
+
+}  // namespace vag

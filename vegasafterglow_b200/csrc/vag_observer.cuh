@@ -68,7 +68,7 @@ VAG_HD RowGeom row_geometry(const EatsModel& M, int i, int j) {
     const double cos_th_lo = (j == 0) ? ct : cos(0.5 * (M.theta[j - 1] + th));
     const double cos_th_hi = (j == last) ? ct : cos(0.5 * (th + M.theta[j + 1]));
     const double dOmega = fabs((cos_th_hi - cos_th_lo) * compute_dphi(h, M.phi, i));
-    g.lg2_dOmega = log2(dOmega);
+    g.lg2_dOmega = rlog2(dOmega);
     g.rep = M.rep_of[j];
     return g;
 }
@@ -87,9 +87,9 @@ VAG_HD void node_logs(const EatsModel& M, const RowGeom& g, int n_t, int k, doub
     const double r = M.r[o];
     const double dop_lin = gamma_ - sqrt((gamma_ - 1) * (gamma_ + 1)) * g.cos_v;
     const double time = M.t_rows[o] * M.one_plus_z + g.t_coeff * r;
-    lg2_dop = -log2(dop_lin);
-    lg2_t = log2(time);
-    lg2_geom = (g.lg2_dOmega + 2.0 * log2(r)) + 3.0 * lg2_dop;
+    lg2_dop = -rlog2(dop_lin);
+    lg2_t = rlog2(time);
+    lg2_geom = (g.lg2_dOmega + 2.0 * rlog2(r)) + 3.0 * lg2_dop;
 }
 
 VAG_HD double cell_log2_I_nu(const EatsModel& M, int rep, int n_t, int k, double log2_nu) {
@@ -132,7 +132,7 @@ VAG_HD int find_interval(const double* t_row, int n_t, double x, bool series) {
 VAG_HD double interp_contrib2(double lo, double hi, double inv_dt, double dx) {
     const double s = (hi - lo) * inv_dt;
     if (!isfinite(s)) return 0.0;
-    return exp2(lo + dx * s);
+    return rexp2(lo + dx * s);
 }
 VAG_HD double interp_contrib(double lo, double hi, double t_lo, double t_hi, double x) {
     return interp_contrib2(lo, hi, 1.0 / (t_hi - t_lo), x - t_lo);

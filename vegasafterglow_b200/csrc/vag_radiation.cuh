@@ -10,9 +10,24 @@
 // as a SoA of the PH_NCOEF hot coefficients that compute_log2_I_nu reads.
 #pragma once
 
+#include "vag_math.cuh"
 #include "vag_model.cuh"
 
 namespace vag {
+
+// radiation-side log2 / exp2 (vag_math.cuh); the dynamics and grid kernels keep libdevice
+VAG_HD double rlog2(double x) { return dlog2(x); }
+VAG_HD double rexp2(double x) { return dexp2(x); }
+// src/util/fast-math.h:179-185
+VAG_HD double log2_softplus(double x) {
+    if (x > 20.0) return x;
+    if (x < -20.0) return 0.0;
+    return rlog2(1.0 + rexp2(x));
+}
+// src/util/fast-math.h:199-202
+VAG_HD double log2_broken_power_ratio(double log2_x, double log2_x_break, double s_delta_beta, double s) {
+    return -log2_softplus(s_delta_beta * (log2_x - log2_x_break)) / s;
+}
 
 // ---- electrons ------------------------------------------------------------------------------
 struct SynElectrons {
@@ -157,7 +172,7 @@ struct SynPhoton {
     double smooth_thick, log2_x_far;  // functions of p only
 };
 
-VAG_HD double sigmoid2(double x) { return 1.0 / (1.0 + fast_exp2(-x)); }
+VAG_HD double sigmoid2(double x) { return 1.0 / (1.0 + rexp2(-x)); }
 VAG_HD double blend(double w, double a, double b) { return w * a + (1.0 - w) * b; }
 VAG_HD double log2_smooth_one(double log2_a, double log2_b, double s) {
     return log2_a - log2_softplus(s * (log2_a - log2_b)) / s;
@@ -166,7 +181,7 @@ VAG_HD double log2_smooth_one(double log2_a, double log2_b, double s) {
 // p-only constants of build(): smooth-power-law-syn.cpp:102-110
 VAG_HD void photon_p_consts(double p, double& smooth_thick, double& log2_x_far) {
     smooth_thick = (3.44 * p - 1.41) / con::ln2;
-    log2_x_far = 1.5 * fast_log2(20.0 / smooth_thick);
+    log2_x_far = 1.5 * rlog2(20.0 / smooth_thick);
 }
 
 // sharp forms used for the thick normalisation: smooth-power-law-syn.cpp:48-74
@@ -194,14 +209,14 @@ VAG_HD void build_photon(const SynElectrons& e, double B, double p, double* c /*
     const double nu_a = compute_syn_freq(e.gamma_a, B);
     const double I_nu_max = compute_syn_I_peak(B, e.column_den);
 
-    const double log2_nu_m = fast_log2(nu_m);
-    const double log2_nu_c = fast_log2(nu_c);
-    const double log2_nu_a = fast_log2(nu_a);
-    c[PH_LOG2_I_MAX] = fast_log2(I_nu_max);
+    const double log2_nu_m = rlog2(nu_m);
+    const double log2_nu_c = rlog2(nu_c);
+    const double log2_nu_a = rlog2(nu_a);
+    c[PH_LOG2_I_MAX] = rlog2(I_nu_max);
     c[PH_LOG2_NU_M] = log2_nu_m;
     c[PH_LOG2_NU_C] = log2_nu_c;
     c[PH_LOG2_NU_A] = log2_nu_a;
-    c[PH_LOG2_NU_M_MAX] = fast_log2(nu_M);
+    c[PH_LOG2_NU_M_MAX] = rlog2(nu_M);
     c[PH_INV_NU_M_MAX] = 1.0 / nu_M;
 
     constexpr double s_swap = 4.0;
@@ -251,13 +266,13 @@ VAG_HD double photon_log2_I_nu(const Get& get, double smooth_thick, double log2_
     if (log2_x > log2_x_far) {
         thick = 2.5 * log2_x;
     } else {
-        const double s = -smooth_thick * fast_exp2(2. / 3 * log2_x);
+        const double s = -smooth_thick * rexp2(2. / 3 * log2_x);
         thick = 2.5 * log2_x + log2_softplus(-0.5 * log2_x + s);
     }
     const double spec = get(PH_LOG2_I_MAX) +
                         (get(PH_LOG2_NORM) + log2_smooth_one(thin, thick + get(PH_LOG2_THICK_NORM), get(PH_S_A_BLEND)));
     if (log2_nu - get(PH_LOG2_NU_M_MAX) < -20) return spec;
-    return spec - con::log2e * get(PH_INV_NU_M_MAX) * fast_exp2(log2_nu);
+    return spec - con::log2e * get(PH_INV_NU_M_MAX) * rexp2(log2_nu);
 }
 
 // One cell of K2: shock state -> photon coefficients.  For relic cells (k >= injection_idx,
