@@ -9,7 +9,9 @@ A "step" is one pass of the hot path over one batch (per GPU) of `--batch` param
 (SURVEY.md section 8d draw, seed = 1000 + rank).  `value` is timed with CUDA events on the launching
 stream with inputs and outputs resident in HBM; `e2e` goes through the host-buffer C-ABI entry point
 with pinned host memory (H2D of the parameters, D2H of the fluxes inside the timed region).
-L2 is flushed between timed iterations (a 256 MiB device memset outside the event brackets).
+L2 is flushed before every step (a 256 MiB device memset on the step's stream).  Up to `--inflight`
+independent steps (batches) are in flight per GPU, each on its own context/stream; the timed region runs
+from the first launch to the completion of the last kernel (CUDA events on the device timeline).
 """
 from __future__ import annotations
 
@@ -56,7 +58,8 @@ def config_dict(args, n_gpus):
         "n_t": 100,
         "n_nu": 3,
         "parallelism": f"walker-partition x{n_gpus} (no data-path collective)",
-        "l2": "flushed between timed iterations (256 MiB memset outside the event brackets)",
+        "l2": "flushed before every step (256 MiB memset on the step's stream, inside the timed region)",
+        "inflight": f"{args.inflight} independent steps in flight per GPU (one vag_context + stream each)",
     }
 
 
@@ -138,6 +141,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=4096, help="parameter sets per GPU per step")
+    ap.add_argument("--inflight", type=int, default=3, help="independent batches (steps) in flight per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -160,77 +164,114 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    eng = Engine(local)
+    from concurrent.futures import ThreadPoolExecutor
+
     P, t, nu = workload(args.batch, rank)
     n = P.size
-    stream = torch.cuda.current_stream().cuda_stream
-
-    # ---- device-resident inputs/outputs ("value") -------------------------------------------------
-    d_p = torch.from_numpy(P.view(np.uint8).copy()).to(dev)
-    d_t, d_nu = torch.from_numpy(t).to(dev), torch.from_numpy(nu).to(dev)
-    d_out = torch.empty((n, abi.NCOMP, nu.size, t.size), dtype=torch.float64, device=dev)
-    d_st = torch.zeros(n, dtype=torch.int32, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    eng.set_capacity(256, 128)
-
-    def step_dev():
-        eng.flux_density_grid_dev(d_p.data_ptr(), n, d_t.data_ptr(), t.size, d_nu.data_ptr(), nu.size,
-                                  d_out.data_ptr(), d_st.data_ptr(), stream)
+    S = max(1, args.inflight)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step_dev()
+    # One slot = one vag_context (own CUDA stream + HBM workspaces) + its own I/O buffers.  Steps are
+    # independent batches, so up to `--inflight` of them are in flight at once: while one batch sits in
+    # the dependent-latency-bound ODE kernel (1 warp/SM at 4096 rows) the EATS kernel of another fills
+    # the SMs.  Every step still runs the full pipeline on its full batch.
+    class Slot:
+        def __init__(self):
+            self.eng = Engine(local)
+            self.eng.set_capacity(256, 128)
+            self.stream = torch.cuda.Stream(device=dev)
+            self.d_p = torch.from_numpy(P.view(np.uint8).copy()).to(dev)
+            self.d_t, self.d_nu = torch.from_numpy(t).to(dev), torch.from_numpy(nu).to(dev)
+            self.d_out = torch.empty((n, abi.NCOMP, nu.size, t.size), dtype=torch.float64, device=dev)
+            self.d_st = torch.zeros(n, dtype=torch.int32, device=dev)
+            self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+            self.launches = 0
+            # pinned host buffers of the end-to-end arm
+            self.h_p = torch.from_numpy(P.view(np.uint8).copy()).pin_memory()
+            self.h_t, self.h_nu = torch.from_numpy(t.copy()).pin_memory(), torch.from_numpy(nu.copy()).pin_memory()
+            self.h_out = torch.empty((n, abi.NCOMP, nu.size, t.size), dtype=torch.float64).pin_memory()
+            self.h_st = torch.zeros(n, dtype=torch.int32).pin_memory()
+
+        def step_dev(self):
+            with torch.cuda.stream(self.stream):
+                self.flush.zero_()  # L2 flush between iterations (256 MiB > 126 MB L2)
+            self.eng.flux_density_grid_dev(self.d_p.data_ptr(), n, self.d_t.data_ptr(), t.size, self.d_nu.data_ptr(),
+                                           nu.size, self.d_out.data_ptr(), self.d_st.data_ptr(), self.stream.cuda_stream)
+            self.launches += self.eng.last_launch_count()
+
+        def step_e2e(self):
+            lib = self.eng._lib
+            rc = lib.vag_flux_density_grid(self.eng._h, self.h_p.data_ptr(), n, self.h_t.data_ptr(), t.size,
+                                           self.h_nu.data_ptr(), nu.size, self.h_out.data_ptr(), self.h_st.data_ptr())
+            assert rc == 0, lib.vag_last_error()
+
+    slots = [Slot() for _ in range(S)]
+    eng = slots[0].eng
+    pool = ThreadPoolExecutor(max_workers=S)
+
+    def run_steps(method, k):
+        """k steps, round-robin over the slots; each slot's steps run in order on its own thread."""
+        def worker(si):
+            for _ in range(si, k, S):
+                getattr(slots[si], method)()
+        list(pool.map(worker, range(min(S, k))))
+
+    def timed(method, k):
+        """Device-timeline duration [ms] from the first launch to the completion of the last kernel."""
+        main = torch.cuda.current_stream()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record(main)
+        for sl in slots:
+            sl.stream.wait_event(ev0)
+        w0 = time.perf_counter()
+        run_steps(method, k)
+        for sl in slots:
+            e = torch.cuda.Event()
+            e.record(sl.stream)
+            main.wait_event(e)
+        ev1.record(main)
+        barrier()
+        return ev0.elapsed_time(ev1), (time.perf_counter() - w0) * 1e3
+
+    run_steps("step_dev", args.warmup * S)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for sl in slots:
+        sl.launches = 0
+    dev_ms, wall_ms_local = timed("step_dev", args.steps)
+    launches = sum(sl.launches for sl in slots)
+    for sl in slots:
+        assert int(sl.d_st.abs().sum()) == 0, "a model reported a status bit"
+        assert bool(torch.isfinite(sl.d_out).all())
+    wall = wall_ms_local * 1e-3
+
+    # per-stage device times (CUDA events inside the library), sequential, one slot, not overlapped
     eng.set_profiling(True)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     stage_acc = {}
-    launches = 0
-    barrier()
-    wall0 = time.perf_counter()
-    for i in range(args.steps):
-        flush.zero_()
-        ev[i][0].record()
-        step_dev()
-        ev[i][1].record()
+    n_prof = 5
+    for _ in range(n_prof):
+        slots[0].step_dev()
         torch.cuda.synchronize()
-        for k, v in eng.last_stage_ms().items():
-            stage_acc[k] = stage_acc.get(k, 0.0) + v
-        launches += eng.last_launch_count()
-    barrier()
-    wall = time.perf_counter() - wall0
+        for k_, v in eng.last_stage_ms().items():
+            stage_acc[k_] = stage_acc.get(k_, 0.0) + v
     eng.set_profiling(False)
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    assert int(d_st.abs().sum()) == 0, "a model reported a status bit"
-    assert bool(torch.isfinite(d_out).all())
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory) -----------------------
-    h_p = torch.from_numpy(P.view(np.uint8).copy()).pin_memory()
-    h_t, h_nu = torch.from_numpy(t.copy()).pin_memory(), torch.from_numpy(nu.copy()).pin_memory()
-    h_out = torch.empty((n, abi.NCOMP, nu.size, t.size), dtype=torch.float64).pin_memory()
-    h_st = torch.zeros(n, dtype=torch.int32).pin_memory()
-    lib = eng._lib
-
-    def step_e2e():
-        rc = lib.vag_flux_density_grid(eng._h, h_p.data_ptr(), n, h_t.data_ptr(), t.size, h_nu.data_ptr(), nu.size,
-                                       h_out.data_ptr(), h_st.data_ptr())
-        assert rc == 0, lib.vag_last_error()
-
-    for _ in range(args.warmup):
-        step_e2e()
+    run_steps("step_e2e", args.warmup * S)
     barrier()
     e0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
+    run_steps("step_e2e", args.steps)
     barrier()
     e2e_s = time.perf_counter() - e0
     clocks = sampler.stop() if rank == 0 else None
+    h_out, h_st = slots[0].h_out, slots[0].h_st
 
     # ---- config 5: batched log-likelihood (series chi2), device-resident ---------------------------
     Pl, ts, nus = loglike_workload(args.batch, rank)
@@ -238,25 +279,43 @@ def main():
     lnF = np.log(1e-26 * (1 + 0.05 * rng.standard_normal(ts.size)) * (ts / 1e3) ** -1.0)
     sig = np.full(ts.size, 0.1)
     wgt = np.ones(ts.size)
-    d_pl = torch.from_numpy(Pl.view(np.uint8).copy()).to(dev)
-    d_arr = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (ts, nus, lnF, sig, wgt)]
-    d_chi2 = torch.empty(n, dtype=torch.float64, device=dev)
     gathered = torch.empty(n * world, dtype=torch.float64, device=dev) if world > 1 else None
+    for sl in slots:
+        sl.d_pl = torch.from_numpy(Pl.view(np.uint8).copy()).to(dev)
+        sl.d_arr = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (ts, nus, lnF, sig, wgt)]
+        sl.d_chi2 = torch.empty(n, dtype=torch.float64, device=dev)
 
-    def step_ll():
-        eng.chi2_series_dev(d_pl.data_ptr(), n, *[a.data_ptr() for a in d_arr], ts.size, d_chi2.data_ptr(),
-                            d_st.data_ptr(), stream)
-        if world > 1:  # the only inter-GPU traffic of the path: gather of float64[n] log-likelihoods
-            dist.all_gather_into_tensor(gathered, d_chi2)
+        def step_ll(self=sl):
+            self.eng.chi2_series_dev(self.d_pl.data_ptr(), n, *[a.data_ptr() for a in self.d_arr], ts.size,
+                                     self.d_chi2.data_ptr(), self.d_st.data_ptr(), self.stream.cuda_stream)
+            if world > 1:  # the only inter-GPU traffic of the path: gather of float64[n] log-likelihoods
+                with torch.cuda.stream(self.stream):
+                    dist.all_gather_into_tensor(gathered, self.d_chi2)
+        sl.step_ll = step_ll
 
-    for _ in range(args.warmup):
-        step_ll()
+    # with a collective in the step, keep one batch in flight per rank (NCCL ops must be issued in the
+    # same order on every rank)
+    S_ll = 1 if world > 1 else S
+
+    def run_ll(k):
+        def worker(si):
+            for _ in range(si, k, S_ll):
+                slots[si].step_ll()
+        list(pool.map(worker, range(min(S_ll, k))))
+
+    run_ll(args.warmup * S_ll)
     barrier()
+    main = torch.cuda.current_stream()
     la, lb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    la.record()
-    for _ in range(args.steps):
-        step_ll()
-    lb.record()
+    la.record(main)
+    for sl in slots:
+        sl.stream.wait_event(la)
+    run_ll(args.steps)
+    for sl in slots:
+        e = torch.cuda.Event()
+        e.record(sl.stream)
+        main.wait_event(e)
+    lb.record(main)
     barrier()
     ll_ms = la.elapsed_time(lb)
 
@@ -276,7 +335,7 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         fp64_peak = eng.measure_fp64_peak()
-        per = {k: v / args.steps for k, v in stage_acc.items()}  # ms per step of rank 0
+        per = {k: v / n_prof for k, v in stage_acc.items()}  # ms per (un-overlapped) step of rank 0
         # algorithmic work per model evaluation (SURVEY.md 8d / DESIGN.md section 5), C1 shape
         flops = {"dynamics": 4.6e4, "radiation": 2.1e4, "eats": 9.9e5}
         bytes_eats = 23e3
@@ -305,7 +364,7 @@ def main():
             "loglike": {"metric": "MCMC loglike evals/s (4096-walker FS+RS tophat, 100-point 5-band series)",
                         "value": n * world * args.steps / (ll_ms * 1e-3), "unit": UNIT, "ms_per_step": ll_ms / args.steps,
                         "collective": "all_gather float64[n] over NCCL" if world > 1 else "none (1 GPU)"},
-            "wall_ms_per_step_incl_flush": wall_ms / args.steps,
+            "wall_ms_per_step": wall_ms / args.steps,
         }
         if world == 1 and not args.no_cpu_baseline:
             try:

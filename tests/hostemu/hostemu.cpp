@@ -99,14 +99,15 @@ void eats_emulate(const BatchWs& w, int mi, int which, const EatsRequest& rq0, d
     const int n_t = h.n_t;
     const int erows = h.n_theta * h.n_phi_eff;
     const bool series = rq0.series != 0;
-    std::vector<double> smem(eats_shared_doubles(n_t, series, EATS_ROW_CHUNK) + 8);
+    const int nu_tile = series ? 1 : std::min(EATS_NU_TILE, rq0.n_nu);
+    std::vector<double> smem(eats_shared_doubles(n_t, series, EATS_ROW_CHUNK, nu_tile) + 8);
     std::vector<double> acc(EATS_NU_TILE * EATS_T_BLOCK);
-    EatsShared sh = eats_carve(smem.data(), n_t, series, EATS_ROW_CHUNK);
+    EatsShared sh = eats_carve(smem.data(), n_t, series, EATS_ROW_CHUNK, nu_tile);
     EatsRequest rq = rq0;
-    const int n_nu_tiles = series ? 1 : (rq.n_nu + EATS_NU_TILE - 1) / EATS_NU_TILE;
+    const int n_nu_tiles = series ? 1 : (rq.n_nu + nu_tile - 1) / nu_tile;
     for (int tile = 0; tile < n_nu_tiles; ++tile) {
-        const int l0 = tile * EATS_NU_TILE;
-        const int nl = series ? 1 : std::min(EATS_NU_TILE, rq.n_nu - l0);
+        const int l0 = tile * nu_tile;
+        const int nl = series ? 1 : std::min(nu_tile, rq.n_nu - l0);
         for (int i0 = 0; i0 < rq.n_t_obs; i0 += EATS_T_BLOCK) {
             rq.i0 = i0;
             rq.ni = std::min(EATS_T_BLOCK, rq.n_t_obs - i0);

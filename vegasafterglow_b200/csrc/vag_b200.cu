@@ -162,8 +162,8 @@ __global__ void k_band_reduce(const double* __restrict__ F, const double* __rest
 }
 
 // K3.  grid = (model, split, shock).  out[model][comp][n_nu][n_t] (grid) or [model][comp][n] (series)
-__global__ void __launch_bounds__(128) k_eats(BatchWs w, EatsRequest rq0, double* __restrict__ out, int n_split,
-                                              int row_chunk, int max_n_t) {
+__global__ void __launch_bounds__(128, 6) k_eats(BatchWs w, EatsRequest rq0, double* __restrict__ out, int n_split,
+                                                 int row_chunk, int max_n_t, int nu_tile) {
     extern __shared__ double smem[];
     const int mi = blockIdx.x;
     const int split = blockIdx.y;
@@ -174,21 +174,21 @@ __global__ void __launch_bounds__(128) k_eats(BatchWs w, EatsRequest rq0, double
     const int n_t = M.h->n_t;
     const int erows = M.h->n_theta * M.h->n_phi_eff;
     const bool series = rq0.series != 0;
-    double* acc = smem;  // [EATS_NU_TILE][EATS_T_BLOCK]
-    const EatsShared sh = eats_carve(smem + EATS_NU_TILE * EATS_T_BLOCK, max_n_t, series, row_chunk);
+    double* acc = smem;  // [nu_tile][EATS_T_BLOCK]
+    const EatsShared sh = eats_carve(smem + nu_tile * EATS_T_BLOCK, max_n_t, series, row_chunk, nu_tile);
     EatsRequest rq = rq0;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int comp = which ? VAG_C_RVS_SYNC : VAG_C_FWD_SYNC;
     const size_t comp_sz = series ? (size_t)rq.n_t_obs : (size_t)rq.n_nu * rq.n_t_obs;
     double* dst = out + ((size_t)mi * VAG_NCOMP + comp) * comp_sz;
-    const int n_nu_tiles = series ? 1 : (rq.n_nu + EATS_NU_TILE - 1) / EATS_NU_TILE;
+    const int n_nu_tiles = series ? 1 : (rq.n_nu + nu_tile - 1) / nu_tile;
     for (int tile = 0; tile < n_nu_tiles; ++tile) {
-        const int l0 = tile * EATS_NU_TILE;
-        const int nl = series ? 1 : imin(EATS_NU_TILE, rq.n_nu - l0);
+        const int l0 = tile * nu_tile;
+        const int nl = series ? 1 : imin(nu_tile, rq.n_nu - l0);
         for (int i0 = 0; i0 < rq.n_t_obs; i0 += EATS_T_BLOCK) {
             rq.i0 = i0;
             rq.ni = imin(EATS_T_BLOCK, rq.n_t_obs - i0);
-            for (int a = tid; a < EATS_NU_TILE * EATS_T_BLOCK; a += nthr) acc[a] = 0.0;
+            for (int a = tid; a < nu_tile * EATS_T_BLOCK; a += nthr) acc[a] = 0.0;
             for (int q0 = split * row_chunk; q0 < erows; q0 += n_split * row_chunk) {
                 const int nrows = imin(row_chunk, erows - q0);
                 __syncthreads();  // previous pass finished reading the staged rows
@@ -468,8 +468,9 @@ int run_flux(vag_context* ctx, const vag_params* d_params, size_t n, const Reque
         // shared-memory budget -> rows staged per pass
         const size_t budget = 200 * 1024;
         int row_chunk = EATS_ROW_CHUNK;
+        const int nu_tile = rq_in.series ? 1 : (int)std::min<size_t>(EATS_NU_TILE, n_nu);
         auto smem_bytes = [&](int rc_) {
-            return sizeof(double) * (EATS_NU_TILE * EATS_T_BLOCK + eats_shared_doubles(max_n_t, rq_in.series, rc_));
+            return sizeof(double) * (nu_tile * EATS_T_BLOCK + eats_shared_doubles(max_n_t, rq_in.series, rc_, nu_tile));
         };
         while (row_chunk > 1 && smem_bytes(row_chunk) > budget) --row_chunk;
         if (smem_bytes(row_chunk) > budget)
@@ -489,7 +490,7 @@ int run_flux(vag_context* ctx, const vag_params* d_params, size_t n, const Reque
         rq.lg2_t_obs = lg2_t;
         rq.lg2_nu_obs = lg2_nu;
         rq.t_obs_lin = t_lin;
-        k_eats<<<dim3((unsigned)n, (unsigned)n_split, 2), 128, sb, s>>>(w, rq, d_out, n_split, row_chunk, max_n_t);
+        k_eats<<<dim3((unsigned)n, (unsigned)n_split, 2), 128, sb, s>>>(w, rq, d_out, n_split, row_chunk, max_n_t, nu_tile);
         ctx->launches++;
     }
     mark(ctx, 4, s);

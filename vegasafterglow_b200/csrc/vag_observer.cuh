@@ -152,6 +152,7 @@ struct EatsShared {
     double* lg2dop;
     double* lg2geo;
     double* bv;
+    int nu_tile;  // stride of bv along the node axis (= frequencies staged per pass, <= EATS_NU_TILE)
 };
 
 struct EatsRequest {
@@ -166,18 +167,19 @@ struct EatsRequest {
 constexpr int EATS_T_BLOCK = 256;   // observation points accumulated per pass
 
 // row_chunk <= EATS_ROW_CHUNK rows are staged per pass (the host lowers it when n_t is large)
-VAG_HD size_t eats_shared_doubles(int n_t, bool series, int row_chunk) {
+VAG_HD size_t eats_shared_doubles(int n_t, bool series, int row_chunk, int nu_tile) {
     size_t n = (sizeof(RowGeom) * EATS_ROW_CHUNK + 7) / 8;
     n += (size_t)row_chunk * n_t;
     if (series)
         n += 2 * (size_t)row_chunk * n_t;
     else
-        n += (size_t)row_chunk * n_t * EATS_NU_TILE;
+        n += (size_t)row_chunk * n_t * nu_tile;
     return n;
 }
 
-VAG_HD EatsShared eats_carve(double* base, int n_t, bool series, int row_chunk) {
+VAG_HD EatsShared eats_carve(double* base, int n_t, bool series, int row_chunk, int nu_tile) {
     EatsShared s;
+    s.nu_tile = nu_tile;
     s.rowg = reinterpret_cast<RowGeom*>(base);
     double* p = base + (sizeof(RowGeom) * EATS_ROW_CHUNK + 7) / 8;
     s.lg2t = p;
@@ -223,7 +225,7 @@ VAG_HD void eats_phase1(const EatsModel& M, const EatsRequest& rq, const EatsSha
             // here a node is evaluated when one of its two adjacent intervals can hold a point.
             const bool need = (k + 1 >= n_t || node_time(M, g, n_t, k + 1) >= w_lo) &&
                               (k == 0 || node_time(M, g, n_t, k - 1) <= w_hi);
-            double* bv = sh.bv + (size_t)it * EATS_NU_TILE;
+            double* bv = sh.bv + (size_t)it * sh.nu_tile;
             if (need) {
                 for (int l = 0; l < nl; ++l) {
                     const double lg2_nu_src = rq.lg2_nu_obs[l0 + l] + lg2_1pz;
@@ -235,7 +237,7 @@ VAG_HD void eats_phase1(const EatsModel& M, const EatsRequest& rq, const EatsSha
 }
 
 // phase 2 (grid): thread <-> observation time; accumulates the chunk's rows into acc[l][idx]
-// acc layout: [EATS_NU_TILE][EATS_T_BLOCK] (thread-owned columns, no atomics)
+// acc layout: [nu_tile][EATS_T_BLOCK] (thread-owned columns, no atomics)
 VAG_HD void eats_phase2_grid(const EatsModel& M, const EatsRequest& rq, const EatsShared& sh, int nrows, int nl,
                              double* acc, int tid, int nthr) {
     const int n_t = M.h->n_t;
@@ -247,8 +249,8 @@ VAG_HD void eats_phase2_grid(const EatsModel& M, const EatsRequest& rq, const Ea
             const double* t_row = sh.lg2t + (size_t)r * n_t;
             const int k = find_interval(t_row, n_t, x, false);
             if (k < 0) continue;
-            const double* b_lo = sh.bv + ((size_t)r * n_t + k) * EATS_NU_TILE;
-            const double* b_hi = b_lo + EATS_NU_TILE;
+            const double* b_lo = sh.bv + ((size_t)r * n_t + k) * sh.nu_tile;
+            const double* b_hi = b_lo + sh.nu_tile;
             const double inv_dt = 1.0 / (t_row[k + 1] - t_row[k]), dx = x - t_row[k];
             for (int l = 0; l < nl; ++l) sum[l] += interp_contrib2(b_lo[l], b_hi[l], inv_dt, dx);
         }
