@@ -30,7 +30,7 @@ enum {
                             (pybind/error_handling.h:31-69) */
     VAG_ERR_CUDA = 2,    /* CUDA runtime error / no device                                       */
     VAG_ERR_UNSUPPORTED = 3, /* a switch of the reference that this path does not implement yet
-                                (jet spreading, Ejecta/Medium callbacks, k_m != 2)               */
+                                (jet spreading, axisymmetric=False, Ejecta/Medium callbacks, k_m != 2)               */
     VAG_ERR_CAPACITY = 4     /* a per-model grid exceeded the compiled capacity                  */
 };
 
@@ -46,7 +46,9 @@ enum {
     VAG_ST_ODE_STALLED = 2,   /* reverse-shock.tpp:560-566                                       */
     VAG_ST_ODE_FAIL500 = 4,   /* boost max_step_checker.hpp:99-106 (reference throws)            */
     VAG_ST_GRID_NONFINITE = 8, /* grid-refinement.h:633-635                                      */
-    VAG_ST_CAPACITY = 16      /* grid larger than compiled capacity; model output is NaN         */
+    VAG_ST_CAPACITY = 16,     /* grid / SSC lattice larger than compiled capacity; model output is NaN */
+    VAG_ST_IC_BAND = 32       /* an SSC query left the clamped output band (inverse-compton.h:622-635:
+                                 the reference would rebuild that cell's full-range spectrum)      */
 };
 
 /* Radiation(eps_e, eps_B, p, xi_e=1, ssc=False, kn=False): pybind/pymodel.h:303-313 */

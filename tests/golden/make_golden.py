@@ -54,7 +54,7 @@ def main():
             pin[name] = dev
     # 2. BASELINE.json configs C1-C3 (+ dense C2)
     for name, (p, t, nu) in {"C1": configs.C1(), "C2": configs.C2(), "C2_dense": configs.C2(dense=True),
-                             "C3": configs.C3()}.items():
+                             "C3": configs.C3(), "C4": configs.C4()}.items():
         save("config_" + name, p, t, nu)
     # 3. stage tables of C1, C2, C3 (Coord + Shock + observer grids)
     for name, (p, t, nu) in {"C1": configs.C1(), "C2": configs.C2(), "C3": configs.C3()}.items():
@@ -68,6 +68,10 @@ def main():
     save("batch_fs_gauss_offaxis", configs.random_draw(12, seed=13, jet="gaussian", theta_obs_max=0.4), t, nu)
     save("batch_fs_powerlaw_wind", configs.random_draw(12, seed=14, jet="powerlaw", medium="wind", theta_obs_max=0.3), t, nu)
     save("batch_rs_tophat_wind", configs.random_draw(24, seed=15, rvs=True, medium="wind"), t, nu)
+    nu_ssc = np.array([1e9, 1e14, 1e17, 1e22, 1e25])
+    save("batch_ssc_kn_tophat_ism", configs.random_draw(24, seed=21, ssc=True, kn=True), t, nu_ssc)
+    save("batch_ssc_thomson_tophat_wind", configs.random_draw(12, seed=22, ssc=True, kn=False, medium="wind"), t, nu_ssc)
+    save("batch_ssc_kn_rs_tophat_ism", configs.random_draw(12, seed=23, ssc=True, kn=True, rvs=True), t, nu_ssc)
     ts = np.sort(np.tile(np.logspace(2.5, 6.5, 20), 5))
     nus = np.tile([1e9, 5e9, 4.84e14, 1e17, 1e18], 20)
     save("series_rs_tophat_ism", configs.random_draw(48, seed=16, rvs=True), ts, nus, series=True)

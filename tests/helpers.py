@@ -53,7 +53,7 @@ MEDIAN_RTOL = 1e-8
 
 
 def assert_parity(flux, g, what):
-    for comp in (0, 1, 3):
+    for comp in (0, 1, 2, 3, 4):
         err = model_errors(flux, g["flux"], comp)
         spread = model_errors(g["flux_alt"], g["flux"], comp)
         tol = np.maximum(FLUX_RTOL, SPREAD_FACTOR * spread)

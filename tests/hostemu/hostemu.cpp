@@ -56,6 +56,7 @@ void run_front(HostBatch& hb, const vag_params* params, size_t n, double t_min, 
     w.row_model = hb.alloc<int>(rows);
     w.row_rep = hb.alloc<int>(rows);
     w.inj_idx = hb.alloc<int>(rows);
+    w.row_cell_off = hb.alloc<long long>(rows + 1);
     w.t_rows = hb.alloc<double>(cells);
     for (int a = 0; a < 6; ++a) {
         w.fwd[a] = hb.alloc<double>(cells);
@@ -63,14 +64,57 @@ void run_front(HostBatch& hb, const vag_params* params, size_t n, double t_min, 
     }
     w.coef_fwd = hb.alloc<double>((size_t)cells * PH_NCOEF);
     w.coef_rvs = hb.alloc<double>((size_t)cells * PH_NCOEF);
+    w.max_n_t = std::max(w.totals[TOT_MAX_NT], 1);
+    w.max_erows = std::max(w.totals[TOT_MAX_EROWS], 1);
+    w.any_ssc = 0;
+    for (size_t i = 0; i < n; ++i) w.any_ssc |= (params[i].fwd.ssc || (params[i].has_rvs && params[i].rvs.ssc)) ? 1 : 0;
     for (size_t i = 0; i < n; ++i) k0c_rowmap_body(w, (int)i);
     for (int r = 0; r < rows; ++r) k1_dynamics_body(w, r);
+    if (w.any_ssc) {
+        for (int sft = 0; sft < 2; ++sft) {
+            w.ic[sft] = hb.alloc<IcCell>(cells);
+            w.ictab_h[sft] = hb.alloc<IcTable>(cells);
+            w.ictab[sft] = hb.alloc<double>((size_t)cells * IC_CAP_OUT);
+        }
+        w.rowcos = hb.alloc<double>(n * w.max_erows);
+        w.dop_min = hb.alloc<double>(n * w.max_n_t);
+        w.dop_max = hb.alloc<double>(n * w.max_n_t);
+        KnLut* lut = hb.alloc<KnLut>(1);
+        for (int i = 0; i < KN_LUT_N; ++i) kn_lut_entry(i, lut->ratio[i], lut->lg2_ratio[i]);
+        w.lut = lut;
+        w.ic_scratch = hb.alloc<double>(IC_SCRATCH_DOUBLES);
+    }
     for (int r = 0; r < rows; ++r) {
         const GridHeader& h = w.hdr[w.row_model[r]];
-        const bool rvs = w.cfg[w.row_model[r]].has_rvs;
-        for (int k = 0; k < h.n_t; ++k) {
-            k2_radiation_cell(w, r, k, 0);
-            if (rvs) k2_radiation_cell(w, r, k, 1);
+        const ModelCfg& cfg = w.cfg[w.row_model[r]];
+        for (int sft = 0; sft < (cfg.has_rvs ? 2 : 1); ++sft) {
+            if ((sft ? cfg.rvs : cfg.fwd).ssc) {
+                k2_ic_cool_row(w, r, sft);
+            } else {
+                for (int k = 0; k < h.n_t; ++k) k2_radiation_cell(w, r, k, sft);
+            }
+        }
+    }
+}
+
+// SSC tables need the observation band: run after the request is known
+void run_ic_tables(HostBatch& hb, const double* nu_range) {
+    BatchWs& w = hb.w;
+    if (!w.any_ssc) return;
+    w.nu_range = nu_range;
+    for (int mi = 0; mi < w.n_models; ++mi) {
+        const GridHeader& h = w.hdr[mi];
+        for (int q = 0; q < h.n_theta * h.n_phi_eff; ++q) k_rowcos_body(w, mi, q);
+        for (int k = 0; k < h.n_t; ++k) k_dop_extrema_body(w, mi, k);
+    }
+    const int rows = w.totals[TOT_ROWS];
+    for (int r = 0; r < rows; ++r) {
+        const int mi = w.row_model[r];
+        const GridHeader& h = w.hdr[mi];
+        const ModelCfg& cfg = w.cfg[mi];
+        for (int sft = 0; sft < (cfg.has_rvs ? 2 : 1); ++sft) {
+            if (!(sft ? cfg.rvs : cfg.fwd).ssc) continue;
+            for (int k = 0; k < h.n_t; ++k) w.status[mi] |= k2b_ic_spectrum_cell(SeqPar{}, w, r, k, sft, w.ic_scratch);
         }
     }
 }
@@ -153,12 +197,16 @@ int run_flux(const vag_params* params, size_t n, const double* t, size_t n_t, co
     rq.lg2_nu_obs = lg2nu.data();
     rq.t_obs_lin = tl.data();
     const size_t comp = series ? n_t : n_nu * n_t;
+    double nu_range[2] = {*std::min_element(lg2nu.begin(), lg2nu.end()), *std::max_element(lg2nu.begin(), lg2nu.end())};
+    run_ic_tables(hb, nu_range);
     for (size_t mi = 0; mi < n; ++mi) {
         double* o = out + mi * VAG_NCOMP * comp;
         std::memset(o, 0, sizeof(double) * VAG_NCOMP * comp);
         if (hb.w.hdr[mi].status & VAG_ST_CAPACITY) continue;
         eats_emulate(hb.w, (int)mi, 0, rq, o + VAG_C_FWD_SYNC * comp);
         if (params[mi].has_rvs) eats_emulate(hb.w, (int)mi, 1, rq, o + VAG_C_RVS_SYNC * comp);
+        if (params[mi].fwd.ssc) eats_emulate(hb.w, (int)mi, 2, rq, o + VAG_C_FWD_SSC * comp);
+        if (params[mi].has_rvs && params[mi].rvs.ssc) eats_emulate(hb.w, (int)mi, 3, rq, o + VAG_C_RVS_SSC * comp);
         for (size_t i = 0; i < comp; ++i)
             o[i] = o[VAG_C_FWD_SYNC * comp + i] + o[VAG_C_FWD_SSC * comp + i] + o[VAG_C_RVS_SYNC * comp + i] +
                    o[VAG_C_RVS_SSC * comp + i];

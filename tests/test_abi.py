@@ -86,6 +86,8 @@ def test_unsupported_switches_say_so():
     p = configs.make()
     p["axisymmetric"] = 0
     assert lib.vag_params_validate(p.ctypes.data) == abi.VAG_ERR_UNSUPPORTED
+    p = configs.make(ssc=True, kn=True)  # inverse Compton is implemented
+    assert lib.vag_params_validate(p.ctypes.data) == abi.VAG_OK
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -71,7 +71,11 @@ def test_exact_invariants(engine):
     f2 = engine.flux_density_grid(q, t, nu)
     np.testing.assert_allclose(f2[0, 0] * 9.0, f1[0, 0], rtol=1e-9)
     np.testing.assert_allclose(f1[0, 0], f1[0, 1] + f1[0, 3], rtol=1e-12)
-    assert np.all(f1[0, 2] == 0) and np.all(f1[0, 4] == 0)  # no SSC components
+    assert np.all(f1[0, 2] == 0) and np.all(f1[0, 4] == 0)  # no SSC components requested
+    ps, ts_, nus_ = configs.C4()
+    fs = engine.flux_density_grid(ps, ts_[::5], nus_[::4])
+    np.testing.assert_allclose(fs[0, 0], fs[0, 1] + fs[0, 2], rtol=1e-12)
+    assert (fs[0, 2] > 0).any()
 
 
 def test_batch_is_independent_of_order_and_size(engine):
@@ -142,7 +146,7 @@ def test_error_conventions(engine):
     with pytest.raises(ValueError, match="eps_e"):
         engine.flux_density_grid(q, t, nu)
     q = p.copy()
-    q["fwd"]["ssc"] = 1
+    q["spreading"] = 1
     with pytest.raises(NotImplementedError):
         engine.flux_density_grid(q, t, nu)
     assert engine.flux_density_grid(p[:0], t, nu).shape == (0, abi.NCOMP, nu.size, t.size)

@@ -38,7 +38,7 @@ def test_stage_tables(name):
             assert _rel(d["rvs_shock"][a], g["rvs_shock"][a]) < 5e-6, nm
 
 
-@pytest.mark.parametrize("name", [n for n in golden_names() if n not in ("config_C2_dense", "golden_gauss_ism_rs")])
+@pytest.mark.parametrize("name", [n for n in golden_names() if n not in ("config_C2_dense", "config_C4", "golden_gauss_ism_rs")])
 def test_flux_parity(name):
     g = load_golden(name)
     fn = emu.flux_density_series if bool(g["series"]) else emu.flux_density_grid

@@ -9,7 +9,8 @@ from . import abi
 
 def make(jet="tophat", theta_c=0.1, E_iso=1e52, Gamma0=300.0, k_e=2.0, k_g=2.0, duration=1.0, medium="ism",
          n_ism=1.0, A_star=0.1, n0=np.inf, lumi_dist=1e26, z=0.1, theta_obs=0.0, fwd=(0.1, 1e-3, 2.3), rvs=None,
-         resolutions=None, rtol=0.0, radiative_fireball=True, xi_e=1.0, rvs_xi_e=1.0):
+         resolutions=None, rtol=0.0, radiative_fireball=True, xi_e=1.0, rvs_xi_e=1.0, ssc=False, kn=False,
+         rvs_ssc=False, rvs_kn=False):
     p = abi.default_params(1)
     p["jet_type"] = {"tophat": abi.JET_TOPHAT, "gaussian": abi.JET_GAUSSIAN, "powerlaw": abi.JET_POWERLAW}[jet]
     p["theta_c"], p["E_iso"], p["Gamma0"], p["k_e"], p["k_g"], p["duration"] = theta_c, E_iso, Gamma0, k_e, k_g, duration
@@ -20,10 +21,12 @@ def make(jet="tophat", theta_c=0.1, E_iso=1e52, Gamma0=300.0, k_e=2.0, k_g=2.0, 
     p["lumi_dist"], p["z"], p["theta_obs"] = lumi_dist, z, theta_obs
     p["fwd"]["eps_e"], p["fwd"]["eps_B"], p["fwd"]["p"] = fwd
     p["fwd"]["xi_e"] = xi_e
+    p["fwd"]["ssc"], p["fwd"]["kn"] = int(ssc), int(kn)
     if rvs is not None:
         p["has_rvs"] = 1
         p["rvs"]["eps_e"], p["rvs"]["eps_B"], p["rvs"]["p"] = rvs
         p["rvs"]["xi_e"] = rvs_xi_e
+        p["rvs"]["ssc"], p["rvs"]["kn"] = int(rvs_ssc), int(rvs_kn)
     if resolutions is not None:
         p["phi_resol"], p["theta_resol"], p["t_resol"] = resolutions
     p["rtol"] = rtol
@@ -46,7 +49,12 @@ def C3():
     return p, np.logspace(1, 7, 100), np.array([1e9, 4.84e14, 1e18])
 
 
-# in-scope goldens of the reference (typed jets, no SSC, no magnetisation)
+def C4():
+    p = make(jet="powerlaw", k_e=2.0, k_g=2.0, theta_obs=0.2, fwd=(0.1, 0.01, 2.3), ssc=True, kn=True)
+    return p, np.logspace(2, 7, 50), np.logspace(9, 27, 40)
+
+
+# in-scope goldens of the reference (typed jets, no magnetisation)
 GOLDEN_T = np.logspace(2, 8, 40)
 GOLDEN_NU = np.array([1e9, 1e14, 1e17, 1e22])
 GOLDEN = {
@@ -57,6 +65,10 @@ GOLDEN = {
                          rvs=(0.1, 0.01, 2.3), resolutions=(0.1, 1.2, 10)),
     "powerlaw_wind_rs": dict(jet="powerlaw", medium="wind", A_star=0.1, lumi_dist=1e28, z=1.0, theta_obs=0.3,
                              fwd=(0.1, 0.01, 2.3), rvs=(0.1, 0.01, 2.3)),
+    "gauss_wind_ssc": dict(jet="gaussian", E_iso=1e53, medium="wind", A_star=0.1, lumi_dist=3e28, z=1.0, theta_obs=0.2,
+                           fwd=(0.1, 1e-4, 2.3), ssc=True, kn=True),
+    "dense_ism_ssa_ssc": dict(n_ism=1e5, fwd=(0.1, 3e-2, 2.5), ssc=True, kn=True),
+    "ism_absorbed_slow_ssc": dict(n_ism=1e3, fwd=(0.1, 1e-6, 2.5), ssc=True, kn=True),
 }
 
 
@@ -64,7 +76,7 @@ def golden(name):
     return make(**GOLDEN[name])
 
 
-def random_draw(n, seed=0, rvs=False, jet="tophat", medium="ism", theta_obs_max=0.0):
+def random_draw(n, seed=0, rvs=False, jet="tophat", medium="ism", theta_obs_max=0.0, ssc=False, kn=False):
     """Common synthetic draw of SURVEY.md section 8d (numpy default_rng(seed))."""
     rng = np.random.default_rng(seed)
     p = np.repeat(make(jet=jet, medium=medium), n)
@@ -86,4 +98,8 @@ def random_draw(n, seed=0, rvs=False, jet="tophat", medium="ism", theta_obs_max=
         p["duration"] = 10 ** rng.uniform(0, 4, n)
     if theta_obs_max > 0:
         p["theta_obs"] = rng.uniform(0, theta_obs_max, n)
+    if ssc:
+        p["fwd"]["ssc"], p["fwd"]["kn"] = 1, int(kn)
+        if rvs:
+            p["rvs"]["ssc"], p["rvs"]["kn"] = 1, int(kn)
     return p

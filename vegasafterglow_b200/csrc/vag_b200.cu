@@ -52,6 +52,8 @@ __global__ void __launch_bounds__(1024) k_scan(BatchWs w) {
     long long cells = 0;
     for (int mi = m0; mi < m1; ++mi) {
         const GridHeader& h = w.hdr[mi];
+        const ModelCfg& cfg = w.cfg[mi];
+        if (cfg.fwd.ssc || (cfg.has_rvs && cfg.rvs.ssc)) st |= (1 << 30);  // carries "any ssc" through the OR
         rows += h.n_reps;
         cells += (long long)h.n_reps * h.n_t;
         max_nt = max(max_nt, h.n_t);
@@ -111,7 +113,8 @@ __global__ void __launch_bounds__(1024) k_scan(BatchWs w) {
         w.totals[TOT_MAX_NT] = max_nt;
         w.totals[TOT_MAX_NTHETA] = max_nth;
         w.totals[TOT_MAX_EROWS] = max_er;
-        w.totals[TOT_STATUS_OR] = st;
+        w.totals[TOT_STATUS_OR] = st & ~(1 << 30);
+        w.totals[TOT_ANY_SSC] = (st >> 30) & 1;
     }
 }
 
@@ -132,8 +135,95 @@ __global__ void __launch_bounds__(64) k_radiation(BatchWs w) {
     const int which = blockIdx.y;
     const int mi = w.row_model[row];
     if (which && !w.cfg[mi].has_rvs) return;
+    if ((which ? w.cfg[mi].rvs : w.cfg[mi].fwd).ssc) return;  // handled by k_ic_cooling
     const int n_t = w.hdr[mi].n_t;
     for (int k = threadIdx.x; k < n_t; k += blockDim.x) k2_radiation_cell(w, row, k, which);
+}
+
+// K2 for shocks with ssc=True: one thread per (row, shock), sequential in k (IC cooling of cell k
+// starts from gamma_c of cell k-1)
+__global__ void __launch_bounds__(32) k_ic_cooling(BatchWs w, int n_rows) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    const int which = blockIdx.y;
+    if (row >= n_rows) return;
+    const int mi = w.row_model[row];
+    if (which && !w.cfg[mi].has_rvs) return;
+    if (!(which ? w.cfg[mi].rvs : w.cfg[mi].fwd).ssc) return;
+    k2_ic_cool_row(w, row, which);
+}
+
+__global__ void k_kn_lut(KnLut* lut) {
+    const int i = threadIdx.x;
+    if (i < KN_LUT_N) kn_lut_entry(i, lut->ratio[i], lut->lg2_ratio[i]);
+}
+
+// log2 of the smallest / largest observation frequency (code units, without the 1+z shift)
+__global__ void k_nu_range(const double* __restrict__ lg2_nu, int n, double* out) {
+    __shared__ double s_lo[256], s_hi[256];
+    double lo = kInf, hi = -kInf;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        lo = fmin(lo, lg2_nu[i]);
+        hi = fmax(hi, lg2_nu[i]);
+    }
+    s_lo[threadIdx.x] = lo;
+    s_hi[threadIdx.x] = hi;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            s_lo[threadIdx.x] = fmin(s_lo[threadIdx.x], s_lo[threadIdx.x + o]);
+            s_hi[threadIdx.x] = fmax(s_hi[threadIdx.x], s_hi[threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[0] = s_lo[0];
+        out[1] = s_hi[0];
+    }
+}
+
+__global__ void k_rowcos(BatchWs w) {
+    const int mi = blockIdx.y;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const ModelCfg& cfg = w.cfg[mi];
+    if (!(cfg.fwd.ssc || (cfg.has_rvs && cfg.rvs.ssc))) return;
+    if (q >= w.hdr[mi].n_theta * w.hdr[mi].n_phi_eff) return;
+    k_rowcos_body(w, mi, q);
+}
+__global__ void k_dop_extrema(BatchWs w) {
+    const int mi = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const ModelCfg& cfg = w.cfg[mi];
+    if (!(cfg.fwd.ssc || (cfg.has_rvs && cfg.rvs.ssc))) return;
+    if (k >= w.hdr[mi].n_t) return;
+    k_dop_extrema_body(w, mi, k);
+}
+
+// K2b: SSC spectrum tables, one warp per unique cell (both shocks); warps stride over the batch's cells
+__global__ void __launch_bounds__(128) k_ic_spectrum(BatchWs w, int n_rows, int n_warps) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const WarpPar par{(int)(threadIdx.x & 31)};
+    double* scratch = w.ic_scratch + (size_t)warp * IC_SCRATCH_DOUBLES;
+    for (long long g = warp; g < w.n_cells; g += n_warps) {
+        // row of global cell g: last row whose first cell is <= g
+        int lo = 0, hi = n_rows;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (w.row_cell_off[mid] <= g)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const int row = lo;
+        const int k = (int)(g - w.row_cell_off[row]);
+        const int mi = w.row_model[row];
+        const ModelCfg& cfg = w.cfg[mi];
+        for (int which = 0; which < 2; ++which) {
+            if (which && !cfg.has_rvs) continue;
+            if (!(which ? cfg.rvs : cfg.fwd).ssc) continue;
+            const int st = k2b_ic_spectrum_cell(par, w, row, k, which, scratch);
+            if (st && par.lane == 0) atomicOr(&w.status[mi], st);
+        }
+    }
 }
 
 // observation request pre-pass: log2 of the (unit-scaled) times and frequencies
@@ -167,10 +257,15 @@ __global__ void __launch_bounds__(128, 6) k_eats(BatchWs w, EatsRequest rq0, dou
     extern __shared__ double smem[];
     const int mi = blockIdx.x;
     const int split = blockIdx.y;
-    const int which = blockIdx.z;
-    if (which && !w.cfg[mi].has_rvs) return;
-    if (w.hdr[mi].status & VAG_ST_CAPACITY) return;
-    const EatsModel M = make_eats_model(w, mi, which);
+    const int which = blockIdx.z;  // 0 fwd sync, 1 rvs sync, 2 fwd ssc, 3 rvs ssc
+    {
+        const ModelCfg& cfg = w.cfg[mi];
+        if ((which & 1) && !cfg.has_rvs) return;
+        if (which >= 2 && !((which & 1) ? cfg.rvs : cfg.fwd).ssc) return;
+    }
+    if (w.status[mi] & VAG_ST_CAPACITY) return;
+    EatsModel M = make_eats_model(w, mi, which);
+    M.breach = &w.status[mi];
     const int n_t = M.h->n_t;
     const int erows = M.h->n_theta * M.h->n_phi_eff;
     const bool series = rq0.series != 0;
@@ -178,7 +273,7 @@ __global__ void __launch_bounds__(128, 6) k_eats(BatchWs w, EatsRequest rq0, dou
     const EatsShared sh = eats_carve(smem + nu_tile * EATS_T_BLOCK, max_n_t, series, row_chunk, nu_tile);
     EatsRequest rq = rq0;
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int comp = which ? VAG_C_RVS_SYNC : VAG_C_FWD_SYNC;
+    const int comp = which == 0 ? VAG_C_FWD_SYNC : which == 1 ? VAG_C_RVS_SYNC : which == 2 ? VAG_C_FWD_SSC : VAG_C_RVS_SSC;
     const size_t comp_sz = series ? (size_t)rq.n_t_obs : (size_t)rq.n_nu * rq.n_t_obs;
     double* dst = out + ((size_t)mi * VAG_NCOMP + comp) * comp_sz;
     const int n_nu_tiles = series ? 1 : (rq.n_nu + nu_tile - 1) / nu_tile;
@@ -244,7 +339,7 @@ __global__ void k_chi2(const double* __restrict__ flux, size_t n_models, int n, 
 __global__ void k_nan_capacity(BatchWs w, double* out, size_t comp_sz_total) {
     // models whose grid exceeded the compiled capacity produce NaN, never a silent partial result
     const int mi = blockIdx.x;
-    if (!(w.hdr[mi].status & VAG_ST_CAPACITY)) return;
+    if (!(w.status[mi] & VAG_ST_CAPACITY)) return;
     for (size_t i = threadIdx.x; i < comp_sz_total; i += blockDim.x) out[(size_t)mi * comp_sz_total + i] = NAN;
 }
 
@@ -304,7 +399,7 @@ struct DevBuf {
 struct vag_context {
     int device = 0;
     cudaStream_t stream = nullptr;
-    DevBuf model_buf, row_buf, cell_buf, obs_buf, io_params, io_t, io_nu, io_out, io_status, io_aux;
+    DevBuf model_buf, row_buf, cell_buf, obs_buf, io_params, io_t, io_nu, io_out, io_status, io_aux, ic_buf, lut_buf;
     int* h_totals = nullptr;        // pinned
     long long* h_cells = nullptr;   // pinned
     int cap_theta = 384, cap_phi = 128;
@@ -383,11 +478,12 @@ int setup_models(vag_context* ctx, BatchWs& w, const vag_params* d_params, size_
 
 int setup_rows(vag_context* ctx, BatchWs& w, int rows, long long cells) {
     w.n_cells = cells;
-    CK(ctx->row_buf.ensure(carve_sz<int>(rows) * 3));
+    CK(ctx->row_buf.ensure(carve_sz<int>(rows) * 3 + carve_sz<long long>(rows + 1)));
     char* p = static_cast<char*>(ctx->row_buf.p);
     w.row_model = carve<int>(p, rows);
     w.row_rep = carve<int>(p, rows);
     w.inj_idx = carve<int>(p, rows);
+    w.row_cell_off = carve<long long>(p, rows + 1);
     const size_t plane = carve_sz<double>((size_t)cells);
     CK(ctx->cell_buf.ensure(plane * (1 + 12) + carve_sz<double>((size_t)cells * PH_NCOEF) * 2));
     p = static_cast<char*>(ctx->cell_buf.p);
@@ -396,6 +492,31 @@ int setup_rows(vag_context* ctx, BatchWs& w, int rows, long long cells) {
     for (int a = 0; a < 6; ++a) w.rvs[a] = carve<double>(p, (size_t)cells);
     w.coef_fwd = carve<double>(p, (size_t)cells * PH_NCOEF);
     w.coef_rvs = carve<double>(p, (size_t)cells * PH_NCOEF);
+    return VAG_OK;
+}
+
+// inverse-Compton workspaces (only when some model of the batch has ssc=True)
+int setup_ic(vag_context* ctx, BatchWs& w, size_t n, long long cells, int n_ic_warps, cudaStream_t s) {
+    const size_t nc = (size_t)cells;
+    const size_t bytes = 2 * (carve_sz<IcCell>(nc) + carve_sz<IcTable>(nc) + carve_sz<double>(nc * IC_CAP_OUT)) +
+                         carve_sz<double>(n * w.max_erows) + 2 * carve_sz<double>(n * w.max_n_t) +
+                         carve_sz<double>((size_t)n_ic_warps * IC_SCRATCH_DOUBLES);
+    CK(ctx->ic_buf.ensure(bytes));
+    char* p = static_cast<char*>(ctx->ic_buf.p);
+    for (int a = 0; a < 2; ++a) {
+        w.ic[a] = carve<IcCell>(p, nc);
+        w.ictab_h[a] = carve<IcTable>(p, nc);
+        w.ictab[a] = carve<double>(p, nc * IC_CAP_OUT);
+    }
+    w.rowcos = carve<double>(p, n * w.max_erows);
+    w.dop_min = carve<double>(p, n * w.max_n_t);
+    w.dop_max = carve<double>(p, n * w.max_n_t);
+    w.ic_scratch = carve<double>(p, (size_t)n_ic_warps * IC_SCRATCH_DOUBLES);
+    if (!ctx->lut_buf.p) {
+        CK(ctx->lut_buf.ensure(sizeof(KnLut)));
+        k_kn_lut<<<1, KN_LUT_N, 0, s>>>(static_cast<KnLut*>(ctx->lut_buf.p));
+    }
+    w.lut = static_cast<const KnLut*>(ctx->lut_buf.p);
     return VAG_OK;
 }
 
@@ -421,6 +542,14 @@ int run_front(vag_context* ctx, BatchWs& w, const vag_params* d_params, size_t n
     *cells_out = cells;
     rc = setup_rows(ctx, w, std::max(rows, 1), std::max<long long>(cells, 1));
     if (rc) return rc;
+    w.max_n_t = std::max(ctx->h_totals[TOT_MAX_NT], 1);
+    w.max_erows = std::max(ctx->h_totals[TOT_MAX_EROWS], 1);
+    w.any_ssc = ctx->h_totals[TOT_ANY_SSC];
+    if (w.any_ssc) {
+        const int n_ic_warps = (int)std::min<long long>(std::max<long long>(cells, 1), (long long)ctx->sm_count * 16);
+        rc = setup_ic(ctx, w, n, std::max<long long>(cells, 1), n_ic_warps, s);
+        if (rc) return rc;
+    }
     if (rows > 0) {
         k_rowmap<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(w);
         mark(ctx, 1, s);
@@ -428,6 +557,10 @@ int run_front(vag_context* ctx, BatchWs& w, const vag_params* d_params, size_t n
         mark(ctx, 2, s);
         k_radiation<<<dim3((unsigned)rows, 2), 64, 0, s>>>(w);
         ctx->launches += 3;
+        if (w.any_ssc) {
+            k_ic_cooling<<<dim3((unsigned)((rows + 31) / 32), 2), 32, 0, s>>>(w, rows);
+            ctx->launches++;
+        }
     } else {
         mark(ctx, 1, s);
         mark(ctx, 2, s);
@@ -448,6 +581,7 @@ int run_flux(vag_context* ctx, const vag_params* d_params, size_t n, const Reque
     double* lg2_t = static_cast<double*>(ctx->obs_buf.p);
     double* t_lin = lg2_t + n_t;
     double* lg2_nu = t_lin + n_t;
+    double* nu_range = lg2_nu + n_nu;
     {
         const size_t m = std::max(n_t, n_nu);
         k_prep_obs<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(rq_in.d_t, (int)n_t, rq_in.d_nu, (int)n_nu, lg2_t, t_lin,
@@ -460,6 +594,16 @@ int run_flux(vag_context* ctx, const vag_params* d_params, size_t n, const Reque
     int rc = run_front(ctx, w, d_params, n, rq_in.d_t, n_t, s, totals, &cells);
     if (rc) return rc;
 
+    if (w.any_ssc && totals[TOT_ROWS] > 0) {
+        // SSC tables: observation band -> per-row line-of-sight cosines -> per-k Doppler extrema -> tables
+        w.nu_range = nu_range;
+        k_nu_range<<<1, 256, 0, s>>>(lg2_nu, (int)n_nu, nu_range);
+        k_rowcos<<<dim3((unsigned)((w.max_erows + 127) / 128), (unsigned)n), 128, 0, s>>>(w);
+        k_dop_extrema<<<dim3((unsigned)((w.max_n_t + 63) / 64), (unsigned)n), 64, 0, s>>>(w);
+        const int n_ic_warps = (int)std::min<long long>(std::max<long long>(cells, 1), (long long)ctx->sm_count * 16);
+        k_ic_spectrum<<<(unsigned)((n_ic_warps * 32 + 127) / 128), 128, 0, s>>>(w, totals[TOT_ROWS], n_ic_warps);
+        ctx->launches += 4;
+    }
     const size_t comp_sz = rq_in.series ? n_t : n_nu * n_t;
     CK(cudaMemsetAsync(d_out, 0, sizeof(double) * n * VAG_NCOMP * comp_sz, s));
     const int max_n_t = std::max(totals[TOT_MAX_NT], 2);
@@ -490,7 +634,7 @@ int run_flux(vag_context* ctx, const vag_params* d_params, size_t n, const Reque
         rq.lg2_t_obs = lg2_t;
         rq.lg2_nu_obs = lg2_nu;
         rq.t_obs_lin = t_lin;
-        k_eats<<<dim3((unsigned)n, (unsigned)n_split, 2), 128, sb, s>>>(w, rq, d_out, n_split, row_chunk, max_n_t, nu_tile);
+        k_eats<<<dim3((unsigned)n, (unsigned)n_split, w.any_ssc ? 4 : 2), 128, sb, s>>>(w, rq, d_out, n_split, row_chunk, max_n_t, nu_tile);
         ctx->launches++;
     }
     mark(ctx, 4, s);
@@ -578,8 +722,6 @@ int vag_params_validate(const vag_params* p) {
         if (!rng_oi(r.eps_B, 0.0, 1.0)) return bad(std::string(who) + ".eps_B must be in (0, 1]");
         if (!rng_oi(r.xi_e, 0.0, 1.0)) return bad(std::string(who) + ".xi_e must be in (0, 1]");
         if (!(std::isfinite(r.p) && r.p > 1.0)) return bad(std::string(who) + ".p must be > 1");
-        if (r.ssc || r.kn)
-            return fail(VAG_ERR_UNSUPPORTED, std::string(who) + ": ssc/kn (inverse Compton) is not implemented on the GPU path yet");
         return VAG_OK;
     };
     if (int rc = chk_rad(p->fwd, "fwd_rad")) return rc;
@@ -624,7 +766,7 @@ void vag_destroy(vag_context* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->model_buf, &c->row_buf, &c->cell_buf, &c->obs_buf, &c->io_params, &c->io_t, &c->io_nu,
-                      &c->io_out, &c->io_status, &c->io_aux})
+                      &c->io_out, &c->io_status, &c->io_aux, &c->ic_buf, &c->lut_buf})
         b->release();
     if (c->h_totals) cudaFreeHost(c->h_totals);
     if (c->h_cells) cudaFreeHost(c->h_cells);

@@ -14,6 +14,7 @@
 #pragma once
 
 #include "vag_grid.cuh"
+#include "vag_ic.cuh"
 #include "vag_radiation.cuh"
 
 namespace vag {
@@ -34,6 +35,13 @@ struct EatsModel {
     long coef_stride;        // distance between coefficient planes (= total cells of the batch)
     double smooth_thick, log2_x_far;
     double one_plus_z, lumi_dist, theta_v;
+    // emission model of this pass: 0 synchrotron, 1 synchrotron with the IC correction of a shock
+    // with ssc=True, 2 SSC (per-cell tables)
+    int mode;
+    const IcCell* ic;         // [n_reps][n_t]
+    const IcTable* ictab_h;   // [n_reps][n_t]
+    const double* ictab;      // [n_reps][n_t][IC_CAP_OUT]
+    int* breach;              // model status word: gets VAG_ST_IC_BAND when an SSC query leaves the clamped band
 };
 
 // compute_dphi: src/core/observer.cpp:17-37
@@ -93,8 +101,24 @@ VAG_HD void node_logs(const EatsModel& M, const RowGeom& g, int n_t, int k, doub
 }
 
 VAG_HD double cell_log2_I_nu(const EatsModel& M, int rep, int n_t, int k, double log2_nu) {
-    const double* base = M.coef + (long)rep * n_t + k;
+    const long cell = (long)rep * n_t + k;
+    if (M.mode == 2) {
+        bool breach = false;
+        const double v = ic_table_log2_I_nu(M.ictab_h[cell], M.ictab + (size_t)cell * IC_CAP_OUT, log2_nu, breach);
+        if (breach && M.breach) {
+#if defined(__CUDA_ARCH__)
+            atomicOr(M.breach, VAG_ST_IC_BAND);
+#else
+            *M.breach |= VAG_ST_IC_BAND;
+#endif
+        }
+        return v;
+    }
+    const double* base = M.coef + cell;
     const long stride = M.coef_stride;
+    if (M.mode == 1)
+        return photon_log2_I_nu_ic([&](int c) { return base[c * stride]; }, M.smooth_thick, M.log2_x_far, M.ic[cell],
+                                   log2_nu);
     return photon_log2_I_nu([&](int c) { return base[c * stride]; }, M.smooth_thick, M.log2_x_far, log2_nu);
 }
 

@@ -13,13 +13,14 @@
 #pragma once
 
 #include "vag_grid.cuh"
+#include "vag_ic.cuh"
 #include "vag_observer.cuh"
 #include "vag_radiation.cuh"
 #include "vag_shock.cuh"
 
 namespace vag {
 
-enum { TOT_ROWS = 0, TOT_MAX_NT, TOT_MAX_NTHETA, TOT_MAX_EROWS, TOT_STATUS_OR, TOT_N };
+enum { TOT_ROWS = 0, TOT_MAX_NT, TOT_MAX_NTHETA, TOT_MAX_EROWS, TOT_STATUS_OR, TOT_ANY_SSC, TOT_N };
 
 struct BatchWs {
     int n_models;
@@ -42,6 +43,7 @@ struct BatchWs {
     int* row_model;
     int* row_rep;
     int* inj_idx;
+    long long* row_cell_off;  // first global cell of each row
     // per unique cell
     long long n_cells;
     double* t_rows;
@@ -49,6 +51,18 @@ struct BatchWs {
     double* rvs[6];
     double* coef_fwd;  // [PH_NCOEF][n_cells]
     double* coef_rvs;
+    // inverse-Compton data: allocated only when some model of the batch has ssc=True
+    int any_ssc;
+    int max_n_t, max_erows;   // batch maxima (known after K0b)
+    IcCell* ic[2];            // [n_cells] per shock
+    IcTable* ictab_h[2];      // [n_cells]
+    double* ictab[2];         // [n_cells][IC_CAP_OUT]
+    double* rowcos;           // [n_models][max_erows]  cos of the angle to the line of sight per (phi,theta) row
+    double* dop_min;          // [n_models][max_n_t]    min / max over rows of the linear Doppler denominator
+    double* dop_max;
+    const KnLut* lut;
+    double* ic_scratch;       // [n_ic_warps][IC_SCRATCH_DOUBLES]
+    const double* nu_range;   // [2] log2 of min / max observation frequency (code units)
 };
 
 // ---- K0 ---------------------------------------------------------------------------------------
@@ -93,6 +107,9 @@ VAG_HD void k0b_scan_body(const BatchWs& w) {
     w.totals[TOT_MAX_NTHETA] = max_nth;
     w.totals[TOT_MAX_EROWS] = max_erows;
     w.totals[TOT_STATUS_OR] = st;
+    int any = 0;
+    for (int mi = 0; mi < w.n_models; ++mi) any |= (w.cfg[mi].fwd.ssc || (w.cfg[mi].has_rvs && w.cfg[mi].rvs.ssc)) ? 1 : 0;
+    w.totals[TOT_ANY_SSC] = any;
 }
 
 // ---- K0c --------------------------------------------------------------------------------------
@@ -104,6 +121,7 @@ VAG_HD void k0c_rowmap_body(const BatchWs& w, int mi) {
     for (int r = 0; r < h.n_reps; ++r) {
         w.row_model[ro + r] = mi;
         w.row_rep[ro + r] = r;
+        w.row_cell_off[ro + r] = w.cell_off[mi] + (long long)r * h.n_t;
         const int j0 = reps[r];
         const int j1 = (r + 1 < h.n_reps) ? reps[r + 1] : h.n_theta;
         for (int j = j0; j < j1; ++j) rep_of[j] = r;
@@ -184,6 +202,74 @@ VAG_HD void k2_radiation_cell(const BatchWs& w, int row, int k, int which) {
     for (int c = 0; c < PH_NCOEF; ++c) out[(long long)c * w.n_cells] = coef[c];
 }
 
+// ---- K2 for shocks with ssc=True: IC cooling along one row (sequential in k) ----------------------
+VAG_HD void k2_ic_cool_row(const BatchWs& w, int row, int which) {
+    const int mi = w.row_model[row];
+    const GridHeader& h = w.hdr[mi];
+    const ModelCfg& cfg = w.cfg[mi];
+    const long long off = w.cell_off[mi] + (long long)w.row_rep[row] * h.n_t;
+    double* const* pl = which ? w.rvs : w.fwd;
+    const RadCfg& rad = which ? cfg.rvs : cfg.fwd;
+    const int inj = which ? w.inj_idx[row] : h.n_t;
+    double* coef = (which ? w.coef_rvs : w.coef_fwd) + off;
+    const long long plane = w.n_cells;
+    ic_cool_row(rad, h.n_t, inj, pl[0] + off, pl[1] + off, pl[3] + off, pl[4] + off, pl[5] + off, w.ic[which] + off,
+                [&](int k, int q, double v) { coef[(long long)q * plane + k] = v; });
+}
+
+// ---- per-row line-of-sight cosine and per-k Doppler extrema (SSC output band, pymodel.h:897-909) ---
+VAG_HD EatsModel make_eats_model(const BatchWs& w, int mi, int which);
+VAG_HD void k_rowcos_body(const BatchWs& w, int mi, int q) {
+    const EatsModel M = make_eats_model(w, mi, 0);
+    const int n_theta = M.h->n_theta;
+    w.rowcos[(size_t)mi * w.max_erows + q] = row_geometry(M, q / n_theta, q % n_theta).cos_v;
+}
+VAG_HD void k_dop_extrema_body(const BatchWs& w, int mi, int k) {
+    const GridHeader& h = w.hdr[mi];
+    const int erows = h.n_theta * h.n_phi_eff;
+    const double* Gam = w.fwd[2] + w.cell_off[mi];
+    const int* rep_of = w.rep_of + (size_t)mi * w.cap_theta;
+    const double* rc = w.rowcos + (size_t)mi * w.max_erows;
+    double lo = kInf, hi = -kInf;
+    for (int q = 0; q < erows; ++q) {
+        const double g = Gam[(size_t)rep_of[q % h.n_theta] * h.n_t + k];
+        const double d = g - sqrt((g - 1) * (g + 1)) * rc[q];
+        lo = vmin(lo, d);
+        hi = vmax(hi, d);
+    }
+    w.dop_min[(size_t)mi * w.max_n_t + k] = lo;
+    w.dop_max[(size_t)mi * w.max_n_t + k] = hi;
+}
+
+// ---- K2b: SSC spectrum of one cell (one warp) -------------------------------------------------------
+template <class Par>
+VAG_HD int k2b_ic_spectrum_cell(const Par& par, const BatchWs& w, int row, int k, int which, double* scratch) {
+    const int mi = w.row_model[row];
+    const GridHeader& h = w.hdr[mi];
+    const ModelCfg& cfg = w.cfg[mi];
+    const long long cell = w.cell_off[mi] + (long long)w.row_rep[row] * h.n_t + k;
+    const RadCfg& rad = which ? cfg.rvs : cfg.fwd;
+    const IcCell& c = w.ic[which][cell];
+    const double* base = (which ? w.coef_rvs : w.coef_fwd) + cell;
+    const long long stride = w.n_cells;
+    double smooth_thick, log2_x_far;
+    photon_p_consts(rad.p, smooth_thick, log2_x_far);
+    auto seed = [&](double log2_nu) {
+        return photon_log2_I_nu_ic([&](int q) { return base[(long long)q * stride]; }, smooth_thick, log2_x_far, c, log2_nu);
+    };
+    // comoving evaluation band of this time index (pybind/pymodel.h:897-909): lg2_doppler = -log2(dop_lin)
+    const double lg2_1pz = fast_log2(1 + cfg.z);
+    const double lg2_dop_max = -rlog2(w.dop_min[(size_t)mi * w.max_n_t + k]);
+    const double lg2_dop_min = -rlog2(w.dop_max[(size_t)mi * w.max_n_t + k]);
+    const double nu_eval_min = fast_exp2((w.nu_range[0] + lg2_1pz) - lg2_dop_max);
+    const double nu_eval_max = fast_exp2((w.nu_range[1] + lg2_1pz) - lg2_dop_min);
+    IcTable hdr;
+    const int st = ic_generate(par, c, seed, rad.kn != 0, *w.lut, nu_eval_min, nu_eval_max, scratch, hdr,
+                               w.ictab[which] + (size_t)cell * IC_CAP_OUT);
+    w.ictab_h[which][cell] = hdr;
+    return st;
+}
+
 VAG_HD EatsModel make_eats_model(const BatchWs& w, int mi, int which) {
     const GridHeader& h = w.hdr[mi];
     const ModelCfg& cfg = w.cfg[mi];
@@ -196,9 +282,16 @@ VAG_HD EatsModel make_eats_model(const BatchWs& w, int mi, int which) {
     M.t_rows = w.t_rows + off;
     M.r = w.fwd[1] + off;      // the pair solver gives both shocks identical kinematics
     M.Gamma = w.fwd[2] + off;  // (pybind/pymodel.h:943-950): one EAT geometry serves both
-    M.coef = (which ? w.coef_rvs : w.coef_fwd) + off;
+    const int shock = which & 1;  // which: 0 fwd sync, 1 rvs sync, 2 fwd ssc, 3 rvs ssc
+    const RadCfg& rad = shock ? cfg.rvs : cfg.fwd;
+    M.coef = (shock ? w.coef_rvs : w.coef_fwd) + off;
     M.coef_stride = (long)w.n_cells;
-    photon_p_consts(which ? cfg.rvs.p : cfg.fwd.p, M.smooth_thick, M.log2_x_far);
+    photon_p_consts(rad.p, M.smooth_thick, M.log2_x_far);
+    M.mode = (which >= 2) ? 2 : (rad.ssc ? 1 : 0);
+    M.ic = (w.any_ssc && rad.ssc) ? w.ic[shock] + off : nullptr;
+    M.ictab_h = (w.any_ssc && rad.ssc) ? w.ictab_h[shock] + off : nullptr;
+    M.ictab = (w.any_ssc && rad.ssc) ? w.ictab[shock] + (size_t)off * IC_CAP_OUT : nullptr;
+    M.breach = nullptr;
     M.one_plus_z = 1 + cfg.z;
     M.lumi_dist = cfg.lumi_dist;
     M.theta_v = cfg.theta_v;
