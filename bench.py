@@ -141,7 +141,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=4096, help="parameter sets per GPU per step")
-    ap.add_argument("--inflight", type=int, default=3, help="independent batches (steps) in flight per GPU")
+    ap.add_argument("--inflight", type=int, default=4, help="independent batches (steps) in flight per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
