@@ -36,7 +36,16 @@ enum {
 
 /* jet / medium enumerations: the typed variants of JetVariant / MediumVariant
  * (src/environment/jet.h:272, src/environment/medium.h:144). */
-enum { VAG_JET_TOPHAT = 0, VAG_JET_GAUSSIAN = 1, VAG_JET_POWERLAW = 2 };
+enum {
+    VAG_JET_TOPHAT = 0,
+    VAG_JET_GAUSSIAN = 1,
+    VAG_JET_POWERLAW = 2,
+    /* closed-form members of the reference's Ejecta family (pybind/pymodel.cpp:97-146,
+     * src/environment/jet.h:403-470) as enumerated device profiles */
+    VAG_JET_TWO_COMPONENT = 3, /* TwoComponentJet(theta_c, E_iso, Gamma0, theta_w, E_iso_w, Gamma0_w)        */
+    VAG_JET_STEP_POWERLAW = 4, /* StepPowerLawJet(theta_c, E_iso, Gamma0, E_iso_w, Gamma0_w, k_e, k_g)       */
+    VAG_JET_POWERLAW_WING = 5  /* PowerLawWing(theta_c, E_iso_w, Gamma0_w, k_e, k_g)                         */
+};
 enum { VAG_MEDIUM_ISM = 0, VAG_MEDIUM_WIND = 1 };
 
 /* per-model status bits written by the kernels (the reference prints a
@@ -65,6 +74,9 @@ typedef struct vag_params {
     int32_t jet_type;
     int32_t spreading; /* must be 0 (VAG_ERR_UNSUPPORTED otherwise) */
     double theta_c, E_iso, Gamma0, k_e, k_g, duration;
+    double theta_w, E_iso_w, Gamma0_w; /* wing of the two-component / step-power-law / power-law-wing jets */
+    double sigma0;                     /* ejecta magnetisation (constant; the reference expresses it through
+                                          Ejecta(sigma0=...)); 0 = unmagnetised */
     /* medium: ISM(n_ism) / Wind(A_star, n_ism=0, n0=inf, k_m=2)  pybind/pymodel.cpp:148-186 */
     int32_t medium_type;
     int32_t pad0_;

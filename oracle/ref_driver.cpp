@@ -31,8 +31,51 @@ struct RefModel {
     Real theta_w{con::pi / 2};
 };
 
+// Ejecta-family jets: the named factories of pybind/pymodel.cpp:97-146 followed by convert_unit_jet
+// (pymodel.cpp:188-211).  A constant magnetisation sigma0 > 0 is expressed the only way the reference
+// can express it: an Ejecta with a sigma0 profile (tests/python/golden/regenerate.py:140-148).
+JetVariant make_ejecta(const vag_params& p) {
+    Ejecta jet;
+    const Real tc = p.theta_c;
+    switch (p.jet_type) {
+        case VAG_JET_TOPHAT:
+            jet.eps_k = math::tophat(tc, p.E_iso);
+            jet.Gamma0 = math::tophat_plus_one(tc, p.Gamma0 - 1);
+            break;
+        case VAG_JET_GAUSSIAN:
+            jet.eps_k = math::gaussian(tc, p.E_iso);
+            jet.Gamma0 = math::gaussian_plus_one(tc, p.Gamma0 - 1);
+            break;
+        case VAG_JET_POWERLAW:
+            jet.eps_k = math::powerlaw(tc, p.E_iso, p.k_e);
+            jet.Gamma0 = math::powerlaw_plus_one(tc, p.Gamma0 - 1, p.k_g);
+            break;
+        case VAG_JET_TWO_COMPONENT:
+            jet.eps_k = math::two_component(tc, p.theta_w, p.E_iso, p.E_iso_w);
+            jet.Gamma0 = math::two_component_plus_one(tc, p.theta_w, p.Gamma0 - 1, p.Gamma0_w - 1);
+            break;
+        case VAG_JET_STEP_POWERLAW:
+            jet.eps_k = math::step_powerlaw(tc, p.E_iso, p.E_iso_w, p.k_e);
+            jet.Gamma0 = math::step_powerlaw_plus_one(tc, p.Gamma0 - 1, p.Gamma0_w - 1, p.k_g);
+            break;
+        default:
+            jet.eps_k = math::powerlaw_wing(tc, p.E_iso_w, p.k_e);
+            jet.Gamma0 = math::powerlaw_wing_plus_one(tc, p.Gamma0_w - 1, p.k_g);
+            break;
+    }
+    if (p.sigma0 > 0) jet.sigma0 = math::isotropic(p.sigma0);
+    jet.spreading = p.spreading != 0;
+    jet.T0 = p.duration;
+    // convert_unit_jet
+    const auto eps_k_cgs = jet.eps_k;
+    jet.eps_k = [=](Real phi, Real theta) { return eps_k_cgs(phi, theta) * (unit::erg / (4 * con::pi)); };
+    jet.T0 *= unit::sec;
+    return jet;
+}
+
 // unit conversions exactly as the Py* factories do (pybind/pymodel.cpp:47-186, pymodel.h:190-204)
 JetVariant make_jet(const vag_params& p) {
+    if (p.jet_type >= VAG_JET_TWO_COMPONENT || p.sigma0 > 0) return make_ejecta(p);
     const Real T0 = p.duration * unit::sec;
     switch (p.jet_type) {
         case VAG_JET_TOPHAT:

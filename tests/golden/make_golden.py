@@ -68,6 +68,18 @@ def main():
     save("batch_fs_gauss_offaxis", configs.random_draw(12, seed=13, jet="gaussian", theta_obs_max=0.4), t, nu)
     save("batch_fs_powerlaw_wind", configs.random_draw(12, seed=14, jet="powerlaw", medium="wind", theta_obs_max=0.3), t, nu)
     save("batch_rs_tophat_wind", configs.random_draw(24, seed=15, rvs=True, medium="wind"), t, nu)
+    P2 = configs.random_draw(16, seed=31, jet="two_component", theta_obs_max=0.3)
+    P2["theta_c"] = np.random.default_rng(31).uniform(0.03, 0.1, 16)
+    P2["theta_w"] = P2["theta_c"] * np.random.default_rng(32).uniform(2, 5, 16)
+    P2["E_iso_w"] = P2["E_iso"] * 10 ** np.random.default_rng(33).uniform(-3, -1, 16)
+    P2["Gamma0_w"] = np.maximum(P2["Gamma0"] * 0.2, 5.0)
+    save("batch_fs_two_component", P2, t, nu)
+    P3 = configs.random_draw(8, seed=34, jet="step_powerlaw", rvs=True, theta_obs_max=0.2)
+    P3["E_iso_w"], P3["Gamma0_w"], P3["k_e"], P3["k_g"] = P3["E_iso"] * 0.3, np.maximum(P3["Gamma0"] * 0.5, 5.0), 3.0, 1.5
+    save("batch_rs_step_powerlaw", P3, t, nu)
+    P4 = configs.random_draw(16, seed=35, rvs=True)
+    P4["sigma0"] = 10 ** np.random.default_rng(36).uniform(-2, 1, 16)
+    save("batch_rs_magnetized_tophat", P4, t, nu)
     nu_ssc = np.array([1e9, 1e14, 1e17, 1e22, 1e25])
     save("batch_ssc_kn_tophat_ism", configs.random_draw(24, seed=21, ssc=True, kn=True), t, nu_ssc)
     save("batch_ssc_thomson_tophat_wind", configs.random_draw(12, seed=22, ssc=True, kn=False, medium="wind"), t, nu_ssc)

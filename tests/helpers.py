@@ -67,3 +67,26 @@ def assert_parity(flux, g, what):
         if n >= 16 and np.any(g["flux"][:, comp] > 0):
             assert np.median(err) <= MEDIAN_RTOL, f"{what} comp {comp}: median err {np.median(err):.3e}"
     return model_errors(flux, g["flux"], 0)
+
+
+# Configurations the reference itself only reproduces to ~1e-3 between builds: structured-jet
+# reverse shocks (chaotic wing rows, tests/python/test_golden.py:95) and magnetised shells (the
+# sigma > 0 jump conditions are tolerance-sensitive: "reverse-shock flux vs a deep reference converges as
+# 9.4e-3 / 1.0e-4 / 5.4e-5 at rtol 1e-6 / 1e-7 / 1e-8", src/dynamics/reverse-shock.tpp:529-537).  They are
+# held to the reference's OWN golden acceptance contract |a-b| <= 2e-3 |b| + 1e-2 peak
+# (tests/python/golden/regenerate.py:29-30) plus a median bar that shows the typical model is still
+# reproduced far below it.
+CHAOTIC = ("golden_gauss_ism_rs", "batch_rs_magnetized_tophat", "series_rs_gauss")
+
+
+def assert_reference_contract(flux, g, what, median_rtol=1e-6):
+    ref = g["flux"]
+    for comp in (0, 1, 2, 3, 4):
+        for i in range(ref.shape[0]):
+            a, b = flux[i, comp], ref[i, comp]
+            if not np.any(b > 0):
+                assert np.all(a == 0), (what, comp, i)
+                continue
+            assert np.all(np.abs(a - b) <= 2e-3 * np.abs(b) + 1e-2 * b.max()), (what, comp, i)
+    if ref.shape[0] >= 8:
+        assert np.median(model_errors(flux, ref, 0)) <= median_rtol, what

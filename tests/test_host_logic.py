@@ -21,7 +21,8 @@ def _va():
 
 def test_pybind_mirror_has_the_reference_surface():
     va = _va()
-    for name in ("Model", "TophatJet", "GaussianJet", "PowerLawJet", "ISM", "Wind", "Observer", "Radiation", "FluxDict"):
+    for name in ("Model", "TophatJet", "GaussianJet", "PowerLawJet", "TwoComponentJet", "StepPowerLawJet", "PowerLawWing",
+                 "ISM", "Wind", "Observer", "Radiation", "FluxDict"):
         assert hasattr(va, name), name
     m = va.Model(jet=va.PowerLawJet(0.1, 1e52, 300, 2, 2, duration=10), medium=va.Wind(0.1, n0=1e3),
                  observer=va.Observer(1e28, 1.0, 0.3), fwd_rad=va.Radiation(0.1, 0.01, 2.3),
@@ -57,6 +58,12 @@ def test_pybind_mirror_error_conventions():
         va.Model(jet=va.TophatJet(0.1, 1e52, 300), medium=3, observer=obs, fwd_rad=rad)
     with pytest.raises(NotImplementedError):
         va.Wind(0.1, k_m=1.5)
+    with pytest.raises(ValueError, match="theta_w"):
+        va.TwoComponentJet(0.1, 1e52, 300, 0.05, 1e50, 50)
+    j = va.TwoComponentJet(0.05, 1e52, 300, 0.3, 1e50, 50)
+    mm = va.Model(j, va.ISM(1), obs, rad)
+    pp = np.frombuffer(mm.params_bytes, dtype=abi.PARAMS_DTYPE)[0]
+    assert pp["jet_type"] == abi.JET_TWO_COMPONENT and pp["theta_w"] == 0.3 and pp["Gamma0_w"] == 50
     m = va.Model(va.TophatJet(0.1, 1e52, 300), va.ISM(1), obs, rad)
     with pytest.raises(ValueError, match="same size"):
         m.flux_density(np.array([1.0, 2.0]), np.array([1e9]))

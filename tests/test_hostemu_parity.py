@@ -5,7 +5,7 @@ the C ABI on the device."""
 import numpy as np
 import pytest
 
-from tests.helpers import assert_parity, golden_names, load_golden
+from tests.helpers import CHAOTIC, assert_parity, assert_reference_contract, golden_names, load_golden
 from tests.hostemu import emu
 from vegasafterglow_b200 import configs
 
@@ -44,7 +44,10 @@ def test_flux_parity(name):
     fn = emu.flux_density_series if bool(g["series"]) else emu.flux_density_grid
     f, st = fn(g["params"], g["t"], g["nu"])
     assert (st == 0).all()
-    assert_parity(f, g, name)
+    if name in CHAOTIC:
+        assert_reference_contract(f, g, name)
+    else:
+        assert_parity(f, g, name)
 
 
 def test_series_equals_grid():

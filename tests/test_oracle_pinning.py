@@ -24,8 +24,9 @@ def test_pinning_record_is_within_reference_tolerance():
         for comp, d in dev.items():
             assert d < 2e-3, (name, comp, d)
     # all but the structured-jet reverse shock (chaotic wing rows, test_golden.py:95) pin to < 1e-7
-    for name in ("tophat_ism", "tophat_ism_adiabatic", "rs_thick", "powerlaw_wind_rs"):
+    for name in set(configs.GOLDEN) - {"gauss_ism_rs"}:
         assert max(pin[name].values()) < 1e-7, name
+    assert len(pin) == 12  # every golden configuration of the reference is in scope
 
 
 @needs_ref

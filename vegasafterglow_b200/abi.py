@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 VAG_OK, VAG_ERR_INVALID, VAG_ERR_CUDA, VAG_ERR_UNSUPPORTED, VAG_ERR_CAPACITY = range(5)
-JET_TOPHAT, JET_GAUSSIAN, JET_POWERLAW = 0, 1, 2
+JET_TOPHAT, JET_GAUSSIAN, JET_POWERLAW, JET_TWO_COMPONENT, JET_STEP_POWERLAW, JET_POWERLAW_WING = 0, 1, 2, 3, 4, 5
 MEDIUM_ISM, MEDIUM_WIND = 0, 1
 NCOMP = 5
 COMPONENTS = ("total", "fwd_sync", "fwd_ssc", "rvs_sync", "rvs_ssc")
@@ -31,6 +31,10 @@ PARAMS_DTYPE = np.dtype(
         ("k_e", "f8"),
         ("k_g", "f8"),
         ("duration", "f8"),
+        ("theta_w", "f8"),
+        ("E_iso_w", "f8"),
+        ("Gamma0_w", "f8"),
+        ("sigma0", "f8"),
         ("medium_type", "i4"),
         ("pad0_", "i4"),
         ("n_ism", "f8"),
@@ -77,6 +81,7 @@ def default_params(n: int = 1) -> np.ndarray:
     p = np.zeros(n, dtype=PARAMS_DTYPE)
     p["k_e"] = 2.0
     p["k_g"] = 2.0
+    p["theta_w"], p["E_iso_w"], p["Gamma0_w"] = 0.3, 1e50, 50.0
     p["duration"] = 1.0
     p["n0"] = np.inf
     p["fwd"]["xi_e"] = 1.0

@@ -10,9 +10,12 @@ from . import abi
 def make(jet="tophat", theta_c=0.1, E_iso=1e52, Gamma0=300.0, k_e=2.0, k_g=2.0, duration=1.0, medium="ism",
          n_ism=1.0, A_star=0.1, n0=np.inf, lumi_dist=1e26, z=0.1, theta_obs=0.0, fwd=(0.1, 1e-3, 2.3), rvs=None,
          resolutions=None, rtol=0.0, radiative_fireball=True, xi_e=1.0, rvs_xi_e=1.0, ssc=False, kn=False,
-         rvs_ssc=False, rvs_kn=False):
+         rvs_ssc=False, rvs_kn=False, theta_w=0.3, E_iso_w=1e50, Gamma0_w=50.0, sigma0=0.0):
     p = abi.default_params(1)
-    p["jet_type"] = {"tophat": abi.JET_TOPHAT, "gaussian": abi.JET_GAUSSIAN, "powerlaw": abi.JET_POWERLAW}[jet]
+    p["jet_type"] = {"tophat": abi.JET_TOPHAT, "gaussian": abi.JET_GAUSSIAN, "powerlaw": abi.JET_POWERLAW,
+                     "two_component": abi.JET_TWO_COMPONENT, "step_powerlaw": abi.JET_STEP_POWERLAW,
+                     "powerlaw_wing": abi.JET_POWERLAW_WING}[jet]
+    p["theta_w"], p["E_iso_w"], p["Gamma0_w"], p["sigma0"] = theta_w, E_iso_w, Gamma0_w, sigma0
     p["theta_c"], p["E_iso"], p["Gamma0"], p["k_e"], p["k_g"], p["duration"] = theta_c, E_iso, Gamma0, k_e, k_g, duration
     if medium == "ism":
         p["medium_type"], p["n_ism"] = abi.MEDIUM_ISM, n_ism
@@ -65,6 +68,11 @@ GOLDEN = {
                          rvs=(0.1, 0.01, 2.3), resolutions=(0.1, 1.2, 10)),
     "powerlaw_wind_rs": dict(jet="powerlaw", medium="wind", A_star=0.1, lumi_dist=1e28, z=1.0, theta_obs=0.3,
                              fwd=(0.1, 0.01, 2.3), rvs=(0.1, 0.01, 2.3)),
+    "two_component_ism": dict(jet="two_component", theta_c=0.05, theta_w=0.3, E_iso_w=1e50, Gamma0_w=50.0,
+                              lumi_dist=1e28, z=1.0, theta_obs=0.15, fwd=(0.1, 0.01, 2.3)),
+    "tophat_sigma_rs": dict(sigma0=0.1, lumi_dist=3e28, z=0.5, rvs=(0.1, 1e-2, 2.5)),
+    "tophat_sigma1_rs": dict(sigma0=1.0, lumi_dist=3e28, z=0.5, rvs=(0.1, 1e-2, 2.5)),
+    "tophat_sigma10_rs": dict(sigma0=10.0, lumi_dist=3e28, z=0.5, rvs=(0.1, 1e-2, 2.5)),
     "gauss_wind_ssc": dict(jet="gaussian", E_iso=1e53, medium="wind", A_star=0.1, lumi_dist=3e28, z=1.0, theta_obs=0.2,
                            fwd=(0.1, 1e-4, 2.3), ssc=True, kn=True),
     "dense_ism_ssa_ssc": dict(n_ism=1e5, fwd=(0.1, 3e-2, 2.5), ssc=True, kn=True),

@@ -24,7 +24,7 @@
 
 using namespace vag;
 
-static_assert(sizeof(vag_params) == 248, "vag_params layout must match vegasafterglow_b200/abi.py");
+static_assert(sizeof(vag_params) == 280, "vag_params layout must match vegasafterglow_b200/abi.py");
 
 // ------------------------------------------------------------------------------------------------
 // kernels
@@ -432,7 +432,7 @@ void caps_for(const vag_params* p, size_t n, int& cap_theta, int& cap_phi) {
         const bool r = p[i].has_rvs != 0;
         const double th_res = p[i].theta_resol > 0 ? p[i].theta_resol : (r ? 0.2 : 0.15);
         const double ph_res = p[i].phi_resol > 0 ? p[i].phi_resol : 0.06;
-        const double lg = std::log10(std::max(1.0, p[i].Gamma0 * 1.5708));
+        const double lg = std::log10(std::max(1.0, std::max(p[i].Gamma0, p[i].Gamma0_w) * 1.5708));
         const int ct = 36 + (int)(90 * th_res) + (int)(std::max(0.0, lg - 1) * th_res * 55) + (int)(lg * th_res * 25) + 40;
         const int cp = std::max((int)(360 * ph_res), 1) * 5 + 8;
         cap_theta = std::max(cap_theta, ct);
@@ -683,6 +683,9 @@ void vag_params_default(vag_params* p) {
     std::memset(p, 0, sizeof(*p));
     p->k_e = p->k_g = 2.0;
     p->duration = 1.0;
+    p->theta_w = 0.3;
+    p->E_iso_w = 1e50;
+    p->Gamma0_w = 50.0;
     p->n0 = INFINITY;
     p->fwd = vag_radiation{0.1, 0.01, 2.3, 1.0, 0, 0};
     p->rvs = vag_radiation{0.1, 0.01, 2.3, 1.0, 0, 0};
@@ -693,15 +696,30 @@ void vag_params_default(vag_params* p) {
 int vag_params_validate(const vag_params* p) {
     auto bad = [&](const std::string& m) { return fail(VAG_ERR_INVALID, m); };
     auto rng_oi = [](double v, double lo, double hi) { return std::isfinite(v) && v > lo && v <= hi; };
-    if (p->jet_type < 0 || p->jet_type > 2) return bad("jet_type must be 0 (tophat), 1 (gaussian) or 2 (powerlaw)");
+    if (p->jet_type < 0 || p->jet_type > 5) return bad("jet_type must be one of VAG_JET_* (0..5)");
     if (p->medium_type < 0 || p->medium_type > 1) return bad("medium_type must be 0 (ISM) or 1 (wind)");
     // PyTophatJet / PyGaussianJet / PyPowerLawJet: pybind/pymodel.cpp:47-95
     if (!rng_oi(p->theta_c, 0.0, con::pi / 2)) return bad("theta_c must be in (0, pi/2]");
-    if (!finite_pos(p->E_iso)) return bad("E_iso must be finite and > 0");
-    if (!(std::isfinite(p->Gamma0) && p->Gamma0 > 1.0)) return bad("Gamma0 must be > 1");
+    const bool has_core = p->jet_type != VAG_JET_POWERLAW_WING;
+    const bool has_wing = p->jet_type >= VAG_JET_TWO_COMPONENT;
+    if (has_core && !finite_pos(p->E_iso)) return bad("E_iso must be finite and > 0");
+    if (has_core && !(std::isfinite(p->Gamma0) && p->Gamma0 > 1.0)) return bad("Gamma0 must be > 1");
     if (!finite_pos(p->duration)) return bad("duration must be finite and > 0");
-    if (p->jet_type == VAG_JET_POWERLAW && (!finite_pos(p->k_e) || !finite_pos(p->k_g)))
+    if ((p->jet_type == VAG_JET_POWERLAW || p->jet_type == VAG_JET_STEP_POWERLAW || p->jet_type == VAG_JET_POWERLAW_WING) &&
+        (!finite_pos(p->k_e) || !finite_pos(p->k_g)))
         return bad("k_e and k_g must be finite and > 0");
+    // PyTwoComponentJet / PyStepPowerLawJet / PyPowerLawWing: pybind/pymodel.cpp:97-146
+    if (has_wing) {
+        if (!finite_pos(p->E_iso_w)) return bad("E_iso_w must be finite and > 0");
+        if (!(std::isfinite(p->Gamma0_w) && p->Gamma0_w > 1.0)) return bad("Gamma0_w must be > 1");
+    }
+    if (p->jet_type == VAG_JET_TWO_COMPONENT) {
+        if (!rng_oi(p->theta_w, 0.0, con::pi / 2)) return bad("theta_w must be in (0, pi/2]");
+        if (!(p->theta_w > p->theta_c))
+            return bad("theta_w (wing angle) must be greater than theta_c (core angle), got theta_w=" +
+                       std::to_string(p->theta_w) + ", theta_c=" + std::to_string(p->theta_c));
+    }
+    if (!(std::isfinite(p->sigma0) && p->sigma0 >= 0)) return bad("sigma0 must be finite and >= 0");
     // PyISM / PyWind: pybind/pymodel.cpp:148-186
     if (p->medium_type == VAG_MEDIUM_ISM) {
         if (!(std::isfinite(p->n_ism) && p->n_ism >= 0)) return bad("n_ism must be finite and >= 0");

@@ -441,7 +441,8 @@ VAG_HD int adaptive_phi_grid(const Par& par, const ModelCfg& m, int phi_num, dou
 VAG_HD double estimate_t_dec(const ModelCfg& m, double theta) {
     const double gamma = jet_Gamma0(m, theta);
     const double beta = gamma_to_beta(gamma);
-    const double m_jet = jet_eps_k(m, theta) / (gamma * con::c2);
+    double m_jet = jet_eps_k(m, theta) / (gamma * con::c2);
+    m_jet /= (1.0 + m.sigma0);  // HasSigma branch (grid-refinement.h:407-409); exact no-op for sigma0 = 0
     const double target = m_jet / gamma;
     constexpr double r_min = 1e-3;
     const double r_max = r_min * pow(10.0, 40.0);

@@ -23,6 +23,7 @@ struct ModelCfg {
     // jet
     int jet_type;
     double theta_c, eps_k0, Gamma0, k_e, k_g, gauss_norm, T0;
+    double theta_w, E_iso, E_iso_w, Gamma0_w, sigma0;  // Ejecta-family profiles work on E_iso [erg] heights
     // medium
     int medium_type;
     double rho_ism, wind_A, wind_r02;
@@ -60,6 +61,11 @@ VAG_HD ModelCfg make_cfg(const vag_params& p) {
     m.k_g = p.k_g;
     m.gauss_norm = -1 / (2 * p.theta_c * p.theta_c);  // jet.h:141
     m.T0 = p.duration * unit::sec;
+    m.theta_w = p.theta_w;
+    m.E_iso = p.E_iso;
+    m.E_iso_w = p.E_iso_w;
+    m.Gamma0_w = p.Gamma0_w;
+    m.sigma0 = p.sigma0;
     m.medium_type = p.medium_type;
     const double n_ism = p.n_ism / unit::cm3;
     m.rho_ism = n_ism * con::mp;  // medium.h:52,98
@@ -90,8 +96,15 @@ VAG_HD double jet_Gamma0(const ModelCfg& m, double theta) {
             return theta < m.theta_c ? m.Gamma0 : 1;  // jet.h:116
         case VAG_JET_GAUSSIAN:
             return (m.Gamma0 - 1) * fast_exp(theta * theta * m.gauss_norm) + 1;  // jet.h:175-177
-        default:
+        case VAG_JET_POWERLAW:
             return (m.Gamma0 - 1) / (1 + fast_pow(theta / m.theta_c, m.k_g)) + 1;  // jet.h:243-245
+        // Ejecta family: Gamma0 = profile(Gamma0 - 1, ...) + 1 (math::*_plus_one, jet.h:403-470)
+        case VAG_JET_TWO_COMPONENT:
+            return ((theta <= m.theta_c) ? (m.Gamma0 - 1) : (theta <= m.theta_w) ? (m.Gamma0_w - 1) : 0.) + 1;
+        case VAG_JET_STEP_POWERLAW:
+            return ((theta <= m.theta_c) ? (m.Gamma0 - 1) : (m.Gamma0_w - 1) * fast_pow(theta / m.theta_c, -m.k_g)) + 1;
+        default:  // VAG_JET_POWERLAW_WING
+            return ((theta <= m.theta_c) ? 0. : (m.Gamma0_w - 1) * fast_pow(theta / m.theta_c, -m.k_g)) + 1;
     }
 }
 
@@ -101,8 +114,19 @@ VAG_HD double jet_eps_k(const ModelCfg& m, double theta) {
             return theta < m.theta_c ? m.eps_k0 : 0;  // jet.h:107
         case VAG_JET_GAUSSIAN:
             return m.eps_k0 * fast_exp(theta * theta * m.gauss_norm);  // jet.h:164-166
-        default:
+        case VAG_JET_POWERLAW:
             return m.eps_k0 / (1 + fast_pow(theta / m.theta_c, m.k_e));  // jet.h:232-234
+        default: {
+            // Ejecta family: E_iso(theta) [erg] * (unit::erg / 4 pi)  (convert_unit_jet, pymodel.cpp:188-211)
+            double E;
+            if (m.jet_type == VAG_JET_TWO_COMPONENT)
+                E = (theta <= m.theta_c) ? m.E_iso : (theta <= m.theta_w) ? m.E_iso_w : 0.;
+            else if (m.jet_type == VAG_JET_STEP_POWERLAW)
+                E = (theta <= m.theta_c) ? m.E_iso : m.E_iso_w * fast_pow(theta / m.theta_c, -m.k_e);
+            else
+                E = (theta <= m.theta_c) ? 0. : m.E_iso_w * fast_pow(theta / m.theta_c, -m.k_e);
+            return E * (unit::erg / (4 * con::pi));
+        }
     }
 }
 

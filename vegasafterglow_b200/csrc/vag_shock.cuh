@@ -220,6 +220,7 @@ struct FwdEqn {
 
     VAG_HD FwdEqn(const ModelCfg& m_, double theta) : m(m_) {
         m_jet0 = jet_eps_k(m, theta) / jet_Gamma0(m, theta) / con::c2;  // forward-shock.tpp:20
+        m_jet0 /= 1 + m.sigma0;                                          // :21-23
     }
 
     // ForwardShockEqn::operator(): forward-shock.tpp:27-118
@@ -330,6 +331,7 @@ struct FREqn {
         Gamma4 = jet_Gamma0(m, theta);
         deps0_dt = jet_eps_k(m, theta) / m.T0;
         dm0_dt = deps0_dt / (Gamma4 * con::c2);
+        dm0_dt /= 1 + m.sigma0;  // reverse-shock.tpp:36-38
         u4 = sqrt(Gamma4 * Gamma4 - 1) * con::c;
         u_x = r_x = B3_ordered_x = V3_comv_x = rho3_x = 0;
     }

@@ -21,7 +21,8 @@ from . import abi
 # (fitting/config.py:99-137 registries; Fitter._build_model fitter.py:455-495)
 _FIELDS = {
     "theta_c": ("theta_c",), "E_iso": ("E_iso",), "Gamma0": ("Gamma0",), "k_e": ("k_e",), "k_g": ("k_g",),
-    "duration": ("duration",), "tau": ("duration",), "n_ism": ("n_ism",), "A_star": ("A_star",), "n0": ("n0",),
+    "duration": ("duration",), "tau": ("duration",), "theta_w": ("theta_w",), "E_iso_w": ("E_iso_w",),
+    "Gamma0_w": ("Gamma0_w",), "sigma0": ("sigma0",), "n_ism": ("n_ism",), "A_star": ("A_star",), "n0": ("n0",),
     "theta_v": ("theta_obs",), "eps_e": ("fwd", "eps_e"), "eps_B": ("fwd", "eps_B"), "p": ("fwd", "p"),
     "xi_e": ("fwd", "xi_e"), "eps_e_r": ("rvs", "eps_e"), "eps_B_r": ("rvs", "eps_B"), "p_r": ("rvs", "p"),
     "xi_e_r": ("rvs", "xi_e"),

@@ -65,9 +65,11 @@ struct Jet {
     int type;
     Real theta_c, E_iso, Gamma0, k_e, k_g, duration;
     bool spreading;
+    Real theta_w{0.3}, E_iso_w{1e50}, Gamma0_w{50}, sigma0{0};
     std::string repr() const {
         char buf[200];
-        const char* nm = type == VAG_JET_TOPHAT ? "TophatJet" : type == VAG_JET_GAUSSIAN ? "GaussianJet" : "PowerLawJet";
+        static const char* names[] = {"TophatJet", "GaussianJet", "PowerLawJet", "TwoComponentJet", "StepPowerLawJet", "PowerLawWing"};
+        const char* nm = names[type];
         snprintf(buf, sizeof(buf), "%s(theta_c=%.6g, E_iso=%.6g, Gamma0=%.6g)", nm, theta_c, E_iso, Gamma0);
         return buf;
     }
@@ -99,7 +101,7 @@ Jet make_jet(int type, Real theta_c, Real E_iso, Real Gamma0, Real k_e, Real k_g
     require(std::isfinite(E_iso) && E_iso > 0, "E_iso must be finite and > 0");
     require(std::isfinite(Gamma0) && Gamma0 > 1.0, "Gamma0 must be > 1");
     require(std::isfinite(duration) && duration > 0, "duration must be finite and > 0");
-    if (type == VAG_JET_POWERLAW)
+    if (type == VAG_JET_POWERLAW || type == VAG_JET_STEP_POWERLAW || type == VAG_JET_POWERLAW_WING)
         require(std::isfinite(k_e) && k_e > 0 && std::isfinite(k_g) && k_g > 0, "k_e and k_g must be finite and > 0");
     return Jet{type, theta_c, E_iso, Gamma0, k_e, k_g, duration, spreading};
 }
@@ -133,6 +135,10 @@ class Model {
         p_.k_e = jet.k_e;
         p_.k_g = jet.k_g;
         p_.duration = jet.duration;
+        p_.theta_w = jet.theta_w;
+        p_.E_iso_w = jet.E_iso_w;
+        p_.Gamma0_w = jet.Gamma0_w;
+        p_.sigma0 = jet.sigma0;
         p_.medium_type = med.type;
         p_.n_ism = med.n_ism;
         p_.A_star = med.A_star;
@@ -317,6 +323,67 @@ PYBIND11_MODULE(VegasAfterglowC_b200, m) {
           },
           py::arg("theta_c"), py::arg("E_iso"), py::arg("Gamma0"), py::arg("k_e"), py::arg("k_g"),
           py::arg("spreading") = false, py::arg("duration") = 1, py::arg("magnetar") = py::none());
+
+    // Ejecta-family named factories (pybind/pybind.cpp:215-223, pybind/pymodel.cpp:97-146)
+    auto gt1 = [](Real v, const char* nm) { require(std::isfinite(v) && v > 1.0, std::string(nm) + " must be > 1"); };
+    auto pos = [](Real v, const char* nm) { require(std::isfinite(v) && v > 0, std::string(nm) + " must be finite and > 0"); };
+    auto ang = [](Real v, const char* nm) {
+        require(std::isfinite(v) && v > 0 && v <= 3.14159265358979323846 / 2, std::string(nm) + " must be in (0, pi/2]");
+    };
+    m.def("TwoComponentJet",
+          [=](Real theta_c, Real E_iso, Real Gamma0, Real theta_w, Real E_iso_w, Real Gamma0_w, bool spreading, Real duration,
+              py::object magnetar) {
+              Jet j = make_jet(VAG_JET_TWO_COMPONENT, theta_c, E_iso, Gamma0, 2, 2, spreading, duration, magnetar);
+              ang(theta_w, "theta_w");
+              require(theta_w > theta_c, "theta_w (wing angle) must be greater than theta_c (core angle), got theta_w=" +
+                                             std::to_string(theta_w) + ", theta_c=" + std::to_string(theta_c));
+              pos(E_iso_w, "E_iso_w");
+              gt1(Gamma0_w, "Gamma0_w");
+              j.theta_w = theta_w;
+              j.E_iso_w = E_iso_w;
+              j.Gamma0_w = Gamma0_w;
+              return j;
+          },
+          py::arg("theta_c"), py::arg("E_iso"), py::arg("Gamma0"), py::arg("theta_w"), py::arg("E_iso_w"), py::arg("Gamma0_w"),
+          py::arg("spreading") = false, py::arg("duration") = 1, py::arg("magnetar") = py::none());
+    m.def("StepPowerLawJet",
+          [=](Real theta_c, Real E_iso, Real Gamma0, Real E_iso_w, Real Gamma0_w, Real k_e, Real k_g, bool spreading,
+              Real duration, py::object magnetar) {
+              Jet j = make_jet(VAG_JET_STEP_POWERLAW, theta_c, E_iso, Gamma0, k_e, k_g, spreading, duration, magnetar);
+              pos(E_iso_w, "E_iso_w");
+              gt1(Gamma0_w, "Gamma0_w");
+              pos(k_e, "k_e");
+              pos(k_g, "k_g");
+              j.E_iso_w = E_iso_w;
+              j.Gamma0_w = Gamma0_w;
+              return j;
+          },
+          py::arg("theta_c"), py::arg("E_iso"), py::arg("Gamma0"), py::arg("E_iso_w"), py::arg("Gamma0_w"), py::arg("k_e"),
+          py::arg("k_g"), py::arg("spreading") = false, py::arg("duration") = 1, py::arg("magnetar") = py::none());
+    m.def("PowerLawWing",
+          [=](Real theta_c, Real E_iso_w, Real Gamma0_w, Real k_e, Real k_g, bool spreading, Real duration) {
+              Jet j = make_jet(VAG_JET_POWERLAW_WING, theta_c, 1.0, 2.0, k_e, k_g, spreading, duration, py::none());
+              pos(E_iso_w, "E_iso_w");
+              gt1(Gamma0_w, "Gamma0_w");
+              pos(k_e, "k_e");
+              pos(k_g, "k_g");
+              j.E_iso_w = E_iso_w;
+              j.Gamma0_w = Gamma0_w;
+              return j;
+          },
+          py::arg("theta_c"), py::arg("E_iso_w"), py::arg("Gamma0_w"), py::arg("k_e"), py::arg("k_g"),
+          py::arg("spreading") = false, py::arg("duration") = 1);
+    // Extension (not a named factory of the reference, which needs Ejecta(sigma0=callable) for this):
+    // a tophat jet with constant ejecta magnetisation sigma0.
+    m.def("MagnetizedTophatJet",
+          [](Real theta_c, Real E_iso, Real Gamma0, Real sigma0, bool spreading, Real duration) {
+              Jet j = make_jet(VAG_JET_TOPHAT, theta_c, E_iso, Gamma0, 2, 2, spreading, duration, py::none());
+              require(std::isfinite(sigma0) && sigma0 >= 0, "sigma0 must be finite and >= 0");
+              j.sigma0 = sigma0;
+              return j;
+          },
+          py::arg("theta_c"), py::arg("E_iso"), py::arg("Gamma0"), py::arg("sigma0"), py::arg("spreading") = false,
+          py::arg("duration") = 1);
 
     m.def("ISM",
           [](Real n_ism) {
