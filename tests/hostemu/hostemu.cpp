@@ -159,12 +159,19 @@ void eats_emulate(const BatchWs& w, int mi, int which, const EatsRequest& rq0, d
             for (int q0 = 0; q0 < erows; q0 += EATS_ROW_CHUNK) {
                 const int nrows = std::min(EATS_ROW_CHUNK, erows - q0);
                 for (int tid = 0; tid < NTHR; ++tid) eats_phase0(M, sh, q0, nrows, tid, NTHR);
-                for (int tid = 0; tid < NTHR; ++tid) eats_phase1(M, rq, sh, nrows, l0, nl, tid, NTHR);
                 for (int tid = 0; tid < NTHR; ++tid) {
-                    if (series)
-                        eats_phase2_series(M, rq, sh, nrows, acc.data(), tid, NTHR);
-                    else
+                    if (M.mode == 0) eats_phase1<0>(M, rq, sh, nrows, l0, nl, tid, NTHR);
+                    if (M.mode == 1) eats_phase1<1>(M, rq, sh, nrows, l0, nl, tid, NTHR);
+                    if (M.mode == 2) eats_phase1<2>(M, rq, sh, nrows, l0, nl, tid, NTHR);
+                }
+                for (int tid = 0; tid < NTHR; ++tid) {
+                    if (!series) {
                         eats_phase2_grid(M, rq, sh, nrows, nl, acc.data(), tid, NTHR);
+                    } else {
+                        if (M.mode == 0) eats_phase2_series<0>(M, rq, sh, nrows, acc.data(), tid, NTHR);
+                        if (M.mode == 1) eats_phase2_series<1>(M, rq, sh, nrows, acc.data(), tid, NTHR);
+                        if (M.mode == 2) eats_phase2_series<2>(M, rq, sh, nrows, acc.data(), tid, NTHR);
+                    }
                 }
             }
             if (series) {

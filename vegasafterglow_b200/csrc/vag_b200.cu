@@ -252,16 +252,20 @@ __global__ void k_band_reduce(const double* __restrict__ F, const double* __rest
 }
 
 // K3.  grid = (model, split, shock).  out[model][comp][n_nu][n_t] (grid) or [model][comp][n] (series)
+// MODE 0: synchrotron of shocks without ssc; MODE 1: synchrotron of shocks with ssc (IC-corrected
+// spectrum); MODE 2: SSC component (per-cell tables).  blockIdx.z = shock (0 forward, 1 reverse).
+template <int MODE>
 __global__ void __launch_bounds__(128, 6) k_eats(BatchWs w, EatsRequest rq0, double* __restrict__ out, int n_split,
                                                  int row_chunk, int max_n_t, int nu_tile) {
     extern __shared__ double smem[];
     const int mi = blockIdx.x;
     const int split = blockIdx.y;
-    const int which = blockIdx.z;  // 0 fwd sync, 1 rvs sync, 2 fwd ssc, 3 rvs ssc
+    const int which = (int)blockIdx.z + (MODE == 2 ? 2 : 0);  // 0 fwd sync, 1 rvs sync, 2 fwd ssc, 3 rvs ssc
     {
         const ModelCfg& cfg = w.cfg[mi];
         if ((which & 1) && !cfg.has_rvs) return;
-        if (which >= 2 && !((which & 1) ? cfg.rvs : cfg.fwd).ssc) return;
+        const bool ssc = ((which & 1) ? cfg.rvs : cfg.fwd).ssc != 0;
+        if ((MODE == 0) == ssc) return;  // MODE 0 handles the shocks without ssc, MODE 1/2 those with
     }
     if (w.status[mi] & VAG_ST_CAPACITY) return;
     EatsModel M = make_eats_model(w, mi, which);
@@ -289,10 +293,10 @@ __global__ void __launch_bounds__(128, 6) k_eats(BatchWs w, EatsRequest rq0, dou
                 __syncthreads();  // previous pass finished reading the staged rows
                 eats_phase0(M, sh, q0, nrows, tid, nthr);
                 __syncthreads();
-                eats_phase1(M, rq, sh, nrows, l0, nl, tid, nthr);
+                eats_phase1<MODE>(M, rq, sh, nrows, l0, nl, tid, nthr);
                 __syncthreads();
                 if (series)
-                    eats_phase2_series(M, rq, sh, nrows, acc, tid, nthr);
+                    eats_phase2_series<MODE>(M, rq, sh, nrows, acc, tid, nthr);
                 else
                     eats_phase2_grid(M, rq, sh, nrows, nl, acc, tid, nthr);
             }
@@ -626,7 +630,9 @@ int run_flux(vag_context* ctx, const vag_params* d_params, size_t n, const Reque
         if (n * 2 < target_ctas) n_split = (int)std::min<size_t>(chunks, (target_ctas + n * 2 - 1) / (n * 2));
         n_split = std::max(n_split, 1);
         const size_t sb = smem_bytes(row_chunk);
-        CK(cudaFuncSetAttribute(k_eats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
+        CK(cudaFuncSetAttribute(k_eats<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
+        CK(cudaFuncSetAttribute(k_eats<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
+        CK(cudaFuncSetAttribute(k_eats<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
         EatsRequest rq{};
         rq.series = rq_in.series ? 1 : 0;
         rq.n_t_obs = (int)n_t;
@@ -634,8 +640,14 @@ int run_flux(vag_context* ctx, const vag_params* d_params, size_t n, const Reque
         rq.lg2_t_obs = lg2_t;
         rq.lg2_nu_obs = lg2_nu;
         rq.t_obs_lin = t_lin;
-        k_eats<<<dim3((unsigned)n, (unsigned)n_split, w.any_ssc ? 4 : 2), 128, sb, s>>>(w, rq, d_out, n_split, row_chunk, max_n_t, nu_tile);
+        const dim3 eg((unsigned)n, (unsigned)n_split, 2);
+        k_eats<0><<<eg, 128, sb, s>>>(w, rq, d_out, n_split, row_chunk, max_n_t, nu_tile);
         ctx->launches++;
+        if (w.any_ssc) {
+            k_eats<1><<<eg, 128, sb, s>>>(w, rq, d_out, n_split, row_chunk, max_n_t, nu_tile);
+            k_eats<2><<<eg, 128, sb, s>>>(w, rq, d_out, n_split, row_chunk, max_n_t, nu_tile);
+            ctx->launches += 2;
+        }
     }
     mark(ctx, 4, s);
     {

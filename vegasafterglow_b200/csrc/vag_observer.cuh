@@ -100,9 +100,12 @@ VAG_HD void node_logs(const EatsModel& M, const RowGeom& g, int n_t, int k, doub
     lg2_geom = (g.lg2_dOmega + 2.0 * rlog2(r)) + 3.0 * lg2_dop;
 }
 
+// MODE is a compile-time copy of EatsModel::mode so that the plain synchrotron instantiation of
+// k_eats carries no inverse-Compton code (registers, branches)
+template <int MODE>
 VAG_HD double cell_log2_I_nu(const EatsModel& M, int rep, int n_t, int k, double log2_nu) {
     const long cell = (long)rep * n_t + k;
-    if (M.mode == 2) {
+    if (MODE == 2) {
         bool breach = false;
         const double v = ic_table_log2_I_nu(M.ictab_h[cell], M.ictab + (size_t)cell * IC_CAP_OUT, log2_nu, breach);
         if (breach && M.breach) {
@@ -116,7 +119,7 @@ VAG_HD double cell_log2_I_nu(const EatsModel& M, int rep, int n_t, int k, double
     }
     const double* base = M.coef + cell;
     const long stride = M.coef_stride;
-    if (M.mode == 1)
+    if (MODE == 1)
         return photon_log2_I_nu_ic([&](int c) { return base[c * stride]; }, M.smooth_thick, M.log2_x_far, M.ic[cell],
                                    log2_nu);
     return photon_log2_I_nu([&](int c) { return base[c * stride]; }, M.smooth_thick, M.log2_x_far, log2_nu);
@@ -230,6 +233,7 @@ VAG_HD void eats_phase0(const EatsModel& M, const EatsShared& sh, int q0, int nr
 }
 
 // phase 1: node logs (+ boundary luminosities for the frequency tile [l0, l0+nl) in grid mode)
+template <int MODE>
 VAG_HD void eats_phase1(const EatsModel& M, const EatsRequest& rq, const EatsShared& sh, int nrows, int l0, int nl,
                         int tid, int nthr) {
     const int n_t = M.h->n_t;
@@ -253,7 +257,7 @@ VAG_HD void eats_phase1(const EatsModel& M, const EatsRequest& rq, const EatsSha
             if (need) {
                 for (int l = 0; l < nl; ++l) {
                     const double lg2_nu_src = rq.lg2_nu_obs[l0 + l] + lg2_1pz;
-                    bv[l] = cell_log2_I_nu(M, g.rep, n_t, k, lg2_nu_src - ld) + lg;
+                    bv[l] = cell_log2_I_nu<MODE>(M, g.rep, n_t, k, lg2_nu_src - ld) + lg;
                 }
             }
         }
@@ -283,6 +287,7 @@ VAG_HD void eats_phase2_grid(const EatsModel& M, const EatsRequest& rq, const Ea
 }
 
 // phase 2 (series): thread <-> data point (t_s, nu_s); acc[EATS_T_BLOCK]
+template <int MODE>
 VAG_HD void eats_phase2_series(const EatsModel& M, const EatsRequest& rq, const EatsShared& sh, int nrows, double* acc,
                                int tid, int nthr) {
     const int n_t = M.h->n_t;
@@ -298,8 +303,8 @@ VAG_HD void eats_phase2_series(const EatsModel& M, const EatsRequest& rq, const 
             const int k = find_interval(t_row, n_t, x, true);
             if (k < 0) continue;
             const int rep = sh.rowg[r].rep;
-            const double lo = cell_log2_I_nu(M, rep, n_t, k, lg2_nu - sh.lg2dop[ro + k]) + sh.lg2geo[ro + k];
-            const double hi = cell_log2_I_nu(M, rep, n_t, k + 1, lg2_nu - sh.lg2dop[ro + k + 1]) + sh.lg2geo[ro + k + 1];
+            const double lo = cell_log2_I_nu<MODE>(M, rep, n_t, k, lg2_nu - sh.lg2dop[ro + k]) + sh.lg2geo[ro + k];
+            const double hi = cell_log2_I_nu<MODE>(M, rep, n_t, k + 1, lg2_nu - sh.lg2dop[ro + k + 1]) + sh.lg2geo[ro + k + 1];
             sum += interp_contrib(lo, hi, t_row[k], t_row[k + 1], x);
         }
         acc[ii] += sum;
