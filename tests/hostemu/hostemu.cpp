@@ -62,6 +62,8 @@ void run_front(HostBatch& hb, const vag_params* params, size_t n, double t_min, 
         w.fwd[a] = hb.alloc<double>(cells);
         w.rvs[a] = hb.alloc<double>(cells);
     }
+    w.geo_u = hb.alloc<double>(cells);
+    w.geo_lg2r2 = hb.alloc<double>(cells);
     w.coef_fwd = hb.alloc<double>((size_t)cells * PH_NCOEF);
     w.coef_rvs = hb.alloc<double>((size_t)cells * PH_NCOEF);
     w.max_n_t = std::max(w.totals[TOT_MAX_NT], 1);

@@ -489,11 +489,13 @@ int setup_rows(vag_context* ctx, BatchWs& w, int rows, long long cells) {
     w.inj_idx = carve<int>(p, rows);
     w.row_cell_off = carve<long long>(p, rows + 1);
     const size_t plane = carve_sz<double>((size_t)cells);
-    CK(ctx->cell_buf.ensure(plane * (1 + 12) + carve_sz<double>((size_t)cells * PH_NCOEF) * 2));
+    CK(ctx->cell_buf.ensure(plane * (1 + 12 + 2) + carve_sz<double>((size_t)cells * PH_NCOEF) * 2));
     p = static_cast<char*>(ctx->cell_buf.p);
     w.t_rows = carve<double>(p, (size_t)cells);
     for (int a = 0; a < 6; ++a) w.fwd[a] = carve<double>(p, (size_t)cells);
     for (int a = 0; a < 6; ++a) w.rvs[a] = carve<double>(p, (size_t)cells);
+    w.geo_u = carve<double>(p, (size_t)cells);
+    w.geo_lg2r2 = carve<double>(p, (size_t)cells);
     w.coef_fwd = carve<double>(p, (size_t)cells * PH_NCOEF);
     w.coef_rvs = carve<double>(p, (size_t)cells * PH_NCOEF);
     return VAG_OK;

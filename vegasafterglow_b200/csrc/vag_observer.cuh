@@ -31,6 +31,8 @@ struct EatsModel {
     const double* t_rows;    // [n_reps][n_t] engine-frame lattice
     const double* r;         // [n_reps][n_t]
     const double* Gamma;     // [n_reps][n_t]
+    const double* geo_u;     // [n_reps][n_t] sqrt((Gamma-1)(Gamma+1))
+    const double* geo_lg2r2; // [n_reps][n_t] 2 log2(r)
     const double* coef;      // [PH_NCOEF][n_reps][n_t]  photon coefficients (SoA)
     long coef_stride;        // distance between coefficient planes (= total cells of the batch)
     double smooth_thick, log2_x_far;
@@ -91,13 +93,11 @@ VAG_HD double node_time(const EatsModel& M, const RowGeom& g, int n_t, int k) {
 VAG_HD void node_logs(const EatsModel& M, const RowGeom& g, int n_t, int k, double& lg2_t, double& lg2_dop,
                       double& lg2_geom) {
     const long o = (long)g.rep * n_t + k;
-    const double gamma_ = M.Gamma[o];
-    const double r = M.r[o];
-    const double dop_lin = gamma_ - sqrt((gamma_ - 1) * (gamma_ + 1)) * g.cos_v;
-    const double time = M.t_rows[o] * M.one_plus_z + g.t_coeff * r;
+    const double dop_lin = M.Gamma[o] - M.geo_u[o] * g.cos_v;
+    const double time = M.t_rows[o] * M.one_plus_z + g.t_coeff * M.r[o];
     lg2_dop = -rlog2(dop_lin);
     lg2_t = rlog2(time);
-    lg2_geom = (g.lg2_dOmega + 2.0 * rlog2(r)) + 3.0 * lg2_dop;
+    lg2_geom = (g.lg2_dOmega + M.geo_lg2r2[o]) + 3.0 * lg2_dop;
 }
 
 // MODE is a compile-time copy of EatsModel::mode so that the plain synchrotron instantiation of

@@ -51,6 +51,8 @@ struct BatchWs {
     double* rvs[6];
     double* coef_fwd;  // [PH_NCOEF][n_cells]
     double* coef_rvs;
+    double* geo_u;     // [n_cells] sqrt((Gamma-1)(Gamma+1)) of the forward table (EATS Doppler factor)
+    double* geo_lg2r2; // [n_cells] 2 log2(r)                                   (EATS geometry factor)
     // inverse-Compton data: allocated only when some model of the batch has ssc=True
     int any_ssc;
     int max_n_t, max_erows;   // batch maxima (known after K0b)
@@ -163,6 +165,13 @@ VAG_HD void k1_dynamics_body(const BatchWs& w, int row) {
     } else {
         st |= solve_fwd_row(cfg, theta, t_dec, t_row, h.n_t, sf);
         w.inj_idx[row] = h.n_t;
+    }
+    // node-only pieces of the EATS geometry (observer.cpp:158,200), shared by every (phi,theta) row
+    // that maps onto this representative row
+    for (int k = 0; k < h.n_t; ++k) {
+        const double g = sf.Gamma[k];
+        w.geo_u[off + k] = sqrt((g - 1) * (g + 1));
+        w.geo_lg2r2[off + k] = 2.0 * rlog2(sf.r[k]);
     }
     if (st) {
 #if defined(__CUDA_ARCH__)
@@ -282,6 +291,8 @@ VAG_HD EatsModel make_eats_model(const BatchWs& w, int mi, int which) {
     M.t_rows = w.t_rows + off;
     M.r = w.fwd[1] + off;      // the pair solver gives both shocks identical kinematics
     M.Gamma = w.fwd[2] + off;  // (pybind/pymodel.h:943-950): one EAT geometry serves both
+    M.geo_u = w.geo_u + off;
+    M.geo_lg2r2 = w.geo_lg2r2 + off;
     const int shock = which & 1;  // which: 0 fwd sync, 1 rvs sync, 2 fwd ssc, 3 rvs ssc
     const RadCfg& rad = shock ? cfg.rvs : cfg.fwd;
     M.coef = (shock ? w.coef_rvs : w.coef_fwd) + off;
