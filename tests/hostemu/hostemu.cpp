@@ -56,6 +56,7 @@ void run_front(HostBatch& hb, const vag_params* params, size_t n, double t_min, 
     w.row_model = hb.alloc<int>(rows);
     w.row_rep = hb.alloc<int>(rows);
     w.inj_idx = hb.alloc<int>(rows);
+    w.row_dyn = hb.alloc<RowDyn>(rows);
     w.row_cell_off = hb.alloc<long long>(rows + 1);
     w.t_rows = hb.alloc<double>(cells);
     for (int a = 0; a < 6; ++a) {
@@ -71,7 +72,16 @@ void run_front(HostBatch& hb, const vag_params* params, size_t n, double t_min, 
     w.any_ssc = 0;
     for (size_t i = 0; i < n; ++i) w.any_ssc |= (params[i].fwd.ssc || (params[i].has_rvs && params[i].rvs.ssc)) ? 1 : 0;
     for (size_t i = 0; i < n; ++i) k0c_rowmap_body(w, (int)i);
-    for (int r = 0; r < rows; ++r) k1_dynamics_body(w, r);
+    for (int r = 0; r < rows; ++r) {
+        k1_dynamics_body(w, r);
+        const RowCtx c = row_ctx(w, r);
+        for (int k = 0; k < c.n_t; ++k) k1b_finish_cell(w, r, c, k);
+        if (c.has_rvs && w.row_dyn[r].n_saved >= 0) {
+            const int idx_cut = extrap_scan(shock_row(w.rvs, c.off), c.n_t, 0, 1);
+            for (int k = 0; k < c.n_t; ++k) k1c_extrap_cell(w, r, c, idx_cut, k);
+        }
+        for (int k = 0; k < c.n_t; ++k) k1d_geo_cell(w, c, k);
+    }
     if (w.any_ssc) {
         for (int sft = 0; sft < 2; ++sft) {
             w.ic[sft] = hb.alloc<IcCell>(cells);

@@ -130,14 +130,32 @@ __global__ void __launch_bounds__(32) k_dynamics(BatchWs w, int n_rows) {
     k1_dynamics_body(w, row);
 }
 
+// K1b + K2: one CTA per unique row.  Finishes the row's shock tables from the raw node states the ODE
+// kernel left (thread <-> node), applies the early-time reverse-shock extrapolation, derives the EATS
+// node geometry and then builds the photon coefficients of both shocks (thread <-> node, SoA plane
+// stores coalesced along k).
 __global__ void __launch_bounds__(64) k_radiation(BatchWs w) {
+    __shared__ int s_cut;
     const int row = blockIdx.x;
-    const int which = blockIdx.y;
-    const int mi = w.row_model[row];
-    if (which && !w.cfg[mi].has_rvs) return;
-    if ((which ? w.cfg[mi].rvs : w.cfg[mi].fwd).ssc) return;  // handled by k_ic_cooling
-    const int n_t = w.hdr[mi].n_t;
-    for (int k = threadIdx.x; k < n_t; k += blockDim.x) k2_radiation_cell(w, row, k, which);
+    const RowCtx c = row_ctx(w, row);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    if (tid == 0) s_cut = c.n_t;
+    for (int k = tid; k < c.n_t; k += nthr) k1b_finish_cell(w, row, c, k);
+    __syncthreads();
+    if (c.has_rvs && w.row_dyn[row].n_saved >= 0) {
+        const int mine = extrap_scan(shock_row(w.rvs, c.off), c.n_t, tid, nthr);
+        if (mine < c.n_t) atomicMin(&s_cut, mine);
+        __syncthreads();
+        const int idx_cut = s_cut;
+        for (int k = tid; k < c.n_t; k += nthr) k1c_extrap_cell(w, row, c, idx_cut, k);
+        __syncthreads();
+    }
+    const ModelCfg& cfg = w.cfg[c.mi];
+    for (int k = tid; k < c.n_t; k += nthr) {
+        k1d_geo_cell(w, c, k);
+        if (!cfg.fwd.ssc) k2_radiation_cell(w, row, k, 0);  // ssc shocks: k_ic_cooling
+        if (cfg.has_rvs && !cfg.rvs.ssc) k2_radiation_cell(w, row, k, 1);
+    }
 }
 
 // K2 for shocks with ssc=True: one thread per (row, shock), sequential in k (IC cooling of cell k
@@ -482,11 +500,12 @@ int setup_models(vag_context* ctx, BatchWs& w, const vag_params* d_params, size_
 
 int setup_rows(vag_context* ctx, BatchWs& w, int rows, long long cells) {
     w.n_cells = cells;
-    CK(ctx->row_buf.ensure(carve_sz<int>(rows) * 3 + carve_sz<long long>(rows + 1)));
+    CK(ctx->row_buf.ensure(carve_sz<int>(rows) * 3 + carve_sz<RowDyn>(rows) + carve_sz<long long>(rows + 1)));
     char* p = static_cast<char*>(ctx->row_buf.p);
     w.row_model = carve<int>(p, rows);
     w.row_rep = carve<int>(p, rows);
     w.inj_idx = carve<int>(p, rows);
+    w.row_dyn = carve<RowDyn>(p, rows);
     w.row_cell_off = carve<long long>(p, rows + 1);
     const size_t plane = carve_sz<double>((size_t)cells);
     CK(ctx->cell_buf.ensure(plane * (1 + 12 + 2) + carve_sz<double>((size_t)cells * PH_NCOEF) * 2));
@@ -561,7 +580,7 @@ int run_front(vag_context* ctx, BatchWs& w, const vag_params* d_params, size_t n
         mark(ctx, 1, s);
         k_dynamics<<<(unsigned)((rows + 31) / 32), 32, 0, s>>>(w, rows);
         mark(ctx, 2, s);
-        k_radiation<<<dim3((unsigned)rows, 2), 64, 0, s>>>(w);
+        k_radiation<<<(unsigned)rows, 64, 0, s>>>(w);
         ctx->launches += 3;
         if (w.any_ssc) {
             k_ic_cooling<<<dim3((unsigned)((rows + 31) / 32), 2), 32, 0, s>>>(w, rows);
@@ -786,9 +805,25 @@ int vag_create(int device, vag_context** out) {
     CK(cudaMallocHost(&c->h_totals, sizeof(int) * TOT_N));
     CK(cudaMallocHost(&c->h_cells, sizeof(long long)));
     for (auto& ev : c->ev) CK(cudaEventCreate(&ev));
-    // the dynamics kernel keeps the dopri5 state in registers and spills the rest: prefer L1
-    cudaFuncSetCacheConfig(k_dynamics, cudaFuncCachePreferL1);
-    cudaFuncSetCacheConfig(k_grid, cudaFuncCachePreferL1);
+    // EXPERIMENT: shared-memory carve-out policy (kernels with different carve-outs cannot share an SM)
+    {
+        const char* e = getenv("VAG_CARVEOUT");
+        const int co = e ? atoi(e) : -1;
+        if (co < 0) {
+            cudaFuncSetCacheConfig(k_dynamics, cudaFuncCachePreferL1);
+            cudaFuncSetCacheConfig(k_grid, cudaFuncCachePreferL1);
+        } else {
+            cudaFuncSetAttribute(k_dynamics, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+            cudaFuncSetAttribute(k_grid, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+            cudaFuncSetAttribute(k_radiation, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+            cudaFuncSetAttribute(k_eats<0>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+            cudaFuncSetAttribute(k_total, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+            cudaFuncSetAttribute(k_chi2, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+            cudaFuncSetAttribute(k_rowmap, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+            cudaFuncSetAttribute(k_scan, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+            cudaFuncSetAttribute(k_prep_obs, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+        }
+    }
     *out = c;
     return VAG_OK;
 }

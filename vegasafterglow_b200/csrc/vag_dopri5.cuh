@@ -21,6 +21,17 @@
 
 namespace vag {
 
+#if defined(VAG_INSTRUMENT) && !defined(__CUDA_ARCH__)
+// host-only analysis hook (scripts/step_stats.cpp): attempts / rejections of the current row
+struct StepStats { long attempts = 0, rejects = 0; };
+inline StepStats g_step_stats;
+#define VAG_COUNT_ATTEMPT() (++g_step_stats.attempts)
+#define VAG_COUNT_REJECT() (++g_step_stats.rejects)
+#else
+#define VAG_COUNT_ATTEMPT() ((void)0)
+#define VAG_COUNT_REJECT() ((void)0)
+#endif
+
 template <int N>
 struct Dopri5 {
     double x[N];     // current state
@@ -79,6 +90,7 @@ struct Dopri5 {
                          dc5 = c5 - (-92097.0 / 339200), dc6 = c6 - 187.0 / 2100, dc7 = -1.0 / 40;
 
         {
+            VAG_COUNT_ATTEMPT();
             double xt[N], k2[N], k7[N];
 #pragma unroll
             for (int i = 0; i < N; ++i) xt[i] = 1.0 * x[i] + (dt * b21) * k1[i];
@@ -118,6 +130,7 @@ struct Dopri5 {
             }
 
             if (err > 1.0) {
+                VAG_COUNT_REJECT();
                 dt *= vmax(0.9 * pow(err, -1.0 / 3.0), 0.2);
                 return false;
             }
@@ -136,6 +149,37 @@ struct Dopri5 {
             }
             return true;
         }
+    }
+
+    // Dense-output weights of time tq inside the last accepted step [t_old, t]:
+    // out_i = xo_i + w[0] ko_i + w[1] k3_i + w[2] k4_i + w[3] k5_i + w[4] k6_i + w[5] k1_i
+    VAG_HD void dense_weights(double tq, double* w) const {
+        constexpr double b1 = 35.0 / 384, b3 = 500.0 / 1113, b4 = 125.0 / 192, b5 = -2187.0 / 6784, b6 = 11.0 / 84;
+        const double h = t - t_old;
+        const double th = (tq - t_old) / h;
+        const double X1 = 5.0 * (2558722523.0 - 31403016.0 * th) / 11282082432.0;
+        const double X3 = 100.0 * (882725551.0 - 15701508.0 * th) / 32700410799.0;
+        const double X4 = 25.0 * (443332067.0 - 31403016.0 * th) / 1880347072.0;
+        const double X5 = 32805.0 * (23143187.0 - 3489224.0 * th) / 199316789632.0;
+        const double X6 = 55.0 * (29972135.0 - 7076736.0 * th) / 822651844.0;
+        const double X7 = 10.0 * (7414447.0 - 829305.0 * th) / 29380423.0;
+        const double thm1 = th - 1.0;
+        const double thsq = th * th;
+        const double A = thsq * (3.0 - 2.0 * th);
+        const double B = thsq * thm1;
+        const double C = thsq * thm1 * thm1;
+        const double D = th * thm1 * thm1;
+        w[0] = h * (A * b1 - C * X1 + D);
+        w[1] = h * (A * b3 + C * X3);
+        w[2] = h * (A * b4 - C * X4);
+        w[3] = h * (A * b5 + C * X5);
+        w[4] = h * (A * b6 - C * X6);
+        w[5] = h * (B + C * X7);
+    }
+    // one component of the dense output (same expression as calc_state)
+    template <int I>
+    VAG_HD double dense_component(const double* w) const {
+        return 1.0 * xo[I] + w[0] * ko[I] + w[1] * k3[I] + w[2] * k4[I] + w[3] * k5[I] + w[4] * k6[I] + w[5] * k1[I];
     }
 
     // Dense output at time tq inside the last accepted step [t_old, t].

@@ -43,6 +43,7 @@ struct BatchWs {
     int* row_model;
     int* row_rep;
     int* inj_idx;
+    RowDyn* row_dyn;          // ODE kernel -> finishing pass (raw-state bookkeeping, crossing state)
     long long* row_cell_off;  // first global cell of each row
     // per unique cell
     long long n_cells;
@@ -142,6 +143,16 @@ VAG_HD ShockRow shock_row(double* const* planes, long long off) {
 }
 
 // ---- K1 ---------------------------------------------------------------------------------------
+// The shock-table planes double as the raw-state store of the ODE kernel (vag_shock.cuh RawRow):
+// component c of the state vector -> forward plane c (c < 6) or reverse plane c - 6.
+VAG_HD RawRow raw_row(const BatchWs& w, long long off) {
+    RawRow raw;
+    for (int c = 0; c < 6; ++c) raw.c[c] = w.fwd[c] + off;
+    for (int c = 6; c < 11; ++c) raw.c[c] = w.rvs[c - 6] + off;
+    return raw;
+}
+
+// K1: sequential part of one row -- time lattice + dopri5 integration, raw node states only
 VAG_HD void k1_dynamics_body(const BatchWs& w, int row) {
     const int mi = w.row_model[row];
     const int r = w.row_rep[row];
@@ -157,22 +168,16 @@ VAG_HD void k1_dynamics_body(const BatchWs& w, int row) {
     for (int k = 0; k < h.n_t; ++k) finite = finite && isfinite(t_row[k]);
     if (!finite) st |= VAG_ST_GRID_NONFINITE;
     const ShockRow sf = shock_row(w.fwd, off);
+    const RawRow raw = raw_row(w, off);
+    RowDyn rd;
     if (cfg.has_rvs) {
         const ShockRow sr = shock_row(w.rvs, off);
-        int inj = h.n_t;
-        st |= solve_pair_row(cfg, theta, t_dec, t_row, h.n_t, sf, sr, &inj);
-        w.inj_idx[row] = inj;
+        st |= solve_pair_row(cfg, theta, t_dec, t_row, h.n_t, sf, sr, raw, rd);
     } else {
-        st |= solve_fwd_row(cfg, theta, t_dec, t_row, h.n_t, sf);
-        w.inj_idx[row] = h.n_t;
+        st |= solve_fwd_row(cfg, theta, t_dec, t_row, h.n_t, sf, raw, rd);
     }
-    // node-only pieces of the EATS geometry (observer.cpp:158,200), shared by every (phi,theta) row
-    // that maps onto this representative row
-    for (int k = 0; k < h.n_t; ++k) {
-        const double g = sf.Gamma[k];
-        w.geo_u[off + k] = sqrt((g - 1) * (g + 1));
-        w.geo_lg2r2[off + k] = 2.0 * rlog2(sf.r[k]);
-    }
+    w.row_dyn[row] = rd;
+    w.inj_idx[row] = rd.injection_idx;
     if (st) {
 #if defined(__CUDA_ARCH__)
         atomicOr(&w.status[mi], st);
@@ -180,6 +185,48 @@ VAG_HD void k1_dynamics_body(const BatchWs& w, int row) {
         w.status[mi] |= st;
 #endif
     }
+}
+
+// K1b: per-cell completion of the shock tables from the raw node states (save_fwd_shock_state /
+// save_rvs_shock_state, forward-shock.tpp:151-173, reverse-shock.tpp:403-426); one thread per (row, k)
+struct RowCtx {
+    int mi, n_t, has_rvs;
+    long long off;
+    double theta;
+};
+VAG_HD RowCtx row_ctx(const BatchWs& w, int row) {
+    RowCtx c;
+    c.mi = w.row_model[row];
+    const int r = w.row_rep[row];
+    c.n_t = w.hdr[c.mi].n_t;
+    c.has_rvs = w.cfg[c.mi].has_rvs;
+    c.off = w.cell_off[c.mi] + (long long)r * c.n_t;
+    c.theta = w.theta[(size_t)c.mi * w.cap_theta + w.reps[(size_t)c.mi * w.cap_theta + r]];
+    return c;
+}
+VAG_HD void k1b_finish_cell(const BatchWs& w, int row, const RowCtx& c, int k) {
+    const ModelCfg& cfg = w.cfg[c.mi];
+    const RowDyn& rd = w.row_dyn[row];
+    const ShockRow sf = shock_row(w.fwd, c.off);
+    const RawRow raw = raw_row(w, c.off);
+    if (c.has_rvs)
+        finish_pair_cell(cfg, c.theta, rd, sf, shock_row(w.rvs, c.off), raw, k);
+    else
+        finish_fwd_cell(cfg, rd, sf, raw, k);
+}
+// K1c: reverse_shock_early_extrap of node k (after every cell of the row is finished and idx_cut,
+// the first node with Gamma_th above the thermal cut, is known)
+VAG_HD void k1c_extrap_cell(const BatchWs& w, int row, const RowCtx& c, int idx_cut, int k) {
+    if (!c.has_rvs || w.row_dyn[row].n_saved < 0) return;
+    if (k < idx_cut && extrap_applies(idx_cut, c.n_t, w.row_dyn[row].injection_idx))
+        extrap_cell(shock_row(w.rvs, c.off), idx_cut, k);
+}
+// K1d: node-only pieces of the EATS geometry (observer.cpp:158,200), shared by every (phi,theta) row
+// that maps onto this representative row
+VAG_HD void k1d_geo_cell(const BatchWs& w, const RowCtx& c, int k) {
+    const double g = w.fwd[2][c.off + k];
+    w.geo_u[c.off + k] = sqrt((g - 1) * (g + 1));
+    w.geo_lg2r2[c.off + k] = 2.0 * rlog2(w.fwd[1][c.off + k]);
 }
 
 // ---- K2 ---------------------------------------------------------------------------------------

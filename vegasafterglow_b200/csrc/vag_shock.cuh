@@ -268,38 +268,88 @@ struct FwdEqn {
     }
 };
 
+// Raw dense-output samples of one row.  The ODE kernel stores only the interpolated state vector
+// of every lattice node (component c -> plane[c][k]); the derived shock quantities are computed
+// afterwards, one thread per cell, by finish_*_cell (same arithmetic as save_*_shock_state, moved
+// out of the latency-critical sequential loop).  The planes are the shock-table planes themselves
+// (forward table = components 0..5, reverse table = components 6..10), finished in place.
+struct RawRow {
+    double* c[11];
+};
+// per-row record left by the ODE kernel for the finishing pass
+struct RowDyn {
+    int n_saved;        // nodes [0, n_saved) hold raw states; -1: the tables already hold final values
+    int injection_idx;
+    double V3_comv_x, rho3_x, B3_ordered_x;  // crossing state (reverse-shock.hpp:66-70)
+};
+
 // grid_solve_fwd_shock: forward-shock.tpp:175-208.  Returns VAG_ST_* bits.
-VAG_HD int solve_fwd_row(const ModelCfg& m, double theta, double t_dec, const double* t, int n_t, const ShockRow& s) {
+// The accepted-step loop of integrate_adaptive/dense output is flattened to one dopri5 ATTEMPT per
+// iteration (identical sequence of attempts, step sizes and accepted states): in a warp of 32 rows a
+// rejected attempt of one row then costs the other rows nothing.
+VAG_HD int solve_fwd_row(const ModelCfg& m, double theta, double t_dec, const double* t, int n_t, const ShockRow& s,
+                         const RawRow& raw, RowDyn& rd) {
     FwdEqn eqn(m, theta);
     double x[FwdEqn::N];
     const double t0 = vmin(t[0], vmin(0.1 * unit::sec, 0.1 * t_dec));
     eqn.set_init_state(x, theta, t0);
+    rd.injection_idx = n_t;
+    rd.V3_comv_x = rd.rho3_x = rd.B3_ordered_x = 0;
     if (x[FwdEqn::iG] <= con::Gamma_cut) {
         set_stopping_row(s, n_t, x[FwdEqn::iT], x[FwdEqn::iR]);
+        rd.n_saved = -1;
         return 0;
     }
     Dopri5<FwdEqn::N> st;
     st.initialize(x, t0, 0.01 * t0, m.rtol);
     const double t_back = t[n_t - 1];
-    int k = 0, status = 0;
-    for (int steps = 0; st.t <= t_back;) {
-        if (!st.do_step(eqn)) {
-            status |= VAG_ST_ODE_FAIL500;
-            break;
+    int k = 0, status = 0, fails = 0, steps = 0;
+    st.begin_step(eqn);
+    while (st.t <= t_back) {
+        if (!st.try_step(eqn)) {
+            if (++fails >= 500) {
+                status |= VAG_ST_ODE_FAIL500;
+                break;
+            }
+            continue;
         }
+        fails = 0;
         if (++steps > dflt::max_ode_steps) {
             status |= VAG_ST_ODE_STEP_CAP;
             break;
         }
         while (k < n_t && st.t > t[k]) {
             st.calc_state(t[k], x);
-            save_fwd_state(m, m.fwd.eps_B, s, k, x[FwdEqn::iG], x[FwdEqn::iM2], x[FwdEqn::iU], x[FwdEqn::iR],
-                           x[FwdEqn::iT]);
+#pragma unroll
+            for (int c = 0; c < FwdEqn::N; ++c) raw.c[c][k] = x[c];
             ++k;
         }
+        st.t_old = st.t;  // dense_output_runge_kutta::do_step: the next step starts here
     }
-    fill_default_row(s, k, n_t);
+    rd.n_saved = k;
     return status;
+}
+
+// save_fwd_shock_state of node k from its raw state (forward-only rows), or the Shock-ctor defaults
+// for nodes the integration never reached (shock.cpp:12-25)
+VAG_HD void default_cell(const ShockRow& s, int k) {
+    s.t_comv[k] = 0;
+    s.r[k] = 0;
+    s.Gamma[k] = 1;
+    s.Gamma_th[k] = 1;
+    s.B[k] = 0;
+    s.N_p[k] = 0;
+}
+VAG_HD void finish_fwd_cell(const ModelCfg& m, const RowDyn& rd, const ShockRow& s, const RawRow& raw, int k) {
+    if (rd.n_saved < 0) return;
+    if (k >= rd.n_saved) {
+        default_cell(s, k);
+        return;
+    }
+    double x[FwdEqn::N];
+#pragma unroll
+    for (int c = 0; c < FwdEqn::N; ++c) x[c] = raw.c[c][k];
+    save_fwd_state(m, m.fwd.eps_B, s, k, x[FwdEqn::iG], x[FwdEqn::iM2], x[FwdEqn::iU], x[FwdEqn::iR], x[FwdEqn::iT]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -322,6 +372,7 @@ struct FRState {
 struct FREqn {
     const ModelCfg& m;
     double Gamma4, deps0_dt, dm0_dt, u4;
+    double cs4, beta4;  // compute_sound_speed(Gamma4), gamma_to_beta(Gamma4): row constants of the RHS
     // crossing state: reverse-shock.hpp:66-70
     double u_x, r_x, B3_ordered_x, V3_comv_x, rho3_x;
     enum { iG = 0, iX4, iX3, iM2, iM3, iU2, iU3, iR, iT, iE4, iM4, N };
@@ -333,6 +384,8 @@ struct FREqn {
         dm0_dt = deps0_dt / (Gamma4 * con::c2);
         dm0_dt /= 1 + m.sigma0;  // reverse-shock.tpp:36-38
         u4 = sqrt(Gamma4 * Gamma4 - 1) * con::c;
+        cs4 = compute_sound_speed(Gamma4);
+        beta4 = gamma_to_beta(Gamma4);
         u_x = r_x = B3_ordered_x = V3_comv_x = rho3_x = 0;
     }
 
@@ -344,11 +397,12 @@ struct FREqn {
         const double sigma = eps4 / (Gamma4 * m4 * con::c2) - 1;
         return (sigma > con::sigma_cut) ? sigma : 0;
     }
-    VAG_HD bool crossing_complete(const double* x, double t) const {  // reverse-shock.tpp:49-60
-        if (x[iM3] < 0.999 * x[iM4]) return false;
+    VAG_HD bool crossing_complete_m(double m3, double m4, double t) const {  // reverse-shock.tpp:49-60
+        if (m3 < 0.999 * m4) return false;
         if (smoothstep(m.T0 * 1.5, m.T0 * 0.5, t) > 1e-6) return false;
         return true;
     }
+    VAG_HD bool crossing_complete(const double* x, double t) const { return crossing_complete_m(x[iM3], x[iM4], t); }
 
     // FRShockEqn::operator(): reverse-shock.tpp:252-294 (+ the rate terms :62-250)
     VAG_HD void operator()(const double* xr, double* d, double t) const {
@@ -387,7 +441,7 @@ struct FREqn {
         // compute_dx4_dt :205-213
         double dx4;
         {
-            const double sound_expansion = compute_sound_speed(Gamma4) * dtc;
+            const double sound_expansion = cs4 * dtc;
             dx4 = (f > 1e-6) ? f * u4 + (1 - f) * sound_expansion : sound_expansion;
         }
         d[iX4] = dx4;
@@ -404,7 +458,6 @@ struct FREqn {
                     const double penetration = Gamma * comp_ratio / Gamma4 - 1;
                     if (!(penetration <= 0)) {
                         const double beta3 = gamma_to_beta(Gamma);
-                        const double beta4 = gamma_to_beta(Gamma4);
                         const double dx3dt = (Gamma4 - Gamma) * (Gamma4 + Gamma) * (1 + beta3) * con::c /
                                              (Gamma4 * Gamma4 * (beta3 + beta4) * penetration);
                         double crossing = fabs(dx3dt * Gamma);
@@ -559,13 +612,20 @@ struct FREqn {
     }
 };
 
-// reverse_shock_early_extrap: reverse-shock.tpp:428-467
-VAG_HD void reverse_shock_early_extrap(const ShockRow& s, int n_t, int injection_idx) {
-    int idx_cut = 0;
-    for (; idx_cut < n_t; ++idx_cut)
-        if (s.Gamma_th[idx_cut] > con::gamma_therm_cut) break;
+// reverse_shock_early_extrap: reverse-shock.tpp:428-467, split into the scan for the first thermally
+// resolved node (extrap_scan: strided over `nthr` cooperating threads, combine the results with min)
+// and the per-node rewrite (extrap_cell: independent for every k < idx_cut)
+VAG_HD int extrap_scan(const ShockRow& s, int n_t, int tid, int nthr) {
+    for (int k = tid; k < n_t; k += nthr)
+        if (s.Gamma_th[k] > con::gamma_therm_cut) return k;
+    return n_t;
+}
+VAG_HD bool extrap_applies(int idx_cut, int n_t, int injection_idx) {
     constexpr int offset = 2;
-    if (idx_cut == 0 || idx_cut >= n_t - offset || idx_cut >= injection_idx) return;
+    return !(idx_cut == 0 || idx_cut >= n_t - offset || idx_cut >= injection_idx);
+}
+VAG_HD void extrap_cell(const ShockRow& s, int idx_cut, int k) {
+    constexpr int offset = 2;
     const double log2_r = fast_log2(s.r[idx_cut]);
     const double log2_Gamma_th = fast_log2(s.Gamma_th[idx_cut] - 1);
     const double log2_B = fast_log2(s.B[idx_cut]);
@@ -574,29 +634,29 @@ VAG_HD void reverse_shock_early_extrap(const ShockRow& s, int n_t, int injection
     const double gamma_slope = (fast_log2(s.Gamma_th[idx_cut + offset] - 1) - log2_Gamma_th) / dl;
     const double B_slope = (fast_log2(s.B[idx_cut + offset]) - log2_B) / dl;
     const double N_p_slope = (fast_log2(s.N_p[idx_cut + offset]) - log2_N_p) / dl;
-    for (int k = 0; k < idx_cut; k++) {
-        const double dlog2_r = fast_log2(s.r[k]) - log2_r;
-        s.Gamma_th[k] = 1 + fast_exp2(log2_Gamma_th + gamma_slope * dlog2_r);
-        s.B[k] = fast_exp2(log2_B + B_slope * dlog2_r);
-        s.N_p[k] = fast_exp2(log2_N_p + N_p_slope * dlog2_r);
-    }
+    const double dlog2_r = fast_log2(s.r[k]) - log2_r;
+    s.Gamma_th[k] = 1 + fast_exp2(log2_Gamma_th + gamma_slope * dlog2_r);
+    s.B[k] = fast_exp2(log2_B + B_slope * dlog2_r);
+    s.N_p[k] = fast_exp2(log2_N_p + N_p_slope * dlog2_r);
 }
 
-// grid_solve_shock_pair: reverse-shock.tpp:511-591.  Returns VAG_ST_* bits; *inj_idx_out receives
-// the row's injection_idx (n_t when the crossing never completes inside the lattice).
+// grid_solve_shock_pair: reverse-shock.tpp:511-591, one dopri5 attempt per loop iteration (see
+// solve_fwd_row).  Leaves raw node states + the RowDyn record; finish_pair_cell completes the tables.
 VAG_HD int solve_pair_row(const ModelCfg& m, double theta, double t_dec, const double* t, int n_t, const ShockRow& sf,
-                          const ShockRow& sr, int* inj_idx_out) {
+                          const ShockRow& sr, const RawRow& raw, RowDyn& rd) {
     FREqn eqn(m, theta);
     double x[FREqn::N];
     const double t0 = vmin(t[0], vmin(0.01 * unit::sec, 0.1 * t_dec));
     eqn.set_init_state(x, t0);
     int injection_idx = n_t;
-    *inj_idx_out = injection_idx;
+    rd.injection_idx = n_t;
+    rd.V3_comv_x = rd.rho3_x = rd.B3_ordered_x = 0;
 
     constexpr double RS_Gamma_limit = 1.03;
     if (x[FREqn::iG] <= RS_Gamma_limit) {
         set_stopping_row(sf, n_t, x[FREqn::iT], x[FREqn::iR]);
         set_stopping_row(sr, n_t, x[FREqn::iT], x[FREqn::iR]);
+        rd.n_saved = -1;
         return 0;
     }
     double rtol = m.rtol;
@@ -608,8 +668,8 @@ VAG_HD int solve_pair_row(const ModelCfg& m, double theta, double t_dec, const d
     int k = 0;
     for (; k < n_t && t[k] < t0; k++) {
         eqn.set_init_state(x, t[k]);
-        save_fwd_state(m, m.fwd.eps_B, sf, k, x[FREqn::iG], x[FREqn::iM2], x[FREqn::iU2], x[FREqn::iR], x[FREqn::iT]);
-        eqn.save_rvs_state(m.rvs.eps_B, sr, k, injection_idx, x);
+#pragma unroll
+        for (int c = 0; c < FREqn::N; ++c) raw.c[c][k] = x[c];
     }
 
     bool reverse_shock_crossing = true;
@@ -617,12 +677,17 @@ VAG_HD int solve_pair_row(const ModelCfg& m, double theta, double t_dec, const d
     double t_cross = 0;
     double t_step_start = t0;
     const double t_back = t[n_t - 1];
-    int status = 0;
-    for (int steps = 0; st.t <= t_back;) {
-        if (!st.do_step(eqn)) {
-            status |= VAG_ST_ODE_FAIL500;
-            break;
+    int status = 0, fails = 0, steps = 0;
+    st.begin_step(eqn);
+    while (st.t <= t_back) {
+        if (!st.try_step(eqn)) {
+            if (++fails >= 500) {
+                status |= VAG_ST_ODE_FAIL500;
+                break;
+            }
+            continue;
         }
+        fails = 0;
         if (++steps > dflt::max_ode_steps) {
             status |= VAG_ST_ODE_STEP_CAP;
             break;
@@ -632,12 +697,16 @@ VAG_HD int solve_pair_row(const ModelCfg& m, double theta, double t_dec, const d
             break;
         }
         if (reverse_shock_crossing && eqn.crossing_complete(st.x, st.t)) {
-            // locate_crossing_time: reverse-shock.tpp:482-495
+            // locate_crossing_time: reverse-shock.tpp:482-495.  crossing_complete reads only m3 and m4
+            // of the dense output, so the bisection interpolates just those two components.
             double t_lo = t_step_start, t_hi = st.t;
+            double wd[6];
             for (int iter = 0; iter < 100 && (t_hi - t_lo) > 1e-12 * t_hi; ++iter) {
                 const double t_mid = 0.5 * (t_lo + t_hi);
-                st.calc_state(t_mid, x);
-                if (eqn.crossing_complete(x, t_mid)) {
+                st.dense_weights(t_mid, wd);
+                const double m3 = st.template dense_component<FREqn::iM3>(wd);
+                const double m4 = st.template dense_component<FREqn::iM4>(wd);
+                if (eqn.crossing_complete_m(m3, m4, t_mid)) {
                     t_hi = t_mid;
                 } else {
                     t_lo = t_mid;
@@ -646,6 +715,9 @@ VAG_HD int solve_pair_row(const ModelCfg& m, double theta, double t_dec, const d
             st.calc_state(t_hi, x);
             t_cross = t_hi;
             eqn.save_cross_state(x);
+            rd.V3_comv_x = eqn.V3_comv_x;
+            rd.rho3_x = eqn.rho3_x;
+            rd.B3_ordered_x = eqn.B3_ordered_x;
             reverse_shock_crossing = false;
             injection_idx_pending = true;
         }
@@ -656,17 +728,35 @@ VAG_HD int solve_pair_row(const ModelCfg& m, double theta, double t_dec, const d
                 injection_idx = k > 0 ? k : 1;
                 injection_idx_pending = false;
             }
-            save_fwd_state(m, m.fwd.eps_B, sf, k, x[FREqn::iG], x[FREqn::iM2], x[FREqn::iU2], x[FREqn::iR],
-                           x[FREqn::iT]);
-            eqn.save_rvs_state(m.rvs.eps_B, sr, k, injection_idx, x);
+#pragma unroll
+            for (int c = 0; c < FREqn::N; ++c) raw.c[c][k] = x[c];
             ++k;
         }
+        st.t_old = st.t;
     }
-    fill_default_row(sf, k, n_t);
-    fill_default_row(sr, k, n_t);
-    *inj_idx_out = injection_idx;
-    reverse_shock_early_extrap(sr, n_t, injection_idx);
+    rd.n_saved = k;
+    rd.injection_idx = injection_idx;
     return status;
+}
+
+// save_fwd_shock_state + save_rvs_shock_state of node k from its raw state (pair rows)
+VAG_HD void finish_pair_cell(const ModelCfg& m, double theta, const RowDyn& rd, const ShockRow& sf, const ShockRow& sr,
+                             const RawRow& raw, int k) {
+    if (rd.n_saved < 0) return;
+    if (k >= rd.n_saved) {
+        default_cell(sf, k);
+        default_cell(sr, k);
+        return;
+    }
+    double x[FREqn::N];
+#pragma unroll
+    for (int c = 0; c < FREqn::N; ++c) x[c] = raw.c[c][k];
+    FREqn eqn(m, theta);
+    eqn.V3_comv_x = rd.V3_comv_x;
+    eqn.rho3_x = rd.rho3_x;
+    eqn.B3_ordered_x = rd.B3_ordered_x;
+    save_fwd_state(m, m.fwd.eps_B, sf, k, x[FREqn::iG], x[FREqn::iM2], x[FREqn::iU2], x[FREqn::iR], x[FREqn::iT]);
+    eqn.save_rvs_state(m.rvs.eps_B, sr, k, rd.injection_idx, x);
 }
 
 }  // namespace vag
