@@ -124,10 +124,17 @@ __global__ void k_rowmap(BatchWs w) {
     k0c_rowmap_body(w, mi);
 }
 
-__global__ void __launch_bounds__(32) k_dynamics(BatchWs w, int n_rows) {
-    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+// K1: one thread per unique row, `lanes` rows per 32-thread CTA.  The ODE is a dependent-latency chain
+// and rows of one warp diverge (different accept/reject histories, branches of the RHS), so a small
+// batch is spread thinly -- few rows per warp, about two warps per scheduler -- and only large batches
+// fill whole warps.  The dopri5 stage vectors sit in shared memory, [slot][component][lane]
+// (conflict-free: a lane only ever touches its own column).
+__global__ void __launch_bounds__(32) k_dynamics(BatchWs w, int n_rows, int lanes) {
+    __shared__ double s_col[K1_COL_DOUBLES * 32];
+    if ((int)threadIdx.x >= lanes) return;
+    const int row = blockIdx.x * lanes + threadIdx.x;
     if (row >= n_rows) return;
-    k1_dynamics_body(w, row);
+    k1_dynamics_body(w, row, s_col + threadIdx.x, 32);
 }
 
 // K1b + K2: one CTA per unique row.  Finishes the row's shock tables from the raw node states the ODE
@@ -578,7 +585,13 @@ int run_front(vag_context* ctx, BatchWs& w, const vag_params* d_params, size_t n
     if (rows > 0) {
         k_rowmap<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(w);
         mark(ctx, 1, s);
-        k_dynamics<<<(unsigned)((rows + 31) / 32), 32, 0, s>>>(w, rows);
+        {
+            // rows per warp: up to one warp per scheduler before warps are filled up
+            int lanes = 32;
+            while (lanes > 4 && (rows + lanes / 2 - 1) / (lanes / 2) <= ctx->sm_count * 4) lanes >>= 1;
+            if (const char* e = getenv("VAG_DYN_LANES")) lanes = atoi(e);  // EXPERIMENT
+            k_dynamics<<<(unsigned)((rows + lanes - 1) / lanes), 32, 0, s>>>(w, rows, lanes);
+        }
         mark(ctx, 2, s);
         k_radiation<<<(unsigned)rows, 64, 0, s>>>(w);
         ctx->launches += 3;
@@ -805,25 +818,10 @@ int vag_create(int device, vag_context** out) {
     CK(cudaMallocHost(&c->h_totals, sizeof(int) * TOT_N));
     CK(cudaMallocHost(&c->h_cells, sizeof(long long)));
     for (auto& ev : c->ev) CK(cudaEventCreate(&ev));
-    // EXPERIMENT: shared-memory carve-out policy (kernels with different carve-outs cannot share an SM)
-    {
-        const char* e = getenv("VAG_CARVEOUT");
-        const int co = e ? atoi(e) : -1;
-        if (co < 0) {
-            cudaFuncSetCacheConfig(k_dynamics, cudaFuncCachePreferL1);
-            cudaFuncSetCacheConfig(k_grid, cudaFuncCachePreferL1);
-        } else {
-            cudaFuncSetAttribute(k_dynamics, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-            cudaFuncSetAttribute(k_grid, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-            cudaFuncSetAttribute(k_radiation, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-            cudaFuncSetAttribute(k_eats<0>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-            cudaFuncSetAttribute(k_total, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-            cudaFuncSetAttribute(k_chi2, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-            cudaFuncSetAttribute(k_rowmap, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-            cudaFuncSetAttribute(k_scan, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-            cudaFuncSetAttribute(k_prep_obs, cudaFuncAttributePreferredSharedMemoryCarveout, co);
-        }
-    }
+    // k_grid spills its scratch to local memory: prefer L1.  k_dynamics keeps its dopri5 stage vectors
+    // in shared memory (23 KB per 32-row CTA): give it the full carve-out so several CTAs share an SM.
+    cudaFuncSetCacheConfig(k_grid, cudaFuncCachePreferL1);
+    cudaFuncSetAttribute(k_dynamics, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     *out = c;
     return VAG_OK;
 }

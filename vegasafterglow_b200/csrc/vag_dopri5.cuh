@@ -211,4 +211,198 @@ struct Dopri5 {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Dopri5S: the same integrator with the stage vectors in a caller-provided column of (shared)
+// memory instead of registers.  Used by the shock ODE kernel (N = 5 / 11): only the state x lives in
+// registers, the seven stage derivatives and the step-start state sit in the thread's private column
+// `col[(slot * N + i) * stride]`, and the six stage evaluations run as a rolled loop, so the RHS exists
+// once in the instruction stream (the fully unrolled register version was 40 k SASS instructions and
+// ran out of the instruction cache with one warp per SM).  Same tableau, same operation order.
+// ---------------------------------------------------------------------------------------------
+#define VAG_DP_A {1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0, 1.0}
+#define VAG_DP_B                                                                                             \
+    {                                                                                                        \
+        {1.0 / 5, 0, 0, 0, 0, 0}, {3.0 / 40, 9.0 / 40, 0, 0, 0, 0}, {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0}, \
+            {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0},                           \
+            {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0},                    \
+            {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84}                            \
+    }
+#if defined(__CUDACC__)
+__constant__ double c_dp_a[6] = VAG_DP_A;
+__constant__ double c_dp_b[6][6] = VAG_DP_B;
+#endif
+static const double h_dp_a[6] = VAG_DP_A;
+static const double h_dp_b[6][6] = VAG_DP_B;
+#if defined(__CUDA_ARCH__)
+#define VAG_DPA c_dp_a
+#define VAG_DPB c_dp_b
+#else
+#define VAG_DPA h_dp_a
+#define VAG_DPB h_dp_b
+#endif
+
+template <int N>
+struct Dopri5S {
+    enum { S_K1 = 0, S_K2, S_K3, S_K4, S_K5, S_K6, S_K7, S_XO, NSLOT };
+    static constexpr int kDoublesPerThread = NSLOT * N;
+    double x[N];  // current state
+    double* col;  // this thread's column
+    int stride;
+    double t, t_old, dt, eps;
+
+    VAG_HD double& K(int slot, int i) const { return col[(size_t)(slot * N + i) * stride]; }
+
+    VAG_HD void initialize(double* column, int column_stride, const double* x0, double t0, double dt0, double tol) {
+        col = column;
+        stride = column_stride;
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = x0[i];
+        t = t0;
+        t_old = t0;
+        dt = dt0;
+        eps = tol;
+    }
+
+    // derivative at the initial state (the FSAL slot of the first step)
+    template <class Sys>
+    VAG_HD void begin(Sys& sys) {
+        double kk[N];
+        sys(x, kk, t);
+#pragma unroll
+        for (int i = 0; i < N; ++i) K(S_K1, i) = kk[i];
+        t_old = t;
+    }
+
+    // One attempt with the current dt (controlled_runge_kutta::try_step): true = accepted.  After an
+    // accepted attempt the dense output of [t_old, t] is available until advance() is called.
+    template <class Sys>
+    VAG_HD bool try_step(Sys& sys) {
+        constexpr double c1 = 35.0 / 384, c3 = 500.0 / 1113, c4 = 125.0 / 192, c5 = -2187.0 / 6784, c6 = 11.0 / 84;
+        constexpr double dc1 = c1 - 5179.0 / 57600, dc3 = c3 - 7571.0 / 16695, dc4 = c4 - 393.0 / 640,
+                         dc5 = c5 - (-92097.0 / 339200), dc6 = c6 - 187.0 / 2100, dc7 = -1.0 / 40;
+        VAG_COUNT_ATTEMPT();
+        double xt[N];
+#pragma unroll 1
+        for (int s = 0; s < 6; ++s) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) xt[i] = 1.0 * x[i];
+#pragma unroll 1
+            for (int j = 0; j <= s; ++j) {
+                const double b = VAG_DPB[s][j];
+                if (b == 0) continue;  // k2 does not enter the 5th-order solution
+                const double db = dt * b;
+#pragma unroll
+                for (int i = 0; i < N; ++i) xt[i] = xt[i] + db * K(j, i);
+            }
+            double kk[N];
+            sys(xt, kk, t + dt * VAG_DPA[s]);
+#pragma unroll
+            for (int i = 0; i < N; ++i) K(s + 1, i) = kk[i];
+        }
+        // error estimate and inf-norm of err_i / (eps + eps * (|x_i| + |dt| |k1_i|))
+        double err = 0;
+        const double adt = fabs(dt);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double k1i = K(S_K1, i);
+            const double e = (dt * dc1) * k1i + (dt * dc3) * K(S_K3, i) + (dt * dc4) * K(S_K4, i) + (dt * dc5) * K(S_K5, i) +
+                             (dt * dc6) * K(S_K6, i) + (dt * dc7) * K(S_K7, i);
+            // a component with an identically zero error estimate (e.g. the shell mass after injection
+            // stops) would send 0 / x down the divider's slow path; 0 / x = 0 for the positive scale
+            const double r = (e == 0) ? 0.0 : fabs(e) / (eps + eps * (1.0 * fabs(x[i]) + adt * fabs(k1i)));
+            err = vmax(err, fabs(r));
+        }
+        if (err > 1.0) {
+            VAG_COUNT_REJECT();
+            dt *= vmax(0.9 * pow(err, -1.0 / 3.0), 0.2);
+            return false;
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            K(S_XO, i) = x[i];
+            x[i] = xt[i];
+        }
+        t += dt;
+        if (err < 0.5) {
+            err = vmax(pow(5.0, -5.0), err);
+            dt *= 0.9 * pow(err, -1.0 / 5.0);
+        }
+        return true;
+    }
+
+    // start of the next step: the FSAL derivative k7 becomes k1
+    VAG_HD void advance() {
+#pragma unroll
+        for (int i = 0; i < N; ++i) K(S_K1, i) = K(S_K7, i);
+        t_old = t;
+    }
+
+    // Dense-output weights (runge_kutta_dopri5.hpp:229-275).  The rational constants of the published
+    // formula are folded into reciprocal multipliers (<= 1 ulp per weight against the divisions).
+    VAG_HD double dense_theta(double tq) const { return (tq - t_old) / (t - t_old); }
+    VAG_HD void dense_weights(double tq, double* w) const {
+        constexpr double b1 = 35.0 / 384, b3 = 500.0 / 1113, b4 = 125.0 / 192, b5 = -2187.0 / 6784, b6 = 11.0 / 84;
+        constexpr double r1 = 5.0 / 11282082432.0, r3 = 100.0 / 32700410799.0, r4 = 25.0 / 1880347072.0,
+                         r5 = 32805.0 / 199316789632.0, r6 = 55.0 / 822651844.0, r7 = 10.0 / 29380423.0;
+        const double h = t - t_old;
+        const double th = (tq - t_old) / h;
+        const double X1 = r1 * (2558722523.0 - 31403016.0 * th);
+        const double X3 = r3 * (882725551.0 - 15701508.0 * th);
+        const double X4 = r4 * (443332067.0 - 31403016.0 * th);
+        const double X5 = r5 * (23143187.0 - 3489224.0 * th);
+        const double X6 = r6 * (29972135.0 - 7076736.0 * th);
+        const double X7 = r7 * (7414447.0 - 829305.0 * th);
+        const double thm1 = th - 1.0;
+        const double thsq = th * th;
+        const double A = thsq * (3.0 - 2.0 * th);
+        const double B = thsq * thm1;
+        const double C = thsq * thm1 * thm1;
+        const double D = th * thm1 * thm1;
+        w[0] = h * (A * b1 - C * X1 + D);
+        w[1] = h * (A * b3 + C * X3);
+        w[2] = h * (A * b4 - C * X4);
+        w[3] = h * (A * b5 + C * X5);
+        w[4] = h * (A * b6 - C * X6);
+        w[5] = h * (B + C * X7);
+    }
+    // The same interpolant of ONE component as a polynomial in theta = (tq - t_old) / h, for callers
+    // that evaluate it many times inside one step (the crossing-time bisection):
+    //   x(theta) = p0 + A p1 + C (p2 + p3 theta) + D p4 + B p5,  A..D as in dense_weights
+    VAG_HD void dense_poly(int i, double* p) const {
+        constexpr double b1 = 35.0 / 384, b3 = 500.0 / 1113, b4 = 125.0 / 192, b5 = -2187.0 / 6784, b6 = 11.0 / 84;
+        constexpr double r1 = 5.0 / 11282082432.0, r3 = 100.0 / 32700410799.0, r4 = 25.0 / 1880347072.0,
+                         r5 = 32805.0 / 199316789632.0, r6 = 55.0 / 822651844.0, r7 = 10.0 / 29380423.0;
+        const double h = t - t_old;
+        const double ko = K(S_K1, i), k3 = K(S_K3, i), k4 = K(S_K4, i), k5 = K(S_K5, i), k6 = K(S_K6, i), k7 = K(S_K7, i);
+        p[0] = K(S_XO, i);
+        p[1] = h * (b1 * ko + b3 * k3 + b4 * k4 + b5 * k5 + b6 * k6);
+        p[2] = h * (-(r1 * 2558722523.0) * ko + (r3 * 882725551.0) * k3 - (r4 * 443332067.0) * k4 + (r5 * 23143187.0) * k5 -
+                    (r6 * 29972135.0) * k6 + (r7 * 7414447.0) * k7);
+        p[3] = h * ((r1 * 31403016.0) * ko - (r3 * 15701508.0) * k3 + (r4 * 31403016.0) * k4 - (r5 * 3489224.0) * k5 +
+                    (r6 * 7076736.0) * k6 - (r7 * 829305.0) * k7);
+        p[4] = h * ko;
+        p[5] = h * k7;
+    }
+    VAG_HD double dense_poly_eval(const double* p, double th) const {
+        const double thm1 = th - 1.0;
+        const double thsq = th * th;
+        const double A = thsq * (3.0 - 2.0 * th);
+        const double B = thsq * thm1;
+        const double C = thsq * thm1 * thm1;
+        const double D = th * thm1 * thm1;
+        return p[0] + A * p[1] + C * (p[2] + p[3] * th) + D * p[4] + B * p[5];
+    }
+    VAG_HD double dense_component(const double* w, int i) const {
+        return 1.0 * K(S_XO, i) + w[0] * K(S_K1, i) + w[1] * K(S_K3, i) + w[2] * K(S_K4, i) + w[3] * K(S_K5, i) +
+               w[4] * K(S_K6, i) + w[5] * K(S_K7, i);
+    }
+    // Dense output at time tq inside the last accepted step [t_old, t] (before advance()).
+    VAG_HD void calc_state(double tq, double* out) const {
+        double w[6];
+        dense_weights(tq, w);
+#pragma unroll
+        for (int i = 0; i < N; ++i) out[i] = dense_component(w, i);
+    }
+};
+
 }  // namespace vag

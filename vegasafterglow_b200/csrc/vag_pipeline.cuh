@@ -153,7 +153,8 @@ VAG_HD RawRow raw_row(const BatchWs& w, long long off) {
 }
 
 // K1: sequential part of one row -- time lattice + dopri5 integration, raw node states only
-VAG_HD void k1_dynamics_body(const BatchWs& w, int row) {
+constexpr int K1_COL_DOUBLES = Dopri5S<FREqn::N>::kDoublesPerThread;  // stage-vector column of one row
+VAG_HD void k1_dynamics_body(const BatchWs& w, int row, double* col, int col_stride) {
     const int mi = w.row_model[row];
     const int r = w.row_rep[row];
     const GridHeader& h = w.hdr[mi];
@@ -172,9 +173,9 @@ VAG_HD void k1_dynamics_body(const BatchWs& w, int row) {
     RowDyn rd;
     if (cfg.has_rvs) {
         const ShockRow sr = shock_row(w.rvs, off);
-        st |= solve_pair_row(cfg, theta, t_dec, t_row, h.n_t, sf, sr, raw, rd);
+        st |= solve_pair_row(cfg, theta, t_dec, t_row, h.n_t, sf, sr, raw, rd, col, col_stride);
     } else {
-        st |= solve_fwd_row(cfg, theta, t_dec, t_row, h.n_t, sf, raw, rd);
+        st |= solve_fwd_row(cfg, theta, t_dec, t_row, h.n_t, sf, raw, rd, col, col_stride);
     }
     w.row_dyn[row] = rd;
     w.inj_idx[row] = rd.injection_idx;

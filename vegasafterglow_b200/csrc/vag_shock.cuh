@@ -10,6 +10,7 @@
 
 #include "vag_dopri5.cuh"
 #include "vag_grid.cuh"
+#include "vag_math.cuh"
 #include "vag_model.cuh"
 
 namespace vag {
@@ -63,6 +64,14 @@ VAG_HD double compute_downstr_4vel(double gamma_rel, double sigma) {
     return sqrt(vmax(uds, 0.0));
 }
 
+// sigma = 0 branch of compute_downstr_4vel with the adiabatic index supplied by the caller
+VAG_HD double compute_downstr_4vel_cold(double gamma_rel, double ad_idx) {
+    const double gamma_m_1 = gamma_rel - 1;
+    const double ad_idx_m_2 = ad_idx - 2;
+    const double ad_idx_m_1 = ad_idx - 1;
+    return sqrt(vmax(gamma_m_1 * ad_idx_m_1 * ad_idx_m_1 / (-ad_idx * ad_idx_m_2 * gamma_m_1 + 2), 0.0));
+}
+
 // shock-physics.h:40-66
 VAG_HD double compute_upstr_4vel(double u_down, double gamma_rel) {
     return sqrt((1 + u_down * u_down) * vmax((gamma_rel - 1) * (gamma_rel + 1), 0.0)) + u_down * gamma_rel;
@@ -75,9 +84,19 @@ VAG_HD double compute_4vel_jump(double gamma_rel, double sigma_upstr) {
     return ratio_u;
 }
 // shock-physics.h:75-78
-VAG_HD double compute_sound_speed(double Gamma_rel) {
-    const double ad_idx = adiabatic_idx(Gamma_rel);
+VAG_HD double compute_sound_speed_ad(double Gamma_rel, double ad_idx) {
     return sqrt(vmax(ad_idx * (ad_idx - 1) * (Gamma_rel - 1) / (1 + (Gamma_rel - 1) * ad_idx), 0.0)) * con::c;
+}
+VAG_HD double compute_sound_speed(double Gamma_rel) { return compute_sound_speed_ad(Gamma_rel, adiabatic_idx(Gamma_rel)); }
+// compute_4vel_jump with the adiabatic index of gamma_rel supplied by the caller
+VAG_HD double compute_downstr_4vel(double gamma_rel, double sigma);
+VAG_HD double compute_4vel_jump_ad(double gamma_rel, double sigma_upstr, double ad_idx) {
+    const double u_down_s =
+        (sigma_upstr <= con::sigma_cut) ? compute_downstr_4vel_cold(gamma_rel, ad_idx) : compute_downstr_4vel(gamma_rel, sigma_upstr);
+    const double u_up_s = sqrt((1 + u_down_s * u_down_s) * vmax((gamma_rel - 1) * (gamma_rel + 1), 0.0)) + u_down_s * gamma_rel;
+    double ratio_u = u_up_s / u_down_s;
+    if (u_down_s == 0.) ratio_u = 4 * gamma_rel;
+    return ratio_u;
 }
 // shock-physics.h:88-102
 VAG_HD double compute_effective_Gamma(double adx, double Gamma) { return (adx * Gamma * Gamma - adx + 1) / Gamma; }
@@ -108,7 +127,7 @@ VAG_HD double radiative_efficiency(const RadCfg& rad, double t_comv, double Gamm
     const double gamma_bar = rad.gamma_c_coeff / (e_th * t_comv);
     const double gamma_c = 0.5 * (gamma_bar + sqrt(gamma_bar * gamma_bar + 4));
     const double ratio = gamma_m / gamma_c;
-    if (ratio < 1 && rad.p > 2) return rad.eps_e_rad * fast_pow(ratio, rad.p - 2);
+    if (ratio < 1 && rad.p > 2) return rad.eps_e_rad * dexp2((rad.p - 2) * dlog2(ratio));  // fast_pow
     return rad.eps_e_rad;
 }
 // shock-physics.h:300-312
@@ -288,7 +307,7 @@ struct RowDyn {
 // iteration (identical sequence of attempts, step sizes and accepted states): in a warp of 32 rows a
 // rejected attempt of one row then costs the other rows nothing.
 VAG_HD int solve_fwd_row(const ModelCfg& m, double theta, double t_dec, const double* t, int n_t, const ShockRow& s,
-                         const RawRow& raw, RowDyn& rd) {
+                         const RawRow& raw, RowDyn& rd, double* col, int col_stride) {
     FwdEqn eqn(m, theta);
     double x[FwdEqn::N];
     const double t0 = vmin(t[0], vmin(0.1 * unit::sec, 0.1 * t_dec));
@@ -300,11 +319,11 @@ VAG_HD int solve_fwd_row(const ModelCfg& m, double theta, double t_dec, const do
         rd.n_saved = -1;
         return 0;
     }
-    Dopri5<FwdEqn::N> st;
-    st.initialize(x, t0, 0.01 * t0, m.rtol);
+    Dopri5S<FwdEqn::N> st;
+    st.initialize(col, col_stride, x, t0, 0.01 * t0, m.rtol);
     const double t_back = t[n_t - 1];
     int k = 0, status = 0, fails = 0, steps = 0;
-    st.begin_step(eqn);
+    st.begin(eqn);
     while (st.t <= t_back) {
         if (!st.try_step(eqn)) {
             if (++fails >= 500) {
@@ -324,7 +343,7 @@ VAG_HD int solve_fwd_row(const ModelCfg& m, double theta, double t_dec, const do
             for (int c = 0; c < FwdEqn::N; ++c) raw.c[c][k] = x[c];
             ++k;
         }
-        st.t_old = st.t;  // dense_output_runge_kutta::do_step: the next step starts here
+        st.advance();  // dense_output_runge_kutta::do_step: the next step starts here
     }
     rd.n_saved = k;
     return status;
@@ -433,9 +452,16 @@ struct FREqn {
         d[iE4] = deps4;
         d[iM4] = dm4;
 
+        // quantities several rate terms of the reference recompute: evaluated once here (same
+        // expressions, so the values are identical)
         const double Gamma34 = compute_rel_Gamma(Gamma4, Gamma);
+        const double ad2 = adiabatic_idx(Gamma);
+        const double ad34 = adiabatic_idx(Gamma34);
+        const double cs34 = compute_sound_speed_ad(Gamma34, ad34);
+        const double cs34_dtc = cs34 * dtc;
+        const double dlnv_r = 2 * dr / r;  // compute_adiabatic_cooling_rate2: 2 drdt / r
         const double sigma = shell_sigma(eps4, m4);
-        const double comp_ratio = compute_4vel_jump(Gamma34, sigma);
+        const double comp_ratio = compute_4vel_jump_ad(Gamma34, sigma, ad34);
 
         const double f = injection_efficiency(dm4);
         // compute_dx4_dt :205-213
@@ -447,22 +473,25 @@ struct FREqn {
         d[iX4] = dx4;
 
         // compute_dx3_dt :124-179
+        const double remaining = vmax(m4 - m3, 0.0);
         double dx3;
         {
-            const double sound_expansion = compute_sound_speed(Gamma34) * dtc;
+            const double sound_expansion = cs34_dtc;
             dx3 = sound_expansion;
             if (!(m4 <= 0)) {
-                const double remaining = vmax(m4 - m3, 0.0);
-                const double crossing_w = f + (1.0 - f) * remaining / m4;
+                // (1 - f) * remaining / m4 with remaining = 0 after the crossing: 0 / m4 = 0 exactly;
+                // skipping the division keeps the hardware off its zero-dividend slow path
+                const double w_num = (1.0 - f) * remaining;
+                const double crossing_w = f + ((w_num == 0) ? 0.0 : w_num / m4);
                 if (!(crossing_w < 1e-6)) {
                     const double penetration = Gamma * comp_ratio / Gamma4 - 1;
                     if (!(penetration <= 0)) {
-                        const double beta3 = gamma_to_beta(Gamma);
+                        const double beta3 = u3 / Gamma;  // gamma_to_beta(Gamma)
                         const double dx3dt = (Gamma4 - Gamma) * (Gamma4 + Gamma) * (1 + beta3) * con::c /
                                              (Gamma4 * Gamma4 * (beta3 + beta4) * penetration);
                         double crossing = fabs(dx3dt * Gamma);
                         if (penetration < 1) {
-                            const double cs = compute_sound_speed(Gamma34);
+                            const double cs = cs34;
                             const double va2 = sigma / (1 + sigma);
                             const double cs2 = cs * cs / (con::c * con::c);
                             const double v_ms = sqrt(va2 + cs2 * (1 - va2)) * con::c;
@@ -480,7 +509,6 @@ struct FREqn {
         {
             dm3 = 0.;
             if (!(m4 <= 0)) {
-                const double remaining = vmax(m4 - m3, 0.0);
                 if (!(remaining <= 0 && f < 1e-6)) {
                     const double eff_mass = f * m4 + (1.0 - f) * remaining;
                     const double column_den3 = eff_mass * comp_ratio / x4;
@@ -503,17 +531,19 @@ struct FREqn {
         {
             const double e_th = (Gamma - 1) * 4 * Gamma * rho * con::c2;
             const double eps_rad = radiative_efficiency(m.fwd, t_comv, Gamma, e_th);
-            const double ad_idx = adiabatic_idx(Gamma);
             const double shock_heating = dm2 * (Gamma - 1) * con::c2;
-            const double adiabatic_cooling = compute_adiabatic_cooling_rate2(ad_idx, r, x4, U2, dr, dx4);
+            double dlnvdt = dlnv_r;
+            if (x4 > 0) dlnvdt += dx4 / x4;
+            const double adiabatic_cooling = -(ad2 - 1) * dlnvdt * U2;
             dU2 = (1 - eps_rad) * shock_heating + adiabatic_cooling;
         }
         d[iU2] = dU2;
         // compute_dU3_dt :112-122
         double dU3;
         {
-            const double ad_idx = adiabatic_idx(Gamma34);
-            const double adiabatic_cooling = compute_adiabatic_cooling_rate2(ad_idx, r, x3, U3, dr, dx3);
+            double dlnvdt = dlnv_r;
+            if (x3 > 0) dlnvdt += dx3 / x3;
+            const double adiabatic_cooling = -(ad34 - 1) * dlnvdt * U3;
             const double shock_heating = dm3 * (Gamma34 - 1) * con::c2;
             dU3 = shock_heating + adiabatic_cooling;
         }
@@ -521,12 +551,10 @@ struct FREqn {
 
         // compute_dGamma_dt :62-94
         {
-            const double ad_idx2 = adiabatic_idx(Gamma);
-            const double ad_idx3 = adiabatic_idx(Gamma34);
-            const double Gamma_eff2 = compute_effective_Gamma(ad_idx2, Gamma);
-            const double Gamma_eff3 = compute_effective_Gamma(ad_idx3, Gamma);
-            const double dGamma_eff2 = compute_effective_Gamma_dGamma(ad_idx2, Gamma);
-            const double dGamma_eff3 = compute_effective_Gamma_dGamma(ad_idx3, Gamma);
+            const double Gamma_eff2 = compute_effective_Gamma(ad2, Gamma);
+            const double Gamma_eff3 = compute_effective_Gamma(ad34, Gamma);
+            const double dGamma_eff2 = compute_effective_Gamma_dGamma(ad2, Gamma);
+            const double dGamma_eff3 = compute_effective_Gamma_dGamma(ad34, Gamma);
             const double deps_dt = 0;
             const double a = (Gamma - 1) * con::c2 * dm2 + (Gamma - Gamma4) * con::c2 * dm3 + Gamma_eff2 * dU2 +
                              Gamma_eff3 * dU3 - deps_dt;
@@ -643,7 +671,7 @@ VAG_HD void extrap_cell(const ShockRow& s, int idx_cut, int k) {
 // grid_solve_shock_pair: reverse-shock.tpp:511-591, one dopri5 attempt per loop iteration (see
 // solve_fwd_row).  Leaves raw node states + the RowDyn record; finish_pair_cell completes the tables.
 VAG_HD int solve_pair_row(const ModelCfg& m, double theta, double t_dec, const double* t, int n_t, const ShockRow& sf,
-                          const ShockRow& sr, const RawRow& raw, RowDyn& rd) {
+                          const ShockRow& sr, const RawRow& raw, RowDyn& rd, double* col, int col_stride) {
     FREqn eqn(m, theta);
     double x[FREqn::N];
     const double t0 = vmin(t[0], vmin(0.01 * unit::sec, 0.1 * t_dec));
@@ -662,8 +690,8 @@ VAG_HD int solve_pair_row(const ModelCfg& m, double theta, double t_dec, const d
     double rtol = m.rtol;
     if (eqn.shell_sigma(x[FREqn::iE4], x[FREqn::iM4]) > 0) rtol *= dflt::magnetized_rtol_factor;
 
-    Dopri5<FREqn::N> st;
-    st.initialize(x, t0, 1e-9 * t0, rtol);
+    Dopri5S<FREqn::N> st;
+    st.initialize(col, col_stride, x, t0, 1e-9 * t0, rtol);
 
     int k = 0;
     for (; k < n_t && t[k] < t0; k++) {
@@ -678,7 +706,7 @@ VAG_HD int solve_pair_row(const ModelCfg& m, double theta, double t_dec, const d
     double t_step_start = t0;
     const double t_back = t[n_t - 1];
     int status = 0, fails = 0, steps = 0;
-    st.begin_step(eqn);
+    st.begin(eqn);
     while (st.t <= t_back) {
         if (!st.try_step(eqn)) {
             if (++fails >= 500) {
@@ -700,13 +728,13 @@ VAG_HD int solve_pair_row(const ModelCfg& m, double theta, double t_dec, const d
             // locate_crossing_time: reverse-shock.tpp:482-495.  crossing_complete reads only m3 and m4
             // of the dense output, so the bisection interpolates just those two components.
             double t_lo = t_step_start, t_hi = st.t;
-            double wd[6];
+            double p3[6], p4[6];
+            st.dense_poly(FREqn::iM3, p3);
+            st.dense_poly(FREqn::iM4, p4);
             for (int iter = 0; iter < 100 && (t_hi - t_lo) > 1e-12 * t_hi; ++iter) {
                 const double t_mid = 0.5 * (t_lo + t_hi);
-                st.dense_weights(t_mid, wd);
-                const double m3 = st.template dense_component<FREqn::iM3>(wd);
-                const double m4 = st.template dense_component<FREqn::iM4>(wd);
-                if (eqn.crossing_complete_m(m3, m4, t_mid)) {
+                const double th = st.dense_theta(t_mid);
+                if (eqn.crossing_complete_m(st.dense_poly_eval(p3, th), st.dense_poly_eval(p4, th), t_mid)) {
                     t_hi = t_mid;
                 } else {
                     t_lo = t_mid;
@@ -732,7 +760,7 @@ VAG_HD int solve_pair_row(const ModelCfg& m, double theta, double t_dec, const d
             for (int c = 0; c < FREqn::N; ++c) raw.c[c][k] = x[c];
             ++k;
         }
-        st.t_old = st.t;
+        st.advance();
     }
     rd.n_saved = k;
     rd.injection_idx = injection_idx;
