@@ -30,9 +30,19 @@ struct HostBatch {
 
 void caps_for(const vag_params* p, size_t n, int& cap_theta, int& cap_phi);
 
+const double* softplus_table() {
+    static std::vector<double> lut;
+    if (lut.empty()) {
+        lut.resize(SPL_DOUBLES);
+        build_softplus_lut(lut.data());
+    }
+    return lut.data();
+}
+
 void run_front(HostBatch& hb, const vag_params* params, size_t n, double t_min, double t_max) {
     BatchWs& w = hb.w;
     w.n_models = (int)n;
+    w.sp_lut = softplus_table();
     caps_for(params, n, w.cap_theta, w.cap_phi);
     w.work_per_model = grid_work_doubles(w.cap_theta, w.cap_phi);
     w.params = params;
@@ -238,6 +248,18 @@ int run_flux(const vag_params* params, size_t n, const double* t, size_t n_t, co
 }  // namespace
 
 extern "C" {
+
+// max |log2_softplus_lut - log2(1 + 2^x)| over n points of [-20, 20] (reference in long double)
+double vagemu_softplus_lut_maxerr(int n) {
+    const double* lut = softplus_table();
+    double worst = 0;
+    for (int i = 0; i <= n; ++i) {
+        const double x = -20.0 + 40.0 * (double)i / n;
+        const long double ref = log2l(1.0L + exp2l((long double)x));
+        worst = std::max(worst, (double)fabsl((long double)log2_softplus_lut(lut, x) - ref));
+    }
+    return worst;
+}
 
 int vagemu_flux_density_grid(const vag_params* params, size_t n, const double* t, size_t n_t, const double* nu,
                              size_t n_nu, double* out, int32_t* status) {

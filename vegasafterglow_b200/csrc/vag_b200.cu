@@ -281,7 +281,7 @@ __global__ void k_band_reduce(const double* __restrict__ F, const double* __rest
 // spectrum); MODE 2: SSC component (per-cell tables).  blockIdx.z = shock (0 forward, 1 reverse).
 template <int MODE>
 __global__ void __launch_bounds__(128, 6) k_eats(BatchWs w, EatsRequest rq0, double* __restrict__ out, int n_split,
-                                                 int row_chunk, int max_n_t, int nu_tile) {
+                                                 int row_chunk, int max_n_t, int nu_tile, int smem_doubles) {
     extern __shared__ double smem[];
     const int mi = blockIdx.x;
     const int split = blockIdx.y;
@@ -295,6 +295,12 @@ __global__ void __launch_bounds__(128, 6) k_eats(BatchWs w, EatsRequest rq0, dou
     if (w.status[mi] & VAG_ST_CAPACITY) return;
     EatsModel M = make_eats_model(w, mi, which);
     M.breach = &w.status[mi];
+    {
+        // log2_softplus table -> shared memory (tail of the dynamic allocation)
+        double* lut = smem + smem_doubles - SPL_DOUBLES;
+        for (int a = threadIdx.x; a < SPL_DOUBLES; a += blockDim.x) lut[a] = w.sp_lut[a];
+        M.sp_lut = lut;
+    }
     const int n_t = M.h->n_t;
     const int erows = M.h->n_theta * M.h->n_phi_eff;
     const bool series = rq0.series != 0;
@@ -428,7 +434,7 @@ struct DevBuf {
 struct vag_context {
     int device = 0;
     cudaStream_t stream = nullptr;
-    DevBuf model_buf, row_buf, cell_buf, obs_buf, io_params, io_t, io_nu, io_out, io_status, io_aux, ic_buf, lut_buf;
+    DevBuf model_buf, row_buf, cell_buf, obs_buf, io_params, io_t, io_nu, io_out, io_status, io_aux, ic_buf, lut_buf, sp_buf;
     int* h_totals = nullptr;        // pinned
     long long* h_cells = nullptr;   // pinned
     int cap_theta = 384, cap_phi = 128;
@@ -484,6 +490,7 @@ int setup_models(vag_context* ctx, BatchWs& w, const vag_params* d_params, size_
     w.cap_phi = ctx->cap_phi;
     w.work_per_model = grid_work_doubles(w.cap_theta, w.cap_phi);
     w.params = d_params;
+    w.sp_lut = static_cast<const double*>(ctx->sp_buf.p);
     size_t bytes = carve_sz<ModelCfg>(n) + carve_sz<GridHeader>(n) + carve_sz<double>(n * w.cap_theta) * 2 +
                    carve_sz<double>(n * w.cap_phi) + carve_sz<double>(n * w.work_per_model) +
                    carve_sz<int>(n * w.cap_theta) * 2 + carve_sz<int>(n + 1) + carve_sz<long long>(n + 1) +
@@ -652,7 +659,8 @@ int run_flux(vag_context* ctx, const vag_params* d_params, size_t n, const Reque
         int row_chunk = EATS_ROW_CHUNK;
         const int nu_tile = rq_in.series ? 1 : (int)std::min<size_t>(EATS_NU_TILE, n_nu);
         auto smem_bytes = [&](int rc_) {
-            return sizeof(double) * (nu_tile * EATS_T_BLOCK + eats_shared_doubles(max_n_t, rq_in.series, rc_, nu_tile));
+            return sizeof(double) *
+                   (nu_tile * EATS_T_BLOCK + eats_shared_doubles(max_n_t, rq_in.series, rc_, nu_tile) + SPL_DOUBLES);
         };
         while (row_chunk > 1 && smem_bytes(row_chunk) > budget) --row_chunk;
         if (smem_bytes(row_chunk) > budget)
@@ -675,11 +683,11 @@ int run_flux(vag_context* ctx, const vag_params* d_params, size_t n, const Reque
         rq.lg2_nu_obs = lg2_nu;
         rq.t_obs_lin = t_lin;
         const dim3 eg((unsigned)n, (unsigned)n_split, 2);
-        k_eats<0><<<eg, 128, sb, s>>>(w, rq, d_out, n_split, row_chunk, max_n_t, nu_tile);
+        k_eats<0><<<eg, 128, sb, s>>>(w, rq, d_out, n_split, row_chunk, max_n_t, nu_tile, (int)(sb / 8));
         ctx->launches++;
         if (w.any_ssc) {
-            k_eats<1><<<eg, 128, sb, s>>>(w, rq, d_out, n_split, row_chunk, max_n_t, nu_tile);
-            k_eats<2><<<eg, 128, sb, s>>>(w, rq, d_out, n_split, row_chunk, max_n_t, nu_tile);
+            k_eats<1><<<eg, 128, sb, s>>>(w, rq, d_out, n_split, row_chunk, max_n_t, nu_tile, (int)(sb / 8));
+            k_eats<2><<<eg, 128, sb, s>>>(w, rq, d_out, n_split, row_chunk, max_n_t, nu_tile, (int)(sb / 8));
             ctx->launches += 2;
         }
     }
@@ -818,6 +826,12 @@ int vag_create(int device, vag_context** out) {
     CK(cudaMallocHost(&c->h_totals, sizeof(int) * TOT_N));
     CK(cudaMallocHost(&c->h_cells, sizeof(long long)));
     for (auto& ev : c->ev) CK(cudaEventCreate(&ev));
+    {
+        std::vector<double> lut(SPL_DOUBLES);
+        build_softplus_lut(lut.data());
+        CK(c->sp_buf.ensure(sizeof(double) * SPL_DOUBLES));
+        CK(cudaMemcpy(c->sp_buf.p, lut.data(), sizeof(double) * SPL_DOUBLES, cudaMemcpyHostToDevice));
+    }
     // k_grid spills its scratch to local memory: prefer L1.  k_dynamics keeps its dopri5 stage vectors
     // in shared memory (23 KB per 32-row CTA): give it the full carve-out so several CTAs share an SM.
     cudaFuncSetCacheConfig(k_grid, cudaFuncCachePreferL1);
@@ -831,7 +845,7 @@ void vag_destroy(vag_context* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->model_buf, &c->row_buf, &c->cell_buf, &c->obs_buf, &c->io_params, &c->io_t, &c->io_nu,
-                      &c->io_out, &c->io_status, &c->io_aux, &c->ic_buf, &c->lut_buf})
+                      &c->io_out, &c->io_status, &c->io_aux, &c->ic_buf, &c->lut_buf, &c->sp_buf})
         b->release();
     if (c->h_totals) cudaFreeHost(c->h_totals);
     if (c->h_cells) cudaFreeHost(c->h_cells);

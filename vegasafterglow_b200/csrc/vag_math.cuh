@@ -105,4 +105,74 @@ VAG_HD double dlog2(double x) {
     return fma(s, q, (double)e);
 }
 
+// ---------------------------------------------------------------------------------------------
+// log2(1 + 2^x) on [-20, 20] as a table of local polynomials (the EATS hot loop evaluates this
+// function four times per spectrum point; computing it as log2(1 + exp2(x)) costs two polynomial
+// evaluations, a division and the exponent bookkeeping of both).
+// 81 rows centred at x_i = -20 + i/2, degree 8 in u = 2 (x - x_i) in [-1/2, 1/2]; the function is
+// analytic with its nearest singularities at x = +-i pi/ln 2 (|Im| = 4.53), so the Chebyshev
+// interpolant converges like 36^-n: truncation < 2e-14 absolute (tests/test_host_logic.py checks it).
+// The table is generated on the host in long double (build_softplus_lut) and staged in shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int SPL_ROWS = 81;
+constexpr int SPL_DEG = 8;
+constexpr int SPL_STRIDE = 10;  // doubles per row (80 B: rows stay 16-byte aligned)
+constexpr int SPL_DOUBLES = SPL_ROWS * SPL_STRIDE;
+
+inline void build_softplus_lut(double* lut) {
+    constexpr int n = SPL_DEG + 1;
+    const long double pi = 3.141592653589793238462643383279502884L;
+    for (int row = 0; row < SPL_ROWS; ++row) {
+        const long double xc = -20.0L + 0.5L * row;
+        long double f[n], cheb[n];
+        for (int k = 0; k < n; ++k) {
+            const long double tk = cosl(pi * (k + 0.5L) / n);  // node on [-1, 1]; x = xc + tk / 4
+            f[k] = log2l(1.0L + exp2l(xc + 0.25L * tk));
+        }
+        for (int j = 0; j < n; ++j) {
+            long double acc = 0;
+            for (int k = 0; k < n; ++k) acc += f[k] * cosl(pi * j * (k + 0.5L) / n);
+            cheb[j] = acc * 2.0L / n;
+        }
+        cheb[0] *= 0.5L;
+        // Chebyshev series -> monomials in t (T_0 = 1, T_1 = t, T_{j+1} = 2 t T_j - T_{j-1})
+        long double mono[n] = {0}, Tprev[n] = {0}, Tcur[n] = {0}, Tnext[n];
+        Tprev[0] = 1;
+        Tcur[1] = 1;
+        mono[0] += cheb[0];
+        for (int q = 0; q < n; ++q) mono[q] += cheb[1] * Tcur[q];
+        for (int j = 2; j < n; ++j) {
+            for (int q = 0; q < n; ++q) Tnext[q] = (q > 0 ? 2 * Tcur[q - 1] : 0) - Tprev[q];
+            for (int q = 0; q < n; ++q) {
+                mono[q] += cheb[j] * Tnext[q];
+                Tprev[q] = Tcur[q];
+                Tcur[q] = Tnext[q];
+            }
+        }
+        // t = 2 u  (u = 2 (x - xc) in [-1/2, 1/2])
+        long double scale = 1;
+        for (int q = 0; q < n; ++q) {
+            lut[row * SPL_STRIDE + q] = (double)(mono[q] * scale);
+            scale *= 2;
+        }
+        lut[row * SPL_STRIDE + n] = 0;
+    }
+}
+
+// src/util/fast-math.h:179-185 (log2_softplus) through the table
+VAG_HD double log2_softplus_lut(const double* __restrict__ lut, double x) {
+    if (x > 20.0) return x;
+    if (x < -20.0) return 0.0;
+    const double y = fma(x, 2.0, 40.0);  // [0, 80]
+    const double magic = 6755399441055744.0;
+    const double t = y + magic;
+    const int row = (int)(uint32_t)(double_to_bits(t) & 0xFFFFFFFFull);  // round-to-nearest integer of y
+    const double u = y - (t - magic);                                     // [-1/2, 1/2]
+    const double* c = lut + row * SPL_STRIDE;
+    double p = c[SPL_DEG];
+#pragma unroll
+    for (int j = SPL_DEG - 1; j >= 0; --j) p = fma(p, u, c[j]);
+    return p;
+}
+
 }  // namespace vag

@@ -44,6 +44,7 @@ struct EatsModel {
     const IcTable* ictab_h;   // [n_reps][n_t]
     const double* ictab;      // [n_reps][n_t][IC_CAP_OUT]
     int* breach;              // model status word: gets VAG_ST_IC_BAND when an SSC query leaves the clamped band
+    const double* sp_lut;     // log2_softplus table (vag_math.cuh), in shared memory on the device
 };
 
 // compute_dphi: src/core/observer.cpp:17-37
@@ -122,7 +123,8 @@ VAG_HD double cell_log2_I_nu(const EatsModel& M, int rep, int n_t, int k, double
     if (MODE == 1)
         return photon_log2_I_nu_ic([&](int c) { return base[c * stride]; }, M.smooth_thick, M.log2_x_far, M.ic[cell],
                                    log2_nu);
-    return photon_log2_I_nu([&](int c) { return base[c * stride]; }, M.smooth_thick, M.log2_x_far, log2_nu);
+    const SynCoefRegs cr = load_syn_coefs([&](int c) { return base[c * stride]; });
+    return photon_log2_I_nu_fast(cr, M.sp_lut, M.smooth_thick, M.log2_x_far, log2_nu);
 }
 
 // Interval lookup on a row's log2 observer-time lattice.
@@ -255,9 +257,20 @@ VAG_HD void eats_phase1(const EatsModel& M, const EatsRequest& rq, const EatsSha
                               (k == 0 || node_time(M, g, n_t, k - 1) <= w_hi);
             double* bv = sh.bv + (size_t)it * sh.nu_tile;
             if (need) {
-                for (int l = 0; l < nl; ++l) {
-                    const double lg2_nu_src = rq.lg2_nu_obs[l0 + l] + lg2_1pz;
-                    bv[l] = cell_log2_I_nu<MODE>(M, g.rep, n_t, k, lg2_nu_src - ld) + lg;
+                if (MODE == 0) {
+                    // the cell's coefficients are read once and serve every frequency of the tile
+                    const double* base = M.coef + ((long)g.rep * n_t + k);
+                    const long stride = M.coef_stride;
+                    const SynCoefRegs cr = load_syn_coefs([&](int c) { return base[c * stride]; });
+                    for (int l = 0; l < nl; ++l) {
+                        const double lg2_nu_src = rq.lg2_nu_obs[l0 + l] + lg2_1pz;
+                        bv[l] = photon_log2_I_nu_fast(cr, M.sp_lut, M.smooth_thick, M.log2_x_far, lg2_nu_src - ld) + lg;
+                    }
+                } else {
+                    for (int l = 0; l < nl; ++l) {
+                        const double lg2_nu_src = rq.lg2_nu_obs[l0 + l] + lg2_1pz;
+                        bv[l] = cell_log2_I_nu<MODE>(M, g.rep, n_t, k, lg2_nu_src - ld) + lg;
+                    }
                 }
             }
         }

@@ -66,6 +66,7 @@ struct BatchWs {
     const KnLut* lut;
     double* ic_scratch;       // [n_ic_warps][IC_SCRATCH_DOUBLES]
     const double* nu_range;   // [2] log2 of min / max observation frequency (code units)
+    const double* sp_lut;     // [SPL_DOUBLES] log2_softplus table (vag_math.cuh)
 };
 
 // ---- K0 ---------------------------------------------------------------------------------------
@@ -351,6 +352,7 @@ VAG_HD EatsModel make_eats_model(const BatchWs& w, int mi, int which) {
     M.ictab_h = (w.any_ssc && rad.ssc) ? w.ictab_h[shock] + off : nullptr;
     M.ictab = (w.any_ssc && rad.ssc) ? w.ictab[shock] + (size_t)off * IC_CAP_OUT : nullptr;
     M.breach = nullptr;
+    M.sp_lut = w.sp_lut;
     M.one_plus_z = 1 + cfg.z;
     M.lumi_dist = cfg.lumi_dist;
     M.theta_v = cfg.theta_v;

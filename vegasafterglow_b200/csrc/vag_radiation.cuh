@@ -275,6 +275,51 @@ VAG_HD double photon_log2_I_nu(const Get& get, double smooth_thick, double log2_
     return spec - con::log2e * get(PH_INV_NU_M_MAX) * rexp2(log2_nu);
 }
 
+// The same spectrum for the EATS hot loop: coefficients already in registers (`c`, indexed by PhCoef),
+// log2_softplus through the shared-memory table, divisions by cell constants as multiplications by
+// their reciprocals (<= 1 ulp per term against photon_log2_I_nu).
+struct SynCoefRegs {
+    double log2_I_max, log2_nu_m, log2_nu_M, inv_nu_M, inv_smooth_lo, log2_thick_norm, s_a, log2_nu_lo, log2_nu_hi,
+        smooth_hi, diff_lo, diff_hi;
+    double inv_smooth_hi, inv_s_a;
+};
+template <class Get>
+VAG_HD SynCoefRegs load_syn_coefs(const Get& get) {
+    SynCoefRegs r;
+    r.log2_I_max = get(PH_LOG2_I_MAX);
+    r.log2_nu_m = get(PH_LOG2_NU_M);
+    r.log2_nu_M = get(PH_LOG2_NU_M_MAX);
+    r.inv_nu_M = get(PH_INV_NU_M_MAX);
+    r.inv_smooth_lo = get(PH_LOG2_NORM);
+    r.log2_thick_norm = get(PH_LOG2_THICK_NORM);
+    r.s_a = get(PH_S_A_BLEND);
+    r.log2_nu_lo = get(PH_LOG2_NU_LO);
+    r.log2_nu_hi = get(PH_LOG2_NU_HI);
+    r.smooth_hi = get(PH_SMOOTH_HI);
+    r.diff_lo = get(PH_DIFF_LO);
+    r.diff_hi = get(PH_DIFF_HI);
+    r.inv_smooth_hi = 1.0 / r.smooth_hi;
+    r.inv_s_a = 1.0 / r.s_a;
+    return r;
+}
+VAG_HD double photon_log2_I_nu_fast(const SynCoefRegs& c, const double* __restrict__ sp_lut, double smooth_thick,
+                                    double log2_x_far, double log2_nu) {
+    const double dlo = log2_nu - c.log2_nu_lo;
+    const double thin = dlo * (1.0 / 3.0) - log2_softplus_lut(sp_lut, c.diff_lo * dlo) * c.inv_smooth_lo -
+                        log2_softplus_lut(sp_lut, c.diff_hi * (log2_nu - c.log2_nu_hi)) * c.inv_smooth_hi;
+    const double log2_x = log2_nu - c.log2_nu_m;
+    double thick = 2.5 * log2_x;
+    if (!(log2_x > log2_x_far)) {
+        const double s = -smooth_thick * rexp2((2. / 3) * log2_x);
+        thick += log2_softplus_lut(sp_lut, -0.5 * log2_x + s);
+    }
+    const double b = thick + c.log2_thick_norm;
+    const double smooth = thin - log2_softplus_lut(sp_lut, c.s_a * (thin - b)) * c.inv_s_a;
+    const double spec = c.log2_I_max + (c.inv_smooth_lo + smooth);
+    if (log2_nu - c.log2_nu_M < -20) return spec;
+    return spec - con::log2e * c.inv_nu_M * rexp2(log2_nu);
+}
+
 // One cell of K2: shock state -> photon coefficients.  For relic cells (k >= injection_idx,
 // synchrotron.h:187-201) the injection-time cell k_inj-1 is re-derived from its shock state
 // instead of being read from a neighbour's output, so every cell is independent.
