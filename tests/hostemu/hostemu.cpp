@@ -170,6 +170,9 @@ void eats_emulate(const BatchWs& w, int mi, int which, const EatsRequest& rq0, d
     std::vector<double> smem(eats_shared_doubles(n_t, series, EATS_ROW_CHUNK, nu_tile) + 8);
     std::vector<double> acc(EATS_NU_TILE * EATS_T_BLOCK);
     EatsShared sh = eats_carve(smem.data(), n_t, series, EATS_ROW_CHUNK, nu_tile);
+    std::vector<RowGeom> rowg(erows);
+    for (int q = 0; q < erows; ++q) rowg[q] = row_geometry(M, q / h.n_theta, q % h.n_theta);
+    const int rows_per_pass = eats_rows_per_pass(n_t, EATS_ROW_CHUNK, NTHR);
     EatsRequest rq = rq0;
     const int n_nu_tiles = series ? 1 : (rq.n_nu + nu_tile - 1) / nu_tile;
     for (int tile = 0; tile < n_nu_tiles; ++tile) {
@@ -179,9 +182,9 @@ void eats_emulate(const BatchWs& w, int mi, int which, const EatsRequest& rq0, d
             rq.i0 = i0;
             rq.ni = std::min(EATS_T_BLOCK, rq.n_t_obs - i0);
             std::fill(acc.begin(), acc.end(), 0.0);
-            for (int q0 = 0; q0 < erows; q0 += EATS_ROW_CHUNK) {
-                const int nrows = std::min(EATS_ROW_CHUNK, erows - q0);
-                for (int tid = 0; tid < NTHR; ++tid) eats_phase0(M, sh, q0, nrows, tid, NTHR);
+            for (int q0 = 0; q0 < erows; q0 += rows_per_pass) {
+                const int nrows = std::min(rows_per_pass, erows - q0);
+                sh.rowg = rowg.data() + q0;
                 for (int tid = 0; tid < NTHR; ++tid) {
                     if (M.mode == 0) eats_phase1<0>(M, rq, sh, nrows, l0, nl, tid, NTHR);
                     if (M.mode == 1) eats_phase1<1>(M, rq, sh, nrows, l0, nl, tid, NTHR);

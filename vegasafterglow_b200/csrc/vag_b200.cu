@@ -206,6 +206,16 @@ __global__ void k_nu_range(const double* __restrict__ lg2_nu, int n, double* out
     }
 }
 
+// EATS row constants of every (model, (phi,theta) row): cos to the line of sight, time coefficient,
+// log2 solid angle, representative shock row
+__global__ void k_rowgeom(BatchWs w) {
+    const int mi = blockIdx.y;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w.status[mi] & VAG_ST_CAPACITY) return;
+    if (q >= w.hdr[mi].n_theta * w.hdr[mi].n_phi_eff) return;
+    k_rowgeom_body(w, mi, q);
+}
+
 __global__ void k_rowcos(BatchWs w) {
     const int mi = blockIdx.y;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -281,8 +291,8 @@ __global__ void k_band_reduce(const double* __restrict__ F, const double* __rest
 // spectrum); MODE 2: SSC component (per-cell tables).  blockIdx.z = shock (0 forward, 1 reverse).
 template <int MODE>
 __global__ void __launch_bounds__(128, 6) k_eats(BatchWs w, EatsRequest rq0, double* __restrict__ out, int n_split,
-                                                 int row_chunk, int max_n_t, int nu_tile, int smem_doubles) {
-    extern __shared__ double smem[];
+                                                 int row_chunk, int max_n_t, int nu_tile) {
+    extern __shared__ __align__(16) double smem[];
     const int mi = blockIdx.x;
     const int split = blockIdx.y;
     const int which = (int)blockIdx.z + (MODE == 2 ? 2 : 0);  // 0 fwd sync, 1 rvs sync, 2 fwd ssc, 3 rvs ssc
@@ -296,22 +306,24 @@ __global__ void __launch_bounds__(128, 6) k_eats(BatchWs w, EatsRequest rq0, dou
     EatsModel M = make_eats_model(w, mi, which);
     M.breach = &w.status[mi];
     {
-        // log2_softplus table -> shared memory (tail of the dynamic allocation)
-        double* lut = smem + smem_doubles - SPL_DOUBLES;
-        for (int a = threadIdx.x; a < SPL_DOUBLES; a += blockDim.x) lut[a] = w.sp_lut[a];
-        M.sp_lut = lut;
+        // log2_softplus table -> head of the dynamic shared memory (16-byte aligned rows)
+        for (int a = threadIdx.x; a < SPL_DOUBLES; a += blockDim.x) smem[a] = w.sp_lut[a];
+        M.sp_lut = smem;
     }
     const int n_t = M.h->n_t;
     const int erows = M.h->n_theta * M.h->n_phi_eff;
     const bool series = rq0.series != 0;
-    double* acc = smem;  // [nu_tile][EATS_T_BLOCK]
-    const EatsShared sh = eats_carve(smem + nu_tile * EATS_T_BLOCK, max_n_t, series, row_chunk, nu_tile);
+    double* acc = smem + SPL_DOUBLES;  // [nu_tile][EATS_T_BLOCK]
+    EatsShared sh = eats_carve(acc + nu_tile * EATS_T_BLOCK, max_n_t, series, row_chunk, nu_tile);
     EatsRequest rq = rq0;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int comp = which == 0 ? VAG_C_FWD_SYNC : which == 1 ? VAG_C_RVS_SYNC : which == 2 ? VAG_C_FWD_SSC : VAG_C_RVS_SSC;
     const size_t comp_sz = series ? (size_t)rq.n_t_obs : (size_t)rq.n_nu * rq.n_t_obs;
     double* dst = out + ((size_t)mi * VAG_NCOMP + comp) * comp_sz;
     const int n_nu_tiles = series ? 1 : (rq.n_nu + nu_tile - 1) / nu_tile;
+    const RowGeom* rowg = w.rowgeom + (size_t)mi * w.max_erows;
+    // rows per pass: this model's lattice may be shorter than the batch maximum the buffers are sized for
+    const int rpp = eats_rows_per_pass(n_t, row_chunk, nthr);
     for (int tile = 0; tile < n_nu_tiles; ++tile) {
         const int l0 = tile * nu_tile;
         const int nl = series ? 1 : imin(nu_tile, rq.n_nu - l0);
@@ -319,11 +331,10 @@ __global__ void __launch_bounds__(128, 6) k_eats(BatchWs w, EatsRequest rq0, dou
             rq.i0 = i0;
             rq.ni = imin(EATS_T_BLOCK, rq.n_t_obs - i0);
             for (int a = tid; a < nu_tile * EATS_T_BLOCK; a += nthr) acc[a] = 0.0;
-            for (int q0 = split * row_chunk; q0 < erows; q0 += n_split * row_chunk) {
-                const int nrows = imin(row_chunk, erows - q0);
-                __syncthreads();  // previous pass finished reading the staged rows
-                eats_phase0(M, sh, q0, nrows, tid, nthr);
-                __syncthreads();
+            for (int q0 = split * rpp; q0 < erows; q0 += n_split * rpp) {
+                const int nrows = imin(rpp, erows - q0);
+                sh.rowg = rowg + q0;
+                __syncthreads();  // previous pass finished reading the staged rows (and the table is loaded)
                 eats_phase1<MODE>(M, rq, sh, nrows, l0, nl, tid, nthr);
                 __syncthreads();
                 if (series)
@@ -434,7 +445,7 @@ struct DevBuf {
 struct vag_context {
     int device = 0;
     cudaStream_t stream = nullptr;
-    DevBuf model_buf, row_buf, cell_buf, obs_buf, io_params, io_t, io_nu, io_out, io_status, io_aux, ic_buf, lut_buf, sp_buf;
+    DevBuf model_buf, row_buf, cell_buf, obs_buf, io_params, io_t, io_nu, io_out, io_status, io_aux, ic_buf, lut_buf, sp_buf, geom_buf;
     int* h_totals = nullptr;        // pinned
     long long* h_cells = nullptr;   // pinned
     int cap_theta = 384, cap_phi = 128;
@@ -583,6 +594,8 @@ int run_front(vag_context* ctx, BatchWs& w, const vag_params* d_params, size_t n
     if (rc) return rc;
     w.max_n_t = std::max(ctx->h_totals[TOT_MAX_NT], 1);
     w.max_erows = std::max(ctx->h_totals[TOT_MAX_EROWS], 1);
+    CK(ctx->geom_buf.ensure(sizeof(RowGeom) * n * (size_t)w.max_erows));
+    w.rowgeom = static_cast<RowGeom*>(ctx->geom_buf.p);
     w.any_ssc = ctx->h_totals[TOT_ANY_SSC];
     if (w.any_ssc) {
         const int n_ic_warps = (int)std::min<long long>(std::max<long long>(cells, 1), (long long)ctx->sm_count * 16);
@@ -591,6 +604,8 @@ int run_front(vag_context* ctx, BatchWs& w, const vag_params* d_params, size_t n
     }
     if (rows > 0) {
         k_rowmap<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(w);
+        k_rowgeom<<<dim3((unsigned)((w.max_erows + 127) / 128), (unsigned)n), 128, 0, s>>>(w);
+        ctx->launches++;
         mark(ctx, 1, s);
         {
             // rows per warp: up to one warp per scheduler before warps are filled up
@@ -683,11 +698,11 @@ int run_flux(vag_context* ctx, const vag_params* d_params, size_t n, const Reque
         rq.lg2_nu_obs = lg2_nu;
         rq.t_obs_lin = t_lin;
         const dim3 eg((unsigned)n, (unsigned)n_split, 2);
-        k_eats<0><<<eg, 128, sb, s>>>(w, rq, d_out, n_split, row_chunk, max_n_t, nu_tile, (int)(sb / 8));
+        k_eats<0><<<eg, 128, sb, s>>>(w, rq, d_out, n_split, row_chunk, max_n_t, nu_tile);
         ctx->launches++;
         if (w.any_ssc) {
-            k_eats<1><<<eg, 128, sb, s>>>(w, rq, d_out, n_split, row_chunk, max_n_t, nu_tile, (int)(sb / 8));
-            k_eats<2><<<eg, 128, sb, s>>>(w, rq, d_out, n_split, row_chunk, max_n_t, nu_tile, (int)(sb / 8));
+            k_eats<1><<<eg, 128, sb, s>>>(w, rq, d_out, n_split, row_chunk, max_n_t, nu_tile);
+            k_eats<2><<<eg, 128, sb, s>>>(w, rq, d_out, n_split, row_chunk, max_n_t, nu_tile);
             ctx->launches += 2;
         }
     }
@@ -845,7 +860,7 @@ void vag_destroy(vag_context* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->model_buf, &c->row_buf, &c->cell_buf, &c->obs_buf, &c->io_params, &c->io_t, &c->io_nu,
-                      &c->io_out, &c->io_status, &c->io_aux, &c->ic_buf, &c->lut_buf, &c->sp_buf})
+                      &c->io_out, &c->io_status, &c->io_aux, &c->ic_buf, &c->lut_buf, &c->sp_buf, &c->geom_buf})
         b->release();
     if (c->h_totals) cudaFreeHost(c->h_totals);
     if (c->h_cells) cudaFreeHost(c->h_cells);

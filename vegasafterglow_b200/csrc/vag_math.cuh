@@ -6,7 +6,7 @@
 // issued instructions were such moves).  These versions keep the coefficients in __constant__
 // memory (uniform LDCU.128 loads, two coefficients per instruction), use MUFU.RCP64H + Newton for
 // the one division, and fall back to libdevice outside the fast domain.  Accuracy: <= 1 ulp-ish
-// (exp2: |rel| <= 1.2e-16, log2: |abs| <= 2e-16 + 1.2e-16*|result|), far inside the 1e-6 flux bar.
+// (exp2: |rel| <= 4.5e-16, log2: |abs| <= 2e-16 + 1.2e-16*|result|), far inside the 1e-6 flux bar.
 // Host builds (tests/hostemu) run the same polynomials.
 #pragma once
 
@@ -18,11 +18,13 @@
 
 namespace vag {
 
-// 2^f on [-0.5, 0.5], degree 12 (Chebyshev-node interpolation, scripts/gen_poly.py: 1.1e-17)
+// 2^f on [-0.5, 0.5], degree 10 (Chebyshev-node interpolation, scripts/gen_poly.py: 4.5e-16 with the
+// FP64 Horner evaluation included)
+#define VAG_EXP2_DEG 10
 #define VAG_EXP2_COEF                                                                                          \
-    0x1.0000000000000p+0, 0x1.62e42fefa39efp-1, 0x1.ebfbdff82c58ep-3, 0x1.c6b08d704a0d8p-5, 0x1.3b2ab6fba4eefp-7, \
-        0x1.5d87fe78a143fp-10, 0x1.430912f84f63dp-13, 0x1.ffcbfc78c6f84p-17, 0x1.62c022a64fb88p-20,             \
-        0x1.b524d76e5be40p-24, 0x1.e4cdbf4adcdb1p-28, 0x1.ea0792028e4c7p-32, 0x1.c65f2ac7d2156p-36
+    0x1.0000000000000p+0, 0x1.62e42fefa3a19p-1, 0x1.ebfbdff82c598p-3, 0x1.c6b08d703ce4ap-5, 0x1.3b2ab6fba1e2ep-7, \
+        0x1.5d87fe9d7a2a0p-10, 0x1.430913095b844p-13, 0x1.ffcb5406b78d0p-17, 0x1.62bfd4af386b2p-20,             \
+        0x1.b675bc23e8f7dp-24, 0x1.e605db52afdbfp-28
 // log2(m) = s * sum_n c_n s^(2n), s = (m-1)/(m+1), c_n = 2 / (ln2 (2n+1)), n = 0..10
 #define VAG_LOG2_COEF                                                                                          \
     2.8853900817779268147, 0.96179669392597560491, 0.57707801635558536295, 0.41219858311113240211,            \
@@ -30,10 +32,10 @@ namespace vag {
         0.16972882833987804793, 0.15186263588304878025, 0.13739952770371080070
 
 #if defined(__CUDACC__)
-__constant__ double c_exp2[13] = {VAG_EXP2_COEF};
+__constant__ double c_exp2[VAG_EXP2_DEG + 1] = {VAG_EXP2_COEF};
 __constant__ double c_log2[11] = {VAG_LOG2_COEF};
 #endif
-static const double h_exp2[13] = {VAG_EXP2_COEF};
+static const double h_exp2[VAG_EXP2_DEG + 1] = {VAG_EXP2_COEF};
 static const double h_log2[11] = {VAG_LOG2_COEF};
 
 #if defined(__CUDA_ARCH__)
@@ -71,9 +73,9 @@ VAG_HD double dexp2(double x) {
     const double kf = t - magic;
     const double f = x - kf;  // [-0.5, 0.5]
     const int64_t k = (int64_t)(double_to_bits(t) & 0xFFFFFFFFull) | ((double_to_bits(t) & 0x80000000ull) ? ~0xFFFFFFFFll : 0);
-    double p = VAG_CEXP2[12];
+    double p = VAG_CEXP2[VAG_EXP2_DEG];
 #pragma unroll
-    for (int j = 11; j >= 0; --j) p = fma(p, f, VAG_CEXP2[j]);
+    for (int j = VAG_EXP2_DEG - 1; j >= 0; --j) p = fma(p, f, VAG_CEXP2[j]);
     return bits_to_double(double_to_bits(p) + ((uint64_t)k << 52));
 }
 
@@ -109,14 +111,15 @@ VAG_HD double dlog2(double x) {
 // log2(1 + 2^x) on [-20, 20] as a table of local polynomials (the EATS hot loop evaluates this
 // function four times per spectrum point; computing it as log2(1 + exp2(x)) costs two polynomial
 // evaluations, a division and the exponent bookkeeping of both).
-// 81 rows centred at x_i = -20 + i/2, degree 8 in u = 2 (x - x_i) in [-1/2, 1/2]; the function is
+// 81 rows centred at x_i = -20 + i/2, degree 7 in u = 2 (x - x_i) in [-1/2, 1/2]; the function is
 // analytic with its nearest singularities at x = +-i pi/ln 2 (|Im| = 4.53), so the Chebyshev
-// interpolant converges like 36^-n: truncation < 2e-14 absolute (tests/test_host_logic.py checks it).
+// interpolant converges like 36^-n: truncation < 5e-13 absolute (tests/test_host_logic.py checks it).
+// A row is 8 doubles = 64 B, read as four 16-byte shared-memory loads.
 // The table is generated on the host in long double (build_softplus_lut) and staged in shared memory.
 // ---------------------------------------------------------------------------------------------
 constexpr int SPL_ROWS = 81;
-constexpr int SPL_DEG = 8;
-constexpr int SPL_STRIDE = 10;  // doubles per row (80 B: rows stay 16-byte aligned)
+constexpr int SPL_DEG = 7;
+constexpr int SPL_STRIDE = 8;  // doubles per row
 constexpr int SPL_DOUBLES = SPL_ROWS * SPL_STRIDE;
 
 inline void build_softplus_lut(double* lut) {
@@ -155,7 +158,6 @@ inline void build_softplus_lut(double* lut) {
             lut[row * SPL_STRIDE + q] = (double)(mono[q] * scale);
             scale *= 2;
         }
-        lut[row * SPL_STRIDE + n] = 0;
     }
 }
 
@@ -168,10 +170,21 @@ VAG_HD double log2_softplus_lut(const double* __restrict__ lut, double x) {
     const double t = y + magic;
     const int row = (int)(uint32_t)(double_to_bits(t) & 0xFFFFFFFFull);  // round-to-nearest integer of y
     const double u = y - (t - magic);                                     // [-1/2, 1/2]
+#if defined(__CUDA_ARCH__)
+    const double2* c2 = reinterpret_cast<const double2*>(lut) + row * (SPL_STRIDE / 2);
+    const double2 c01 = c2[0], c23 = c2[1], c45 = c2[2], c67 = c2[3];
+    double p = fma(c67.y, u, c67.x);
+    p = fma(p, u, c45.y);
+    p = fma(p, u, c45.x);
+    p = fma(p, u, c23.y);
+    p = fma(p, u, c23.x);
+    p = fma(p, u, c01.y);
+    p = fma(p, u, c01.x);
+#else
     const double* c = lut + row * SPL_STRIDE;
     double p = c[SPL_DEG];
-#pragma unroll
     for (int j = SPL_DEG - 1; j >= 0; --j) p = fma(p, u, c[j]);
+#endif
     return p;
 }
 

@@ -169,14 +169,13 @@ VAG_HD double interp_contrib(double lo, double hi, double t_lo, double t_hi, dou
 
 // ---------------------------------------------------------------------------------------------
 // CTA work description.  Shared memory layout (doubles):
-//   rowg   [ROW_CHUNK] RowGeom
 //   lg2t   [ROW_CHUNK][n_t]
 //   lg2dop [ROW_CHUNK][n_t]          (series mode only)
 //   lg2geo [ROW_CHUNK][n_t]          (series mode only)
 //   bv     [ROW_CHUNK][n_t][nu_tile] (grid mode only)
 // ---------------------------------------------------------------------------------------------
 struct EatsShared {
-    RowGeom* rowg;
+    const RowGeom* rowg;  // row constants of the current chunk (global memory, written by k_rowgeom)
     double* lg2t;
     double* lg2dop;
     double* lg2geo;
@@ -197,8 +196,7 @@ constexpr int EATS_T_BLOCK = 256;   // observation points accumulated per pass
 
 // row_chunk <= EATS_ROW_CHUNK rows are staged per pass (the host lowers it when n_t is large)
 VAG_HD size_t eats_shared_doubles(int n_t, bool series, int row_chunk, int nu_tile) {
-    size_t n = (sizeof(RowGeom) * EATS_ROW_CHUNK + 7) / 8;
-    n += (size_t)row_chunk * n_t;
+    size_t n = (size_t)row_chunk * n_t;
     if (series)
         n += 2 * (size_t)row_chunk * n_t;
     else
@@ -209,8 +207,8 @@ VAG_HD size_t eats_shared_doubles(int n_t, bool series, int row_chunk, int nu_ti
 VAG_HD EatsShared eats_carve(double* base, int n_t, bool series, int row_chunk, int nu_tile) {
     EatsShared s;
     s.nu_tile = nu_tile;
-    s.rowg = reinterpret_cast<RowGeom*>(base);
-    double* p = base + (sizeof(RowGeom) * EATS_ROW_CHUNK + 7) / 8;
+    s.rowg = nullptr;
+    double* p = base;
     s.lg2t = p;
     p += (size_t)row_chunk * n_t;
     if (series) {
@@ -225,13 +223,20 @@ VAG_HD EatsShared eats_carve(double* base, int n_t, bool series, int row_chunk, 
     return s;
 }
 
-// phase 0: row constants of the chunk [q0, q0+nrows)
-VAG_HD void eats_phase0(const EatsModel& M, const EatsShared& sh, int q0, int nrows, int tid, int nthr) {
-    const int n_theta = M.h->n_theta;
-    for (int r = tid; r < nrows; r += nthr) {
-        const int q = q0 + r;
-        sh.rowg[r] = row_geometry(M, q / n_theta, q % n_theta);
+// Rows staged per pass for a lattice of n_t nodes: the count <= row_chunk that wastes the fewest
+// thread slots of the last phase-1 round (thread <-> (row, node), nthr threads)
+VAG_HD int eats_rows_per_pass(int n_t, int row_chunk, int nthr) {
+    int best = row_chunk;
+    double best_fill = 0;
+    for (int r = row_chunk; r >= 1 && 2 * r > row_chunk; --r) {
+        const int items = r * n_t;
+        const double fill = (double)items / (double)(((items + nthr - 1) / nthr) * nthr);
+        if (fill > best_fill + 1e-9) {
+            best_fill = fill;
+            best = r;
+        }
     }
+    return best;
 }
 
 // phase 1: node logs (+ boundary luminosities for the frequency tile [l0, l0+nl) in grid mode)
@@ -285,6 +290,7 @@ VAG_HD void eats_phase2_grid(const EatsModel& M, const EatsRequest& rq, const Ea
     for (int ii = tid; ii < rq.ni; ii += nthr) {
         const double x = rq.lg2_t_obs[rq.i0 + ii];
         double sum[EATS_NU_TILE];
+#pragma unroll
         for (int l = 0; l < EATS_NU_TILE; ++l) sum[l] = 0;
         for (int r = 0; r < nrows; ++r) {
             const double* t_row = sh.lg2t + (size_t)r * n_t;
@@ -293,9 +299,13 @@ VAG_HD void eats_phase2_grid(const EatsModel& M, const EatsRequest& rq, const Ea
             const double* b_lo = sh.bv + ((size_t)r * n_t + k) * sh.nu_tile;
             const double* b_hi = b_lo + sh.nu_tile;
             const double inv_dt = 1.0 / (t_row[k + 1] - t_row[k]), dx = x - t_row[k];
-            for (int l = 0; l < nl; ++l) sum[l] += interp_contrib2(b_lo[l], b_hi[l], inv_dt, dx);
+#pragma unroll
+            for (int l = 0; l < EATS_NU_TILE; ++l)
+                if (l < nl) sum[l] += interp_contrib2(b_lo[l], b_hi[l], inv_dt, dx);
         }
-        for (int l = 0; l < nl; ++l) acc[l * EATS_T_BLOCK + ii] += sum[l];
+#pragma unroll
+        for (int l = 0; l < EATS_NU_TILE; ++l)
+            if (l < nl) acc[l * EATS_T_BLOCK + ii] += sum[l];
     }
 }
 

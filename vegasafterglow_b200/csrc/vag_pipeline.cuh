@@ -67,6 +67,7 @@ struct BatchWs {
     double* ic_scratch;       // [n_ic_warps][IC_SCRATCH_DOUBLES]
     const double* nu_range;   // [2] log2 of min / max observation frequency (code units)
     const double* sp_lut;     // [SPL_DOUBLES] log2_softplus table (vag_math.cuh)
+    RowGeom* rowgeom;         // [n_models][max_erows] EATS row constants (k_rowgeom)
 };
 
 // ---- K0 ---------------------------------------------------------------------------------------
@@ -281,6 +282,12 @@ VAG_HD void k_rowcos_body(const BatchWs& w, int mi, int q) {
     const EatsModel M = make_eats_model(w, mi, 0);
     const int n_theta = M.h->n_theta;
     w.rowcos[(size_t)mi * w.max_erows + q] = row_geometry(M, q / n_theta, q % n_theta).cos_v;
+}
+// row constants of calc_eat_non_spreading for row q of model mi (observer.cpp:167-192)
+VAG_HD void k_rowgeom_body(const BatchWs& w, int mi, int q) {
+    const EatsModel M = make_eats_model(w, mi, 0);
+    const int n_theta = M.h->n_theta;
+    w.rowgeom[(size_t)mi * w.max_erows + q] = row_geometry(M, q / n_theta, q % n_theta);
 }
 VAG_HD void k_dop_extrema_body(const BatchWs& w, int mi, int k) {
     const GridHeader& h = w.hdr[mi];
