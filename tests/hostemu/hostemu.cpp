@@ -84,7 +84,10 @@ void run_front(HostBatch& hb, const vag_params* params, size_t n, double t_min, 
     for (size_t i = 0; i < n; ++i) k0c_rowmap_body(w, (int)i);
     for (int r = 0; r < rows; ++r) {
         double col[K1_COL_DOUBLES];
-        k1_dynamics_body(w, r, col, 1);
+        if (w.cfg[w.row_model[r]].has_rvs)
+            k1_dynamics_body<true>(w, r, col, 1);
+        else
+            k1_dynamics_body<false>(w, r, col, 1);
         const RowCtx c = row_ctx(w, r);
         for (int k = 0; k < c.n_t; ++k) k1b_finish_cell(w, r, c, k);
         if (c.has_rvs && w.row_dyn[r].n_saved >= 0) {

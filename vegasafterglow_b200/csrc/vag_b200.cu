@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(1024) k_scan(BatchWs w) {
         const GridHeader& h = w.hdr[mi];
         const ModelCfg& cfg = w.cfg[mi];
         if (cfg.fwd.ssc || (cfg.has_rvs && cfg.rvs.ssc)) st |= (1 << 30);  // carries "any ssc" through the OR
+        st |= cfg.has_rvs ? (1 << 29) : (1 << 28);                         // "any pair rows" / "any forward-only rows"
         rows += h.n_reps;
         cells += (long long)h.n_reps * h.n_t;
         max_nt = max(max_nt, h.n_t);
@@ -113,8 +114,10 @@ __global__ void __launch_bounds__(1024) k_scan(BatchWs w) {
         w.totals[TOT_MAX_NT] = max_nt;
         w.totals[TOT_MAX_NTHETA] = max_nth;
         w.totals[TOT_MAX_EROWS] = max_er;
-        w.totals[TOT_STATUS_OR] = st & ~(1 << 30);
+        w.totals[TOT_STATUS_OR] = st & ~(7 << 28);
         w.totals[TOT_ANY_SSC] = (st >> 30) & 1;
+        w.totals[TOT_ANY_PAIR] = (st >> 29) & 1;
+        w.totals[TOT_ANY_FWD_ONLY] = (st >> 28) & 1;
     }
 }
 
@@ -129,12 +132,16 @@ __global__ void k_rowmap(BatchWs w) {
 // batch is spread thinly -- few rows per warp, about two warps per scheduler -- and only large batches
 // fill whole warps.  The dopri5 stage vectors sit in shared memory, [slot][component][lane]
 // (conflict-free: a lane only ever touches its own column).
+// PAIR selects the rows a launch integrates (forward+reverse pairs with the shared-memory stepper, or
+// forward-only rows with the register-resident one, which needs no shared memory).
+template <bool PAIR>
 __global__ void __launch_bounds__(32) k_dynamics(BatchWs w, int n_rows, int lanes) {
-    __shared__ double s_col[K1_COL_DOUBLES * 32];
+    __shared__ double s_col[PAIR ? K1_COL_DOUBLES * 32 : 1];
     if ((int)threadIdx.x >= lanes) return;
     const int row = blockIdx.x * lanes + threadIdx.x;
     if (row >= n_rows) return;
-    k1_dynamics_body(w, row, s_col + threadIdx.x, 32);
+    if ((w.cfg[w.row_model[row]].has_rvs != 0) != PAIR) return;
+    k1_dynamics_body<PAIR>(w, row, s_col + threadIdx.x, 32);
 }
 
 // K1b + K2: one CTA per unique row.  Finishes the row's shock tables from the raw node states the ODE
@@ -612,11 +619,19 @@ int run_front(vag_context* ctx, BatchWs& w, const vag_params* d_params, size_t n
             int lanes = 32;
             while (lanes > 4 && (rows + lanes / 2 - 1) / (lanes / 2) <= ctx->sm_count * 4) lanes >>= 1;
             if (const char* e = getenv("VAG_DYN_LANES")) lanes = atoi(e);  // EXPERIMENT
-            k_dynamics<<<(unsigned)((rows + lanes - 1) / lanes), 32, 0, s>>>(w, rows, lanes);
+            const unsigned nb = (unsigned)((rows + lanes - 1) / lanes);
+            if (ctx->h_totals[TOT_ANY_FWD_ONLY]) {
+                k_dynamics<false><<<nb, 32, 0, s>>>(w, rows, lanes);
+                ctx->launches++;
+            }
+            if (ctx->h_totals[TOT_ANY_PAIR]) {
+                k_dynamics<true><<<nb, 32, 0, s>>>(w, rows, lanes);
+                ctx->launches++;
+            }
         }
         mark(ctx, 2, s);
         k_radiation<<<(unsigned)rows, 64, 0, s>>>(w);
-        ctx->launches += 3;
+        ctx->launches += 2;
         if (w.any_ssc) {
             k_ic_cooling<<<dim3((unsigned)((rows + 31) / 32), 2), 32, 0, s>>>(w, rows);
             ctx->launches++;
@@ -850,7 +865,7 @@ int vag_create(int device, vag_context** out) {
     // k_grid spills its scratch to local memory: prefer L1.  k_dynamics keeps its dopri5 stage vectors
     // in shared memory (23 KB per 32-row CTA): give it the full carve-out so several CTAs share an SM.
     cudaFuncSetCacheConfig(k_grid, cudaFuncCachePreferL1);
-    cudaFuncSetAttribute(k_dynamics, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_dynamics<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     *out = c;
     return VAG_OK;
 }

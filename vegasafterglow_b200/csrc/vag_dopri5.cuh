@@ -124,7 +124,7 @@ struct Dopri5 {
             for (int i = 0; i < N; ++i) {
                 const double e = (dt * dc1) * k1[i] + (dt * dc3) * k3[i] + (dt * dc4) * k4[i] + (dt * dc5) * k5[i] +
                                  (dt * dc6) * k6[i] + (dt * dc7) * k7[i];
-                const double r = fabs(e) / (eps + eps * (1.0 * fabs(x[i]) + adt * fabs(k1[i])));
+                const double r = (e == 0) ? 0.0 : fabs(e) / (eps + eps * (1.0 * fabs(x[i]) + adt * fabs(k1[i])));
                 // boost norm_inf: max over |r| starting from 0 with std::max(init, |r|)
                 err = vmax(err, fabs(r));
             }

@@ -20,7 +20,7 @@
 
 namespace vag {
 
-enum { TOT_ROWS = 0, TOT_MAX_NT, TOT_MAX_NTHETA, TOT_MAX_EROWS, TOT_STATUS_OR, TOT_ANY_SSC, TOT_N };
+enum { TOT_ROWS = 0, TOT_MAX_NT, TOT_MAX_NTHETA, TOT_MAX_EROWS, TOT_STATUS_OR, TOT_ANY_SSC, TOT_ANY_PAIR, TOT_ANY_FWD_ONLY, TOT_N };
 
 struct BatchWs {
     int n_models;
@@ -115,6 +115,10 @@ VAG_HD void k0b_scan_body(const BatchWs& w) {
     int any = 0;
     for (int mi = 0; mi < w.n_models; ++mi) any |= (w.cfg[mi].fwd.ssc || (w.cfg[mi].has_rvs && w.cfg[mi].rvs.ssc)) ? 1 : 0;
     w.totals[TOT_ANY_SSC] = any;
+    int any_pair = 0, any_fwd = 0;
+    for (int mi = 0; mi < w.n_models; ++mi) (w.cfg[mi].has_rvs ? any_pair : any_fwd) = 1;
+    w.totals[TOT_ANY_PAIR] = any_pair;
+    w.totals[TOT_ANY_FWD_ONLY] = any_fwd;
 }
 
 // ---- K0c --------------------------------------------------------------------------------------
@@ -156,6 +160,7 @@ VAG_HD RawRow raw_row(const BatchWs& w, long long off) {
 
 // K1: sequential part of one row -- time lattice + dopri5 integration, raw node states only
 constexpr int K1_COL_DOUBLES = Dopri5S<FREqn::N>::kDoublesPerThread;  // stage-vector column of one row
+template <bool PAIR>
 VAG_HD void k1_dynamics_body(const BatchWs& w, int row, double* col, int col_stride) {
     const int mi = w.row_model[row];
     const int r = w.row_rep[row];
@@ -173,7 +178,7 @@ VAG_HD void k1_dynamics_body(const BatchWs& w, int row, double* col, int col_str
     const ShockRow sf = shock_row(w.fwd, off);
     const RawRow raw = raw_row(w, off);
     RowDyn rd;
-    if (cfg.has_rvs) {
+    if (PAIR) {
         const ShockRow sr = shock_row(w.rvs, off);
         st |= solve_pair_row(cfg, theta, t_dec, t_row, h.n_t, sf, sr, raw, rd, col, col_stride);
     } else {

@@ -319,11 +319,15 @@ VAG_HD int solve_fwd_row(const ModelCfg& m, double theta, double t_dec, const do
         rd.n_saved = -1;
         return 0;
     }
-    Dopri5S<FwdEqn::N> st;
-    st.initialize(col, col_stride, x, t0, 0.01 * t0, m.rtol);
+    // five state variables: the register-resident stepper fits without spills (the 11-variable pair
+    // system uses the shared-memory one)
+    (void)col;
+    (void)col_stride;
+    Dopri5<FwdEqn::N> st;
+    st.initialize(x, t0, 0.01 * t0, m.rtol);
     const double t_back = t[n_t - 1];
     int k = 0, status = 0, fails = 0, steps = 0;
-    st.begin(eqn);
+    st.begin_step(eqn);
     while (st.t <= t_back) {
         if (!st.try_step(eqn)) {
             if (++fails >= 500) {
@@ -343,7 +347,7 @@ VAG_HD int solve_fwd_row(const ModelCfg& m, double theta, double t_dec, const do
             for (int c = 0; c < FwdEqn::N; ++c) raw.c[c][k] = x[c];
             ++k;
         }
-        st.advance();  // dense_output_runge_kutta::do_step: the next step starts here
+        st.t_old = st.t;  // dense_output_runge_kutta::do_step: the next step starts here
     }
     rd.n_saved = k;
     return status;
