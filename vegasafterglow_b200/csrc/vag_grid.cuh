@@ -48,6 +48,13 @@ struct SeqPar {
     VAG_HD void for_each(int n, F f) const {
         for (int i = 0; i < n; ++i) f(i);
     }
+    // smallest j in [begin, end) with pred(j), or end
+    template <class P>
+    VAG_HD int first_true(int begin, int end, P pred) const {
+        for (int j = begin; j < end; ++j)
+            if (pred(j)) return j;
+        return end;
+    }
 };
 #if defined(__CUDACC__)
 // one warp: index space strided over the lanes, warp barrier (with memory ordering) afterwards
@@ -58,6 +65,16 @@ struct WarpPar {
         __syncwarp();
         for (int i = lane; i < n; i += 32) f(i);
         __syncwarp();
+    }
+    // first-hit search of an order-independent predicate: 32 candidates per ballot, in index order
+    template <class P>
+    __device__ __forceinline__ int first_true(int begin, int end, P pred) const {
+        for (int j0 = begin; j0 < end; j0 += 32) {
+            const int j = j0 + lane;
+            const unsigned hits = __ballot_sync(0xffffffffu, j < end && pred(j));
+            if (hits) return j0 + __ffs(hits) - 1;
+        }
+        return end;
     }
 };
 #endif
@@ -94,31 +111,31 @@ VAG_HD int find_jet_jumps(const Par& par, const ModelCfg& m, double gamma_cut, d
         return 1;
     }
     par.for_each(n_scan, [&](int j) { G[j] = jet_Gamma0(m, j == 0 ? theta_lo : theta_lo + dtheta * (double)j); });
+    // The walk's jump test at node j reads only G[j-1] and G[j]: the candidates are found with an
+    // order-preserving parallel search, each hit is then refined exactly as the sequential walk does.
     int n = 0;
-    double prev_th = theta_lo;
-    double prev_G = G[0];
-    for (int j = 1; j < n_scan; ++j) {
+    auto is_jump = [&](int j) {
+        const double prev_G = G[j - 1], cur_G = G[j];
+        if (!(prev_G >= gamma_cut || cur_G >= gamma_cut)) return false;
+        const double dG = fabs(cur_G - prev_G);
+        const double scale = vmax(prev_G - 1, cur_G - 1);
+        return scale > 0 && dG > 0.5 * scale;
+    };
+    for (int j = par.first_true(1, n_scan, is_jump); j < n_scan; j = par.first_true(j + 1, n_scan, is_jump)) {
+        const double prev_th = (j - 1 == 0) ? theta_lo : theta_lo + dtheta * (double)(j - 1);
         const double cur_th = theta_lo + dtheta * (double)j;
-        const double cur_G = G[j];
-        if (prev_G >= gamma_cut || cur_G >= gamma_cut) {
-            const double dG = fabs(cur_G - prev_G);
-            const double scale = vmax(prev_G - 1, cur_G - 1);
-            if (scale > 0 && dG > 0.5 * scale) {
-                double lo = prev_th, hi = cur_th;
-                while (hi - lo > eps) {
-                    const double mid = 0.5 * (lo + hi);
-                    const double G_mid = jet_Gamma0(m, mid);
-                    if (fabs(G_mid - prev_G) < fabs(G_mid - cur_G)) {
-                        lo = mid;
-                    } else {
-                        hi = mid;
-                    }
-                }
-                if (n < cap) jumps[n++] = prev_G > cur_G ? lo : hi;
+        const double prev_G = G[j - 1], cur_G = G[j];
+        double lo = prev_th, hi = cur_th;
+        while (hi - lo > eps) {
+            const double mid = 0.5 * (lo + hi);
+            const double G_mid = jet_Gamma0(m, mid);
+            if (fabs(G_mid - prev_G) < fabs(G_mid - cur_G)) {
+                lo = mid;
+            } else {
+                hi = mid;
             }
         }
-        prev_th = cur_th;
-        prev_G = cur_G;
+        if (n < cap) jumps[n++] = prev_G > cur_G ? lo : hi;
     }
     return n;
 }
@@ -139,19 +156,17 @@ VAG_HD void find_theta_range(const Par& par, const ModelCfg& m, double gamma_cut
     int n = 0;
     for (double th = theta_hi; th >= theta_lo && n < GRID_NSCAN + 6; th -= step) TH[n++] = th;
     par.for_each(n, [&](int j) { G[j] = jet_Gamma0(m, TH[j]); });
-    for (int j = 0; j < n; ++j)
-        if (G[j] >= gamma_cut) {
-            theta_max = TH[j];
-            break;
-        }
+    {
+        const int j = par.first_true(0, n, [&](int q) { return G[q] >= gamma_cut; });
+        if (j < n) theta_max = TH[j];
+    }
     n = 0;
     for (double th = theta_lo; th <= theta_hi && n < GRID_NSCAN + 6; th += step) TH[n++] = th;
     par.for_each(n, [&](int j) { G[j] = jet_Gamma0(m, TH[j]); });
-    for (int j = 0; j < n; ++j)
-        if (G[j] >= gamma_cut) {
-            theta_min = TH[j];
-            break;
-        }
+    {
+        const int j = par.first_true(0, n, [&](int q) { return G[q] >= gamma_cut; });
+        if (j < n) theta_min = TH[j];
+    }
 }
 
 // ---- inverse_CFD_sampling: grid-refinement.h:137-189 -----------------------------------------
