@@ -195,6 +195,16 @@ int vag_details(vag_context* ctx, const vag_params* p, double t_min, double t_ma
                 double* theta, double* phi, int32_t* reps, double* t_rows, double* fwd_shock, double* rvs_shock,
                 int32_t* inj_idx);
 
+/* Output transfer policy of the HOST-buffer flux entry points.
+ * VAG_OUT_DENSE (default): every one of the VAG_NCOMP planes of `out` is written (absent components 0).
+ * VAG_OUT_PRESENT: planes of components that NO model of the batch has (reverse shock: has_rvs;
+ * SSC: fwd.ssc / rvs.ssc) are neither transferred nor written -- the caller's buffer is left
+ * untouched there.  This mirrors the reference's FluxDict, whose absent components are empty
+ * arrays that are never materialised (pybind/pymodel.h:361-383), and saves 3/5 of the device-to-host
+ * traffic of a forward-shock synchrotron batch.  VAG_C_TOTAL and VAG_C_FWD_SYNC are always present. */
+enum { VAG_OUT_DENSE = 0, VAG_OUT_PRESENT = 1 };
+int vag_set_output_mode(vag_context* ctx, int mode);
+
 /* per-stage device time of the most recent batched call on this context, milliseconds:
  * [0]=grid (K0) [1]=dynamics (K1) [2]=radiation (K2) [3]=EATS flux (K3) [4]=likelihood (K4)
  * Only filled when vag_set_profiling(ctx, 1) was called (adds event records + one sync). */

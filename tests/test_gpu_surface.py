@@ -131,3 +131,28 @@ def test_exposure_averaging_matches_reference_fixture(engine):
     np.testing.assert_allclose(fe.total, g["flux"][0], rtol=1e-6)
     with pytest.raises(ValueError):
         m.flux_density_exposures(g["t"], g["nu"], -g["expo"], 10)
+
+
+def test_present_only_output_mode_matches_dense():
+    """VAG_OUT_PRESENT (include/vag.h): planes of components no model of the batch has are not written,
+    every other plane equals the dense transfer bit for bit."""
+    from vegasafterglow_b200.engine import Engine
+
+    eng = Engine(0)
+    t, nu = np.logspace(2, 8, 40), np.array([1e9, 1e14, 1e17])
+    for rvs in (False, True):
+        P = configs.random_draw(8, seed=77, rvs=rvs)
+        dense = eng.flux_density_grid(P, t, nu)
+        eng.set_output_mode(True)
+        try:
+            sparse = eng.flux_density_grid(P, t, nu)
+            sd = eng.flux_density_series(P, np.sort(np.tile(t, 3)), np.tile(nu, 40))
+        finally:
+            eng.set_output_mode(False)
+        dd = eng.flux_density_series(P, np.sort(np.tile(t, 3)), np.tile(nu, 40))
+        present = [abi.COMPONENTS.index("total"), abi.COMPONENTS.index("fwd_sync")] + ([abi.COMPONENTS.index("rvs_sync")] if rvs else [])
+        for c in range(abi.NCOMP):
+            if c in present:
+                assert np.array_equal(sparse[:, c], dense[:, c]) and np.array_equal(sd[:, c], dd[:, c])
+            else:
+                assert not sparse[:, c].any() and not dense[:, c].any()

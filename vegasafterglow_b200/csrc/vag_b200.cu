@@ -457,6 +457,7 @@ struct vag_context {
     long long* h_cells = nullptr;   // pinned
     int cap_theta = 384, cap_phi = 128;
     bool profiling = false;
+    int out_mode = VAG_OUT_DENSE;
     cudaEvent_t ev[8] = {};
     float stage_ms[8] = {};
     int launches = 0;
@@ -899,6 +900,11 @@ int vag_synchronize(vag_context* ctx) {
     CK(cudaStreamSynchronize(ctx->stream));
     return VAG_OK;
 }
+int vag_set_output_mode(vag_context* ctx, int mode) {
+    if (mode != VAG_OUT_DENSE && mode != VAG_OUT_PRESENT) return fail(VAG_ERR_INVALID, "unknown output mode");
+    ctx->out_mode = mode;
+    return VAG_OK;
+}
 int vag_set_capacity(vag_context* ctx, int cap_theta, int cap_phi) {
     if (cap_theta < 40 || cap_phi < 2) return fail(VAG_ERR_INVALID, "capacity too small");
     ctx->cap_theta = cap_theta;
@@ -996,6 +1002,38 @@ static int host_prepare(vag_context* ctx, const vag_params* params, size_t n_mod
     return VAG_OK;
 }
 
+// device -> host transfer of out[n_models][VAG_NCOMP][comp_sz] under the context's output mode
+static int copy_out(vag_context* ctx, const vag_params* params, size_t n_models, size_t comp_sz, double* out,
+                    cudaStream_t s) {
+    const size_t row = sizeof(double) * comp_sz, pitch = row * VAG_NCOMP;
+    if (ctx->out_mode == VAG_OUT_DENSE) {
+        CK(cudaMemcpyAsync(out, ctx->io_out.p, pitch * n_models, cudaMemcpyDeviceToHost, s));
+        return VAG_OK;
+    }
+    bool present[VAG_NCOMP] = {true, true, false, false, false};
+    for (size_t i = 0; i < n_models; ++i) {
+        if (params[i].fwd.ssc) present[VAG_C_FWD_SSC] = true;
+        if (params[i].has_rvs) {
+            present[VAG_C_RVS_SYNC] = true;
+            if (params[i].rvs.ssc) present[VAG_C_RVS_SSC] = true;
+        }
+    }
+    const char* src = static_cast<const char*>(ctx->io_out.p);
+    char* dst = reinterpret_cast<char*>(out);
+    for (int c = 0; c < VAG_NCOMP;) {
+        if (!present[c]) {
+            ++c;
+            continue;
+        }
+        int c1 = c;
+        while (c1 + 1 < VAG_NCOMP && present[c1 + 1]) ++c1;  // adjacent present planes travel together
+        CK(cudaMemcpy2DAsync(dst + row * c, pitch, src + row * c, pitch, row * (c1 - c + 1), n_models,
+                             cudaMemcpyDeviceToHost, s));
+        c = c1 + 1;
+    }
+    return VAG_OK;
+}
+
 int vag_flux_density_grid(vag_context* ctx, const vag_params* params, size_t n_models, const double* t, size_t n_t,
                           const double* nu, size_t n_nu, double* out, int32_t* status) {
     if (int rc = host_prepare(ctx, params, n_models, t, n_t, nu, n_nu, false)) return rc;
@@ -1008,7 +1046,7 @@ int vag_flux_density_grid(vag_context* ctx, const vag_params* params, size_t n_m
                           static_cast<double*>(ctx->io_out.p), static_cast<int32_t*>(ctx->io_status.p), nullptr, nullptr,
                           nullptr, nullptr, s))
         return rc;
-    CK(cudaMemcpyAsync(out, ctx->io_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+    if (int rc = copy_out(ctx, params, n_models, out_bytes / (sizeof(double) * n_models * VAG_NCOMP), out, s)) return rc;
     if (status) CK(cudaMemcpyAsync(status, ctx->io_status.p, sizeof(int32_t) * n_models, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return VAG_OK;
@@ -1026,7 +1064,7 @@ int vag_flux_density_series(vag_context* ctx, const vag_params* params, size_t n
                           static_cast<double*>(ctx->io_out.p), static_cast<int32_t*>(ctx->io_status.p), nullptr, nullptr,
                           nullptr, nullptr, s))
         return rc;
-    CK(cudaMemcpyAsync(out, ctx->io_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+    if (int rc = copy_out(ctx, params, n_models, out_bytes / (sizeof(double) * n_models * VAG_NCOMP), out, s)) return rc;
     if (status) CK(cudaMemcpyAsync(status, ctx->io_status.p, sizeof(int32_t) * n_models, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return VAG_OK;

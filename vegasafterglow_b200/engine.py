@@ -46,7 +46,7 @@ class Engine:
         """Batched ``Model.flux_density_grid`` -> float64[n_models, 5, n_nu, n_t]
         (component order ``abi.COMPONENTS``)."""
         p, t, nu = self._params(params), _f64(t).reshape(-1), _f64(nu).reshape(-1)
-        out = np.empty((p.size, abi.NCOMP, nu.size, t.size))
+        out = (np.zeros if getattr(self, "_present_only", False) else np.empty)((p.size, abi.NCOMP, nu.size, t.size))
         st = np.zeros(p.size, dtype=np.int32)
         _lib.check(self._lib.vag_flux_density_grid(self._h, p.ctypes.data, p.size, t.ctypes.data, t.size,
                                                    nu.ctypes.data, nu.size, out.ctypes.data, st.ctypes.data))
@@ -58,7 +58,7 @@ class Engine:
         if t.size != nu.size:  # pybind/pymodel.cpp:376-379
             raise ValueError("time and frequency arrays must have the same size\nIf you intend to get grid-like "
                              "output, use the generic `flux_density_grid` instead")
-        out = np.empty((p.size, abi.NCOMP, t.size))
+        out = (np.zeros if getattr(self, "_present_only", False) else np.empty)((p.size, abi.NCOMP, t.size))
         st = np.zeros(p.size, dtype=np.int32)
         _lib.check(self._lib.vag_flux_density_series(self._h, p.ctypes.data, p.size, t.ctypes.data, nu.ctypes.data,
                                                      t.size, out.ctypes.data, st.ctypes.data))
@@ -128,6 +128,11 @@ class Engine:
 
     def set_capacity(self, cap_theta, cap_phi):
         _lib.check(self._lib.vag_set_capacity(self._h, int(cap_theta), int(cap_phi)))
+
+    def set_output_mode(self, present_only: bool):
+        """True: host-buffer calls skip the planes of components no model of the batch has (vag.h VAG_OUT_PRESENT)."""
+        _lib.check(self._lib.vag_set_output_mode(self._h, 1 if present_only else 0))
+        self._present_only = bool(present_only)
 
     def set_profiling(self, on=True):
         _lib.check(self._lib.vag_set_profiling(self._h, 1 if on else 0))
