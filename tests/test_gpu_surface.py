@@ -135,7 +135,8 @@ def test_exposure_averaging_matches_reference_fixture(engine):
 
 def test_present_only_output_mode_matches_dense():
     """VAG_OUT_PRESENT (include/vag.h): planes of components no model of the batch has are not written,
-    every other plane equals the dense transfer bit for bit."""
+    every other plane equals the dense transfer (to 1e-13: a batch this small splits a model's rows over
+    several CTAs that combine with atomicAdd, so two runs differ in the last bits)."""
     from vegasafterglow_b200.engine import Engine
 
     eng = Engine(0)
@@ -153,6 +154,7 @@ def test_present_only_output_mode_matches_dense():
         present = [abi.COMPONENTS.index("total"), abi.COMPONENTS.index("fwd_sync")] + ([abi.COMPONENTS.index("rvs_sync")] if rvs else [])
         for c in range(abi.NCOMP):
             if c in present:
-                assert np.array_equal(sparse[:, c], dense[:, c]) and np.array_equal(sd[:, c], dd[:, c])
+                np.testing.assert_allclose(sparse[:, c], dense[:, c], rtol=1e-13)
+                np.testing.assert_allclose(sd[:, c], dd[:, c], rtol=1e-13)
             else:
                 assert not sparse[:, c].any() and not dense[:, c].any()

@@ -94,4 +94,36 @@ VAG_HD double adiabatic_idx(double gamma) { return 4.0 / 3.0 + 1 / (3 * gamma); 
 
 VAG_HD bool vfinite(double x) { return isfinite(x); }
 
+// Branch-free FP64 division / square root for the ODE right-hand sides, where the compiler's IEEE
+// sequences (12-14 instructions each, every one ending in a range check and a branch to a slow-path
+// call) chop the dependent chain into blocks the scheduler cannot overlap.  Reciprocal / rsqrt seed
+// from the MUFU unit, two Newton steps and one residual correction: faithfully rounded (<= 1 ulp).
+// ONLY for operands known to be finite, normal and (divisor / radicand) positive -- zero radicands are
+// handled; callers keep the IEEE operators wherever a zero or infinite operand carries meaning.
+#if defined(__CUDA_ARCH__)
+VAG_HD double vdiv(double a, double b) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    r = fma(r, fma(-b, r, 1.0), r);
+    r = fma(r, fma(-b, r, 1.0), r);
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);
+}
+VAG_HD double vsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x * y, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    e = fma(-x * y, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    const double s = x * y;
+    const double root = fma(0.5 * y, fma(-s, s, x), s);
+    return (x == 0.0) ? 0.0 : root;
+}
+#else
+VAG_HD double vdiv(double a, double b) { return a / b; }
+VAG_HD double vsqrt(double x) { return sqrt(x); }
+#endif
+VAG_HD double adiabatic_idx_fast(double gamma) { return 4.0 / 3.0 + vdiv(1.0, 3 * gamma); }  // gamma >= 1
+
 }  // namespace vag

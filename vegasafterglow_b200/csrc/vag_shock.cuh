@@ -69,7 +69,8 @@ VAG_HD double compute_downstr_4vel_cold(double gamma_rel, double ad_idx) {
     const double gamma_m_1 = gamma_rel - 1;
     const double ad_idx_m_2 = ad_idx - 2;
     const double ad_idx_m_1 = ad_idx - 1;
-    return sqrt(vmax(gamma_m_1 * ad_idx_m_1 * ad_idx_m_1 / (-ad_idx * ad_idx_m_2 * gamma_m_1 + 2), 0.0));
+    // ad_idx in (4/3, 5/3]: the denominator is >= 2
+    return vsqrt(vmax(vdiv(gamma_m_1 * ad_idx_m_1 * ad_idx_m_1, -ad_idx * ad_idx_m_2 * gamma_m_1 + 2), 0.0));
 }
 
 // shock-physics.h:40-66
@@ -85,7 +86,7 @@ VAG_HD double compute_4vel_jump(double gamma_rel, double sigma_upstr) {
 }
 // shock-physics.h:75-78
 VAG_HD double compute_sound_speed_ad(double Gamma_rel, double ad_idx) {
-    return sqrt(vmax(ad_idx * (ad_idx - 1) * (Gamma_rel - 1) / (1 + (Gamma_rel - 1) * ad_idx), 0.0)) * con::c;
+    return vsqrt(vmax(vdiv(ad_idx * (ad_idx - 1) * (Gamma_rel - 1), 1 + (Gamma_rel - 1) * ad_idx), 0.0)) * con::c;
 }
 VAG_HD double compute_sound_speed(double Gamma_rel) { return compute_sound_speed_ad(Gamma_rel, adiabatic_idx(Gamma_rel)); }
 // compute_4vel_jump with the adiabatic index of gamma_rel supplied by the caller
@@ -93,26 +94,27 @@ VAG_HD double compute_downstr_4vel(double gamma_rel, double sigma);
 VAG_HD double compute_4vel_jump_ad(double gamma_rel, double sigma_upstr, double ad_idx) {
     const double u_down_s =
         (sigma_upstr <= con::sigma_cut) ? compute_downstr_4vel_cold(gamma_rel, ad_idx) : compute_downstr_4vel(gamma_rel, sigma_upstr);
-    const double u_up_s = sqrt((1 + u_down_s * u_down_s) * vmax((gamma_rel - 1) * (gamma_rel + 1), 0.0)) + u_down_s * gamma_rel;
-    double ratio_u = u_up_s / u_down_s;
+    const double u_up_s = vsqrt((1 + u_down_s * u_down_s) * vmax((gamma_rel - 1) * (gamma_rel + 1), 0.0)) + u_down_s * gamma_rel;
+    // u_down_s == 0 is overridden below (the quotient is discarded), otherwise it is positive
+    double ratio_u = vdiv(u_up_s, u_down_s);
     if (u_down_s == 0.) ratio_u = 4 * gamma_rel;
     return ratio_u;
 }
 // shock-physics.h:88-102
-VAG_HD double compute_effective_Gamma(double adx, double Gamma) { return (adx * Gamma * Gamma - adx + 1) / Gamma; }
+VAG_HD double compute_effective_Gamma(double adx, double Gamma) { return vdiv(adx * Gamma * Gamma - adx + 1, Gamma); }
 VAG_HD double compute_effective_Gamma_dGamma(double adx, double Gamma) {
     const double Gamma2 = Gamma * Gamma;
-    return (adx * Gamma2 + adx - 1) / Gamma2;
+    return vdiv(adx * Gamma2 + adx - 1, Gamma2);
 }
 // shock-physics.h:179-181
 VAG_HD double compute_upstr_B(double rho_up, double sigma) { return sqrt((4 * con::pi * con::c2) * sigma * rho_up); }
 // shock-physics.h:192-204
 VAG_HD double compute_rel_Gamma(double gamma1, double gamma2) {
-    const double u1u2 = sqrt(vmax((gamma1 - 1) * (gamma1 + 1) * (gamma2 - 1) * (gamma2 + 1), 0.0));
+    const double u1u2 = vsqrt(vmax((gamma1 - 1) * (gamma1 + 1) * (gamma2 - 1) * (gamma2 + 1), 0.0));
     const double d = gamma1 - gamma2;
     const double denom = gamma1 * gamma2 - 1 + u1u2;
     if (denom <= 0) return 1;
-    return 1 + d * d / denom;
+    return 1 + vdiv(d * d, denom);
 }
 // shock-physics.h:223-229
 VAG_HD double compute_adiabatic_cooling_rate2(double ad_idx, double r, double x, double u, double drdt, double dxdt) {
@@ -246,30 +248,31 @@ struct FwdEqn {
     VAG_HD void operator()(const double* x, double* d, double /*t*/) const {
         const double Gamma = x[iG];
         const double u2 = (Gamma - 1) * (Gamma + 1);
-        const double u = sqrt(u2);
+        const double u = sqrt(u2);  // IEEE: a stage value of Gamma below 1 must give NaN as in the reference
         d[iR] = u * (Gamma + u) * con::c;
         d[iT] = Gamma + u;
         const double rho = medium_rho(m, x[iR]);
         d[iM2] = x[iR] * x[iR] * rho * d[iR];
         const double e_th = (Gamma - 1) * 4 * Gamma * rho * con::c2;
         const double eps_rad = radiative_efficiency(m.fwd, x[iT], Gamma, e_th);
-        const double ad_idx = adiabatic_idx(Gamma);
+        const double ad_idx = adiabatic_idx_fast(Gamma);
+        const double dlnV_r = vdiv(3 * d[iR], x[iR]);  // 3 / r * dr/dt, r > 0
         // compute_dGamma_dt
         {
             const double Gamma2 = Gamma * Gamma;
-            const double Gamma_eff = (ad_idx * (Gamma2 - 1) + 1) / Gamma;
-            const double dGamma_eff = (ad_idx * (Gamma2 + 1) - 1) / Gamma2;
-            const double dlnVdt = 3 / x[iR] * d[iR];
+            const double Gamma_eff = vdiv(ad_idx * (Gamma2 - 1) + 1, Gamma);
+            const double dGamma_eff = vdiv(ad_idx * (Gamma2 + 1) - 1, Gamma2);
+            const double dlnVdt = dlnV_r;
             const double U = x[iU];
             const double a1 = -(Gamma - 1) * (Gamma_eff + 1) * con::c2 * d[iM2];
             const double a2 = (ad_idx - 1) * Gamma_eff * U * dlnVdt;
             const double b1 = (m_jet0 + x[iM2]) * con::c2;
-            const double b2 = (dGamma_eff + Gamma_eff * (ad_idx - 1) / Gamma) * U;
+            const double b2 = (dGamma_eff + vdiv(Gamma_eff * (ad_idx - 1), Gamma)) * U;
             d[iG] = (a1 + a2) / (b1 + b2);
         }
         // compute_dU_dt
         {
-            const double dlnVdt = 3 / x[iR] * d[iR] - d[iG] / Gamma;
+            const double dlnVdt = dlnV_r - vdiv(d[iG], Gamma);
             d[iU] = (1 - eps_rad) * (Gamma - 1) * con::c2 * d[iM2] - (ad_idx - 1) * dlnVdt * x[iU];
         }
     }
@@ -437,7 +440,7 @@ struct FREqn {
         const double U3 = vmax(xr[iU3], 0.0);
         const double x4 = xr[iX4], m2 = xr[iM2], U2 = xr[iU2], r = xr[iR], t_comv = xr[iT], eps4 = xr[iE4];
 
-        const double u3 = sqrt((Gamma - 1) * (Gamma + 1));
+        const double u3 = vsqrt((Gamma - 1) * (Gamma + 1));  // Gamma clamped to [1, Gamma4]
         const double dr = u3 * (Gamma + u3) * con::c;
         const double dtc = Gamma + u3;
         d[iR] = dr;
@@ -459,11 +462,11 @@ struct FREqn {
         // quantities several rate terms of the reference recompute: evaluated once here (same
         // expressions, so the values are identical)
         const double Gamma34 = compute_rel_Gamma(Gamma4, Gamma);
-        const double ad2 = adiabatic_idx(Gamma);
-        const double ad34 = adiabatic_idx(Gamma34);
+        const double ad2 = adiabatic_idx_fast(Gamma);
+        const double ad34 = adiabatic_idx_fast(Gamma34);
         const double cs34 = compute_sound_speed_ad(Gamma34, ad34);
         const double cs34_dtc = cs34 * dtc;
-        const double dlnv_r = 2 * dr / r;  // compute_adiabatic_cooling_rate2: 2 drdt / r
+        const double dlnv_r = vdiv(2 * dr, r);  // compute_adiabatic_cooling_rate2: 2 drdt / r  (r > 0)
         const double sigma = shell_sigma(eps4, m4);
         const double comp_ratio = compute_4vel_jump_ad(Gamma34, sigma, ad34);
 
@@ -483,22 +486,20 @@ struct FREqn {
             const double sound_expansion = cs34_dtc;
             dx3 = sound_expansion;
             if (!(m4 <= 0)) {
-                // (1 - f) * remaining / m4 with remaining = 0 after the crossing: 0 / m4 = 0 exactly;
-                // skipping the division keeps the hardware off its zero-dividend slow path
                 const double w_num = (1.0 - f) * remaining;
-                const double crossing_w = f + ((w_num == 0) ? 0.0 : w_num / m4);
+                const double crossing_w = f + vdiv(w_num, m4);  // m4 > 0 here
                 if (!(crossing_w < 1e-6)) {
-                    const double penetration = Gamma * comp_ratio / Gamma4 - 1;
+                    const double penetration = vdiv(Gamma * comp_ratio, Gamma4) - 1;
                     if (!(penetration <= 0)) {
-                        const double beta3 = u3 / Gamma;  // gamma_to_beta(Gamma)
-                        const double dx3dt = (Gamma4 - Gamma) * (Gamma4 + Gamma) * (1 + beta3) * con::c /
-                                             (Gamma4 * Gamma4 * (beta3 + beta4) * penetration);
+                        const double beta3 = vdiv(u3, Gamma);  // gamma_to_beta(Gamma)
+                        const double dx3dt = vdiv((Gamma4 - Gamma) * (Gamma4 + Gamma) * (1 + beta3) * con::c,
+                                                  Gamma4 * Gamma4 * (beta3 + beta4) * penetration);
                         double crossing = fabs(dx3dt * Gamma);
                         if (penetration < 1) {
                             const double cs = cs34;
-                            const double va2 = sigma / (1 + sigma);
+                            const double va2 = vdiv(sigma, 1 + sigma);  // sigma >= 0
                             const double cs2 = cs * cs / (con::c * con::c);
-                            const double v_ms = sqrt(va2 + cs2 * (1 - va2)) * con::c;
+                            const double v_ms = vsqrt(va2 + cs2 * (1 - va2)) * con::c;
                             crossing = vmin(crossing, v_ms * dtc);
                         }
                         dx3 = crossing_w * crossing + (1.0 - crossing_w) * sound_expansion;
@@ -515,10 +516,10 @@ struct FREqn {
             if (!(m4 <= 0)) {
                 if (!(remaining <= 0 && f < 1e-6)) {
                     const double eff_mass = f * m4 + (1.0 - f) * remaining;
-                    const double column_den3 = eff_mass * comp_ratio / x4;
+                    const double column_den3 = eff_mass * comp_ratio / x4;  // IEEE: x4 is an unclamped state
                     const double dm3dt = column_den3 * dx3;
                     if (f > 1e-6) {
-                        const double ratio = m3 / m4;
+                        const double ratio = vdiv(m3, m4);  // m4 > 0 here
                         const double cap_w = smoothstep(0, 1.0, ratio);
                         const double capped_rate = vmin(dm3dt, dm4);
                         dm3 = (1.0 - cap_w) * dm3dt + cap_w * capped_rate;
@@ -537,7 +538,7 @@ struct FREqn {
             const double eps_rad = radiative_efficiency(m.fwd, t_comv, Gamma, e_th);
             const double shock_heating = dm2 * (Gamma - 1) * con::c2;
             double dlnvdt = dlnv_r;
-            if (x4 > 0) dlnvdt += dx4 / x4;
+            if (x4 > 0) dlnvdt += vdiv(dx4, x4);
             const double adiabatic_cooling = -(ad2 - 1) * dlnvdt * U2;
             dU2 = (1 - eps_rad) * shock_heating + adiabatic_cooling;
         }
@@ -546,7 +547,7 @@ struct FREqn {
         double dU3;
         {
             double dlnvdt = dlnv_r;
-            if (x3 > 0) dlnvdt += dx3 / x3;
+            if (x3 > 0) dlnvdt += vdiv(dx3, x3);
             const double adiabatic_cooling = -(ad34 - 1) * dlnvdt * U3;
             const double shock_heating = dm3 * (Gamma34 - 1) * con::c2;
             dU3 = shock_heating + adiabatic_cooling;
