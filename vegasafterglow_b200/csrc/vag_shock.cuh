@@ -126,9 +126,17 @@ VAG_HD double compute_adiabatic_cooling_rate2(double ad_idx, double r, double x,
 VAG_HD double radiative_efficiency(const RadCfg& rad, double t_comv, double Gamma_th, double e_th) {
     if (rad.eps_e_rad == 0) return 0;
     const double gamma_m = rad.gamma_m_coeff * (Gamma_th - 1) + 1;
-    const double gamma_bar = rad.gamma_c_coeff / (e_th * t_comv);
-    const double gamma_c = 0.5 * (gamma_bar + sqrt(gamma_bar * gamma_bar + 4));
-    const double ratio = gamma_m / gamma_c;
+    const double den = e_th * t_comv;
+    double ratio;
+    if (den > 1e-100 && den < 1e100) {  // the ordinary case: branch-free arithmetic
+        const double gamma_bar = vdiv(rad.gamma_c_coeff, den);
+        const double gamma_c = 0.5 * (gamma_bar + vsqrt(gamma_bar * gamma_bar + 4));
+        ratio = vdiv(gamma_m, gamma_c);
+    } else {  // e_th = 0 (Gamma clamped to 1), overflow ...: IEEE semantics as in the reference
+        const double gamma_bar = rad.gamma_c_coeff / den;
+        const double gamma_c = 0.5 * (gamma_bar + sqrt(gamma_bar * gamma_bar + 4));
+        ratio = gamma_m / gamma_c;
+    }
     if (ratio < 1 && rad.p > 2) return rad.eps_e_rad * dexp2((rad.p - 2) * dlog2(ratio));  // fast_pow
     return rad.eps_e_rad;
 }
@@ -383,7 +391,7 @@ VAG_HD void finish_fwd_cell(const ModelCfg& m, const RowDyn& rd, const ShockRow&
 // state = [Gamma, x4, x3, m2, m3, U2_th, U3_th, r, t_comv, eps4, m4]
 // ---------------------------------------------------------------------------------------------
 VAG_HD double smoothstep(double edge0, double edge1, double x) {  // reverse-shock.tpp:11-20
-    double t = (x - edge0) / (edge1 - edge0);
+    double t = vdiv(x - edge0, edge1 - edge0);  // edges are distinct finite constants
     if (t < 0.0)
         t = 0.0;
     else if (t > 1.0)
@@ -416,7 +424,7 @@ struct FREqn {
     }
 
     VAG_HD double injection_efficiency(double dm4) const {  // reverse-shock.tpp:42-47
-        if (dm0_dt > 0 && dm4 > 0) return vmin(dm4 / dm0_dt, 1.0);
+        if (dm0_dt > 0 && dm4 > 0) return vmin(vdiv(dm4, dm0_dt), 1.0);
         return 0.0;
     }
     VAG_HD double shell_sigma(double eps4, double m4) const {  // reverse-shock.tpp:359-363
