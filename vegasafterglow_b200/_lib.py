@@ -8,7 +8,7 @@ import os
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvag_b200.so")
+LIB_PATH = os.environ.get("VAG_LIB_PATH") or os.path.join(_HERE, "libvag_b200.so")  # override: A/B experiments only
 _lib = None
 
 

@@ -296,8 +296,11 @@ __global__ void k_band_reduce(const double* __restrict__ F, const double* __rest
 // K3.  grid = (model, split, shock).  out[model][comp][n_nu][n_t] (grid) or [model][comp][n] (series)
 // MODE 0: synchrotron of shocks without ssc; MODE 1: synchrotron of shocks with ssc (IC-corrected
 // spectrum); MODE 2: SSC component (per-cell tables).  blockIdx.z = shock (0 forward, 1 reverse).
+#ifndef EATS_MIN_BLOCKS
+#define EATS_MIN_BLOCKS 8
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(128, 6) k_eats(BatchWs w, EatsRequest rq0, double* __restrict__ out, int n_split,
+__global__ void __launch_bounds__(128, EATS_MIN_BLOCKS) k_eats(BatchWs w, EatsRequest rq0, double* __restrict__ out, int n_split,
                                                  int row_chunk, int max_n_t, int nu_tile) {
     extern __shared__ __align__(16) double smem[];
     const int mi = blockIdx.x;
@@ -693,6 +696,8 @@ int run_flux(vag_context* ctx, const vag_params* d_params, size_t n, const Reque
             return sizeof(double) *
                    (nu_tile * EATS_T_BLOCK + eats_shared_doubles(max_n_t, rq_in.series, rc_, nu_tile) + SPL_DOUBLES);
         };
+        // fewer staged rows per pass while that buys residency: 8 CTAs / SM need <= 28 KB each
+        while (row_chunk > 4 && smem_bytes(row_chunk) > 28 * 1024) --row_chunk;
         while (row_chunk > 1 && smem_bytes(row_chunk) > budget) --row_chunk;
         if (smem_bytes(row_chunk) > budget)
             return fail(VAG_ERR_CAPACITY, "time lattice too long for the EATS shared-memory stage");
