@@ -140,7 +140,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=4096, help="parameter sets per GPU per step")
+    ap.add_argument("--batch", type=int, default=16384, help="parameter sets per GPU per step")
+    ap.add_argument("--ll-batch", type=int, default=4096, help="walkers per GPU per log-likelihood step (config 5)")
     ap.add_argument("--inflight", type=int, default=4, help="independent batches (steps) in flight per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -277,20 +278,22 @@ def main():
     h_out, h_st = slots[0].h_out, slots[0].h_st
 
     # ---- config 5: batched log-likelihood (series chi2), device-resident ---------------------------
-    Pl, ts, nus = loglike_workload(args.batch, rank)
+    Pl, ts, nus = loglike_workload(args.ll_batch, rank)
+    n_ll = Pl.size
     rng = np.random.default_rng(42)
     lnF = np.log(1e-26 * (1 + 0.05 * rng.standard_normal(ts.size)) * (ts / 1e3) ** -1.0)
     sig = np.full(ts.size, 0.1)
     wgt = np.ones(ts.size)
-    gathered = torch.empty(n * world, dtype=torch.float64, device=dev) if world > 1 else None
+    gathered = torch.empty(n_ll * world, dtype=torch.float64, device=dev) if world > 1 else None
     for sl in slots:
         sl.d_pl = torch.from_numpy(Pl.view(np.uint8).copy()).to(dev)
         sl.d_arr = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (ts, nus, lnF, sig, wgt)]
-        sl.d_chi2 = torch.empty(n, dtype=torch.float64, device=dev)
+        sl.d_chi2 = torch.empty(n_ll, dtype=torch.float64, device=dev)
+        sl.d_st_ll = torch.zeros(n_ll, dtype=torch.int32, device=dev)
 
         def step_ll(self=sl):
-            self.eng.chi2_series_dev(self.d_pl.data_ptr(), n, *[a.data_ptr() for a in self.d_arr], ts.size,
-                                     self.d_chi2.data_ptr(), self.d_st.data_ptr(), self.stream.cuda_stream)
+            self.eng.chi2_series_dev(self.d_pl.data_ptr(), n_ll, *[a.data_ptr() for a in self.d_arr], ts.size,
+                                     self.d_chi2.data_ptr(), self.d_st_ll.data_ptr(), self.stream.cuda_stream)
             if world > 1:  # the only inter-GPU traffic of the path: gather of float64[n] log-likelihoods
                 with torch.cuda.stream(self.stream):
                     dist.all_gather_into_tensor(gathered, self.d_chi2)
@@ -344,8 +347,17 @@ def main():
         bytes_eats = 23e3
         dominant = max(("grid", "dynamics", "eats"), key=lambda k: per.get(k, 0.0))
         eats_s = per["eats"] * 1e-3
+        # DRAM bytes of one k_eats launch from the committed `ncu --set full` capture (profiles/), when it was
+        # taken at this batch size
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["k_eats_fs_grid"]
+            if int(tj["batch"]) == n:
+                traffic = float(tj["dram_bytes_per_launch"])
+        except (OSError, KeyError, ValueError):
+            pass
         roofline = {"bound": "hbm", "kernel": "k_eats", "achieved": n * bytes_eats / eats_s / 1e9, "peak": hbm_peak,
-                    "unit": "GB/s", "frac": n * bytes_eats / eats_s / 1e9 / hbm_peak, "traffic": None,
+                    "unit": "GB/s", "frac": n * bytes_eats / eats_s / 1e9 / hbm_peak, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                     "note": "the path is FP64-pipe / dependent-latency bound, not HBM bound (SURVEY.md 8d): see "
                             "roofline_fp64 for the per-kernel FP64 fractions"}
@@ -366,8 +378,9 @@ def main():
             "clocks": clocks,
             "roofline": roofline,
             "roofline_fp64": roofline_fp64,
-            "loglike": {"metric": "MCMC loglike evals/s (4096-walker FS+RS tophat, 100-point 5-band series)",
-                        "value": n * world * args.steps / (ll_ms * 1e-3), "unit": UNIT, "ms_per_step": ll_ms / args.steps,
+            "loglike": {"metric": f"MCMC loglike evals/s ({n_ll}-walker batch per GPU per step, FS+RS tophat, 100-point "
+                                  f"5-band series, {S_ll} steps in flight)",
+                        "value": n_ll * world * args.steps / (ll_ms * 1e-3), "unit": UNIT, "ms_per_step": ll_ms / args.steps,
                         "collective": "all_gather float64[n] over NCCL" if world > 1 else "none (1 GPU)"},
             "wall_ms_per_step": wall_ms / args.steps,
         }
