@@ -30,7 +30,7 @@ static_assert(sizeof(vag_params) == 280, "vag_params layout must match vegasafte
 // kernels
 // ------------------------------------------------------------------------------------------------
 // K0: one warp per model (vag_grid.cuh), 4 warps per CTA
-__global__ void __launch_bounds__(128) k_grid(BatchWs w, const double* __restrict__ t_obs, int n_t_obs) {
+__global__ void __launch_bounds__(128, 4) k_grid(BatchWs w, const double* __restrict__ t_obs, int n_t_obs) {
     const int mi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (mi >= w.n_models) return;  // whole warps exit together
     const WarpPar par{(int)(threadIdx.x & 31)};
