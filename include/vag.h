@@ -95,6 +95,12 @@ typedef struct vag_params {
      * (src/config/simulation-defaults.h:71-83, pybind/pymodel.h:633-640) */
     double phi_resol, theta_resol, t_resol;
     double rtol; /* <= 0 selects defaults::solver::dynamics_rtol = 1e-6 */
+    /* magnetar=Magnetar(L0 [erg/s], t0 [s], q) of the jet factories (pybind/pymodel.h:34-58): energy injection
+     * L0 (1 + t/t0)^-q for theta <= theta_c (src/environment/jet.h:518-528).  As in the reference the jet then
+     * takes the generic-Ejecta code path (pybind/pymodel.cpp:53-59). */
+    int32_t has_magnetar;
+    int32_t pad2_;
+    double magnetar_L0, magnetar_t0, magnetar_q;
 } vag_params;
 
 /* Fill *p with the reference defaults (Tophat/ISM values are NOT set, only the switches). */

@@ -66,16 +66,22 @@ JetVariant make_ejecta(const vag_params& p) {
     if (p.sigma0 > 0) jet.sigma0 = math::isotropic(p.sigma0);
     jet.spreading = p.spreading != 0;
     jet.T0 = p.duration;
+    // initialize_ejecta (pybind/pymodel.cpp:38-45)
+    if (p.has_magnetar) jet.deps_dt = math::magnetar_injection(p.magnetar_t0, p.magnetar_q, p.magnetar_L0, tc);
     // convert_unit_jet
     const auto eps_k_cgs = jet.eps_k;
     jet.eps_k = [=](Real phi, Real theta) { return eps_k_cgs(phi, theta) * (unit::erg / (4 * con::pi)); };
+    const auto deps_dt_cgs = jet.deps_dt;
+    jet.deps_dt = [=](Real phi, Real theta, Real t) {
+        return deps_dt_cgs(phi, theta, t / unit::sec) * (unit::erg / (4 * con::pi * unit::sec));
+    };
     jet.T0 *= unit::sec;
     return jet;
 }
 
 // unit conversions exactly as the Py* factories do (pybind/pymodel.cpp:47-186, pymodel.h:190-204)
 JetVariant make_jet(const vag_params& p) {
-    if (p.jet_type >= VAG_JET_TWO_COMPONENT || p.sigma0 > 0) return make_ejecta(p);
+    if (p.jet_type >= VAG_JET_TWO_COMPONENT || p.sigma0 > 0 || p.has_magnetar) return make_ejecta(p);
     const Real T0 = p.duration * unit::sec;
     switch (p.jet_type) {
         case VAG_JET_TOPHAT:

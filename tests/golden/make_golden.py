@@ -80,6 +80,16 @@ def main():
     P4 = configs.random_draw(16, seed=35, rvs=True)
     P4["sigma0"] = 10 ** np.random.default_rng(36).uniform(-2, 1, 16)
     save("batch_rs_magnetized_tophat", P4, t, nu)
+    # magnetar energy injection (jet factories' magnetar=Magnetar(L0, t0, q); the jet takes the Ejecta path)
+    rng = np.random.default_rng(41)
+    for nm, P5 in (("batch_fs_magnetar_tophat", configs.random_draw(16, seed=37)),
+                   ("batch_rs_magnetar_tophat", configs.random_draw(12, seed=38, rvs=True)),
+                   ("batch_fs_magnetar_gauss_offaxis", configs.random_draw(8, seed=39, jet="gaussian", theta_obs_max=0.3))):
+        P5["has_magnetar"] = 1
+        P5["magnetar_L0"] = 10 ** rng.uniform(46, 49.5, P5.size)
+        P5["magnetar_t0"] = 10 ** rng.uniform(2, 4.5, P5.size)
+        P5["magnetar_q"] = rng.uniform(1.0, 3.0, P5.size)
+        save(nm, P5, t, nu)
     nu_ssc = np.array([1e9, 1e14, 1e17, 1e22, 1e25])
     save("batch_ssc_kn_tophat_ism", configs.random_draw(24, seed=21, ssc=True, kn=True), t, nu_ssc)
     save("batch_ssc_thomson_tophat_wind", configs.random_draw(12, seed=22, ssc=True, kn=False, medium="wind"), t, nu_ssc)

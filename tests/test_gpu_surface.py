@@ -158,3 +158,20 @@ def test_present_only_output_mode_matches_dense():
                 np.testing.assert_allclose(sd[:, c], dd[:, c], rtol=1e-13)
             else:
                 assert not sparse[:, c].any() and not dense[:, c].any()
+
+
+def test_magnetar_side_by_side():
+    """TophatJet(..., magnetar=Magnetar(L0, t0, q)) through both pybind11 modules (pybind/pybind.cpp:198-209)."""
+    ours, theirs = _both()
+    t, nu = np.logspace(2, 7, 40), np.array([1e9, 1e14, 1e17])
+    out = []
+    for va in (ours, theirs):
+        m = va.Model(jet=va.TophatJet(0.1, 1e52, 300, magnetar=va.Magnetar(1e48, 1e3, 2.0)), medium=va.ISM(1),
+                     observer=va.Observer(1e26, 0.1, 0), fwd_rad=va.Radiation(0.1, 1e-3, 2.3))
+        out.append(np.asarray(m.flux_density_grid(t, nu).total))
+    np.testing.assert_allclose(out[0], out[1], rtol=1e-6)
+    plain = np.asarray(_build(ours).flux_density_grid(t, nu).total)
+    assert np.max(np.abs(out[0] / plain - 1)) > 0.05  # the injection visibly re-brightens the afterglow
+    for va in (ours, theirs):
+        with pytest.raises(ValueError):
+            va.Magnetar(-1.0, 1e3, 2.0)

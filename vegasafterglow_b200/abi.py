@@ -54,6 +54,11 @@ PARAMS_DTYPE = np.dtype(
         ("theta_resol", "f8"),
         ("t_resol", "f8"),
         ("rtol", "f8"),
+        ("has_magnetar", "i4"),
+        ("pad2_", "i4"),
+        ("magnetar_L0", "f8"),
+        ("magnetar_t0", "f8"),
+        ("magnetar_q", "f8"),
     ],
     align=True,
 )

@@ -10,12 +10,15 @@ from . import abi
 def make(jet="tophat", theta_c=0.1, E_iso=1e52, Gamma0=300.0, k_e=2.0, k_g=2.0, duration=1.0, medium="ism",
          n_ism=1.0, A_star=0.1, n0=np.inf, lumi_dist=1e26, z=0.1, theta_obs=0.0, fwd=(0.1, 1e-3, 2.3), rvs=None,
          resolutions=None, rtol=0.0, radiative_fireball=True, xi_e=1.0, rvs_xi_e=1.0, ssc=False, kn=False,
-         rvs_ssc=False, rvs_kn=False, theta_w=0.3, E_iso_w=1e50, Gamma0_w=50.0, sigma0=0.0):
+         rvs_ssc=False, rvs_kn=False, theta_w=0.3, E_iso_w=1e50, Gamma0_w=50.0, sigma0=0.0, magnetar=None):
     p = abi.default_params(1)
     p["jet_type"] = {"tophat": abi.JET_TOPHAT, "gaussian": abi.JET_GAUSSIAN, "powerlaw": abi.JET_POWERLAW,
                      "two_component": abi.JET_TWO_COMPONENT, "step_powerlaw": abi.JET_STEP_POWERLAW,
                      "powerlaw_wing": abi.JET_POWERLAW_WING}[jet]
     p["theta_w"], p["E_iso_w"], p["Gamma0_w"], p["sigma0"] = theta_w, E_iso_w, Gamma0_w, sigma0
+    if magnetar is not None:  # (L0 [erg/s], t0 [s], q)
+        p["has_magnetar"] = 1
+        p["magnetar_L0"], p["magnetar_t0"], p["magnetar_q"] = magnetar
     p["theta_c"], p["E_iso"], p["Gamma0"], p["k_e"], p["k_g"], p["duration"] = theta_c, E_iso, Gamma0, k_e, k_g, duration
     if medium == "ism":
         p["medium_type"], p["n_ism"] = abi.MEDIUM_ISM, n_ism

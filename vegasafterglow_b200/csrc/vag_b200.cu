@@ -24,7 +24,7 @@
 
 using namespace vag;
 
-static_assert(sizeof(vag_params) == 280, "vag_params layout must match vegasafterglow_b200/abi.py");
+static_assert(sizeof(vag_params) == 312, "vag_params layout must match vegasafterglow_b200/abi.py");
 
 // ------------------------------------------------------------------------------------------------
 // kernels
@@ -810,6 +810,12 @@ int vag_params_validate(const vag_params* p) {
                        std::to_string(p->theta_w) + ", theta_c=" + std::to_string(p->theta_c));
     }
     if (!(std::isfinite(p->sigma0) && p->sigma0 >= 0)) return bad("sigma0 must be finite and >= 0");
+    if (p->has_magnetar) {  // PyMagnetar: pybind/pymodel.h:45-49
+        if (!finite_pos(p->magnetar_L0)) return bad("L0 must be finite and > 0");
+        if (!finite_pos(p->magnetar_t0)) return bad("t0 must be finite and > 0");
+        if (!finite_pos(p->magnetar_q)) return bad("q must be finite and > 0");
+        if (p->jet_type == VAG_JET_POWERLAW_WING) return bad("PowerLawWing takes no magnetar (pybind/pybind.cpp:220-223)");
+    }
     // PyISM / PyWind: pybind/pymodel.cpp:148-186
     if (p->medium_type == VAG_MEDIUM_ISM) {
         if (!(std::isfinite(p->n_ism) && p->n_ism >= 0)) return bad("n_ism must be finite and >= 0");

@@ -24,6 +24,8 @@ struct ModelCfg {
     int jet_type;
     double theta_c, eps_k0, Gamma0, k_e, k_g, gauss_norm, T0;
     double theta_w, E_iso, E_iso_w, Gamma0_w, sigma0;  // Ejecta-family profiles work on E_iso [erg] heights
+    int has_magnetar;
+    double mag_L, mag_t0, mag_q;  // L0 [code units / 4 pi], t0 [s], q
     // medium
     int medium_type;
     double rho_ism, wind_A, wind_r02;
@@ -66,6 +68,11 @@ VAG_HD ModelCfg make_cfg(const vag_params& p) {
     m.E_iso_w = p.E_iso_w;
     m.Gamma0_w = p.Gamma0_w;
     m.sigma0 = p.sigma0;
+    m.has_magnetar = p.has_magnetar;
+    // convert_unit_jet (pybind/pymodel.cpp:196-199): deps_dt_cgs(t / unit::sec) * (unit::erg / (4 pi unit::sec))
+    m.mag_L = p.magnetar_L0;
+    m.mag_t0 = p.magnetar_t0;
+    m.mag_q = p.magnetar_q;
     m.medium_type = p.medium_type;
     const double n_ism = p.n_ism / unit::cm3;
     m.rho_ism = n_ism * con::mp;  // medium.h:52,98
@@ -128,6 +135,18 @@ VAG_HD double jet_eps_k(const ModelCfg& m, double theta) {
             return E * (unit::erg / (4 * con::pi));
         }
     }
+}
+
+// energy injection rate per solid angle: math::magnetar_injection (jet.h:518-528) behind the unit wrapper
+// of convert_unit_jet (pybind/pymodel.cpp:196-199); t in code units
+VAG_HD double jet_deps_dt(const ModelCfg& m, double theta, double t) {
+    if (!m.has_magnetar) return 0.;
+    double cgs = 0.;
+    if (theta <= m.theta_c) {
+        const double tt = 1 + (t / unit::sec) / m.mag_t0;
+        cgs = m.mag_L * fast_pow(tt, -m.mag_q);
+    }
+    return cgs * (unit::erg / (4 * con::pi * unit::sec));
 }
 
 // ---- medium profiles (isotropic) ------------------------------------------------------------

@@ -182,7 +182,8 @@ VAG_HD void k1_dynamics_body(const BatchWs& w, int row, double* col, int col_str
         const ShockRow sr = shock_row(w.rvs, off);
         st |= solve_pair_row(cfg, theta, t_dec, t_row, h.n_t, sf, sr, raw, rd, col, col_stride);
     } else {
-        st |= solve_fwd_row(cfg, theta, t_dec, t_row, h.n_t, sf, raw, rd, col, col_stride);
+        st |= cfg.has_magnetar ? solve_fwd_row<true>(cfg, theta, t_dec, t_row, h.n_t, sf, raw, rd, col, col_stride)
+                               : solve_fwd_row<false>(cfg, theta, t_dec, t_row, h.n_t, sf, raw, rd, col, col_stride);
     }
     w.row_dyn[row] = rd;
     w.inj_idx[row] = rd.injection_idx;

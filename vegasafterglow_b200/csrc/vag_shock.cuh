@@ -242,19 +242,24 @@ VAG_HD void save_fwd_state(const ModelCfg& m, double eps_B, const ShockRow& s, i
 // ---------------------------------------------------------------------------------------------
 // forward shock: state = [Gamma, m2, U2_th, r, t_comv]
 // ---------------------------------------------------------------------------------------------
-struct FwdEqn {
+// INJ: the jet injects energy (magnetar): the reference's ForwardState then carries eps_jet, whose
+// derivative deps_dt(t) enters the step-size control (forward-shock.hpp:23-26, forward-shock.tpp:46-48,89-91)
+template <bool INJ>
+struct FwdEqnT {
     const ModelCfg& m;
-    double m_jet0;
-    enum { iG = 0, iM2 = 1, iU = 2, iR = 3, iT = 4, N = 5 };
+    double m_jet0, theta0;
+    enum { iG = 0, iM2 = 1, iU = 2, iR = 3, iT = 4, iE = 5, N = INJ ? 6 : 5 };
 
-    VAG_HD FwdEqn(const ModelCfg& m_, double theta) : m(m_) {
+    VAG_HD FwdEqnT(const ModelCfg& m_, double theta) : m(m_), theta0(theta) {
         m_jet0 = jet_eps_k(m, theta) / jet_Gamma0(m, theta) / con::c2;  // forward-shock.tpp:20
         m_jet0 /= 1 + m.sigma0;                                          // :21-23
     }
 
     // ForwardShockEqn::operator(): forward-shock.tpp:27-118
-    VAG_HD void operator()(const double* x, double* d, double /*t*/) const {
+    VAG_HD void operator()(const double* x, double* d, double t) const {
         const double Gamma = x[iG];
+        const double deps = INJ ? jet_deps_dt(m, theta0, t) : 0.0;
+        if (INJ) d[INJ ? iE : 0] = deps;
         const double u2 = (Gamma - 1) * (Gamma + 1);
         const double u = sqrt(u2);  // IEEE: a stage value of Gamma below 1 must give NaN as in the reference
         d[iR] = u * (Gamma + u) * con::c;
@@ -272,7 +277,8 @@ struct FwdEqn {
             const double dGamma_eff = vdiv(ad_idx * (Gamma2 + 1) - 1, Gamma2);
             const double dlnVdt = dlnV_r;
             const double U = x[iU];
-            const double a1 = -(Gamma - 1) * (Gamma_eff + 1) * con::c2 * d[iM2];
+            double a1 = -(Gamma - 1) * (Gamma_eff + 1) * con::c2 * d[iM2];
+            if (INJ) a1 += deps;
             const double a2 = (ad_idx - 1) * Gamma_eff * U * dlnVdt;
             const double b1 = (m_jet0 + x[iM2]) * con::c2;
             const double b2 = (dGamma_eff + vdiv(Gamma_eff * (ad_idx - 1), Gamma)) * U;
@@ -293,10 +299,12 @@ struct FwdEqn {
         x[iT] = x[iR] / sqrt((Gamma4 - 1) * (Gamma4 + 1)) / con::c;
         x[iM2] = medium_mass(m, x[iR]);
         x[iG] = Gamma4;
+        if (INJ) x[INJ ? iE : 0] = jet_eps_k(m, theta);
         const double ad_idx = adiabatic_idx(Gamma4);
         x[iU] = enclosed_thermal_energy_medium(m, x[iR], Gamma4, ad_idx, m.fwd.radiative ? m.fwd.eps_e : 0.0);
     }
 };
+using FwdEqn = FwdEqnT<false>;
 
 // Raw dense-output samples of one row.  The ODE kernel stores only the interpolated state vector
 // of every lattice node (component c -> plane[c][k]); the derived shock quantities are computed
@@ -317,10 +325,12 @@ struct RowDyn {
 // The accepted-step loop of integrate_adaptive/dense output is flattened to one dopri5 ATTEMPT per
 // iteration (identical sequence of attempts, step sizes and accepted states): in a warp of 32 rows a
 // rejected attempt of one row then costs the other rows nothing.
+template <bool INJ>
 VAG_HD int solve_fwd_row(const ModelCfg& m, double theta, double t_dec, const double* t, int n_t, const ShockRow& s,
                          const RawRow& raw, RowDyn& rd, double* col, int col_stride) {
-    FwdEqn eqn(m, theta);
-    double x[FwdEqn::N];
+    using Eqn = FwdEqnT<INJ>;
+    Eqn eqn(m, theta);
+    double x[Eqn::N];
     const double t0 = vmin(t[0], vmin(0.1 * unit::sec, 0.1 * t_dec));
     eqn.set_init_state(x, theta, t0);
     rd.injection_idx = n_t;
@@ -334,7 +344,7 @@ VAG_HD int solve_fwd_row(const ModelCfg& m, double theta, double t_dec, const do
     // system uses the shared-memory one)
     (void)col;
     (void)col_stride;
-    Dopri5<FwdEqn::N> st;
+    Dopri5<Eqn::N> st;
     st.initialize(x, t0, 0.01 * t0, m.rtol);
     const double t_back = t[n_t - 1];
     int k = 0, status = 0, fails = 0, steps = 0;
@@ -405,14 +415,14 @@ struct FRState {
 
 struct FREqn {
     const ModelCfg& m;
-    double Gamma4, deps0_dt, dm0_dt, u4;
+    double Gamma4, deps0_dt, dm0_dt, u4, theta0;
     double cs4, beta4;  // compute_sound_speed(Gamma4), gamma_to_beta(Gamma4): row constants of the RHS
     // crossing state: reverse-shock.hpp:66-70
     double u_x, r_x, B3_ordered_x, V3_comv_x, rho3_x;
     enum { iG = 0, iX4, iX3, iM2, iM3, iU2, iU3, iR, iT, iE4, iM4, N };
 
     // FRShockEqn ctor: reverse-shock.tpp:22-40
-    VAG_HD FREqn(const ModelCfg& m_, double theta) : m(m_) {
+    VAG_HD FREqn(const ModelCfg& m_, double theta) : m(m_), theta0(theta) {
         Gamma4 = jet_Gamma0(m, theta);
         deps0_dt = jet_eps_k(m, theta) / m.T0;
         dm0_dt = deps0_dt / (Gamma4 * con::c2);
@@ -464,6 +474,8 @@ struct FREqn {
             deps4 = inject_w * deps0_dt;
             dm4 = inject_w * dm0_dt;
         }
+        const double deps_inj = jet_deps_dt(m, theta0, t);  // 0 without a magnetar
+        deps4 += deps_inj;                                   // compute_deps4_dt :231-233
         d[iE4] = deps4;
         d[iM4] = dm4;
 
@@ -568,7 +580,7 @@ struct FREqn {
             const double Gamma_eff3 = compute_effective_Gamma(ad34, Gamma);
             const double dGamma_eff2 = compute_effective_Gamma_dGamma(ad2, Gamma);
             const double dGamma_eff3 = compute_effective_Gamma_dGamma(ad34, Gamma);
-            const double deps_dt = 0;
+            const double deps_dt = deps_inj;  // :75-77
             const double a = (Gamma - 1) * con::c2 * dm2 + (Gamma - Gamma4) * con::c2 * dm3 + Gamma_eff2 * dU2 +
                              Gamma_eff3 * dU3 - deps_dt;
             const double b = (m2 + m3) * con::c2 + dGamma_eff2 * U2 + dGamma_eff3 * U3;

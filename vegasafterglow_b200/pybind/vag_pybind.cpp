@@ -61,11 +61,28 @@ std::shared_ptr<Ctx> context(int device) {
 }
 
 // ---- parameter carriers (the typed variants of JetVariant / MediumVariant) ----------------------
+// Magnetar(L0, t0, q=2): pybind/pymodel.h:34-58, pybind/pybind.cpp:198-203
+struct Magnetar {
+    Real L0, t0, q;
+    Magnetar(Real L0_, Real t0_, Real q_) : L0(L0_), t0(t0_), q(q_) {
+        if (!(std::isfinite(L0) && L0 > 0)) throw std::invalid_argument("L0 must be finite and > 0");
+        if (!(std::isfinite(t0) && t0 > 0)) throw std::invalid_argument("t0 must be finite and > 0");
+        if (!(std::isfinite(q) && q > 0)) throw std::invalid_argument("q must be finite and > 0");
+    }
+    std::string repr() const {
+        char buf[128];
+        std::snprintf(buf, sizeof(buf), "Magnetar(L0=%g, t0=%g, q=%g)", L0, t0, q);
+        return buf;
+    }
+};
+
 struct Jet {
     int type;
     Real theta_c, E_iso, Gamma0, k_e, k_g, duration;
     bool spreading;
     Real theta_w{0.3}, E_iso_w{1e50}, Gamma0_w{50}, sigma0{0};
+    bool has_magnetar{false};
+    Real mag_L0{0}, mag_t0{0}, mag_q{0};
     std::string repr() const {
         char buf[200];
         static const char* names[] = {"TophatJet", "GaussianJet", "PowerLawJet", "TwoComponentJet", "StepPowerLawJet", "PowerLawWing"};
@@ -92,10 +109,6 @@ void require(bool ok, const std::string& msg) {
 
 Jet make_jet(int type, Real theta_c, Real E_iso, Real Gamma0, Real k_e, Real k_g, bool spreading, Real duration,
              const py::object& magnetar) {
-    if (!magnetar.is_none()) {
-        PyErr_SetString(PyExc_NotImplementedError, "magnetar injection is not implemented on the GPU path yet");
-        throw py::error_already_set();
-    }
     // pybind/pymodel.cpp:47-95
     require(std::isfinite(theta_c) && theta_c > 0 && theta_c <= 3.14159265358979323846 / 2, "theta_c must be in (0, pi/2]");
     require(std::isfinite(E_iso) && E_iso > 0, "E_iso must be finite and > 0");
@@ -103,7 +116,15 @@ Jet make_jet(int type, Real theta_c, Real E_iso, Real Gamma0, Real k_e, Real k_g
     require(std::isfinite(duration) && duration > 0, "duration must be finite and > 0");
     if (type == VAG_JET_POWERLAW || type == VAG_JET_STEP_POWERLAW || type == VAG_JET_POWERLAW_WING)
         require(std::isfinite(k_e) && k_e > 0 && std::isfinite(k_g) && k_g > 0, "k_e and k_g must be finite and > 0");
-    return Jet{type, theta_c, E_iso, Gamma0, k_e, k_g, duration, spreading};
+    Jet j{type, theta_c, E_iso, Gamma0, k_e, k_g, duration, spreading};
+    if (!magnetar.is_none()) {
+        const Magnetar mg = magnetar.cast<Magnetar>();
+        j.has_magnetar = true;
+        j.mag_L0 = mg.L0;
+        j.mag_t0 = mg.t0;
+        j.mag_q = mg.q;
+    }
+    return j;
 }
 
 struct Flux {
@@ -139,6 +160,10 @@ class Model {
         p_.E_iso_w = jet.E_iso_w;
         p_.Gamma0_w = jet.Gamma0_w;
         p_.sigma0 = jet.sigma0;
+        p_.has_magnetar = jet.has_magnetar ? 1 : 0;
+        p_.magnetar_L0 = jet.mag_L0;
+        p_.magnetar_t0 = jet.mag_t0;
+        p_.magnetar_q = jet.mag_q;
         p_.medium_type = med.type;
         p_.n_ism = med.n_ism;
         p_.A_star = med.A_star;
@@ -303,6 +328,12 @@ PYBIND11_MODULE(VegasAfterglowC_b200, m) {
     m.attr("backend") = vag_version();
 
     py::class_<Jet>(m, "_Jet").def("__repr__", &Jet::repr);
+    py::class_<Magnetar>(m, "Magnetar")
+        .def(py::init<Real, Real, Real>(), py::arg("L0"), py::arg("t0"), py::arg("q") = 2)
+        .def_readonly("L0", &Magnetar::L0)
+        .def_readonly("t0", &Magnetar::t0)
+        .def_readonly("q", &Magnetar::q)
+        .def("__repr__", &Magnetar::repr);
     py::class_<MediumP>(m, "_Medium");
 
     m.def("TophatJet",
