@@ -90,6 +90,14 @@ def main():
         P5["magnetar_t0"] = 10 ** rng.uniform(2, 4.5, P5.size)
         P5["magnetar_q"] = rng.uniform(1.0, 3.0, P5.size)
         save(nm, P5, t, nu)
+    # lateral spreading (spreading=True of the jet factories): theta(k) dynamics for forward-shock models,
+    # Symmetry::structured lattices for both
+    for nm, P6 in (("batch_fs_spreading_tophat", configs.random_draw(16, seed=42, theta_obs_max=0.3)),
+                   ("batch_fs_spreading_gauss", configs.random_draw(8, seed=43, jet="gaussian", theta_obs_max=0.4)),
+                   ("batch_fs_spreading_powerlaw_wind", configs.random_draw(8, seed=44, jet="powerlaw", medium="wind", theta_obs_max=0.2)),
+                   ("batch_rs_spreading_tophat", configs.random_draw(8, seed=45, rvs=True, theta_obs_max=0.2))):
+        P6["spreading"] = 1
+        save(nm, P6, t, nu)
     nu_ssc = np.array([1e9, 1e14, 1e17, 1e22, 1e25])
     save("batch_ssc_kn_tophat_ism", configs.random_draw(24, seed=21, ssc=True, kn=True), t, nu_ssc)
     save("batch_ssc_thomson_tophat_wind", configs.random_draw(12, seed=22, ssc=True, kn=False, medium="wind"), t, nu_ssc)

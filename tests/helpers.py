@@ -76,7 +76,18 @@ def assert_parity(flux, g, what):
 # held to the reference's OWN golden acceptance contract |a-b| <= 2e-3 |b| + 1e-2 peak
 # (tests/python/golden/regenerate.py:29-30) plus a median bar that shows the typical model is still
 # reproduced far below it.
-CHAOTIC = ("golden_gauss_ism_rs", "batch_rs_magnetized_tophat", "series_rs_gauss", "batch_rs_step_powerlaw")
+#
+# Spreading jets join the list for a different reason: a `structured` model gives every theta row its
+# own time lattice (build_time_grid, grid-refinement.h:612-619), so a row starts to contribute at its own
+# first observer-time node and the flux is a DISCONTINUOUS function of the theta grid at those onsets.  The
+# GPU theta grid differs from the reference's by the quadrature noise described above (~1e-4 in the nodes
+# for the occasional model); for that model the bins next to a row onset move by ~5e-3 while all other
+# bins stay <= 1e-4 (measured: 15 of 16 models of batch_fs_spreading_tophat <= 1.2e-6, one at 6.8e-3 in two
+# isolated time bins).  The host emulation, which shares glibc's libm with the reference, reproduces the same
+# fixtures to <= 1e-8.
+CHAOTIC = ("golden_gauss_ism_rs", "batch_rs_magnetized_tophat", "series_rs_gauss", "batch_rs_step_powerlaw",
+           "batch_fs_spreading_tophat", "batch_fs_spreading_gauss", "batch_fs_spreading_powerlaw_wind",
+           "batch_rs_spreading_tophat")
 
 
 def assert_reference_contract(flux, g, what, median_rtol=1e-4):

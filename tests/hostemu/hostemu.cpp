@@ -75,6 +75,13 @@ void run_front(HostBatch& hb, const vag_params* params, size_t n, double t_min, 
     }
     w.geo_u = hb.alloc<double>(cells);
     w.geo_lg2r2 = hb.alloc<double>(cells);
+    w.sh_theta = w.geo_cth = w.geo_sth = w.geo_dcos = nullptr;
+    if (w.totals[TOT_ANY_SPREAD]) {
+        w.sh_theta = hb.alloc<double>(cells);
+        w.geo_cth = hb.alloc<double>(cells);
+        w.geo_sth = hb.alloc<double>(cells);
+        w.geo_dcos = hb.alloc<double>(cells);
+    }
     w.coef_fwd = hb.alloc<double>((size_t)cells * PH_NCOEF);
     w.coef_rvs = hb.alloc<double>((size_t)cells * PH_NCOEF);
     w.max_n_t = std::max(w.totals[TOT_MAX_NT], 1);
@@ -88,13 +95,18 @@ void run_front(HostBatch& hb, const vag_params* params, size_t n, double t_min, 
             k1_dynamics_body<true>(w, r, col, 1);
         else
             k1_dynamics_body<false>(w, r, col, 1);
+    }
+    for (int r = 0; r < rows; ++r) {
         const RowCtx c = row_ctx(w, r);
         for (int k = 0; k < c.n_t; ++k) k1b_finish_cell(w, r, c, k);
         if (c.has_rvs && w.row_dyn[r].n_saved >= 0) {
             const int idx_cut = extrap_scan(shock_row(w.rvs, c.off), c.n_t, 0, 1);
             for (int k = 0; k < c.n_t; ++k) k1c_extrap_cell(w, r, c, idx_cut, k);
         }
-        for (int k = 0; k < c.n_t; ++k) k1d_geo_cell(w, c, k);
+        for (int k = 0; k < c.n_t; ++k) {
+            k1d_geo_cell(w, c, k);
+            if (w.cfg[c.mi].spreading && w.sh_theta) k1e_spread_geo_cell(w, r, c, k);
+        }
     }
     if (w.any_ssc) {
         for (int sft = 0; sft < 2; ++sft) {
@@ -307,7 +319,7 @@ int vagemu_details(const vag_params* p, double t_min, double t_max, vag_grid_inf
             for (int r = 0; r < h.n_reps; ++r)
                 for (int k = 0; k < h.n_t; ++k)
                     o[((size_t)a * h.n_reps + r) * h.n_t + k] =
-                        map[a] < 0 ? w.theta[w.reps[r]] : pl[map[a]][(size_t)r * h.n_t + k];
+                        map[a] < 0 ? (w.sh_theta ? w.sh_theta[(size_t)r * h.n_t + k] : w.theta[w.reps[r]]) : pl[map[a]][(size_t)r * h.n_t + k];
     };
     if (fwd_shock) dump(w.fwd, fwd_shock);
     if (rvs_shock && p->has_rvs) dump(w.rvs, rvs_shock);

@@ -79,10 +79,9 @@ def test_validation_radiation_ranges():
 
 def test_unsupported_switches_say_so():
     lib = _lib.load()
-    for k in ("spreading",):
-        p = configs.make()
-        p[k] = 1
-        assert lib.vag_params_validate(p.ctypes.data) == abi.VAG_ERR_UNSUPPORTED
+    p = configs.make()
+    p["spreading"] = 1  # lateral spreading is implemented
+    assert lib.vag_params_validate(p.ctypes.data) == abi.VAG_OK
     p = configs.make()
     p["axisymmetric"] = 0
     assert lib.vag_params_validate(p.ctypes.data) == abi.VAG_ERR_UNSUPPORTED

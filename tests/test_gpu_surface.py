@@ -175,3 +175,19 @@ def test_magnetar_side_by_side():
     for va in (ours, theirs):
         with pytest.raises(ValueError):
             va.Magnetar(-1.0, 1e3, 2.0)
+
+
+def test_spreading_side_by_side():
+    """GaussianJet(..., spreading=True) off-axis through both pybind11 modules: theta(k) dynamics
+    (forward-shock.tpp:36-40) and the per-node EATS geometry (observer.cpp:51-141)."""
+    ours, theirs = _both()
+    t, nu = np.logspace(2, 8, 50), np.array([1e9, 1e14, 1e17])
+    out = []
+    for va in (ours, theirs):
+        m = va.Model(jet=va.GaussianJet(0.1, 1e52, 300, spreading=True), medium=va.ISM(1),
+                     observer=va.Observer(1e26, 0.1, 0.3), fwd_rad=va.Radiation(0.1, 1e-3, 2.3))
+        out.append(np.asarray(m.flux_density_grid(t, nu).total))
+    np.testing.assert_allclose(out[0], out[1], rtol=1e-6)
+    m0 = ours.Model(jet=ours.GaussianJet(0.1, 1e52, 300), medium=ours.ISM(1), observer=ours.Observer(1e26, 0.1, 0.3),
+                    fwd_rad=ours.Radiation(0.1, 1e-3, 2.3))
+    assert np.max(np.abs(out[0] / np.asarray(m0.flux_density_grid(t, nu).total) - 1)) > 0.5

@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(1024) k_scan(BatchWs w) {
         const ModelCfg& cfg = w.cfg[mi];
         if (cfg.fwd.ssc || (cfg.has_rvs && cfg.rvs.ssc)) st |= (1 << 30);  // carries "any ssc" through the OR
         st |= cfg.has_rvs ? (1 << 29) : (1 << 28);                         // "any pair rows" / "any forward-only rows"
+        if (cfg.spreading) st |= (1 << 27);                                // "any spreading model"
         rows += h.n_reps;
         cells += (long long)h.n_reps * h.n_t;
         max_nt = max(max_nt, h.n_t);
@@ -114,7 +115,8 @@ __global__ void __launch_bounds__(1024) k_scan(BatchWs w) {
         w.totals[TOT_MAX_NT] = max_nt;
         w.totals[TOT_MAX_NTHETA] = max_nth;
         w.totals[TOT_MAX_EROWS] = max_er;
-        w.totals[TOT_STATUS_OR] = st & ~(7 << 28);
+        w.totals[TOT_STATUS_OR] = st & ~(15 << 27);
+        w.totals[TOT_ANY_SPREAD] = (st >> 27) & 1;
         w.totals[TOT_ANY_SSC] = (st >> 30) & 1;
         w.totals[TOT_ANY_PAIR] = (st >> 29) & 1;
         w.totals[TOT_ANY_FWD_ONLY] = (st >> 28) & 1;
@@ -167,6 +169,7 @@ __global__ void __launch_bounds__(64) k_radiation(BatchWs w) {
     const ModelCfg& cfg = w.cfg[c.mi];
     for (int k = tid; k < c.n_t; k += nthr) {
         k1d_geo_cell(w, c, k);
+        if (cfg.spreading && w.sh_theta) k1e_spread_geo_cell(w, row, c, k);
         if (!cfg.fwd.ssc) k2_radiation_cell(w, row, k, 0);  // ssc shocks: k_ic_cooling
         if (cfg.has_rvs && !cfg.rvs.ssc) k2_radiation_cell(w, row, k, 1);
     }
@@ -534,7 +537,7 @@ int setup_models(vag_context* ctx, BatchWs& w, const vag_params* d_params, size_
     return VAG_OK;
 }
 
-int setup_rows(vag_context* ctx, BatchWs& w, int rows, long long cells) {
+int setup_rows(vag_context* ctx, BatchWs& w, int rows, long long cells, bool any_spread) {
     w.n_cells = cells;
     CK(ctx->row_buf.ensure(carve_sz<int>(rows) * 3 + carve_sz<RowDyn>(rows) + carve_sz<long long>(rows + 1)));
     char* p = static_cast<char*>(ctx->row_buf.p);
@@ -544,7 +547,7 @@ int setup_rows(vag_context* ctx, BatchWs& w, int rows, long long cells) {
     w.row_dyn = carve<RowDyn>(p, rows);
     w.row_cell_off = carve<long long>(p, rows + 1);
     const size_t plane = carve_sz<double>((size_t)cells);
-    CK(ctx->cell_buf.ensure(plane * (1 + 12 + 2) + carve_sz<double>((size_t)cells * PH_NCOEF) * 2));
+    CK(ctx->cell_buf.ensure(plane * (1 + 12 + 2 + (any_spread ? 4 : 0)) + carve_sz<double>((size_t)cells * PH_NCOEF) * 2));
     p = static_cast<char*>(ctx->cell_buf.p);
     w.t_rows = carve<double>(p, (size_t)cells);
     for (int a = 0; a < 6; ++a) w.fwd[a] = carve<double>(p, (size_t)cells);
@@ -553,6 +556,13 @@ int setup_rows(vag_context* ctx, BatchWs& w, int rows, long long cells) {
     w.geo_lg2r2 = carve<double>(p, (size_t)cells);
     w.coef_fwd = carve<double>(p, (size_t)cells * PH_NCOEF);
     w.coef_rvs = carve<double>(p, (size_t)cells * PH_NCOEF);
+    w.sh_theta = w.geo_cth = w.geo_sth = w.geo_dcos = nullptr;
+    if (any_spread) {
+        w.sh_theta = carve<double>(p, (size_t)cells);
+        w.geo_cth = carve<double>(p, (size_t)cells);
+        w.geo_sth = carve<double>(p, (size_t)cells);
+        w.geo_dcos = carve<double>(p, (size_t)cells);
+    }
     return VAG_OK;
 }
 
@@ -601,7 +611,7 @@ int run_front(vag_context* ctx, BatchWs& w, const vag_params* d_params, size_t n
     const long long cells = *ctx->h_cells;
     std::memcpy(totals_out, ctx->h_totals, sizeof(int) * TOT_N);
     *cells_out = cells;
-    rc = setup_rows(ctx, w, std::max(rows, 1), std::max<long long>(cells, 1));
+    rc = setup_rows(ctx, w, std::max(rows, 1), std::max<long long>(cells, 1), ctx->h_totals[TOT_ANY_SPREAD] != 0);
     if (rc) return rc;
     w.max_n_t = std::max(ctx->h_totals[TOT_MAX_NT], 1);
     w.max_erows = std::max(ctx->h_totals[TOT_MAX_EROWS], 1);
@@ -846,7 +856,6 @@ int vag_params_validate(const vag_params* p) {
     if (!std::isfinite(p->rtol) || !std::isfinite(p->phi_resol) || !std::isfinite(p->theta_resol) ||
         !std::isfinite(p->t_resol))
         return bad("resolutions and rtol must be finite");
-    if (p->spreading) return fail(VAG_ERR_UNSUPPORTED, "jet spreading is not implemented on the GPU path yet");
     if (!p->axisymmetric) return fail(VAG_ERR_UNSUPPORTED, "axisymmetric=False is not implemented on the GPU path yet");
     return VAG_OK;
 }
@@ -1237,6 +1246,10 @@ int vag_details(vag_context* ctx, const vag_params* p, double t_min, double t_ma
             for (int k = 0; k < h.n_t; ++k) o[(2 * (size_t)h.n_reps + r) * h.n_t + k] = th_host[reps_host[r]];
     };
     if (fwd_shock) fill_theta(fwd_shock);
+    if (fwd_shock && w.sh_theta) {  // spreading model: Shock::theta varies along k
+        CK(cudaMemcpyAsync(fwd_shock + 2 * nc, w.sh_theta, sizeof(double) * nc, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
     if (rvs_shock && p->has_rvs) fill_theta(rvs_shock);
     return VAG_OK;
 }

@@ -30,6 +30,8 @@ struct GridHeader {
     int n_reps, symmetry, phi_mirrored, status;
     int t_num_tot, t_num_base, has_early, is_rvs;
     double t_end, min_t_start, min_t_early;
+    int spreading, structured;
+    double theta_s;  // jet_spreading_edge (spreading models)
 };
 
 // Slab of per-model arrays (capacities fixed per batch by the host).
@@ -549,16 +551,21 @@ VAG_HD void logspace_with_cross_refinement(double t_start, double t_end, double 
     }
 }
 
-// Lattice of one representative row: make_time_grid + store_time_grid (grid-refinement.h:571-591)
-VAG_HD void build_row_lattice(const GridHeader& h, double t_dec, double T0, double* t_row) {
+// Lattice of one representative row: make_time_grid + store_time_grid (grid-refinement.h:571-591).
+// Symmetric models share the global start / early point; a `structured` (spreading) model gives every
+// row its own (build_time_grid, grid-refinement.h:612-619): row_start = max(t_raw, cut),
+// row_early = 0.99 min(t_raw, cut), left by build_grid in the model's scratch slab.
+VAG_HD void build_row_lattice(const GridHeader& h, double t_dec, double T0, double row_start, double row_early,
+                              double* t_row) {
     double* grid = t_row + (h.has_early ? 1 : 0);
+    const double ts = h.structured ? row_start : h.min_t_start;
     if (h.is_rvs) {
         const double t_cross_limit = vmax(t_dec, T0);
-        logspace_with_cross_refinement(h.min_t_start, h.t_end, 10 * t_cross_limit, h.t_num_tot, h.t_num_base, grid);
+        logspace_with_cross_refinement(ts, h.t_end, 10 * t_cross_limit, h.t_num_tot, h.t_num_base, grid);
     } else {
-        logspace_with_band_refinement(h.min_t_start, h.t_end, t_dec / 3, 3 * t_dec, h.t_num_tot, 3.0, grid);
+        logspace_with_band_refinement(ts, h.t_end, t_dec / 3, 3 * t_dec, h.t_num_tot, 3.0, grid);
     }
-    if (h.has_early) t_row[0] = h.min_t_early;
+    if (h.has_early) t_row[0] = h.structured ? row_early : h.min_t_early;
 }
 
 // ---- auto_grid: grid-refinement.h:638-706 (axisymmetric, typed jets) --------------------------
@@ -644,7 +651,36 @@ VAG_HD void build_grid(const Par& par, const ModelCfg& m, double t_obs_min, doub
     // phi extent 1 (jet_3d = 0), so an on-axis observer needs a single phi sample.
     h.n_phi_eff = (theta_view == 0) ? 1 : n_phi;
 
-    // detect_symmetry (mesh.h:120-185): non-spreading jet in an isotropic medium.
+    // jet_spreading_edge (grid-refinement.h:113-135): angle of the steepest decline of Gamma0 between the
+    // first and last theta node.  The walk's nodes are a running sum; the profile is evaluated at all of
+    // them (and their clamped neighbours) in parallel, the minimum is taken in walk order.
+    h.spreading = m.spreading;
+    h.structured = m.structured;
+    h.theta_s = 0;
+    if (m.spreading) {
+        const double th_min = s.theta[0], th_max = s.theta[n_theta - 1];
+        const double step = (th_max - th_min) / 256;
+        int nn = 0;
+        for (double th = th_min; th <= th_max && nn < GRID_NSCAN + 6; th += step) A[nn++] = th;
+        {
+            const int cnt = nn;
+            par.for_each(cnt, [&](int q) {
+                const double th = A[q];
+                const double lo = vmax(th - step, th_min), hi = vmin(th + step, th_max);
+                B[q] = (jet_Gamma0(m, hi) - jet_Gamma0(m, lo)) / (hi - lo);
+            });
+        }
+        double theta_s = th_min, dp_min = 0;
+        for (int q = 0; q < nn; ++q)
+            if (B[q] < dp_min) {
+                dp_min = B[q];
+                theta_s = A[q];
+            }
+        if (dp_min == 0) theta_s = th_max;
+        h.theta_s = theta_s;
+    }
+
+    // detect_symmetry (mesh.h:120-185): a spreading jet is `structured` (every theta row is solved)
     // per-theta probes in parallel: pt[0..n) = eps_k, pt[n..2n) = Gamma0, then an ordered scan.
     double* e_arr = pt;
     double* g_arr = pt + n_theta;
@@ -665,9 +701,10 @@ VAG_HD void build_grid(const Par& par, const ModelCfg& m, double t_obs_min, doub
     int n_reps = 0;
     s.reps[n_reps++] = 0;
     for (int j = 1; j < n_theta; ++j)
-        if (e_arr[j - 1] != e_arr[j] || g_arr[j - 1] != g_arr[j]) s.reps[n_reps++] = j;
+        if (m.structured || e_arr[j - 1] != e_arr[j] || g_arr[j - 1] != g_arr[j]) s.reps[n_reps++] = j;
     h.n_reps = n_reps;
-    h.symmetry = (n_reps == 1) ? SYM_ISOTROPIC : (n_reps < n_theta ? SYM_PIECEWISE : SYM_PHI_SYMMETRIC);
+    h.symmetry = m.structured ? SYM_STRUCTURED
+                             : (n_reps == 1) ? SYM_ISOTROPIC : (n_reps < n_theta ? SYM_PIECEWISE : SYM_PHI_SYMMETRIC);
 
     // build_time_grid (grid-refinement.h:593-636) with phi_size = 1.  t_dec only depends on
     // (eps_k, Gamma0), so it is evaluated once per representative group.
@@ -690,6 +727,10 @@ VAG_HD void build_grid(const Par& par, const ModelCfg& m, double t_obs_min, doub
             min_raw = vmin(min_raw, ts);
             min_guarded = vmin(min_guarded, vmax(ts, cut));
             min_cut = vmin(min_cut, cut);
+            if (m.structured) {  // per-row lattice bounds (TimeScanResult::t_start / early_t); e_arr is dead by now
+                base_theta[j] = vmax(ts, cut);
+                pt[j] = 0.99 * vmin(ts, cut);
+            }
         }
     }
     h.min_t_early = min_raw;

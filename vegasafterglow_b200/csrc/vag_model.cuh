@@ -25,7 +25,9 @@ struct ModelCfg {
     double theta_c, eps_k0, Gamma0, k_e, k_g, gauss_norm, T0;
     double theta_w, E_iso, E_iso_w, Gamma0_w, sigma0;  // Ejecta-family profiles work on E_iso [erg] heights
     int has_magnetar;
-    double mag_L, mag_t0, mag_q;  // L0 [code units / 4 pi], t0 [s], q
+    double mag_L, mag_t0, mag_q;
+    int spreading;   // lateral spreading of a forward-shock-only model (the pair solver has none, reverse-shock.tpp)
+    int structured;  // jet.spreading: Symmetry::structured, every theta row solved on its own lattice (mesh.h:125-130)  // L0 [code units / 4 pi], t0 [s], q
     // medium
     int medium_type;
     double rho_ism, wind_A, wind_r02;
@@ -68,6 +70,8 @@ VAG_HD ModelCfg make_cfg(const vag_params& p) {
     m.E_iso_w = p.E_iso_w;
     m.Gamma0_w = p.Gamma0_w;
     m.sigma0 = p.sigma0;
+    m.spreading = (p.spreading && !p.has_rvs) ? 1 : 0;
+    m.structured = p.spreading ? 1 : 0;
     m.has_magnetar = p.has_magnetar;
     // convert_unit_jet (pybind/pymodel.cpp:196-199): deps_dt_cgs(t / unit::sec) * (unit::erg / (4 pi unit::sec))
     m.mag_L = p.magnetar_L0;

@@ -45,6 +45,12 @@ struct EatsModel {
     const double* ictab;      // [n_reps][n_t][IC_CAP_OUT]
     int* breach;              // model status word: gets VAG_ST_IC_BAND when an SSC query leaves the clamped band
     const double* sp_lut;     // log2_softplus table (vag_math.cuh), in shared memory on the device
+    // spreading jets (calc_t_obs / calc_solid_angle, observer.cpp:51-141): theta varies along k, so the line
+    // of sight cosine and the solid angle are per-node quantities built from these per-cell tables
+    int spreading;
+    const double* geo_cth;    // [n_reps][n_t] cos(theta(k))
+    const double* geo_sth;    // [n_reps][n_t] sin(theta(k))
+    const double* geo_dcos;   // [n_reps][n_t] cos(theta_hi(k)) - cos(theta_lo(k))
 };
 
 // compute_dphi: src/core/observer.cpp:17-37
@@ -61,6 +67,7 @@ VAG_HD double compute_dphi(const GridHeader& h, const double* phi, int i) {
 }
 
 // Row constants of calc_eat_non_spreading (observer.cpp:167-192): t_coeff and log2(dOmega)
+// Spreading models reuse the record as (cos(phi) sin(theta_obs), cos(theta_obs), dphi, rep).
 struct RowGeom {
     double cos_v, t_coeff, lg2_dOmega;
     int rep;  // representative row index
@@ -73,6 +80,13 @@ VAG_HD RowGeom row_geometry(const EatsModel& M, int i, int j) {
     const double th = M.theta[j];
     const double ct = cos(th), st = sin(th);
     RowGeom g;
+    if (M.spreading) {
+        g.cos_v = cos_phi * sin_obs;
+        g.t_coeff = cos_obs;
+        g.lg2_dOmega = compute_dphi(h, M.phi, i);
+        g.rep = M.rep_of[j];
+        return g;
+    }
     g.cos_v = st * cos_phi * sin_obs + ct * cos_obs;
     g.t_coeff = (1 - g.cos_v) / con::c * M.one_plus_z;
     const int last = h.n_theta - 1;
@@ -84,16 +98,33 @@ VAG_HD RowGeom row_geometry(const EatsModel& M, int i, int j) {
     return g;
 }
 
-// Linear observer time of node k of a row (observer.cpp:201)
+// line-of-sight cosine of node o of a spreading row (observer.cpp:82)
+VAG_HD double spread_cos_v(const EatsModel& M, const RowGeom& g, long o) {
+    return M.geo_sth[o] * g.cos_v + M.geo_cth[o] * g.t_coeff;
+}
+
+// Linear observer time of node k of a row (observer.cpp:201; spreading: :87)
 VAG_HD double node_time(const EatsModel& M, const RowGeom& g, int n_t, int k) {
     const long o = (long)g.rep * n_t + k;
+    if (M.spreading) return (M.t_rows[o] + (1 - spread_cos_v(M, g, o)) * M.r[o] / con::c) * M.one_plus_z;
     return M.t_rows[o] * M.one_plus_z + g.t_coeff * M.r[o];
 }
 
-// log2 grids of one node: finalize_log_grids (observer.cpp:439-454) on the pre-logged geometry path
+// log2 grids of one node: finalize_log_grids (observer.cpp:439-454) on the pre-logged geometry path, or on
+// the linear dOmega r^2 of a spreading jet (observer.cpp:131-139)
 VAG_HD void node_logs(const EatsModel& M, const RowGeom& g, int n_t, int k, double& lg2_t, double& lg2_dop,
                       double& lg2_geom) {
     const long o = (long)g.rep * n_t + k;
+    if (M.spreading) {
+        const double cos_v = spread_cos_v(M, g, o);
+        const double dop_lin = M.Gamma[o] - M.geo_u[o] * cos_v;
+        const double time = (M.t_rows[o] + (1 - cos_v) * M.r[o] / con::c) * M.one_plus_z;
+        const double dOmega = fabs(M.geo_dcos[o] * g.lg2_dOmega);
+        lg2_dop = -rlog2(dop_lin);
+        lg2_t = rlog2(time);
+        lg2_geom = rlog2(dOmega * M.r[o] * M.r[o]) + 3.0 * lg2_dop;
+        return;
+    }
     const double dop_lin = M.Gamma[o] - M.geo_u[o] * g.cos_v;
     const double time = M.t_rows[o] * M.one_plus_z + g.t_coeff * M.r[o];
     lg2_dop = -rlog2(dop_lin);

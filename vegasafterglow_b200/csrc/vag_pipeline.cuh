@@ -20,7 +20,8 @@
 
 namespace vag {
 
-enum { TOT_ROWS = 0, TOT_MAX_NT, TOT_MAX_NTHETA, TOT_MAX_EROWS, TOT_STATUS_OR, TOT_ANY_SSC, TOT_ANY_PAIR, TOT_ANY_FWD_ONLY, TOT_N };
+enum { TOT_ROWS = 0, TOT_MAX_NT, TOT_MAX_NTHETA, TOT_MAX_EROWS, TOT_STATUS_OR, TOT_ANY_SSC, TOT_ANY_PAIR, TOT_ANY_FWD_ONLY,
+       TOT_ANY_SPREAD, TOT_N };
 
 struct BatchWs {
     int n_models;
@@ -54,6 +55,11 @@ struct BatchWs {
     double* coef_rvs;
     double* geo_u;     // [n_cells] sqrt((Gamma-1)(Gamma+1)) of the forward table (EATS Doppler factor)
     double* geo_lg2r2; // [n_cells] 2 log2(r)                                   (EATS geometry factor)
+    // spreading models only (allocated when the batch has one): Shock::theta and the per-node EATS geometry
+    double* sh_theta;  // [n_cells] theta(k) of the row
+    double* geo_cth;   // [n_cells] cos theta(k)
+    double* geo_sth;   // [n_cells] sin theta(k)
+    double* geo_dcos;  // [n_cells] cos(theta_hi) - cos(theta_lo) against the neighbour rows (observer.cpp:112-122)
     // inverse-Compton data: allocated only when some model of the batch has ssc=True
     int any_ssc;
     int max_n_t, max_erows;   // batch maxima (known after K0b)
@@ -119,6 +125,9 @@ VAG_HD void k0b_scan_body(const BatchWs& w) {
     for (int mi = 0; mi < w.n_models; ++mi) (w.cfg[mi].has_rvs ? any_pair : any_fwd) = 1;
     w.totals[TOT_ANY_PAIR] = any_pair;
     w.totals[TOT_ANY_FWD_ONLY] = any_fwd;
+    int any_spread = 0;
+    for (int mi = 0; mi < w.n_models; ++mi) any_spread |= w.cfg[mi].spreading;
+    w.totals[TOT_ANY_SPREAD] = any_spread;
 }
 
 // ---- K0c --------------------------------------------------------------------------------------
@@ -155,6 +164,7 @@ VAG_HD RawRow raw_row(const BatchWs& w, long long off) {
     RawRow raw;
     for (int c = 0; c < 6; ++c) raw.c[c] = w.fwd[c] + off;
     for (int c = 6; c < 11; ++c) raw.c[c] = w.rvs[c - 6] + off;
+    raw.theta = w.sh_theta ? w.sh_theta + off : nullptr;
     return raw;
 }
 
@@ -170,7 +180,9 @@ VAG_HD void k1_dynamics_body(const BatchWs& w, int row, double* col, int col_str
     double* t_row = w.t_rows + off;
     const double t_dec = w.t_dec[(size_t)mi * w.cap_theta + r];
     const double theta = w.theta[(size_t)mi * w.cap_theta + w.reps[(size_t)mi * w.cap_theta + r]];
-    build_row_lattice(h, t_dec, cfg.T0, t_row);
+    // per-row lattice bounds of a structured model: work[j] and work[cap_theta + j] (build_grid)
+    const double* work = w.work + (size_t)mi * w.work_per_model;
+    build_row_lattice(h, t_dec, cfg.T0, h.structured ? work[r] : 0.0, h.structured ? work[w.cap_theta + r] : 0.0, t_row);
     int st = 0;
     bool finite = true;
     for (int k = 0; k < h.n_t; ++k) finite = finite && isfinite(t_row[k]);
@@ -182,8 +194,15 @@ VAG_HD void k1_dynamics_body(const BatchWs& w, int row, double* col, int col_str
         const ShockRow sr = shock_row(w.rvs, off);
         st |= solve_pair_row(cfg, theta, t_dec, t_row, h.n_t, sf, sr, raw, rd, col, col_stride);
     } else {
-        st |= cfg.has_magnetar ? solve_fwd_row<true>(cfg, theta, t_dec, t_row, h.n_t, sf, raw, rd, col, col_stride)
-                               : solve_fwd_row<false>(cfg, theta, t_dec, t_row, h.n_t, sf, raw, rd, col, col_stride);
+        (void)col;
+        (void)col_stride;
+        const double ths = h.theta_s;
+        if (cfg.spreading)
+            st |= cfg.has_magnetar ? solve_fwd_row<true, true>(cfg, theta, ths, t_dec, t_row, h.n_t, sf, raw, rd)
+                                   : solve_fwd_row<false, true>(cfg, theta, ths, t_dec, t_row, h.n_t, sf, raw, rd);
+        else
+            st |= cfg.has_magnetar ? solve_fwd_row<true, false>(cfg, theta, ths, t_dec, t_row, h.n_t, sf, raw, rd)
+                                   : solve_fwd_row<false, false>(cfg, theta, ths, t_dec, t_row, h.n_t, sf, raw, rd);
     }
     w.row_dyn[row] = rd;
     w.inj_idx[row] = rd.injection_idx;
@@ -236,6 +255,37 @@ VAG_HD void k1d_geo_cell(const BatchWs& w, const RowCtx& c, int k) {
     const double g = w.fwd[2][c.off + k];
     w.geo_u[c.off + k] = sqrt((g - 1) * (g + 1));
     w.geo_lg2r2[c.off + k] = 2.0 * rlog2(w.fwd[1][c.off + k]);
+}
+// K1e (spreading models): per-node trigonometry and solid-angle width of calc_t_obs / calc_solid_angle
+// (observer.cpp:51-141).  Row j's boundaries at engine time t(j,k) use the neighbour rows' theta
+// interpolated at that time; with every theta row a representative, the neighbours are rows +-1.
+VAG_HD double interp_theta_nb(const double* t_nb, const double* th_nb, int n_t, double t_target) {
+    int h = 0;  // the reference's monotone k_hint walk, restarted (same result for an ascending lattice)
+    int lo = 0, hi = n_t - 1;  // largest h with t_nb[h] < t_target for h >= 1 (0 if none)
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (t_nb[mid] < t_target)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    h = lo;
+    if (h + 1 >= n_t) return th_nb[n_t - 1];
+    const double wgt = (t_target - t_nb[h]) / (t_nb[h + 1] - t_nb[h]);
+    return th_nb[h] + wgt * (th_nb[h + 1] - th_nb[h]);
+}
+VAG_HD void k1e_spread_geo_cell(const BatchWs& w, int row, const RowCtx& c, int k) {
+    const int j = w.row_rep[row];
+    const int last = w.hdr[c.mi].n_reps - 1;
+    const long long o = c.off + k;
+    const double th = w.sh_theta[o];
+    w.geo_cth[o] = cos(th);
+    w.geo_sth[o] = sin(th);
+    const double t_target = w.t_rows[o];
+    double th_lo = th, th_hi = th;
+    if (j > 0) th_lo = 0.5 * (th + interp_theta_nb(w.t_rows + c.off - c.n_t, w.sh_theta + c.off - c.n_t, c.n_t, t_target));
+    if (j < last) th_hi = 0.5 * (th + interp_theta_nb(w.t_rows + c.off + c.n_t, w.sh_theta + c.off + c.n_t, c.n_t, t_target));
+    w.geo_dcos[o] = cos(th_hi) - cos(th_lo);
 }
 
 // ---- K2 ---------------------------------------------------------------------------------------
@@ -366,6 +416,10 @@ VAG_HD EatsModel make_eats_model(const BatchWs& w, int mi, int which) {
     M.ictab = (w.any_ssc && rad.ssc) ? w.ictab[shock] + (size_t)off * IC_CAP_OUT : nullptr;
     M.breach = nullptr;
     M.sp_lut = w.sp_lut;
+    M.spreading = (cfg.spreading && w.sh_theta) ? 1 : 0;
+    M.geo_cth = M.spreading ? w.geo_cth + off : nullptr;
+    M.geo_sth = M.spreading ? w.geo_sth + off : nullptr;
+    M.geo_dcos = M.spreading ? w.geo_dcos + off : nullptr;
     M.one_plus_z = 1 + cfg.z;
     M.lumi_dist = cfg.lumi_dist;
     M.theta_v = cfg.theta_v;

@@ -243,16 +243,18 @@ VAG_HD void save_fwd_state(const ModelCfg& m, double eps_B, const ShockRow& s, i
 // forward shock: state = [Gamma, m2, U2_th, r, t_comv]
 // ---------------------------------------------------------------------------------------------
 // INJ: the jet injects energy (magnetar): the reference's ForwardState then carries eps_jet, whose
-// derivative deps_dt(t) enters the step-size control (forward-shock.hpp:23-26, forward-shock.tpp:46-48,89-91)
-template <bool INJ>
+// derivative deps_dt(t) enters the step-size control (forward-shock.hpp:23-26, forward-shock.tpp:46-48,89-91).
+// SPREAD: lateral spreading, theta becomes a state variable (forward-shock.tpp:36-40,57-60,78-84,110-115).
+template <bool INJ, bool SPREAD>
 struct FwdEqnT {
     const ModelCfg& m;
-    double m_jet0, theta0;
-    enum { iG = 0, iM2 = 1, iU = 2, iR = 3, iT = 4, iE = 5, N = INJ ? 6 : 5 };
+    double m_jet0, theta0, dOmega0, theta_s;
+    enum { iG = 0, iM2 = 1, iU = 2, iR = 3, iT = 4, iTh = 5, iE = SPREAD ? 6 : 5, N = 5 + (INJ ? 1 : 0) + (SPREAD ? 1 : 0) };
 
-    VAG_HD FwdEqnT(const ModelCfg& m_, double theta) : m(m_), theta0(theta) {
+    VAG_HD FwdEqnT(const ModelCfg& m_, double theta, double theta_s_) : m(m_), theta0(theta), theta_s(theta_s_) {
         m_jet0 = jet_eps_k(m, theta) / jet_Gamma0(m, theta) / con::c2;  // forward-shock.tpp:20
         m_jet0 /= 1 + m.sigma0;                                          // :21-23
+        dOmega0 = 1 - cos(theta);                                        // :18
     }
 
     // ForwardShockEqn::operator(): forward-shock.tpp:27-118
@@ -264,30 +266,59 @@ struct FwdEqnT {
         const double u = sqrt(u2);  // IEEE: a stage value of Gamma below 1 must give NaN as in the reference
         d[iR] = u * (Gamma + u) * con::c;
         d[iT] = Gamma + u;
+        double dth = 0, sin_theta = 0, cos_theta = 1;
+        if (SPREAD) {
+            const double th = x[SPREAD ? iTh : 0];
+            if (th < 0.5 * con::pi) {  // compute_dtheta_dt: shock-physics.h:154-158
+                constexpr double Q = 7;
+                const double f = 1 / (1 + u * theta_s * Q);
+                dth = d[iR] / (2 * Gamma * x[iR]) * sqrt((2 * u2 + 3) / (4 * u2 + 3)) * f;
+            }
+            d[SPREAD ? iTh : 0] = dth;
+            sin_theta = sin(th);
+            cos_theta = cos(th);
+        }
         const double rho = medium_rho(m, x[iR]);
         d[iM2] = x[iR] * x[iR] * rho * d[iR];
         const double e_th = (Gamma - 1) * 4 * Gamma * rho * con::c2;
         const double eps_rad = radiative_efficiency(m.fwd, x[iT], Gamma, e_th);
         const double ad_idx = adiabatic_idx_fast(Gamma);
         const double dlnV_r = vdiv(3 * d[iR], x[iR]);  // 3 / r * dr/dt, r > 0
+        // lateral-expansion term sin(theta) / (1 - cos(theta)) * dtheta/dt of both rate equations
+        const double lat = SPREAD ? sin_theta / (1 - cos_theta) * dth : 0.0;
         // compute_dGamma_dt
         {
             const double Gamma2 = Gamma * Gamma;
             const double Gamma_eff = vdiv(ad_idx * (Gamma2 - 1) + 1, Gamma);
             const double dGamma_eff = vdiv(ad_idx * (Gamma2 + 1) - 1, Gamma2);
-            const double dlnVdt = dlnV_r;
-            const double U = x[iU];
-            double a1 = -(Gamma - 1) * (Gamma_eff + 1) * con::c2 * d[iM2];
+            double dlnVdt = dlnV_r;
+            double U = x[iU];
+            double dm_dt_swept = d[iM2];
+            double m_swept = x[iM2];
+            if (SPREAD) {
+                const double f_spread = (1 - cos_theta) / dOmega0;
+                dm_dt_swept = dm_dt_swept * f_spread + m_swept / dOmega0 * sin_theta * dth;
+                m_swept *= f_spread;
+                dlnVdt += lat;
+                U *= f_spread;
+            }
+            double a1 = -(Gamma - 1) * (Gamma_eff + 1) * con::c2 * dm_dt_swept;
             if (INJ) a1 += deps;
             const double a2 = (ad_idx - 1) * Gamma_eff * U * dlnVdt;
-            const double b1 = (m_jet0 + x[iM2]) * con::c2;
+            const double b1 = (m_jet0 + m_swept) * con::c2;
             const double b2 = (dGamma_eff + vdiv(Gamma_eff * (ad_idx - 1), Gamma)) * U;
             d[iG] = (a1 + a2) / (b1 + b2);
         }
         // compute_dU_dt
         {
-            const double dlnVdt = dlnV_r - vdiv(d[iG], Gamma);
-            d[iU] = (1 - eps_rad) * (Gamma - 1) * con::c2 * d[iM2] - (ad_idx - 1) * dlnVdt * x[iU];
+            double dm_dt_swept = d[iM2];
+            double dlnVdt = dlnV_r - vdiv(d[iG], Gamma);
+            if (SPREAD) {
+                dm_dt_swept = dm_dt_swept + x[iM2] * lat;
+                dlnVdt += lat;
+                dlnVdt += lat / (ad_idx - 1);
+            }
+            d[iU] = (1 - eps_rad) * (Gamma - 1) * con::c2 * dm_dt_swept - (ad_idx - 1) * dlnVdt * x[iU];
         }
     }
 
@@ -299,12 +330,13 @@ struct FwdEqnT {
         x[iT] = x[iR] / sqrt((Gamma4 - 1) * (Gamma4 + 1)) / con::c;
         x[iM2] = medium_mass(m, x[iR]);
         x[iG] = Gamma4;
+        if (SPREAD) x[SPREAD ? iTh : 0] = theta;
         if (INJ) x[INJ ? iE : 0] = jet_eps_k(m, theta);
         const double ad_idx = adiabatic_idx(Gamma4);
         x[iU] = enclosed_thermal_energy_medium(m, x[iR], Gamma4, ad_idx, m.fwd.radiative ? m.fwd.eps_e : 0.0);
     }
 };
-using FwdEqn = FwdEqnT<false>;
+using FwdEqn = FwdEqnT<false, false>;
 
 // Raw dense-output samples of one row.  The ODE kernel stores only the interpolated state vector
 // of every lattice node (component c -> plane[c][k]); the derived shock quantities are computed
@@ -313,6 +345,7 @@ using FwdEqn = FwdEqnT<false>;
 // (forward table = components 0..5, reverse table = components 6..10), finished in place.
 struct RawRow {
     double* c[11];
+    double* theta;  // Shock::theta of a spreading row (nullptr otherwise)
 };
 // per-row record left by the ODE kernel for the finishing pass
 struct RowDyn {
@@ -325,25 +358,25 @@ struct RowDyn {
 // The accepted-step loop of integrate_adaptive/dense output is flattened to one dopri5 ATTEMPT per
 // iteration (identical sequence of attempts, step sizes and accepted states): in a warp of 32 rows a
 // rejected attempt of one row then costs the other rows nothing.
-template <bool INJ>
-VAG_HD int solve_fwd_row(const ModelCfg& m, double theta, double t_dec, const double* t, int n_t, const ShockRow& s,
-                         const RawRow& raw, RowDyn& rd, double* col, int col_stride) {
-    using Eqn = FwdEqnT<INJ>;
-    Eqn eqn(m, theta);
+template <bool INJ, bool SPREAD>
+VAG_HD int solve_fwd_row(const ModelCfg& m, double theta, double theta_s, double t_dec, const double* t, int n_t,
+                         const ShockRow& s, const RawRow& raw, RowDyn& rd) {
+    using Eqn = FwdEqnT<INJ, SPREAD>;
+    Eqn eqn(m, theta, theta_s);
     double x[Eqn::N];
     const double t0 = vmin(t[0], vmin(0.1 * unit::sec, 0.1 * t_dec));
     eqn.set_init_state(x, theta, t0);
     rd.injection_idx = n_t;
     rd.V3_comv_x = rd.rho3_x = rd.B3_ordered_x = 0;
-    if (x[FwdEqn::iG] <= con::Gamma_cut) {
-        set_stopping_row(s, n_t, x[FwdEqn::iT], x[FwdEqn::iR]);
+    if (x[Eqn::iG] <= con::Gamma_cut) {
+        set_stopping_row(s, n_t, x[Eqn::iT], x[Eqn::iR]);
+        if (SPREAD)
+            for (int k = 0; k < n_t; ++k) raw.theta[k] = theta;  // set_stopping_shock: shock-physics.h:392
         rd.n_saved = -1;
         return 0;
     }
-    // five state variables: the register-resident stepper fits without spills (the 11-variable pair
-    // system uses the shared-memory one)
-    (void)col;
-    (void)col_stride;
+    // five to seven state variables: the register-resident stepper fits without spills (the 11-variable
+    // pair system uses the shared-memory one)
     Dopri5<Eqn::N> st;
     st.initialize(x, t0, 0.01 * t0, m.rtol);
     const double t_back = t[n_t - 1];
@@ -365,11 +398,14 @@ VAG_HD int solve_fwd_row(const ModelCfg& m, double theta, double t_dec, const do
         while (k < n_t && st.t > t[k]) {
             st.calc_state(t[k], x);
 #pragma unroll
-            for (int c = 0; c < FwdEqn::N; ++c) raw.c[c][k] = x[c];
+            for (int c = 0; c < 5; ++c) raw.c[c][k] = x[c];
+            if (SPREAD) raw.theta[k] = x[SPREAD ? Eqn::iTh : 0];
             ++k;
         }
         st.t_old = st.t;  // dense_output_runge_kutta::do_step: the next step starts here
     }
+    if (SPREAD)
+        for (int q = k; q < n_t; ++q) raw.theta[q] = 0;  // Shock ctor default (shock.cpp:15)
     rd.n_saved = k;
     return status;
 }
