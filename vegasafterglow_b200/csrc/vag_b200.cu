@@ -29,11 +29,15 @@ static_assert(sizeof(vag_params) == 312, "vag_params layout must match vegasafte
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-// K0: one warp per model (vag_grid.cuh), 4 warps per CTA
+// K0: GRID_GROUP lanes per model (vag_grid.cuh GroupPar), 32 / GRID_GROUP models per warp, 4 warps per CTA
+constexpr int GRID_GROUP = 8;
 __global__ void __launch_bounds__(128, 4) k_grid(BatchWs w, const double* __restrict__ t_obs, int n_t_obs) {
-    const int mi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (mi >= w.n_models) return;  // whole warps exit together
-    const WarpPar par{(int)(threadIdx.x & 31)};
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int mi = gt / GRID_GROUP;
+    if (mi >= w.n_models) return;  // whole groups exit together
+    const int lane = threadIdx.x & 31;
+    const int shift = lane & ~(GRID_GROUP - 1);
+    const GroupPar<GRID_GROUP> par{lane & (GRID_GROUP - 1), ((1u << GRID_GROUP) - 1u) << shift, shift};
     k0_grid_body(par, w, mi, t_obs[0], t_obs[n_t_obs - 1]);
 }
 
@@ -601,7 +605,7 @@ int run_front(vag_context* ctx, BatchWs& w, const vag_params* d_params, size_t n
     int rc = setup_models(ctx, w, d_params, n);
     if (rc) return rc;
     mark(ctx, 0, s);
-    k_grid<<<(unsigned)((n * 32 + 127) / 128), 128, 0, s>>>(w, d_t, (int)n_t);
+    k_grid<<<(unsigned)((n * GRID_GROUP + 127) / 128), 128, 0, s>>>(w, d_t, (int)n_t);
     k_scan<<<1, 1024, 0, s>>>(w);
     ctx->launches += 2;
     CK(cudaMemcpyAsync(ctx->h_totals, w.totals, sizeof(int) * TOT_N, cudaMemcpyDeviceToHost, s));

@@ -79,6 +79,31 @@ struct WarpPar {
         return end;
     }
 };
+// G lanes of a warp (G = 8): the same contract for a sub-warp group, so that 32 / G models share one warp.
+// The grid builder is mostly uniform (scalar) code that every cooperating lane executes redundantly;
+// with narrower groups the same instruction stream serves 32 / G models at once, while the strided
+// regions keep all lanes busy.  Groups synchronise with their own lane mask (they diverge freely).
+template <int G>
+struct GroupPar {
+    int lane;       // 0 .. G-1 within the group
+    unsigned mask;  // lanes of this group within the warp
+    int shift;      // first lane of the group
+    template <class F>
+    __device__ __forceinline__ void for_each(int n, F f) const {
+        __syncwarp(mask);
+        for (int i = lane; i < n; i += G) f(i);
+        __syncwarp(mask);
+    }
+    template <class P>
+    __device__ __forceinline__ int first_true(int begin, int end, P pred) const {
+        for (int j0 = begin; j0 < end; j0 += G) {
+            const int j = j0 + lane;
+            const unsigned hits = (__ballot_sync(mask, j < end && pred(j)) & mask) >> shift;
+            if (hits) return j0 + __ffs(hits) - 1;
+        }
+        return end;
+    }
+};
 #endif
 
 constexpr int GRID_NSCAN = 513;  // longest scan (find_theta_range visits at most 513 nodes)
