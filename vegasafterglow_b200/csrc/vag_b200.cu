@@ -29,15 +29,17 @@ static_assert(sizeof(vag_params) == 312, "vag_params layout must match vegasafte
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-// K0: GRID_GROUP lanes per model (vag_grid.cuh GroupPar), 32 / GRID_GROUP models per warp, 4 warps per CTA
-constexpr int GRID_GROUP = 8;
+// K0: G lanes per model (vag_grid.cuh GroupPar), 32 / G models per warp, 4 warps per CTA.  Narrow groups
+// share the scalar instruction stream between more models (throughput, large batches); wide groups
+// finish one model sooner (latency, small batches).
+template <int G>
 __global__ void __launch_bounds__(128, 4) k_grid(BatchWs w, const double* __restrict__ t_obs, int n_t_obs) {
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
-    const int mi = gt / GRID_GROUP;
+    const int mi = gt / G;
     if (mi >= w.n_models) return;  // whole groups exit together
     const int lane = threadIdx.x & 31;
-    const int shift = lane & ~(GRID_GROUP - 1);
-    const GroupPar<GRID_GROUP> par{lane & (GRID_GROUP - 1), ((1u << GRID_GROUP) - 1u) << shift, shift};
+    const int shift = lane & ~(G - 1);
+    const GroupPar<G> par{lane & (G - 1), (G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u)) << shift, shift};
     k0_grid_body(par, w, mi, t_obs[0], t_obs[n_t_obs - 1]);
 }
 
@@ -605,7 +607,12 @@ int run_front(vag_context* ctx, BatchWs& w, const vag_params* d_params, size_t n
     int rc = setup_models(ctx, w, d_params, n);
     if (rc) return rc;
     mark(ctx, 0, s);
-    k_grid<<<(unsigned)((n * GRID_GROUP + 127) / 128), 128, 0, s>>>(w, d_t, (int)n_t);
+    if (n >= 8192)
+        k_grid<8><<<(unsigned)((n * 8 + 127) / 128), 128, 0, s>>>(w, d_t, (int)n_t);
+    else if (n >= 1024)
+        k_grid<16><<<(unsigned)((n * 16 + 127) / 128), 128, 0, s>>>(w, d_t, (int)n_t);
+    else
+        k_grid<32><<<(unsigned)((n * 32 + 127) / 128), 128, 0, s>>>(w, d_t, (int)n_t);
     k_scan<<<1, 1024, 0, s>>>(w);
     ctx->launches += 2;
     CK(cudaMemcpyAsync(ctx->h_totals, w.totals, sizeof(int) * TOT_N, cudaMemcpyDeviceToHost, s));
@@ -889,7 +896,9 @@ int vag_create(int device, vag_context** out) {
     }
     // k_grid spills its scratch to local memory: prefer L1.  k_dynamics keeps its dopri5 stage vectors
     // in shared memory (23 KB per 32-row CTA): give it the full carve-out so several CTAs share an SM.
-    cudaFuncSetCacheConfig(k_grid, cudaFuncCachePreferL1);
+    cudaFuncSetCacheConfig(k_grid<8>, cudaFuncCachePreferL1);
+    cudaFuncSetCacheConfig(k_grid<16>, cudaFuncCachePreferL1);
+    cudaFuncSetCacheConfig(k_grid<32>, cudaFuncCachePreferL1);
     cudaFuncSetAttribute(k_dynamics<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     *out = c;
     return VAG_OK;
