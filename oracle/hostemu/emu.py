@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE ONLY: ctypes binding of tests/hostemu/libvagemu.so (the kernel bodies of
+"""TEST INFRASTRUCTURE ONLY: ctypes binding of oracle/hostemu/libvagemu.so (the kernel bodies of
 vegasafterglow_b200/csrc executed sequentially on the host)."""
 import ctypes as C
 import os

@@ -5,7 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
-#include "../tests/hostemu/hostemu.cpp"
+#include "../oracle/hostemu/hostemu.cpp"
 
 int main(int argc, char** argv) {
     FILE* f = fopen(argv[1], "rb");

@@ -99,7 +99,7 @@ _GLOO_WORKER = textwrap.dedent("""
     sys.path.insert(0, {root!r})
     import numpy as np, torch.distributed as dist
     from vegasafterglow_b200 import configs, parallel
-    from tests.hostemu import emu
+    from oracle.hostemu import emu
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
     P = configs.random_draw(7, seed=3, rvs=True)
     ts = np.sort(np.tile(np.logspace(3, 6, 4), 2)); nus = np.tile([1e9, 1e17], 4)

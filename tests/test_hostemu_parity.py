@@ -1,12 +1,12 @@
 """CPU tier: the kernel bodies of vegasafterglow_b200/csrc executed sequentially on the host
-(tests/hostemu) against the committed reference fixtures -- stage by stage (grid, dynamics) and end
+(oracle/hostemu) against the committed reference fixtures -- stage by stage (grid, dynamics) and end
 to end (flux).  This is the same code the GPU runs; the -m gpu tier repeats the flux checks through
 the C ABI on the device."""
 import numpy as np
 import pytest
 
 from tests.helpers import CHAOTIC, assert_parity, assert_reference_contract, golden_names, load_golden
-from tests.hostemu import emu
+from oracle.hostemu import emu
 from vegasafterglow_b200 import configs
 
 

@@ -14,7 +14,7 @@
 //   * the inverse-CDF look-ups, the per-theta symmetry probes, t_dec and the time-bound scan.
 // Order-dependent reductions (running peaks, sums whose rounding matters, first-hit searches) stay
 // in uniform code over the precomputed values, so results equal the sequential restatement's.
-// On the host (tests/hostemu) `Par` is a plain loop.
+// On the host (oracle/hostemu) `Par` is a plain loop.
 #pragma once
 
 #include "vag_dopri5.cuh"

@@ -7,7 +7,7 @@
 // memory (uniform LDCU.128 loads, two coefficients per instruction), use MUFU.RCP64H + Newton for
 // the one division, and fall back to libdevice outside the fast domain.  Accuracy: <= 1 ulp-ish
 // (exp2: |rel| <= 4.5e-16, log2: |abs| <= 2e-16 + 1.2e-16*|result|), far inside the 1e-6 flux bar.
-// Host builds (tests/hostemu) run the same polynomials.
+// Host builds (oracle/hostemu) run the same polynomials.
 #pragma once
 
 #include <cmath>

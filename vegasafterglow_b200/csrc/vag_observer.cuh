@@ -10,7 +10,7 @@
 //
 // The work of one CTA is expressed as barrier-separated phases, each an HD function of the
 // thread index, so the same code runs as a CUDA block (vag_kernels.cu) and as a sequential
-// host emulation in the CPU test-suite (tests/hostemu).
+// host emulation in the CPU test-suite (oracle/hostemu).
 #pragma once
 
 #include "vag_grid.cuh"
