@@ -2,13 +2,13 @@
 // VegasAfterglow model-evaluation path.  Kernel bodies live in vag_pipeline.cuh / vag_observer.cuh.
 //
 // Launch geometry (B200: 148 SMs, FP64 path, no tensor cores -- nothing here is a contraction):
-//   k_grid / k_dynamics : one thread per model / unique row, 32-thread CTAs so that a 4096-row
-//                         batch spreads over all SMs (the ODE is dependent-latency bound; the
-//                         state lives in registers).
-//   k_radiation         : one 64-thread CTA per unique row, threads stride over the time lattice,
-//                         SoA plane stores are coalesced along k.
-//   k_eats              : one 128-thread CTA per (model, row-split, shock); cell tables and
-//                         per-node log2-luminosities staged in dynamic shared memory.
+//   k_grid<G>        : G = 8 / 16 / 32 lanes per model (32 / G models share a warp's scalar instruction stream)
+//   k_dynamics<PAIR> : one thread per unique ODE row, 8 rows per warp for small batches; forward-only rows on a
+//                      register-resident dopri5, pair rows with the stage vectors in shared memory
+//   k_radiation      : one 64-thread CTA per unique row: finishes the shock tables from the raw node states,
+//                      EATS node geometry, photon coefficients (SoA planes, stores coalesced along k)
+//   k_eats<MODE>     : one 128-thread CTA per (model, row-split, shock), 8 CTAs / SM; staged rows, the
+//                      log2_softplus table and the accumulators in dynamic shared memory
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -643,7 +643,6 @@ int run_front(vag_context* ctx, BatchWs& w, const vag_params* d_params, size_t n
             // rows per warp: up to one warp per scheduler before warps are filled up
             int lanes = 32;
             while (lanes > 4 && (rows + lanes / 2 - 1) / (lanes / 2) <= ctx->sm_count * 4) lanes >>= 1;
-            if (const char* e = getenv("VAG_DYN_LANES")) lanes = atoi(e);  // EXPERIMENT
             const unsigned nb = (unsigned)((rows + lanes - 1) / lanes);
             if (ctx->h_totals[TOT_ANY_FWD_ONLY]) {
                 k_dynamics<false><<<nb, 32, 0, s>>>(w, rows, lanes);
