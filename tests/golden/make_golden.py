@@ -98,6 +98,13 @@ def main():
                    ("batch_rs_spreading_tophat", configs.random_draw(8, seed=45, rvs=True, theta_obs_max=0.2))):
         P6["spreading"] = 1
         save(nm, P6, t, nu)
+    # Model(axisymmetric=False): unmirrored phi grid, every phi row observed (jet_3d = 1)
+    for nm, P7 in (("batch_fs_nonaxisym_mixed", np.concatenate([configs.random_draw(6, seed=46, theta_obs_max=0.3),
+                                                                configs.random_draw(5, seed=47, jet="gaussian", theta_obs_max=0.4),
+                                                                configs.random_draw(5, seed=48, jet="powerlaw", medium="wind", theta_obs_max=0.2)])),
+                   ("batch_rs_nonaxisym_tophat", configs.random_draw(8, seed=49, rvs=True, theta_obs_max=0.2))):
+        P7["axisymmetric"] = 0
+        save(nm, P7, t, nu)
     nu_ssc = np.array([1e9, 1e14, 1e17, 1e22, 1e25])
     save("batch_ssc_kn_tophat_ism", configs.random_draw(24, seed=21, ssc=True, kn=True), t, nu_ssc)
     save("batch_ssc_thomson_tophat_wind", configs.random_draw(12, seed=22, ssc=True, kn=False, medium="wind"), t, nu_ssc)

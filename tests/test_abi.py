@@ -83,7 +83,9 @@ def test_unsupported_switches_say_so():
     p["spreading"] = 1  # lateral spreading is implemented
     assert lib.vag_params_validate(p.ctypes.data) == abi.VAG_OK
     p = configs.make()
-    p["axisymmetric"] = 0
+    p["axisymmetric"] = 0  # implemented ...
+    assert lib.vag_params_validate(p.ctypes.data) == abi.VAG_OK
+    p["spreading"] = 1     # ... except together with spreading (per-(phi,theta) lattices)
     assert lib.vag_params_validate(p.ctypes.data) == abi.VAG_ERR_UNSUPPORTED
     p = configs.make(ssc=True, kn=True)  # inverse Compton is implemented
     assert lib.vag_params_validate(p.ctypes.data) == abi.VAG_OK

@@ -866,7 +866,9 @@ int vag_params_validate(const vag_params* p) {
     if (!std::isfinite(p->rtol) || !std::isfinite(p->phi_resol) || !std::isfinite(p->theta_resol) ||
         !std::isfinite(p->t_resol))
         return bad("resolutions and rtol must be finite");
-    if (!p->axisymmetric) return fail(VAG_ERR_UNSUPPORTED, "axisymmetric=False is not implemented on the GPU path yet");
+    if (!p->axisymmetric && p->spreading)
+        return fail(VAG_ERR_UNSUPPORTED,
+                    "axisymmetric=False together with spreading=True (per-(phi,theta) lattices) is not implemented on the GPU path");
     return VAG_OK;
 }
 

@@ -635,14 +635,15 @@ VAG_HD void build_grid(const Par& par, const ModelCfg& m, double t_obs_min, doub
     if (n_theta > s.cap_theta) return fail_capacity();
     h.n_theta = n_theta;
 
-    // phi grid (grid-refinement.h:664-693); is_axisymmetric = true on this path
+    // phi grid (grid-refinement.h:664-693)
+    const bool axis = m.axisymmetric != 0;
     const long long phi_base_ll = (long long)(360 * m.phi_resol);
     const int phi_base = (int)(phi_base_ll > 1 ? phi_base_ll : 1);
-    const bool mirror_phi = theta_view != 0 && phi_base > 4;
+    const bool mirror_phi = axis && theta_view != 0 && phi_base > 4;
     int n_phi;
     if (mirror_phi) {
         const int n_half = (phi_base + 1) / 2;
-        n_phi = adaptive_phi_grid(par, m, n_half, theta_view, s.theta, n_theta, true, con::pi, 5.0, s.phi, s.cap_phi, pt,
+        n_phi = adaptive_phi_grid(par, m, n_half, theta_view, s.theta, n_theta, axis, con::pi, 5.0, s.phi, s.cap_phi, pt,
                                   A, samp, kk);
         h.phi_mirrored = 1;
     } else {
@@ -658,7 +659,7 @@ VAG_HD void build_grid(const Par& par, const ModelCfg& m, double t_obs_min, doub
             else
                 n_phi = -n_phi;
         } else {
-            n_phi = adaptive_phi_grid(par, m, (int)phi_num, theta_view, s.theta, n_theta, true, 2 * con::pi, 0.0, s.phi,
+            n_phi = adaptive_phi_grid(par, m, (int)phi_num, theta_view, s.theta, n_theta, axis, 2 * con::pi, 0.0, s.phi,
                                       s.cap_phi, pt, A, samp, kk);
         }
         if (n_phi >= 2) {
@@ -673,8 +674,9 @@ VAG_HD void build_grid(const Par& par, const ModelCfg& m, double t_obs_min, doub
     if (n_phi < 0) return fail_capacity();
     h.n_phi = n_phi;
     // Observer::build_time_grid (src/core/observer.cpp:211-222): axisymmetric shock tables have
-    // phi extent 1 (jet_3d = 0), so an on-axis observer needs a single phi sample.
-    h.n_phi_eff = (theta_view == 0) ? 1 : n_phi;
+    // phi extent 1 (jet_3d = 0), so an on-axis observer needs a single phi sample; with
+    // axisymmetric=False the tables carry every phi (jet_3d = 1) and all of them are observed.
+    h.n_phi_eff = (theta_view == 0 && axis) ? 1 : n_phi;
 
     // jet_spreading_edge (grid-refinement.h:113-135): angle of the steepest decline of Gamma0 between the
     // first and last theta node.  The walk's nodes are a running sum; the profile is evaluated at all of
@@ -712,16 +714,22 @@ VAG_HD void build_grid(const Par& par, const ModelCfg& m, double t_obs_min, doub
     double* ts_arr = pt + 2 * (size_t)n_theta;
     const double t_end = 1.01 * t_obs_max / (1 + m.z);
     const double cos_tv = cos(theta_view), sin_tv = sin(theta_view);
-    const double cos_phi0 = cos(s.phi[0]);
+    // scan_time_bounds walks phi_size = (axisymmetric ? 1 : N_phi) azimuths (grid-refinement.h:597,484-511);
+    // every bound it keeps is monotone in the raw start time, so the per-theta minimum over phi suffices
+    const int n_phi_scan = axis ? 1 : n_phi;
     par.for_each(n_theta, [&](int j) {
         const double th = s.theta[j];
         const double G = jet_Gamma0(m, th);
         e_arr[j] = jet_eps_k(m, th);
         g_arr[j] = G;
-        // scan_time_bounds (grid-refinement.h:471-514): raw start time of cell (0, j)
+        // scan_time_bounds (grid-refinement.h:471-514): raw start time of cell (i, j)
         const double b = gamma_to_beta(G);
-        const double cos_a = cos(th) * cos_tv + sin(th) * sin_tv * cos_phi0;
-        ts_arr[j] = 0.99 * t_obs_min * (1 - b) / (1 - cos_a * b) / (1 + m.z);
+        double ts_min = kInf;
+        for (int i = 0; i < n_phi_scan; ++i) {
+            const double cos_a = cos(th) * cos_tv + sin(th) * sin_tv * cos(s.phi[i]);
+            ts_min = vmin(ts_min, 0.99 * t_obs_min * (1 - b) / (1 - cos_a * b) / (1 + m.z));
+        }
+        ts_arr[j] = ts_min;
     });
     int n_reps = 0;
     s.reps[n_reps++] = 0;

@@ -27,6 +27,7 @@ struct ModelCfg {
     int has_magnetar;
     double mag_L, mag_t0, mag_q;
     int spreading;   // lateral spreading of a forward-shock-only model (the pair solver has none, reverse-shock.tpp)
+    int axisymmetric;  // Model(axisymmetric=): False = full unmirrored phi grid, every phi row observed (jet_3d = 1)
     int structured;  // jet.spreading: Symmetry::structured, every theta row solved on its own lattice (mesh.h:125-130)  // L0 [code units / 4 pi], t0 [s], q
     // medium
     int medium_type;
@@ -72,6 +73,7 @@ VAG_HD ModelCfg make_cfg(const vag_params& p) {
     m.sigma0 = p.sigma0;
     m.spreading = (p.spreading && !p.has_rvs) ? 1 : 0;
     m.structured = p.spreading ? 1 : 0;
+    m.axisymmetric = p.axisymmetric ? 1 : 0;
     m.has_magnetar = p.has_magnetar;
     // convert_unit_jet (pybind/pymodel.cpp:196-199): deps_dt_cgs(t / unit::sec) * (unit::erg / (4 pi unit::sec))
     m.mag_L = p.magnetar_L0;
