@@ -101,6 +101,10 @@ typedef struct vag_params {
     int32_t has_magnetar;
     int32_t pad2_;
     double magnetar_L0, magnetar_t0, magnetar_q;
+    /* Wind(..., k_m): density slope of the wind, rho = A / (r0^k + r^k) + rho_ism.  2 (or <= 0) selects the typed
+     * Wind of the reference; any other value takes its generic-Medium path (pybind/pymodel.cpp:169-185:
+     * numeric enclosed mass / thermal energy, CGS profile behind convert_unit_medium). */
+    double wind_k_m;
 } vag_params;
 
 /* Fill *p with the reference defaults (Tophat/ISM values are NOT set, only the switches). */

@@ -97,6 +97,22 @@ MediumVariant make_medium(const vag_params& p) {
     if (p.medium_type == VAG_MEDIUM_ISM) {
         return ISM(p.n_ism / unit::cm3);
     }
+    if (p.wind_k_m > 0 && p.wind_k_m != 2) {
+        // PyWind, general k_m (pybind/pymodel.cpp:169-185) followed by convert_unit_medium (:211-222)
+        const Real k_m = p.wind_k_m;
+        constexpr Real r0_cgs = 1e17;
+        const Real mp_cgs = con::mp / unit::g;
+        const Real A_cgs = p.A_star * 5e11 * std::pow(r0_cgs, k_m - 2);
+        const Real rho_ism_cgs = p.n_ism * mp_cgs;
+        const Real r0k_cgs = A_cgs / (p.n0 * 1.3 * mp_cgs);
+        Medium medium;
+        const auto rho_cgs = [=](Real /*phi*/, Real /*theta*/, Real r) noexcept {
+            return A_cgs / (r0k_cgs + std::pow(r, k_m)) + rho_ism_cgs;
+        };
+        medium.rho = [=](Real phi, Real theta, Real r) { return rho_cgs(phi, theta, r / unit::cm) * (unit::g / unit::cm3); };
+        medium.isotropic = true;
+        return medium;
+    }
     return Wind(p.A_star, p.n_ism / unit::cm3, p.n0 / unit::cm3);
 }
 

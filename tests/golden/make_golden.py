@@ -22,7 +22,13 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 REF_GOLDEN = "/root/reference/tests/python/golden"
 
 
+ONLY = tuple(sys.argv[1:])  # optional fixture-name prefixes: regenerate just those, keep the other files
+
+
 def save(name, params, t, nu, series=False, **extra):
+    path = os.path.join(OUT, name + ".npz")
+    if ONLY and not name.startswith(ONLY) and os.path.exists(path):
+        return np.load(path)["flux"]
     fn = ref.flux_density_series if series else ref.flux_density_grid
     f = fn(params, t, nu, n_threads=8)
     # the same unmodified reference built with different code generation (oracle/Makefile,
@@ -57,7 +63,7 @@ def main():
                              "C3": configs.C3(), "C4": configs.C4()}.items():
         save("config_" + name, p, t, nu)
     # 3. stage tables of C1, C2, C3 (Coord + Shock + observer grids)
-    for name, (p, t, nu) in {"C1": configs.C1(), "C2": configs.C2(), "C3": configs.C3()}.items():
+    for name, (p, t, nu) in ({} if ONLY else {"C1": configs.C1(), "C2": configs.C2(), "C3": configs.C3()}).items():
         d = ref.details(p, t[0], t[-1])
         np.savez_compressed(os.path.join(OUT, "stages_" + name + ".npz"), params=p, t_min=t[0], t_max=t[-1],
                             info=np.array(tuple(d["info"].tolist())), **{k: v for k, v in d.items() if k != "info"})
@@ -105,6 +111,14 @@ def main():
                    ("batch_rs_nonaxisym_tophat", configs.random_draw(8, seed=49, rvs=True, theta_obs_max=0.2))):
         P7["axisymmetric"] = 0
         save(nm, P7, t, nu)
+    # Wind(A_star, n_ism, n0, k_m != 2): the reference's generic-Medium path (pybind/pymodel.cpp:169-185)
+    P8 = np.concatenate([configs.random_draw(6, seed=50, medium="wind", theta_obs_max=0.2),
+                         configs.random_draw(5, seed=51, jet="gaussian", medium="wind", theta_obs_max=0.3),
+                         configs.random_draw(5, seed=52, medium="wind", rvs=True)])
+    P8["wind_k_m"] = np.random.default_rng(53).uniform(0.5, 2.8, P8.size)
+    P8["n0"][::3] = 1e5
+    P8["n_ism"][1::4] = 1e-3
+    save("batch_mixed_wind_k", P8, t, nu)
     nu_ssc = np.array([1e9, 1e14, 1e17, 1e22, 1e25])
     save("batch_ssc_kn_tophat_ism", configs.random_draw(24, seed=21, ssc=True, kn=True), t, nu_ssc)
     save("batch_ssc_thomson_tophat_wind", configs.random_draw(12, seed=22, ssc=True, kn=False, medium="wind"), t, nu_ssc)
@@ -139,6 +153,8 @@ def main():
         configs.make(z=3.0, lumi_dist=8e28, rtol=1e-8),
     ])
     save("edge_parameter_corners", corners, np.logspace(1, 8, 30), np.array([1e8, 1e11, 1e14, 1e18, 1e22]))
+    if ONLY:
+        return
     # 6. Model.flux (band integration) and Model.flux_density_exposures through the reference's own
     #    pybind11 module (oracle/_ref/VegasAfterglowC*.so)
     va = ref.pymodule()

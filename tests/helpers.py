@@ -9,7 +9,12 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 def load_golden(name):
     g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
-    return {k: g[k] for k in g.files}
+    d = {k: g[k] for k in g.files}
+    if "params" in d:
+        from vegasafterglow_b200 import abi
+
+        d["params"] = abi.upgrade_params(d["params"])
+    return d
 
 
 def golden_names(prefix=""):

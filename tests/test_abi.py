@@ -37,7 +37,7 @@ def test_params_layout_matches_header(tmp_path):
     out = dict(line.split() for line in subprocess.check_output([str(exe)]).decode().splitlines())
     for k in fields:
         assert int(out[k]) == abi.PARAMS_DTYPE.fields[k][1], k
-    assert int(out["sizeof"]) == abi.PARAMS_DTYPE.itemsize == 312
+    assert int(out["sizeof"]) == abi.PARAMS_DTYPE.itemsize == 320
     assert int(out["info"]) == abi.GRID_INFO_DTYPE.itemsize
 
 

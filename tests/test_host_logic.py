@@ -56,8 +56,9 @@ def test_pybind_mirror_error_conventions():
         va.Model(jet="tophat", medium=va.ISM(1), observer=obs, fwd_rad=rad)
     with pytest.raises(TypeError):
         va.Model(jet=va.TophatJet(0.1, 1e52, 300), medium=3, observer=obs, fwd_rad=rad)
-    with pytest.raises(NotImplementedError):
-        va.Wind(0.1, k_m=1.5)
+    va.Wind(0.1, k_m=1.5)  # general wind slope: the reference's generic-Medium path, on the GPU path too
+    with pytest.raises(ValueError, match="k_m"):
+        va.Wind(0.1, k_m=-1.0)
     with pytest.raises(ValueError, match="theta_w"):
         va.TwoComponentJet(0.1, 1e52, 300, 0.05, 1e50, 50)
     j = va.TwoComponentJet(0.05, 1e52, 300, 0.3, 1e50, 50)

@@ -59,6 +59,7 @@ PARAMS_DTYPE = np.dtype(
         ("magnetar_L0", "f8"),
         ("magnetar_t0", "f8"),
         ("magnetar_q", "f8"),
+        ("wind_k_m", "f8"),
     ],
     align=True,
 )
@@ -81,6 +82,19 @@ c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
 
 
+def upgrade_params(old) -> np.ndarray:
+    """Records written with an earlier (shorter) ``vag_params`` layout -> the current one: fields are copied by
+    name, new fields keep their defaults (committed fixtures stay valid when the struct grows)."""
+    old = np.asarray(old)
+    if old.dtype == PARAMS_DTYPE:
+        return old
+    new = default_params(old.size).reshape(old.shape)
+    for name in old.dtype.names:
+        if name in PARAMS_DTYPE.names:
+            new[name] = old[name]
+    return new
+
+
 def default_params(n: int = 1) -> np.ndarray:
     """``n`` records initialised with the reference defaults (pybind/pybind.cpp:419-422)."""
     p = np.zeros(n, dtype=PARAMS_DTYPE)
@@ -94,6 +108,7 @@ def default_params(n: int = 1) -> np.ndarray:
     p["fwd"]["eps_e"], p["fwd"]["eps_B"], p["fwd"]["p"] = 0.1, 0.01, 2.3
     p["rvs"]["eps_e"], p["rvs"]["eps_B"], p["rvs"]["p"] = 0.1, 0.01, 2.3
     p["axisymmetric"] = 1
+    p["wind_k_m"] = 2.0
     p["radiative_fireball"] = 1
     p["phi_resol"] = p["theta_resol"] = p["t_resol"] = 0.0  # <=0 -> reference defaults
     p["rtol"] = 0.0

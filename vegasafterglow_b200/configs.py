@@ -10,7 +10,7 @@ from . import abi
 def make(jet="tophat", theta_c=0.1, E_iso=1e52, Gamma0=300.0, k_e=2.0, k_g=2.0, duration=1.0, medium="ism",
          n_ism=1.0, A_star=0.1, n0=np.inf, lumi_dist=1e26, z=0.1, theta_obs=0.0, fwd=(0.1, 1e-3, 2.3), rvs=None,
          resolutions=None, rtol=0.0, radiative_fireball=True, xi_e=1.0, rvs_xi_e=1.0, ssc=False, kn=False,
-         rvs_ssc=False, rvs_kn=False, theta_w=0.3, E_iso_w=1e50, Gamma0_w=50.0, sigma0=0.0, magnetar=None):
+         rvs_ssc=False, rvs_kn=False, theta_w=0.3, E_iso_w=1e50, Gamma0_w=50.0, sigma0=0.0, magnetar=None, k_m=2.0):
     p = abi.default_params(1)
     p["jet_type"] = {"tophat": abi.JET_TOPHAT, "gaussian": abi.JET_GAUSSIAN, "powerlaw": abi.JET_POWERLAW,
                      "two_component": abi.JET_TWO_COMPONENT, "step_powerlaw": abi.JET_STEP_POWERLAW,
@@ -24,6 +24,7 @@ def make(jet="tophat", theta_c=0.1, E_iso=1e52, Gamma0=300.0, k_e=2.0, k_g=2.0, 
         p["medium_type"], p["n_ism"] = abi.MEDIUM_ISM, n_ism
     else:
         p["medium_type"], p["A_star"], p["n_ism"], p["n0"] = abi.MEDIUM_WIND, A_star, 0.0 if medium == "wind" else n_ism, n0
+        p["wind_k_m"] = k_m
     p["lumi_dist"], p["z"], p["theta_obs"] = lumi_dist, z, theta_obs
     p["fwd"]["eps_e"], p["fwd"]["eps_B"], p["fwd"]["p"] = fwd
     p["fwd"]["xi_e"] = xi_e

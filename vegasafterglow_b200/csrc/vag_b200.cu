@@ -24,7 +24,7 @@
 
 using namespace vag;
 
-static_assert(sizeof(vag_params) == 312, "vag_params layout must match vegasafterglow_b200/abi.py");
+static_assert(sizeof(vag_params) == 320, "vag_params layout must match vegasafterglow_b200/abi.py");
 
 // ------------------------------------------------------------------------------------------------
 // kernels
@@ -801,6 +801,7 @@ void vag_params_default(vag_params* p) {
     p->rvs = vag_radiation{0.1, 0.01, 2.3, 1.0, 0, 0};
     p->axisymmetric = 1;
     p->radiative_fireball = 1;
+    p->wind_k_m = 2.0;
 }
 
 int vag_params_validate(const vag_params* p) {
@@ -843,6 +844,7 @@ int vag_params_validate(const vag_params* p) {
         if (!finite_pos(p->A_star)) return bad("A_star must be finite and > 0");
         if (!(std::isfinite(p->n_ism) && p->n_ism >= 0)) return bad("n_ism must be finite and >= 0");
         if (!(p->n0 > 0)) return bad("n0 must be > 0 (or +inf for no floor)");
+        if (!(std::isfinite(p->wind_k_m))) return bad("k_m must be finite and > 0");
     }
     // PyObserver: pybind/pymodel.h:190-204
     if (!finite_pos(p->lumi_dist)) return bad("lumi_dist must be finite and > 0");

@@ -32,6 +32,9 @@ struct ModelCfg {
     // medium
     int medium_type;
     double rho_ism, wind_A, wind_r02;
+    // Wind(k_m != 2): generic-Medium profile in CGS, rho = A_cgs / (r0k_cgs + r_cgs^k) + rho_ism_cgs
+    int wind_generic;
+    double wind_k, wind_A_cgs, wind_r0k_cgs, wind_rho_ism_cgs;
     // observer
     double lumi_dist, z, theta_v;
     // radiation
@@ -87,6 +90,18 @@ VAG_HD ModelCfg make_cfg(const vag_params& p) {
     if (p.medium_type == VAG_MEDIUM_WIND) {
         m.wind_A = p.A_star * 5e11 * unit::g / unit::cm;           // medium.h:98
         m.wind_r02 = m.wind_A / ((p.n0 / unit::cm3) * 1.3 * con::mp);  // 0 when n0 = inf
+    }
+    m.wind_generic = 0;
+    m.wind_k = 2;
+    m.wind_A_cgs = m.wind_r0k_cgs = m.wind_rho_ism_cgs = 0;
+    if (p.medium_type == VAG_MEDIUM_WIND && p.wind_k_m > 0 && p.wind_k_m != 2) {  // pybind/pymodel.cpp:169-185
+        constexpr double r0_cgs = 1e17;
+        const double mp_cgs = con::mp / unit::g;
+        m.wind_generic = 1;
+        m.wind_k = p.wind_k_m;
+        m.wind_A_cgs = p.A_star * 5e11 * pow(r0_cgs, p.wind_k_m - 2);
+        m.wind_rho_ism_cgs = p.n_ism * mp_cgs;
+        m.wind_r0k_cgs = m.wind_A_cgs / (p.n0 * 1.3 * mp_cgs);
     }
     m.lumi_dist = p.lumi_dist * unit::cm;
     m.z = p.z;
@@ -158,6 +173,8 @@ VAG_HD double jet_deps_dt(const ModelCfg& m, double theta, double t) {
 // ---- medium profiles (isotropic) ------------------------------------------------------------
 VAG_HD double medium_rho(const ModelCfg& m, double r) {
     if (m.medium_type == VAG_MEDIUM_ISM) return m.rho_ism;  // medium.h:58
+    if (m.wind_generic)                                     // PyWind's Medium behind convert_unit_medium
+        return (m.wind_A_cgs / (m.wind_r0k_cgs + pow(r / unit::cm, m.wind_k)) + m.wind_rho_ism_cgs) * (unit::g / unit::cm3);
     return m.wind_A / (m.wind_r02 + r * r) + m.rho_ism;     // medium.h:107-109
 }
 

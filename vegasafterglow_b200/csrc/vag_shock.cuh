@@ -328,7 +328,8 @@ struct FwdEqnT {
         const double beta4 = gamma_to_beta(Gamma4);
         x[iR] = beta4 * con::c * t0 * Gamma4 * Gamma4 * (1 + beta4);
         x[iT] = x[iR] / sqrt((Gamma4 - 1) * (Gamma4 + 1)) / con::c;
-        x[iM2] = medium_mass(m, x[iR]);
+        // enclosed_mass_medium (shock-physics.h:442-449): analytic for ISM / Wind, Simpson for a generic Medium
+        x[iM2] = m.wind_generic ? enclosed_mass_numeric(m, x[iR]) : medium_mass(m, x[iR]);
         x[iG] = Gamma4;
         if (SPREAD) x[SPREAD ? iTh : 0] = theta;
         if (INJ) x[INJ ? iE : 0] = jet_eps_k(m, theta);

@@ -94,6 +94,7 @@ struct Jet {
 struct MediumP {
     int type;
     Real n_ism, A_star, n0;
+    Real k_m{2};
 };
 struct Observer {
     Real lumi_dist, z, theta_obs, phi_obs;
@@ -168,6 +169,7 @@ class Model {
         p_.n_ism = med.n_ism;
         p_.A_star = med.A_star;
         p_.n0 = med.n0;
+        p_.wind_k_m = med.k_m;
         p_.lumi_dist = observer.lumi_dist;
         p_.z = observer.z;
         p_.theta_obs = observer.theta_obs;
@@ -428,11 +430,7 @@ PYBIND11_MODULE(VegasAfterglowC_b200, m) {
               require(std::isfinite(k_m) && k_m > 0, "k_m must be finite and > 0");
               if (n_ism) require(std::isfinite(*n_ism) && *n_ism >= 0, "n_ism must be finite and >= 0");
               if (n0) require(*n0 > 0, "n0 must be > 0 (or +inf for no floor), got " + std::to_string(*n0));
-              if (k_m != 2) {
-                  PyErr_SetString(PyExc_NotImplementedError, "Wind(k_m != 2) is a host-callback medium in the reference; not on the GPU path");
-                  throw py::error_already_set();
-              }
-              return MediumP{VAG_MEDIUM_WIND, n_ism.value_or(0), A_star, n0.value_or(INFINITY)};
+              return MediumP{VAG_MEDIUM_WIND, n_ism.value_or(0), A_star, n0.value_or(INFINITY), k_m};
           },
           py::arg("A_star"), py::arg("n_ism") = py::none(), py::arg("n0") = py::none(), py::arg("k_m") = 2);
 
