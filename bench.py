@@ -325,11 +325,48 @@ def main():
     barrier()
     ll_ms = la.elapsed_time(lb)
 
+    # ---- config 5 as stated (north_star): ONE 4096-walker ensemble partitioned over the N GPUs by walker,
+    # one evaluation at a time (an MCMC step needs the whole ensemble's log-likelihoods before it can move):
+    # per rank a contiguous block of ceil(4096 / N) walkers, then the NCCL all-gather of the chi2 vector.
+    from vegasafterglow_b200 import parallel
+
+    n_ens = 4096
+    Pe = loglike_workload(n_ens, 0)[0]
+    lo, hi = parallel.partition(n_ens, world, rank)
+    per_rank = -(-n_ens // world)
+    sl0 = slots[0]
+    d_pe = torch.from_numpy(Pe[lo:hi].view(np.uint8).copy()).to(dev)
+    d_blk = torch.full((per_rank,), float("inf"), dtype=torch.float64, device=dev)
+    d_ens = torch.empty(per_rank * world, dtype=torch.float64, device=dev)
+    d_st_e = torch.zeros(per_rank, dtype=torch.int32, device=dev)
+
+    def step_ensemble():
+        sl0.eng.chi2_series_dev(d_pe.data_ptr(), hi - lo, *[a.data_ptr() for a in sl0.d_arr], ts.size,
+                                d_blk.data_ptr(), d_st_e.data_ptr(), sl0.stream.cuda_stream)
+        if world > 1:
+            with torch.cuda.stream(sl0.stream):
+                dist.all_gather_into_tensor(d_ens, d_blk)
+
+    for _ in range(args.warmup):
+        step_ensemble()
+    barrier()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record(main)
+    sl0.stream.wait_event(ea)
+    for _ in range(args.steps):
+        step_ensemble()
+    e = torch.cuda.Event()
+    e.record(sl0.stream)
+    main.wait_event(e)
+    eb.record(main)
+    barrier()
+    ens_ms = ea.elapsed_time(eb)
+
     # ---- max over ranks ------------------------------------------------------------------------------
-    times = torch.tensor([dev_ms, e2e_s * 1e3, ll_ms, wall * 1e3], dtype=torch.float64, device=dev)
+    times = torch.tensor([dev_ms, e2e_s * 1e3, ll_ms, wall * 1e3, ens_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, ll_ms, wall_ms = (float(x) for x in times.tolist())
+    dev_ms, e2e_ms, ll_ms, wall_ms, ens_ms = (float(x) for x in times.tolist())
 
     if rank == 0:
         total_models = n * world * args.steps
@@ -381,7 +418,12 @@ def main():
             "loglike": {"metric": f"MCMC loglike evals/s ({n_ll}-walker batch per GPU per step, FS+RS tophat, 100-point "
                                   f"5-band series, {S_ll} steps in flight)",
                         "value": n_ll * world * args.steps / (ll_ms * 1e-3), "unit": UNIT, "ms_per_step": ll_ms / args.steps,
-                        "collective": "all_gather float64[n] over NCCL" if world > 1 else "none (1 GPU)"},
+                        "collective": "all_gather float64[n] over NCCL" if world > 1 else "none (1 GPU)",
+                        "ensemble_4096": {
+                            "what": f"one 4096-walker ensemble split over {world} GPU(s) by walker ({per_rank} per GPU), one "
+                                    f"evaluation in flight, chi2 all-gathered over NCCL (strong scaling of config 5)",
+                            "ms_per_ensemble": ens_ms / args.steps,
+                            "value": n_ens * args.steps / (ens_ms * 1e-3), "unit": UNIT}},
             "wall_ms_per_step": wall_ms / args.steps,
         }
         if world == 1 and not args.no_cpu_baseline:
