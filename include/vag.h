@@ -205,6 +205,12 @@ int vag_details(vag_context* ctx, const vag_params* p, double t_min, double t_ma
                 double* theta, double* phi, int32_t* reps, double* t_rows, double* fwd_shock, double* rvs_shock,
                 int32_t* inj_idx);
 
+/* Photon tables of one model (same front end as vag_details): for each shock [6][n_reps][n_t] in the order
+ * log2 nu_m, log2 nu_c, log2 nu_a, log2 nu_M, log2 I_nu_max (code units) and 1/nu_M -- what
+ * save_photon_details exports (pybind/pymodel.cpp:263-291).  rvs may be NULL; it is untouched without a
+ * reverse shock.  Shocks with ssc=True are not covered (VAG_ERR_UNSUPPORTED). */
+int vag_details_photons(vag_context* ctx, const vag_params* p, double t_min, double t_max, double* fwd, double* rvs);
+
 /* Output transfer policy of the HOST-buffer flux entry points.
  * VAG_OUT_DENSE (default): every one of the VAG_NCOMP planes of `out` is written (absent components 0).
  * VAG_OUT_PRESENT: planes of components that NO model of the batch has (reverse shock: has_rvs;

@@ -1270,4 +1270,38 @@ int vag_details(vag_context* ctx, const vag_params* p, double t_min, double t_ma
     return VAG_OK;
 }
 
+int vag_details_photons(vag_context* ctx, const vag_params* p, double t_min, double t_max, double* fwd, double* rvs) {
+    if (!ctx || !p || !fwd) return fail(VAG_ERR_INVALID, "NULL argument");
+    if (int rc = vag_params_validate(p)) return rc;
+    if (p->fwd.ssc || (p->has_rvs && p->rvs.ssc))
+        return fail(VAG_ERR_UNSUPPORTED, "vag_details_photons covers shocks without inverse Compton only");
+    CK(cudaSetDevice(ctx->device));
+    int ct, cp;
+    caps_for(p, 1, ct, cp);
+    ctx->cap_theta = ct;
+    ctx->cap_phi = cp;
+    cudaStream_t s = ctx->stream;
+    CK(ctx->io_params.ensure(sizeof(vag_params)));
+    CK(ctx->io_t.ensure(sizeof(double) * 2));
+    const double tt[2] = {t_min, t_max};
+    CK(cudaMemcpyAsync(ctx->io_params.p, p, sizeof(vag_params), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->io_t.p, tt, sizeof(tt), cudaMemcpyHostToDevice, s));
+    BatchWs w;
+    int totals[TOT_N];
+    long long cells = 0;
+    ctx->launches = 0;
+    if (int rc = run_front(ctx, w, static_cast<vag_params*>(ctx->io_params.p), 1, static_cast<double*>(ctx->io_t.p), 2,
+                           s, totals, &cells))
+        return rc;
+    const int planes[6] = {PH_LOG2_NU_M, PH_LOG2_NU_C, PH_LOG2_NU_A, PH_LOG2_NU_M_MAX, PH_LOG2_I_MAX, PH_INV_NU_M_MAX};
+    const size_t nc = (size_t)cells;
+    for (int a = 0; a < 6; ++a) {
+        CK(cudaMemcpyAsync(fwd + a * nc, w.coef_fwd + (size_t)planes[a] * nc, sizeof(double) * nc, cudaMemcpyDeviceToHost, s));
+        if (rvs && p->has_rvs)
+            CK(cudaMemcpyAsync(rvs + a * nc, w.coef_rvs + (size_t)planes[a] * nc, sizeof(double) * nc, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    return VAG_OK;
+}
+
 }  // extern "C"

@@ -1,0 +1,100 @@
+"""``Model.details(t_min, t_max)`` on the GPU path: the reference's ``SimulationDetails`` / ``ShockDetails``
+(pybind/pymodel.cpp:213-348, pybind/pybind.cpp:522-584) assembled from the device stage tables.
+
+The device keeps only the UNIQUE shock rows (symmetry collapse) and the photon coefficients; this module
+broadcasts them over theta (and phi for ``axisymmetric=False``), converts to the reference's CGS / second
+units and rebuilds the observer-frame grids (``t_obs``, ``Doppler``: observer.cpp:51-205) and the electron
+break Lorentz factors from the break frequencies (gamma = sqrt(nu / (K B)), synchrotron.cpp:107-116).
+Inverse-Compton bookkeeping (``Y_T``, ``*_hat``) is not exported: those fields are zero, as they are in the
+reference for ``Radiation(ssc=False)``.
+"""
+from __future__ import annotations
+
+import types
+
+import numpy as np
+
+from . import abi
+
+# unit system of the reference (src/util/macros.h:43-77), same expressions as csrc/vag_common.cuh
+_LEN = 1.5e13
+CM = 1 / _LEN
+SEC = 3e10 / _LEN
+G = 1 / 2e33
+HZ = 1 / SEC
+ERG = G * CM * CM / SEC / SEC
+FLUX_DEN_CGS = ERG / (CM * CM) / SEC / HZ
+GAUSS = 8.66e-11 / SEC
+MP = 1.67e-24 * G
+ME = MP / 1836
+E_CHARGE = 4.8e-10 / 4.472136e16 / 5.809475e19 / SEC
+C = 1.0
+_K_SYN = 3 * E_CHARGE / (4 * np.pi * ME * C)  # nu = K B gamma^2
+
+
+def _shock(tab, rep_of, n_ext):
+    """[7, n_reps, n_t] device table -> dict of [n_ext, n_theta, n_t] arrays in the reference's units."""
+    names = ("t_comv", "r", "theta", "Gamma", "Gamma_th", "B_comv", "N_p")
+    scale = (1 / SEC, 1 / CM, 1.0, 1.0, 1.0, 1 / GAUSS, 1.0)
+    return {n: np.broadcast_to(tab[a][rep_of] * s, (n_ext,) + tab[a][rep_of].shape).copy() for a, (n, s) in enumerate(zip(names, scale))}
+
+
+def simulation_details(engine, param, t_min, t_max):
+    p = np.ascontiguousarray(param, dtype=abi.PARAMS_DTYPE).reshape(-1)
+    assert p.size == 1
+    d = engine.details(p, float(t_min), float(t_max))
+    n_theta, n_t = d["theta"].size, d["t_rows"].shape[1]
+    reps = d["reps"]
+    rep_of = np.searchsorted(reps, np.arange(n_theta), side="right") - 1
+    axis = bool(p["axisymmetric"][0])
+    has_rvs = bool(p["has_rvs"][0])
+    spreading = bool(p["spreading"][0]) and not has_rvs
+    n_ext = 1 if axis else d["phi"].size
+    theta_v, z = float(p["theta_obs"][0]), float(p["z"][0])
+    n_phi_eff = int(d["info"]["n_phi_eff"])
+    ph_f, ph_r = engine.details_photons(p, float(t_min), float(t_max), reps.size, n_t)
+
+    out = types.SimpleNamespace()
+    out.phi, out.theta = d["phi"].copy(), d["theta"].copy()
+    t_code = d["t_rows"][rep_of]                        # [n_theta, n_t]
+    out.t_src = np.broadcast_to(t_code / SEC, (n_ext, n_theta, n_t)).copy()
+
+    # observer grids (one EAT geometry serves both shocks: pybind/pymodel.cpp:337)
+    fwd_tab = d["fwd_shock"]
+    Gam, r = fwd_tab[3][rep_of], fwd_tab[1][rep_of]
+    th_k = fwd_tab[2][rep_of] if spreading else np.broadcast_to(d["theta"][:, None], (n_theta, n_t))
+    cos_phi = np.cos(d["phi"][:n_phi_eff])[:, None, None]
+    cos_v = np.sin(th_k)[None] * cos_phi * np.sin(theta_v) + np.cos(th_k)[None] * np.cos(theta_v)
+    u = np.sqrt((Gam - 1) * (Gam + 1))
+    doppler = 1.0 / (Gam[None] - u[None] * cos_v)
+    t_obs = (t_code[None] + (1 - cos_v) * r[None] / C) * (1 + z) / SEC
+
+    def shock_details(tab, coef, rad):
+        s = types.SimpleNamespace(**_shock(tab, rep_of, n_ext))
+        if not spreading:  # Shock::broadcast_groups gives every row its own coord.theta(j) (shock.cpp:41-88)
+            s.theta = np.broadcast_to(d["theta"][None, :, None], (n_ext, n_theta, n_t)).copy()
+        s.t_obs, s.Doppler = t_obs.copy(), doppler.copy()
+        B = tab[5][rep_of]
+        ext = lambda a: np.broadcast_to(a, (n_ext,) + a.shape).copy()  # noqa: E731
+        with np.errstate(over="ignore", divide="ignore", invalid="ignore"):
+            nu = {k: np.exp2(coef[i][rep_of]) for i, k in enumerate(("nu_m", "nu_c", "nu_a"))}
+            nu["nu_M"] = 1.0 / coef[5][rep_of]
+            for k, v in nu.items():
+                setattr(s, k, ext(v / HZ))
+                setattr(s, "gamma_" + k[3:], ext(np.sqrt(v / (_K_SYN * B))))
+            s.I_nu_max = ext(np.exp2(coef[4][rep_of]) / FLUX_DEN_CGS)
+            gm = np.sqrt(nu["nu_m"] / (_K_SYN * B))
+            f_syn = (gm - 1) / gm
+            if rad["p"] > 3:
+                f_syn = f_syn ** ((rad["p"] - 1) / 2)
+            s.N_e = ext(tab[6][rep_of] * rad["xi_e"] * f_syn)
+        for k in ("gamma_m_hat", "gamma_c_hat", "nu_m_hat", "nu_c_hat", "Y_T"):
+            setattr(s, k, np.zeros((n_ext, n_theta, n_t)))
+        return s
+
+    out.fwd = shock_details(fwd_tab, ph_f, p["fwd"][0])
+    if has_rvs:
+        out.rvs = shock_details(d["rvs_shock"], ph_r, p["rvs"][0])
+    else:  # the reference leaves the absent shock's arrays default-constructed (0-d)
+        out.rvs = types.SimpleNamespace(**{k: np.zeros(()) for k in vars(out.fwd)})
+    return out

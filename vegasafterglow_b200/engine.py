@@ -174,3 +174,13 @@ class Engine:
                      d["phi"].ctypes.data, d["reps"].ctypes.data, d["t_rows"].ctypes.data,
                      d["fwd_shock"].ctypes.data, d["rvs_shock"].ctypes.data, d["inj_idx"].ctypes.data))
         return d
+
+    def details_photons(self, param, t_min, t_max, n_reps, n_t):
+        """Photon tables of one model: (fwd, rvs) each [6, n_reps, n_t] -- log2 nu_m, nu_c, nu_a, nu_M, I_nu_max (code
+        units) and 1/nu_M (include/vag.h vag_details_photons)."""
+        p = self._params(param)
+        assert p.size == 1
+        fwd = np.zeros((6, n_reps, n_t))
+        rvs = np.zeros((6, n_reps, n_t))
+        _lib.check(self._lib.vag_details_photons(self._h, p.ctypes.data, t_min, t_max, fwd.ctypes.data, rvs.ctypes.data))
+        return fwd, rvs

@@ -288,6 +288,17 @@ class Model {
         return pack(out, {(py::ssize_t)n});
     }
 
+    // Model.details (pybind/pymodel.cpp:315-348): assembled in Python from the device stage tables
+    // (vegasafterglow_b200/details.py) -- broadcasting, unit conversion and the observer grids are host work
+    py::object details(Real t_min, Real t_max) const {
+        require(std::isfinite(t_min) && t_min > 0 && std::isfinite(t_max) && t_max > t_min, "need 0 < t_min < t_max");
+        py::object engine = py::module_::import("vegasafterglow_b200.engine").attr("Engine")(device_);
+        py::object dtype = py::module_::import("vegasafterglow_b200.abi").attr("PARAMS_DTYPE");
+        py::bytes raw(reinterpret_cast<const char*>(&p_), sizeof(p_));
+        py::object arr = py::module_::import("numpy").attr("frombuffer")(raw, dtype);
+        return py::module_::import("vegasafterglow_b200.details").attr("simulation_details")(engine, arr, t_min, t_max);
+    }
+
     const vag_params& params() const { return p_; }
     Observer obs_;
     Radiation fwd_;
@@ -494,5 +505,6 @@ PYBIND11_MODULE(VegasAfterglowC_b200, m) {
         .def_property_readonly("radiative_fireball", [](const Model& mdl) { return mdl.params().radiative_fireball != 0; })
         .def_property_readonly("params_bytes",
                                [](const Model& mdl) { return py::bytes(reinterpret_cast<const char*>(&mdl.params()), sizeof(vag_params)); })
+        .def("details", &Model::details, py::arg("t_min"), py::arg("t_max"))
         .def("__repr__", &Model::repr);
 }
