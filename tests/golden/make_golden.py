@@ -123,6 +123,9 @@ def main():
     save("batch_ssc_kn_tophat_ism", configs.random_draw(24, seed=21, ssc=True, kn=True), t, nu_ssc)
     save("batch_ssc_thomson_tophat_wind", configs.random_draw(12, seed=22, ssc=True, kn=False, medium="wind"), t, nu_ssc)
     save("batch_ssc_kn_rs_tophat_ism", configs.random_draw(12, seed=23, ssc=True, kn=True, rvs=True), t, nu_ssc)
+    P9 = configs.random_draw(6, seed=24, ssc=True, kn=True, theta_obs_max=0.3)
+    P9["spreading"] = 1  # SSC output band of a spreading jet: per-node Doppler extrema
+    save("batch_ssc_spreading_tophat", P9, t, nu_ssc)
     ts = np.sort(np.tile(np.logspace(2.5, 6.5, 20), 5))
     nus = np.tile([1e9, 5e9, 4.84e14, 1e17, 1e18], 20)
     save("series_rs_tophat_ism", configs.random_draw(48, seed=16, rvs=True), ts, nus, series=True)

@@ -92,7 +92,7 @@ def assert_parity(flux, g, what):
 # fixtures to <= 1e-8.
 CHAOTIC = ("golden_gauss_ism_rs", "batch_rs_magnetized_tophat", "series_rs_gauss", "batch_rs_step_powerlaw",
            "batch_fs_spreading_tophat", "batch_fs_spreading_gauss", "batch_fs_spreading_powerlaw_wind",
-           "batch_rs_spreading_tophat")
+           "batch_rs_spreading_tophat", "batch_ssc_spreading_tophat")
 
 
 def assert_reference_contract(flux, g, what, median_rtol=1e-4):

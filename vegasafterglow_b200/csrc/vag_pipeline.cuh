@@ -351,10 +351,17 @@ VAG_HD void k_dop_extrema_body(const BatchWs& w, int mi, int k) {
     const double* Gam = w.fwd[2] + w.cell_off[mi];
     const int* rep_of = w.rep_of + (size_t)mi * w.cap_theta;
     const double* rc = w.rowcos + (size_t)mi * w.max_erows;
+    // spreading jets: the line-of-sight cosine is a per-node quantity (observer.cpp:82); rowcos then holds
+    // cos(phi) sin(theta_obs) and the node tables supply cos / sin of theta(k)
+    const bool spread = w.cfg[mi].spreading && w.sh_theta;
+    const double cos_obs = cos(w.cfg[mi].theta_v);
     double lo = kInf, hi = -kInf;
     for (int q = 0; q < erows; ++q) {
-        const double g = Gam[(size_t)rep_of[q % h.n_theta] * h.n_t + k];
-        const double d = g - sqrt((g - 1) * (g + 1)) * rc[q];
+        const size_t o = (size_t)rep_of[q % h.n_theta] * h.n_t + k;
+        const double g = Gam[o];
+        const long long cell = w.cell_off[mi] + (long long)o;
+        const double cos_v = spread ? w.geo_sth[cell] * rc[q] + w.geo_cth[cell] * cos_obs : rc[q];
+        const double d = g - sqrt((g - 1) * (g + 1)) * cos_v;
         lo = vmin(lo, d);
         hi = vmax(hi, d);
     }
