@@ -166,7 +166,7 @@ void caps_for(const vag_params* p, size_t n, int& cap_theta, int& cap_phi) {
         const double th_res = p[i].theta_resol > 0 ? p[i].theta_resol : (r ? 0.2 : 0.15);
         const double ph_res = p[i].phi_resol > 0 ? p[i].phi_resol : 0.06;
         const double lg = std::log10(std::max(1.0, std::max(p[i].Gamma0, p[i].Gamma0_w) * 1.5708));
-        const int ct = 36 + (int)(90 * th_res) + (int)(std::max(0.0, lg - 1) * th_res * 55) + (int)(lg * th_res * 25) + 40;
+        const int ct = 36 + (int)(90 * th_res) + (int)(std::max(0.0, lg - 1) * th_res * 55) + (int)(lg * th_res * 25) + 64;
         const int cp = std::max((int)(360 * ph_res), 1) * 5 + 8;
         cap_theta = std::max(cap_theta, ct);
         cap_phi = std::max(cap_phi, cp);

@@ -86,6 +86,11 @@ def main():
     P4 = configs.random_draw(16, seed=35, rvs=True)
     P4["sigma0"] = 10 ** np.random.default_rng(36).uniform(-2, 1, 16)
     save("batch_rs_magnetized_tophat", P4, t, nu)
+    # narrow structured cores: the steep Gaussian trips find_jet_jumps' discontinuity test at up to 14 scan
+    # intervals (grid-refinement.h:40-86), each of which adds refinement nodes
+    PN = configs.random_draw(12, seed=54, jet="gaussian", theta_obs_max=0.1)
+    PN["theta_c"] = 10 ** np.random.default_rng(55).uniform(-2.4, -1.5, PN.size)
+    save("batch_fs_narrow_gauss", PN, t, nu)
     # magnetar energy injection (jet factories' magnetar=Magnetar(L0, t0, q); the jet takes the Ejecta path)
     rng = np.random.default_rng(41)
     for nm, P5 in (("batch_fs_magnetar_tophat", configs.random_draw(16, seed=37)),

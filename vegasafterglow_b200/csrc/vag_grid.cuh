@@ -162,7 +162,8 @@ VAG_HD int find_jet_jumps(const Par& par, const ModelCfg& m, double gamma_cut, d
                 hi = mid;
             }
         }
-        if (n < cap) jumps[n++] = prev_G > cur_G ? lo : hi;
+        if (n >= cap) return -1;  // more discontinuities than the compiled capacity: reported, never truncated
+        jumps[n++] = prev_G > cur_G ? lo : hi;
     }
     return n;
 }
@@ -614,8 +615,12 @@ VAG_HD void build_grid(const Par& par, const ModelCfg& m, double t_obs_min, doub
     double* samp = B + (GRID_NSCAN + 7);               // [2*theta_samples]
     double* kk = samp + 2 * dflt::theta_samples;       // [8]
 
-    double jumps[8];
-    const int n_jumps = find_jet_jumps(par, m, con::Gamma_cut, jumps, 8, A);
+    // A steep smooth profile trips the jump test too (adjacent scan nodes differing by more than half):
+    // a Gaussian core of theta_c ~ 0.014 rad yields 14 "jumps", the most any typed profile produces.
+    constexpr int JUMP_CAP = 48;
+    double jumps[JUMP_CAP];
+    const int n_jumps = find_jet_jumps(par, m, con::Gamma_cut, jumps, JUMP_CAP, A);
+    if (n_jumps < 0) return fail_capacity();
     double inner_edge, outer_edge;
     find_theta_range(par, m, con::Gamma_cut, inner_edge, outer_edge, A, B);
     for (int i = 0; i < n_jumps; ++i) outer_edge = vmax(outer_edge, jumps[i]);
@@ -629,7 +634,7 @@ VAG_HD void build_grid(const Par& par, const ModelCfg& m, double t_obs_min, doub
                                            base_theta, s.cap_theta, A, B, samp, kk);
     if (n_base < 0) return fail_capacity();
     const double avg_spacing = (theta_max - theta_min) / n_base;
-    double feat[24];
+    double feat[3 * JUMP_CAP];
     const int n_feat = jump_refinement_grid(jumps, n_jumps, theta_min, theta_max, avg_spacing, feat);
     const int n_theta = merge_grids(base_theta, n_base, feat, n_feat, s.theta, s.cap_theta);
     if (n_theta > s.cap_theta) return fail_capacity();
