@@ -68,6 +68,8 @@ for q, i in enumerate(idx):
 errs = np.array(errs)
 print(f"parity vs the unmodified reference on {idx.size} sampled models: median {np.median(errs):.2e}, "
       f"90% {np.percentile(errs, 90):.2e}, max {errs.max():.2e}; > 1e-6: {np.count_nonzero(errs > 1e-6)}, > 1e-3: {np.count_nonzero(errs > 1e-3)}")
+fs_only = np.array([P["has_rvs"][i] == 0 for i in idx])
+print(f"  forward-shock-only models: {fs_only.sum()}, of which > 1e-6: {np.count_nonzero(errs[fs_only] > 1e-6)}, max {errs[fs_only].max() if fs_only.any() else 0:.2e}")
 for q in np.argsort(-errs)[:8]:
     i = idx[q]
     print(f"  err {errs[q]:.2e} model {i}:", {k: (float(P[k][i]) if P[k][i].dtype.kind == 'f' else int(P[k][i])) for k in ("jet_type", "medium_type", "has_rvs", "spreading", "axisymmetric", "has_magnetar", "sigma0", "wind_k_m", "theta_obs")}, "ssc", int(P["fwd"]["ssc"][i]))
