@@ -79,6 +79,21 @@ VAG_HD double dexp2(double x) {
     return bits_to_double(double_to_bits(p) + ((uint64_t)k << 52));
 }
 
+// Guard-free variants for callers that guarantee a finite argument in (-1000, 1000) / a positive normal
+// finite argument: no range check, no libm fallback, hence no branch in the caller's instruction stream.
+VAG_HD double dexp2_nc(double x) {
+    const double magic = 6755399441055744.0;
+    const double t = x + magic;
+    const double kf = t - magic;
+    const double f = x - kf;
+    const int64_t k = (int64_t)(double_to_bits(t) & 0xFFFFFFFFull) | ((double_to_bits(t) & 0x80000000ull) ? ~0xFFFFFFFFll : 0);
+    double p = VAG_CEXP2[VAG_EXP2_DEG];
+#pragma unroll
+    for (int j = VAG_EXP2_DEG - 1; j >= 0; --j) p = fma(p, f, VAG_CEXP2[j]);
+    return bits_to_double(double_to_bits(p) + ((uint64_t)k << 52));
+}
+VAG_HD double dlog2_nc(double x);
+
 VAG_HD double dlog2(double x) {
     if (!(x >= 2.2250738585072014e-308 && x < kInf)) return log2(x);  // 0, negative, subnormal, inf, NaN
     uint64_t u = double_to_bits(x);
@@ -89,6 +104,32 @@ VAG_HD double dlog2(double x) {
         m *= 0.5;
         e += 1;
     }
+    const double num = m - 1.0, den = m + 1.0;
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+    r = fma(r, fma(-den, r, 1.0), r);
+    r = fma(r, fma(-den, r, 1.0), r);
+    double s = num * r;
+    s = fma(fma(-den, s, num), r, s);
+#else
+    const double s = num / den;
+#endif
+    const double z = s * s;
+    double q = VAG_CLOG2[10];
+#pragma unroll
+    for (int j = 9; j >= 0; --j) q = fma(q, z, VAG_CLOG2[j]);
+    return fma(s, q, (double)e);
+}
+
+VAG_HD double dlog2_nc(double x) {
+    uint64_t u = double_to_bits(x);
+    int e = (int)(u >> 52) - 1023;
+    u = (u & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull;
+    double m = bits_to_double(u);
+    const bool hi = m > 1.4142135623730951;
+    m = hi ? m * 0.5 : m;
+    e = hi ? e + 1 : e;
     const double num = m - 1.0, den = m + 1.0;
 #if defined(__CUDA_ARCH__)
     double r;

@@ -127,17 +127,22 @@ VAG_HD double radiative_efficiency(const RadCfg& rad, double t_comv, double Gamm
     if (rad.eps_e_rad == 0) return 0;
     const double gamma_m = rad.gamma_m_coeff * (Gamma_th - 1) + 1;
     const double den = e_th * t_comv;
-    double ratio;
-    if (den > 1e-100 && den < 1e100) {  // the ordinary case: branch-free arithmetic
-        const double gamma_bar = vdiv(rad.gamma_c_coeff, den);
-        const double gamma_c = 0.5 * (gamma_bar + vsqrt(gamma_bar * gamma_bar + 4));
-        ratio = vdiv(gamma_m, gamma_c);
-    } else {  // e_th = 0 (Gamma clamped to 1), overflow ...: IEEE semantics as in the reference
+    const bool ok = den > 1e-100 && den < 1e100;  // the ordinary case: branch-free arithmetic
+    const double den_s = ok ? den : 1.0;
+    const double gamma_bar_f = vdiv(rad.gamma_c_coeff, den_s);
+    const double gamma_c_f = 0.5 * (gamma_bar_f + vsqrt(gamma_bar_f * gamma_bar_f + 4));
+    double ratio = vdiv(gamma_m, gamma_c_f);
+    if (!ok) {  // e_th = 0 (Gamma clamped to 1), overflow ...: IEEE semantics as in the reference
         const double gamma_bar = rad.gamma_c_coeff / den;
         const double gamma_c = 0.5 * (gamma_bar + sqrt(gamma_bar * gamma_bar + 4));
         ratio = gamma_m / gamma_c;
     }
-    if (ratio < 1 && rad.p > 2) return rad.eps_e_rad * dexp2((rad.p - 2) * dlog2(ratio));  // fast_pow
+    // fast_pow(ratio, p - 2) evaluated unconditionally on a safe argument and selected afterwards, so that the
+    // chain can overlap with the rest of the right-hand side instead of sitting behind a branch
+    const bool slow_cooling = ratio < 1 && rad.p > 2;
+    const double ratio_s = (slow_cooling && ratio > 1e-300) ? ratio : 0.5;
+    const double pw = dexp2_nc(vmax((rad.p - 2) * dlog2_nc(ratio_s), -1000.0));
+    if (slow_cooling) return rad.eps_e_rad * ((ratio > 1e-300) ? pw : 0.0);
     return rad.eps_e_rad;
 }
 // shock-physics.h:300-312
@@ -536,66 +541,57 @@ struct FREqn {
         }
         d[iX4] = dx4;
 
+        // The nested conditions of the reference's rate terms are evaluated as straight-line code and selected
+        // afterwards (same arithmetic on the taken side): with one warp per scheduler a branch ends the window
+        // in which the independent chains of this right-hand side can overlap.
+        // compute_dU2_dt :96-110 -- the radiative efficiency only needs (Gamma, rho, t_comv): start it early
+        const double e_th = (Gamma - 1) * 4 * Gamma * rho * con::c2;
+        const double eps_rad = radiative_efficiency(m.fwd, t_comv, Gamma, e_th);
+
         // compute_dx3_dt :124-179
         const double remaining = vmax(m4 - m3, 0.0);
+        const bool has_shell = !(m4 <= 0);
+        const double m4_s = has_shell ? m4 : 1.0;
+        const double crossing_w = f + vdiv((1.0 - f) * remaining, m4_s);
+        const double penetration = vdiv(Gamma * comp_ratio, Gamma4) - 1;
+        const bool crossing_on = has_shell && !(crossing_w < 1e-6) && !(penetration <= 0);
         double dx3;
         {
             const double sound_expansion = cs34_dtc;
-            dx3 = sound_expansion;
-            if (!(m4 <= 0)) {
-                const double w_num = (1.0 - f) * remaining;
-                const double crossing_w = f + vdiv(w_num, m4);  // m4 > 0 here
-                if (!(crossing_w < 1e-6)) {
-                    const double penetration = vdiv(Gamma * comp_ratio, Gamma4) - 1;
-                    if (!(penetration <= 0)) {
-                        const double beta3 = vdiv(u3, Gamma);  // gamma_to_beta(Gamma)
-                        const double dx3dt = vdiv((Gamma4 - Gamma) * (Gamma4 + Gamma) * (1 + beta3) * con::c,
-                                                  Gamma4 * Gamma4 * (beta3 + beta4) * penetration);
-                        double crossing = fabs(dx3dt * Gamma);
-                        if (penetration < 1) {
-                            const double cs = cs34;
-                            const double va2 = vdiv(sigma, 1 + sigma);  // sigma >= 0
-                            const double cs2 = cs * cs / (con::c * con::c);
-                            const double v_ms = vsqrt(va2 + cs2 * (1 - va2)) * con::c;
-                            crossing = vmin(crossing, v_ms * dtc);
-                        }
-                        dx3 = crossing_w * crossing + (1.0 - crossing_w) * sound_expansion;
-                    }
-                }
-            }
+            const double pen_s = crossing_on ? penetration : 1.0;
+            const double beta3 = vdiv(u3, Gamma);  // gamma_to_beta(Gamma)
+            const double dx3dt = vdiv((Gamma4 - Gamma) * (Gamma4 + Gamma) * (1 + beta3) * con::c,
+                                      Gamma4 * Gamma4 * (beta3 + beta4) * pen_s);
+            double crossing = fabs(dx3dt * Gamma);
+            const double va2 = vdiv(sigma, 1 + sigma);  // sigma >= 0
+            const double cs2 = cs34 * cs34 / (con::c * con::c);
+            const double v_ms = vsqrt(va2 + cs2 * (1 - va2)) * con::c;
+            crossing = (penetration < 1) ? vmin(crossing, v_ms * dtc) : crossing;
+            dx3 = crossing_on ? crossing_w * crossing + (1.0 - crossing_w) * sound_expansion : sound_expansion;
         }
         d[iX3] = dx3;
 
         // compute_dm3_dt :181-203
         double dm3;
         {
-            dm3 = 0.;
-            if (!(m4 <= 0)) {
-                if (!(remaining <= 0 && f < 1e-6)) {
-                    const double eff_mass = f * m4 + (1.0 - f) * remaining;
-                    const double column_den3 = eff_mass * comp_ratio / x4;  // IEEE: x4 is an unclamped state
-                    const double dm3dt = column_den3 * dx3;
-                    if (f > 1e-6) {
-                        const double ratio = vdiv(m3, m4);  // m4 > 0 here
-                        const double cap_w = smoothstep(0, 1.0, ratio);
-                        const double capped_rate = vmin(dm3dt, dm4);
-                        dm3 = (1.0 - cap_w) * dm3dt + cap_w * capped_rate;
-                    } else {
-                        dm3 = dm3dt;
-                    }
-                }
-            }
+            const bool feeding = has_shell && !(remaining <= 0 && f < 1e-6);
+            const double eff_mass = f * m4 + (1.0 - f) * remaining;
+            const double column_den3 = eff_mass * comp_ratio / x4;  // IEEE: x4 is an unclamped state
+            const double dm3dt = column_den3 * dx3;
+            const double ratio = vdiv(m3, m4_s);
+            const double cap_w = smoothstep(0, 1.0, ratio);
+            const double capped_rate = vmin(dm3dt, dm4);
+            const double injected = (1.0 - cap_w) * dm3dt + cap_w * capped_rate;
+            dm3 = feeding ? ((f > 1e-6) ? injected : dm3dt) : 0.;
         }
         d[iM3] = dm3;
 
         // compute_dU2_dt :96-110
         double dU2;
         {
-            const double e_th = (Gamma - 1) * 4 * Gamma * rho * con::c2;
-            const double eps_rad = radiative_efficiency(m.fwd, t_comv, Gamma, e_th);
             const double shock_heating = dm2 * (Gamma - 1) * con::c2;
-            double dlnvdt = dlnv_r;
-            if (x4 > 0) dlnvdt += vdiv(dx4, x4);
+            const double x4_s = (x4 > 0) ? x4 : 1.0;
+            const double dlnvdt = dlnv_r + ((x4 > 0) ? vdiv(dx4, x4_s) : 0.0);
             const double adiabatic_cooling = -(ad2 - 1) * dlnvdt * U2;
             dU2 = (1 - eps_rad) * shock_heating + adiabatic_cooling;
         }
@@ -603,8 +599,8 @@ struct FREqn {
         // compute_dU3_dt :112-122
         double dU3;
         {
-            double dlnvdt = dlnv_r;
-            if (x3 > 0) dlnvdt += vdiv(dx3, x3);
+            const double x3_s = (x3 > 0) ? x3 : 1.0;
+            const double dlnvdt = dlnv_r + ((x3 > 0) ? vdiv(dx3, x3_s) : 0.0);
             const double adiabatic_cooling = -(ad34 - 1) * dlnvdt * U3;
             const double shock_heating = dm3 * (Gamma34 - 1) * con::c2;
             dU3 = shock_heating + adiabatic_cooling;
