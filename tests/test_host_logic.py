@@ -128,3 +128,30 @@ def test_walker_partition_gather_gloo_world2(tmp_path):
         out, err = p.communicate(timeout=300)
         assert p.returncode == 0, err[-2000:]
         assert "ok" in out
+
+
+def test_softplus_table_accuracy():
+    """log2(1 + 2^x) table of the EATS kernel (vag_math.cuh): absolute error against long double over [-20, 20]."""
+    import ctypes
+
+    from oracle.hostemu import emu
+
+    lib = emu.lib()
+    lib.vagemu_softplus_lut_maxerr.restype = ctypes.c_double
+    assert lib.vagemu_softplus_lut_maxerr(400001) < 5e-13
+
+
+def test_params_layout_upgrade():
+    """Fixtures written with an earlier, shorter vag_params layout load by field name; new fields keep defaults."""
+    from vegasafterglow_b200 import abi, configs
+
+    cur = configs.make(jet="gaussian", theta_obs=0.3, rvs=(0.1, 0.01, 2.4), duration=50.0)
+    old_dtype = np.dtype({n: abi.PARAMS_DTYPE.fields[n] for n in abi.PARAMS_DTYPE.names[:-6]})  # before the magnetar / k_m fields
+    old = np.zeros(1, dtype=old_dtype)
+    for n in old_dtype.names:
+        old[n] = cur[n]
+    up = abi.upgrade_params(old)
+    assert up.dtype == abi.PARAMS_DTYPE and up["wind_k_m"][0] == 2.0 and up["has_magnetar"][0] == 0
+    for n in old_dtype.names:
+        assert np.array_equal(up[n], cur[n]), n
+    assert abi.upgrade_params(cur) is cur
