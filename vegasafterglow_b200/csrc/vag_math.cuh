@@ -93,6 +93,30 @@ VAG_HD double dexp2_nc(double x) {
     return bits_to_double(double_to_bits(p) + ((uint64_t)k << 52));
 }
 VAG_HD double dlog2_nc(double x);
+// NL independent exp2 evaluations with the Horner recurrences interleaved (one coefficient fetch serves all of
+// them, and the NL dependent chains overlap); arguments as for dexp2_nc
+template <int NL>
+VAG_HD void dexp2_nc_vec(const double* x, double* out) {
+    const double magic = 6755399441055744.0;
+    double f[NL], p[NL];
+    uint64_t sh[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        const double t = x[l] + magic;
+        f[l] = x[l] - (t - magic);
+        const int64_t k = (int64_t)(double_to_bits(t) & 0xFFFFFFFFull) | ((double_to_bits(t) & 0x80000000ull) ? ~0xFFFFFFFFll : 0);
+        sh[l] = (uint64_t)k << 52;
+        p[l] = VAG_CEXP2[VAG_EXP2_DEG];
+    }
+#pragma unroll
+    for (int j = VAG_EXP2_DEG - 1; j >= 0; --j) {
+        const double c = VAG_CEXP2[j];
+#pragma unroll
+        for (int l = 0; l < NL; ++l) p[l] = fma(p[l], f[l], c);
+    }
+#pragma unroll
+    for (int l = 0; l < NL; ++l) out[l] = bits_to_double(double_to_bits(p[l]) + sh[l]);
+}
 
 VAG_HD double dlog2(double x) {
     if (!(x >= 2.2250738585072014e-308 && x < kInf)) return log2(x);  // 0, negative, subnormal, inf, NaN
@@ -209,8 +233,9 @@ VAG_HD double log2_softplus_lut(const double* __restrict__ lut, double x) {
     const double y = fma(x, 2.0, 40.0);  // [0, 80]
     const double magic = 6755399441055744.0;
     const double t = y + magic;
-    const int row = (int)(uint32_t)(double_to_bits(t) & 0xFFFFFFFFull);  // round-to-nearest integer of y
-    const double u = y - (t - magic);                                     // [-1/2, 1/2]
+    int row = (int)(uint32_t)(double_to_bits(t) & 0xFFFFFFFFull);  // round-to-nearest integer of y
+    row = imin(imax(row, 0), SPL_ROWS - 1);                        // a NaN argument must not index outside the table
+    const double u = y - (t - magic);                              // [-1/2, 1/2]
 #if defined(__CUDA_ARCH__)
     const double2* c2 = reinterpret_cast<const double2*>(lut) + row * (SPL_STRIDE / 2);
     const double2 c01 = c2[0], c23 = c2[1], c45 = c2[2], c67 = c2[3];

@@ -314,15 +314,19 @@ VAG_HD void eats_phase1(const EatsModel& M, const EatsRequest& rq, const EatsSha
 }
 
 // phase 2 (grid): thread <-> observation time; accumulates the chunk's rows into acc[l][idx]
-// acc layout: [nu_tile][EATS_T_BLOCK] (thread-owned columns, no atomics)
-VAG_HD void eats_phase2_grid(const EatsModel& M, const EatsRequest& rq, const EatsShared& sh, int nrows, int nl,
-                             double* acc, int tid, int nthr) {
+// acc layout: [nu_tile][EATS_T_BLOCK] (thread-owned columns, no atomics).  NLC = compile-time number of
+// frequencies of the tile: their NLC interpolation exponentials are evaluated as one interleaved batch.
+// exp2 arguments are clamped to [-1000, 1020]: below, the reference's term is < 1e-301 of anything it is
+// added to (it underflows there); above, it would have overflowed.
+template <int NLC>
+VAG_HD void eats_phase2_grid_n(const EatsModel& M, const EatsRequest& rq, const EatsShared& sh, int nrows, double* acc,
+                               int tid, int nthr) {
     const int n_t = M.h->n_t;
     for (int ii = tid; ii < rq.ni; ii += nthr) {
         const double x = rq.lg2_t_obs[rq.i0 + ii];
-        double sum[EATS_NU_TILE];
+        double sum[NLC];
 #pragma unroll
-        for (int l = 0; l < EATS_NU_TILE; ++l) sum[l] = 0;
+        for (int l = 0; l < NLC; ++l) sum[l] = 0;
         for (int r = 0; r < nrows; ++r) {
             const double* t_row = sh.lg2t + (size_t)r * n_t;
             const int k = find_interval(t_row, n_t, x, false);
@@ -330,13 +334,35 @@ VAG_HD void eats_phase2_grid(const EatsModel& M, const EatsRequest& rq, const Ea
             const double* b_lo = sh.bv + ((size_t)r * n_t + k) * sh.nu_tile;
             const double* b_hi = b_lo + sh.nu_tile;
             const double inv_dt = 1.0 / (t_row[k + 1] - t_row[k]), dx = x - t_row[k];
+            double arg[NLC], val[NLC];
+            bool fin[NLC];
 #pragma unroll
-            for (int l = 0; l < EATS_NU_TILE; ++l)
-                if (l < nl) sum[l] += interp_contrib2(b_lo[l], b_hi[l], inv_dt, dx);
+            for (int l = 0; l < NLC; ++l) {  // interp_contrib2 (observer.h:417-433)
+                const double lo = b_lo[l];
+                const double s = (b_hi[l] - lo) * inv_dt;
+                fin[l] = isfinite(s);
+                const double a = lo + dx * s;
+                arg[l] = fin[l] ? vclamp(a, -1000.0, 1020.0) : 0.0;
+            }
+            dexp2_nc_vec<NLC>(arg, val);
+#pragma unroll
+            for (int l = 0; l < NLC; ++l) sum[l] += fin[l] ? val[l] : 0.0;
         }
 #pragma unroll
-        for (int l = 0; l < EATS_NU_TILE; ++l)
-            if (l < nl) acc[l * EATS_T_BLOCK + ii] += sum[l];
+        for (int l = 0; l < NLC; ++l) acc[l * EATS_T_BLOCK + ii] += sum[l];
+    }
+}
+VAG_HD void eats_phase2_grid(const EatsModel& M, const EatsRequest& rq, const EatsShared& sh, int nrows, int nl,
+                             double* acc, int tid, int nthr) {
+    switch (nl) {
+        case 1: return eats_phase2_grid_n<1>(M, rq, sh, nrows, acc, tid, nthr);
+        case 2: return eats_phase2_grid_n<2>(M, rq, sh, nrows, acc, tid, nthr);
+        case 3: return eats_phase2_grid_n<3>(M, rq, sh, nrows, acc, tid, nthr);
+        case 4: return eats_phase2_grid_n<4>(M, rq, sh, nrows, acc, tid, nthr);
+        case 5: return eats_phase2_grid_n<5>(M, rq, sh, nrows, acc, tid, nthr);
+        case 6: return eats_phase2_grid_n<6>(M, rq, sh, nrows, acc, tid, nthr);
+        case 7: return eats_phase2_grid_n<7>(M, rq, sh, nrows, acc, tid, nthr);
+        default: return eats_phase2_grid_n<8>(M, rq, sh, nrows, acc, tid, nthr);
     }
 }
 
