@@ -1,0 +1,400 @@
+"""TEST INFRASTRUCTURE ONLY -- an independent numpy / pure-Python restatement of the reference's physics stages
+for forward-shock synchrotron models: blast-wave ODE, synchrotron
+electrons and photons, equal-arrival-time-surface flux integration.  It shares no code with the product
+(`vegasafterglow_b200/csrc`): different language, different structure (row-vectorised numpy, scalar dopri5).
+
+Scope: TophatJet / GaussianJet / PowerLawJet, ISM / Wind(k_m = 2), forward shock, no inverse Compton, no
+spreading, axisymmetric.  The adaptive (phi, theta, t) grid (row a1) is an INPUT here -- taken from the
+reference's own `details()` tables -- so that this file stays small enough to audit; the grid stage is pinned
+separately, directly against the reference's Coord (tests/test_hostemu_parity.py::test_stage_tables).
+
+Pinned by tests/test_restatement.py: flux of BASELINE configs C1 (tophat) and C2 (Gaussian off-axis) against the
+unmodified reference (oracle/_ref) to <= 1e-8.  Citations are `path:line` in the reference repository.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+# ---- unit system and constants: src/util/macros.h:43-107 -----------------------------------------------------------
+LEN = 1.5e13
+CM = 1 / LEN
+SEC = 3e10 / LEN
+G = 1 / 2e33
+HZ = 1 / SEC
+ERG = G * CM * CM / SEC / SEC
+FLUX_DEN_CGS = ERG / (CM * CM) / SEC / HZ
+C = 1.0
+MP = 1.67e-24 * G
+ME = MP / 1836
+E = 4.8e-10 / 4.472136e16 / 5.809475e19 / SEC
+SIGMA_T = 6.65e-25 * CM * CM
+PI = math.pi
+GAMMA_CUT = 1 + 1e-6          # src/config/simulation-defaults.h:41
+LN2 = math.log(2.0)
+LOG2E = 1 / LN2
+
+
+# ---- jets and media: src/environment/jet.h:84-257, medium.h:50-140 -------------------------------------------------
+class Model:
+    def __init__(self, p):
+        g = lambda k: float(np.asarray(p[k]).reshape(-1)[0])  # noqa: E731
+        self.jet, self.theta_c = int(g("jet_type")), g("theta_c")
+        self.eps_k0 = g("E_iso") * ERG / (4 * PI)
+        self.Gamma0, self.k_e, self.k_g = g("Gamma0"), g("k_e"), g("k_g")
+        self.ism = int(g("medium_type")) == 0
+        self.rho_ism = g("n_ism") / CM**3 * MP
+        self.wind_A = g("A_star") * 5e11 * G / CM if not self.ism else 0.0
+        n0 = g("n0")
+        self.wind_r02 = self.wind_A / ((n0 / CM**3) * 1.3 * MP) if (not self.ism and math.isfinite(n0)) else 0.0
+        f = np.asarray(p["fwd"]).reshape(-1)[0]
+        self.eps_e, self.eps_B, self.p, self.xi_e = (float(f[k]) for k in ("eps_e", "eps_B", "p", "xi_e"))
+        self.radiative = bool(g("radiative_fireball"))
+        self.z, self.d_L, self.theta_v = g("z"), g("lumi_dist") * CM, g("theta_obs")
+        rtol = g("rtol")
+        self.rtol = rtol if rtol > 0 else 1e-6
+        # RadiativeEfficiency coefficients: src/dynamics/shock-physics.h:251-261
+        self.gm_coeff = (self.p - 2) / (self.p - 1) * self.eps_e * MP / ME / self.xi_e
+        self.gc_coeff = 6 * PI * ME * C / SIGMA_T / (8 * PI * self.eps_B)
+
+    def Gamma0_of(self, th):
+        if self.jet == 0:
+            return self.Gamma0 if th < self.theta_c else 1.0
+        if self.jet == 1:
+            return (self.Gamma0 - 1) * math.exp(th * th * (-1 / (2 * self.theta_c**2))) + 1
+        return (self.Gamma0 - 1) / (1 + 2.0 ** (self.k_g * math.log2(th / self.theta_c))) + 1
+
+    def eps_k_of(self, th):
+        if self.jet == 0:
+            return self.eps_k0 if th < self.theta_c else 0.0
+        if self.jet == 1:
+            return self.eps_k0 * math.exp(th * th * (-1 / (2 * self.theta_c**2)))
+        return self.eps_k0 / (1 + 2.0 ** (self.k_e * math.log2(th / self.theta_c)))
+
+    def rho(self, r):
+        return self.rho_ism if self.ism else self.wind_A / (self.wind_r02 + r * r) + self.rho_ism
+
+    def mass(self, r):  # enclosed mass per solid angle: medium.h:61,115-127
+        m = self.rho_ism * r**3 / 3.0
+        if not self.ism and self.wind_A != 0:
+            if self.wind_r02 > 0:
+                a = math.sqrt(self.wind_r02)
+                m += self.wind_A * (r - a * math.atan(r / a))
+            else:
+                m += self.wind_A * r
+        return m
+
+
+def adiabatic_idx(g):  # src/core/physics.h:59-61
+    return 4.0 / 3.0 + 1 / (3 * g)
+
+
+def simpson_logspace(f, r):  # shock-physics.h:401-416
+    n, u1 = 32, math.log(r)
+    u0 = u1 - 18
+    h = (u1 - u0) / n
+    s = f(u0) + f(u1)
+    s += sum(4 * f(u0 + i * h) for i in range(1, n, 2)) + sum(2 * f(u0 + i * h) for i in range(2, n, 2))
+    return s * h / 3
+
+
+def enclosed_thermal_energy(m: Model, r, Gamma, ad, eps_e):  # shock-physics.h:452-469
+    cool = 3 * (ad - 1)
+    if m.ism:
+        pe = 3 + cool
+        return (1 - eps_e) * (Gamma - 1) * C * C * m.rho_ism * r**3 * (1 - math.exp(-18.0) ** pe) / pe
+    return (1 - eps_e) * (Gamma - 1) * C * C * simpson_logspace(
+        lambda u: m.rho(math.exp(u)) * math.exp(u) ** 3 * (math.exp(u) / r) ** cool, r)
+
+
+def estimate_t_dec(m: Model, th):  # src/core/grid-refinement.h:401-453
+    g = m.Gamma0_of(th)
+    beta = math.sqrt((g - 1) * (g + 1)) / g
+    target = m.eps_k_of(th) / (g * C * C) / g
+    r_min = 1e-3
+    r_max = r_min * 10.0**40
+    if target <= 0:
+        return r_min * (1 - beta) / (beta * C)
+    if m.ism:
+        if m.rho_ism > 0:
+            r_dec = np.cbrt(max(r_min**3 + 3 * target / m.rho_ism, 0.0))
+            return min(float(r_dec), r_max) * (1 - beta) / (beta * C)
+        return r_max * (1 - beta) / (beta * C)
+    n, u0 = 256, math.log(1e-3)
+    du = (u0 + 40 * math.log(10.0) - u0) / n
+    mass, r_prev = 0.0, math.exp(u0)
+    f_prev = m.rho(r_prev) * r_prev**2
+    for i in range(1, n + 1):
+        r_i = math.exp(u0 + i * du)
+        f_i = m.rho(r_i) * r_i**2
+        dr = r_i - r_prev
+        mass += 0.5 * (f_prev + f_i) * dr
+        if mass >= target:
+            return (r_prev + (target - (mass - 0.5 * (f_prev + f_i) * dr)) / f_i) * (1 - beta) / (beta * C)
+        f_prev, r_prev = f_i, r_i
+    return math.exp(u0 + 40 * math.log(10.0)) * (1 - beta) / (beta * C)
+
+
+# ---- Dormand-Prince 5(4) with the Boost.odeint 1.82 controller and dense output ------------------------------------
+# tableau: external/boost/numeric/odeint/stepper/runge_kutta_dopri5.hpp:92-198, dense output :229-275,
+# controller: stepper/controlled_runge_kutta.hpp:64-153
+_A = (1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0, 1.0)
+_B = ((1 / 5,), (3 / 40, 9 / 40), (44 / 45, -56 / 15, 32 / 9), (19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729),
+      (9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656), (35 / 384, 0.0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84))
+_C = (35 / 384, 0.0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84)
+_DC = (35 / 384 - 5179 / 57600, 0.0, 500 / 1113 - 7571 / 16695, 125 / 192 - 393 / 640, -2187 / 6784 + 92097 / 339200,
+       11 / 84 - 187 / 2100, -1 / 40)
+
+
+def integrate_dense(f, x0, t0, dt0, tol, t_out, max_steps=100000):
+    """make_dense_output(tol, tol, dopri5) stepped until every t_out has been passed; states at t_out."""
+    x, t, dt = np.array(x0, dtype=float), t0, dt0
+    k1 = f(x, t)
+    out = np.full((len(t_out), x.size), np.nan)
+    k_out, steps = 0, 0
+    while t <= t_out[-1]:
+        fails = 0
+        while True:  # controlled_runge_kutta::try_step until success (max_step_checker: 500)
+            ks = [k1]
+            for s in range(6):
+                xt = 1.0 * x
+                for j, b in enumerate(_B[s]):
+                    if b != 0.0:
+                        xt = xt + (dt * b) * ks[j]
+                ks.append(f(xt, t + dt * _A[s]))
+            x_new, k7 = xt, ks[6]
+            err_vec = sum((dt * dc) * kk for dc, kk in zip(_DC, ks) if dc != 0.0)
+            err = float(np.max(np.abs(err_vec) / (tol + tol * (np.abs(x) + abs(dt) * np.abs(k1)))))
+            if err > 1.0:
+                dt *= max(0.9 * err ** (-1 / 3), 0.2)
+                fails += 1
+                if fails >= 500:
+                    return out
+                continue
+            break
+        x_old, k_old, t_old = x, k1, t
+        x, k1, t = x_new, k7, t + dt
+        if err < 0.5:
+            dt *= 0.9 * max(5.0**-5, err) ** (-1 / 5)
+        steps += 1
+        if steps > max_steps:
+            return out
+        while k_out < len(t_out) and t > t_out[k_out]:  # dense output (Hairer-Norsett-Wanner I, p. 191)
+            h = t - t_old
+            th = (t_out[k_out] - t_old) / h
+            X1 = 5.0 * (2558722523.0 - 31403016.0 * th) / 11282082432.0
+            X3 = 100.0 * (882725551.0 - 15701508.0 * th) / 32700410799.0
+            X4 = 25.0 * (443332067.0 - 31403016.0 * th) / 1880347072.0
+            X5 = 32805.0 * (23143187.0 - 3489224.0 * th) / 199316789632.0
+            X6 = 55.0 * (29972135.0 - 7076736.0 * th) / 822651844.0
+            X7 = 10.0 * (7414447.0 - 829305.0 * th) / 29380423.0
+            A, Bc, Cc, D = th * th * (3 - 2 * th), th * th * (th - 1), th * th * (th - 1) ** 2, th * (th - 1) ** 2
+            out[k_out] = (x_old + h * (A * _C[0] - Cc * X1 + D) * k_old + h * (A * _C[2] + Cc * X3) * ks[2]
+                          + h * (A * _C[3] - Cc * X4) * ks[3] + h * (A * _C[4] + Cc * X5) * ks[4]
+                          + h * (A * _C[5] - Cc * X6) * ks[5] + h * (Bc + Cc * X7) * k7)
+            k_out += 1
+    return out
+
+
+# ---- forward shock: src/dynamics/forward-shock.tpp:17-208 ----------------------------------------------------------
+def radiative_efficiency(m: Model, t_comv, Gamma, e_th):  # shock-physics.h:247-288
+    eps = m.eps_e if m.radiative else 0.0
+    if eps == 0:
+        return 0.0
+    gm = m.gm_coeff * (Gamma - 1) + 1
+    with np.errstate(divide="ignore"):
+        gbar = m.gc_coeff / (e_th * t_comv) if e_th * t_comv != 0 else math.inf
+    gc = 0.5 * (gbar + math.sqrt(gbar * gbar + 4)) if math.isfinite(gbar) else math.inf
+    ratio = gm / gc
+    if ratio < 1 and m.p > 2:
+        return eps * (2.0 ** ((m.p - 2) * math.log2(ratio)) if ratio > 0 else 0.0)
+    return eps
+
+
+def solve_forward_row(m: Model, theta, t_lat):
+    """Shock table of one row: t_comv, r, Gamma, Gamma_th, B, N_p at the lattice t_lat (code units)."""
+    G4 = m.Gamma0_of(theta)
+    m_jet0 = m.eps_k_of(theta) / G4 / (C * C)
+    n = len(t_lat)
+    t0 = min(t_lat[0], 0.1 * SEC, 0.1 * estimate_t_dec(m, theta))
+    beta4 = math.sqrt((G4 - 1) * (G4 + 1)) / G4
+    r0 = beta4 * C * t0 * G4 * G4 * (1 + beta4)
+    tc0 = r0 / math.sqrt((G4 - 1) * (G4 + 1)) / C if G4 > 1 else math.inf
+    if G4 <= GAMMA_CUT:  # set_stopping_shock: shock-physics.h:388-397
+        tc0 = r0 / math.sqrt((G4 - 1) * (G4 + 1)) / C if G4 > 1 else math.nan
+        return dict(t_comv=np.full(n, tc0), r=np.full(n, r0), Gamma=np.ones(n), Gamma_th=np.ones(n), B=np.zeros(n), N_p=np.zeros(n))
+    U0 = enclosed_thermal_energy(m, r0, G4, adiabatic_idx(G4), m.eps_e if m.radiative else 0.0)
+    x0 = [G4, m.mass(r0), U0, r0, tc0]  # Gamma, m2, U2_th, r, t_comv
+
+    def rhs(x, _t):  # ForwardShockEqn::operator(): forward-shock.tpp:27-118
+        Gm, m2, U, r, tc = x
+        u2 = (Gm - 1) * (Gm + 1)
+        u = math.sqrt(u2) if u2 >= 0 else math.nan
+        dr = u * (Gm + u) * C
+        rho = m.rho(r)
+        dm2 = r * r * rho * dr
+        e_th = (Gm - 1) * 4 * Gm * rho * C * C
+        eps_rad = radiative_efficiency(m, tc, Gm, e_th)
+        ad = adiabatic_idx(Gm)
+        G2 = Gm * Gm
+        Geff = (ad * (G2 - 1) + 1) / Gm
+        dGeff = (ad * (G2 + 1) - 1) / G2
+        dlnV = 3 / r * dr
+        dG = (-(Gm - 1) * (Geff + 1) * C * C * dm2 + (ad - 1) * Geff * U * dlnV) / (
+            (m_jet0 + m2) * C * C + (dGeff + Geff * (ad - 1) / Gm) * U)
+        dU = (1 - eps_rad) * (Gm - 1) * C * C * dm2 - (ad - 1) * (dlnV - dG / Gm) * U
+        return np.array([dG, dm2, dU, dr, Gm + u])
+
+    X = integrate_dense(rhs, x0, t0, 0.01 * t0, m.rtol, list(t_lat))
+    tab = dict(t_comv=np.zeros(n), r=np.zeros(n), Gamma=np.ones(n), Gamma_th=np.ones(n), B=np.zeros(n), N_p=np.zeros(n))
+    for k in range(n):  # save_fwd_shock_state: forward-shock.tpp:151-173
+        if not np.isfinite(X[k, 0]):
+            continue
+        Gm, m2, U, r, tc = X[k]
+        ad = adiabatic_idx(Gm)  # compute_compression(1, Gamma, 0): shock.cpp:90-138, shock-physics.h:40-66,352-355
+        u_down = math.sqrt(max((Gm - 1) * (ad - 1) ** 2 / (-ad * (ad - 2) * (Gm - 1) + 2), 0.0))
+        u_up = math.sqrt((1 + u_down**2) * max((Gm - 1) * (Gm + 1), 0.0)) + u_down * Gm
+        comp = u_up / u_down if u_down != 0 else 4 * Gm
+        Gth = U / (m2 * C * C) + 1 if m2 != 0 else 1.0
+        e_th = (Gth - 1) * m.rho(r) * comp * C * C
+        tab["t_comv"][k], tab["r"][k], tab["Gamma"][k], tab["Gamma_th"][k] = tc, r, Gm, Gth
+        tab["B"][k], tab["N_p"][k] = math.sqrt(8 * PI * m.eps_B * e_th), m2 / MP
+    return tab
+
+
+# ---- synchrotron electrons and photons: src/radiation/synchrotron.cpp:45-408, smooth-power-law-syn.cpp:26-166 ------
+_KS = 3 * E / (4 * PI * ME * C)
+
+
+def _softplus2(x):  # src/util/fast-math.h:179-185
+    x = np.asarray(x, dtype=float)
+    with np.errstate(over="ignore", invalid="ignore"):
+        mid = np.log2(1.0 + np.exp2(np.clip(x, -20, 20)))
+    return np.where(x > 20, x, np.where(x < -20, 0.0, mid))
+
+
+def photon_tables(m: Model, tab):
+    """Per-cell spectral coefficients (generate_syn_electrons + generate_syn_photons + SmoothPowerLawSyn::build)."""
+    B, r, Gth, Np, tc, p = tab["B"], tab["r"], tab["Gamma_th"], tab["N_p"], tab["t_comv"], m.p
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        gM = np.where(B == 0, np.inf, np.sqrt(6 * PI * E / SIGMA_T / B))
+        gave = m.eps_e * (Gth - 1) * (MP / ME) / m.xi_e
+        if p > 2:
+            gm = (p - 2) / (p - 1) * gave + 1
+        else:  # 1 < p < 2 (p == 2 root-finding is not restated)
+            gm = ((2 - p) / (p - 1) * gave * gM ** (p - 2)) ** (1 / (p - 1)) + 1
+        fsyn = (gm - 1) / gm
+        if p > 3:
+            fsyn = np.exp2((p - 1) / 2 * np.log2(fsyn))
+        Ne = Np * m.xi_e * fsyn
+        col = Ne / (r * r)
+        gbar = (6 * PI * ME * C / SIGMA_T) / (B * B * tc)
+        gc = (gbar + np.sqrt(gbar * gbar + 4)) / 2
+        I_peak = B * ((PI / 4) * 0.92 * math.sqrt(3.0) * E**3 / (ME * C * C)) * col / (4 * PI)
+        freq = lambda g: np.where((B == 0) | ~np.isfinite(g), 0.0, _KS * B * g * g)  # noqa: E731
+        # compute_syn_gamma_a: synchrotron.cpp:212-246 (no inverse Compton: every ic factor is 1)
+        gpk = np.minimum(gm, gc)
+        nu_pk, kT = freq(gpk), (gpk - 1) * (ME * C * C) / 3
+        pw = lambda a, b: np.exp2(b * np.log2(a))  # noqa: E731  fast_pow
+        base = I_peak * C * C / (2 * kT)
+        nu_m, nu_c = freq(gm), freq(gc)
+        nu_a = pw(I_peak * C * C / (np.cbrt(nu_pk) * 2 * kT), 0.6)
+        slow = gc > gm
+        a_mid_slow = pw(base * pw(nu_m, p / 2), 2 / (p + 4))
+        a_hi = pw(base * np.sqrt(nu_c) * pw(nu_m, p / 2), 2 / (p + 5))
+        a_mid_fast = pw(base * np.sqrt(nu_c), 0.4)
+        over = nu_a > nu_pk
+        nu_a_slow = np.where(a_mid_slow > nu_c, a_hi, a_mid_slow)
+        nu_a_fast = np.where(a_mid_fast > nu_m, a_hi, a_mid_fast)
+        nu_a = np.where(over, np.where(slow, nu_a_slow, nu_a_fast), nu_a)
+        ga = np.sqrt((4 * PI * ME * C / (3 * E)) * (nu_a / B)) + 1
+        nu_a = freq(ga)
+        nu_M = freq(gM)
+        l2m, l2c, l2a = np.log2(nu_m), np.log2(nu_c), np.log2(nu_a)
+        c = dict(l2I=np.log2(I_peak), l2m=l2m, l2M=np.log2(nu_M), inv_M=1.0 / nu_M)
+        sig = lambda x: 1.0 / (1.0 + np.exp2(-x))  # noqa: E731
+        w_slow = sig(4.0 * (l2c - l2m))
+        soft = _softplus2(-4.0 * np.abs(l2c - l2m)) / 4.0
+        c["lo"], c["hi"] = np.minimum(l2m, l2c) - soft, np.maximum(l2m, l2c) + soft
+        blend = lambda w, a, b: w * a + (1 - w) * b  # noqa: E731
+        s_lo = blend(w_slow, max(1.84 - 0.40 * p, 0.1), 0.597)
+        s_hi = blend(w_slow, max(1.15 - 0.06 * p, 0.1), max(3.34 - 0.82 * p, 0.1))
+        a_mid = blend(w_slow, -0.5 * (p - 1.0), -0.5)
+        c["s_lo"], c["s_hi"] = s_lo, s_hi
+        c["d_lo"], c["d_hi"] = s_lo * (1 / 3 - a_mid), s_hi * (a_mid + 0.5 * p)
+        u, v = sig(4.0 * (l2a - l2m)), sig(4.0 * (l2a - l2c))
+        wb, wa = (1 - u) * (1 - v), u * v
+        c["s_a"] = wb * 1.64 + wa * max(0.94 - 0.14 * p, 0.1) + (1 - wb - wa) * max(1.47 - 0.21 * p, 0.1)
+        c["norm"] = 1.0 / s_lo
+        # sharp forms for the thick normalisation: smooth-power-law-syn.cpp:48-74
+        thick_sharp = np.where(l2a < l2m, 2.0 * (l2a - l2m), 2.5 * (l2a - l2m))
+        thin_slow = np.where(l2a < l2m, (l2a - l2m) / 3, np.where(l2a < l2c, 0.5 * (1 - p) * (l2a - l2m),
+                             0.5 * (1 - p) * (l2c - l2m) - 0.5 * p * (l2a - l2c)))
+        thin_fast = np.where(l2a < l2c, (l2a - l2c) / 3, np.where(l2a < l2m, -0.5 * (l2a - l2c),
+                             -0.5 * (l2m - l2c) - 0.5 * p * (l2a - l2m)))
+        c["thick_norm"] = np.where(l2m < l2c, thin_slow, thin_fast) - thick_sharp
+    return c
+
+
+def log2_I_nu(m: Model, c, l2nu):
+    """SmoothPowerLawSyn::compute_log2_I_nu (smooth-power-law-syn.cpp:26-46,80-92,159-166); arrays broadcast."""
+    smooth_thick = (3.44 * m.p - 1.41) / LN2
+    x_far = 1.5 * math.log2(20.0 / smooth_thick)
+    with np.errstate(over="ignore", invalid="ignore"):
+        thin = ((l2nu - c["lo"]) / 3.0 - _softplus2(c["d_lo"] * (l2nu - c["lo"])) / c["s_lo"]
+                - _softplus2(c["d_hi"] * (l2nu - c["hi"])) / c["s_hi"])
+        lx = l2nu - c["l2m"]
+        s = -smooth_thick * np.exp2(2.0 / 3 * lx)
+        thick = np.where(lx > x_far, 2.5 * lx, 2.5 * lx + _softplus2(-0.5 * lx + s))
+        b = thick + c["thick_norm"]
+        smooth = thin - _softplus2(c["s_a"] * (thin - b)) / c["s_a"]
+        spec = c["l2I"] + (c["norm"] + smooth)
+        return np.where(l2nu - c["l2M"] < -20, spec, spec - LOG2E * c["inv_M"] * np.exp2(l2nu))
+
+
+# ---- observer: src/core/observer.cpp:17-37,143-205,439-454, observer.h:355-445 -------------------------------------
+def flux_density_grid(p, theta, phi, t_rows, reps, phi_mirrored, n_phi_eff, t_obs, nu_obs):
+    """F_nu[n_nu, n_t] (erg cm^-2 s^-1 Hz^-1) of one forward-shock model on the GIVEN grid: theta[N_theta],
+    phi[N_phi], t_rows[n_reps, N_t] (engine-frame lattice of each representative row, code units), reps."""
+    m = Model(p)
+    theta, phi = np.asarray(theta, float), np.asarray(phi, float)
+    n_th = theta.size
+    tabs = [solve_forward_row(m, theta[j0], t_rows[r]) for r, j0 in enumerate(reps)]
+    coefs = [photon_tables(m, tb) for tb in tabs]
+    rep_of = np.searchsorted(np.asarray(reps), np.arange(n_th), side="right") - 1
+    l2t_obs = np.log2(np.asarray(t_obs, float) * SEC)
+    l2nu = np.log2(np.asarray(nu_obs, float) * HZ) + math.log2(1 + m.z)
+    F = np.zeros((l2nu.size, l2t_obs.size))
+    cos_o, sin_o = math.cos(m.theta_v), math.sin(m.theta_v)
+    last = n_phi_eff - 1
+    for i in range(n_phi_eff):
+        if n_phi_eff == 1:
+            dphi = 2 * PI
+        elif phi_mirrored:
+            left = 0.5 * (phi[i - 1] + phi[i]) if i > 0 else 0.0
+            right = 0.5 * (phi[i] + phi[i + 1]) if i < last else PI
+            dphi = 2 * (right - left)
+        else:
+            dphi = 0.5 * (phi[min(i + 1, last)] - phi[max(i - 1, 0)])
+        for j in range(n_th):
+            tb, cf = tabs[rep_of[j]], coefs[rep_of[j]]
+            t_eng = np.asarray(t_rows[rep_of[j]], float)
+            cos_v = math.sin(theta[j]) * math.cos(phi[i]) * sin_o + math.cos(theta[j]) * cos_o
+            c_lo = math.cos(theta[j]) if j == 0 else math.cos(0.5 * (theta[j - 1] + theta[j]))
+            c_hi = math.cos(theta[j]) if j == n_th - 1 else math.cos(0.5 * (theta[j] + theta[j + 1]))
+            dOmega = abs((c_hi - c_lo) * dphi)
+            Gm, r = tb["Gamma"], tb["r"]
+            with np.errstate(divide="ignore", invalid="ignore"):
+                l2dop = -np.log2(Gm - np.sqrt((Gm - 1) * (Gm + 1)) * cos_v)
+                l2t = np.log2(t_eng * (1 + m.z) + (1 - cos_v) / C * (1 + m.z) * r)
+                l2geom = (np.log2(np.float64(dOmega)) + 2 * np.log2(r)) + 3 * l2dop
+                L = log2_I_nu(m, cf, l2nu[:, None] - l2dop[None, :]) + l2geom[None, :]  # [n_nu, N_t]
+                # iterate_to: t_row[k] <= x < t_row[k+1] (observer.h:309-313,405-433)
+                k = np.searchsorted(l2t, l2t_obs, side="right") - 1
+                ok = (k >= 0) & (k <= l2t.size - 2)
+                kk = np.clip(k, 0, l2t.size - 2)
+                slope = (L[:, kk + 1] - L[:, kk]) / (l2t[kk + 1] - l2t[kk])[None, :]
+                val = np.exp2(L[:, kk] + (l2t_obs - l2t[kk])[None, :] * slope)
+            F += np.where(ok[None, :] & np.isfinite(slope), val, 0.0)
+    return F * ((1 + m.z) / (m.d_L * m.d_L)) / FLUX_DEN_CGS
