@@ -147,15 +147,20 @@ _DC = (35 / 384 - 5179 / 57600, 0.0, 500 / 1113 - 7571 / 16695, 125 / 192 - 393 
        11 / 84 - 187 / 2100, -1 / 40)
 
 
-def integrate_dense(f, x0, t0, dt0, tol, t_out, max_steps=100000):
-    """make_dense_output(tol, tol, dopri5) stepped until every t_out has been passed; states at t_out."""
-    x, t, dt = np.array(x0, dtype=float), t0, dt0
-    k1 = f(x, t)
-    out = np.full((len(t_out), x.size), np.nan)
-    k_out, steps = 0, 0
-    while t <= t_out[-1]:
+class DenseDopri5:
+    """make_dense_output(tol, tol, runge_kutta_dopri5): do_step() advances one accepted step, dense(tq) evaluates
+    the continuous extension inside it."""
+
+    def __init__(self, f, x0, t0, dt0, tol):
+        self.f, self.x, self.t, self.dt, self.tol = f, np.array(x0, dtype=float), t0, dt0, tol
+        self.k1 = f(self.x, t0)
+        self.t_old = t0
+
+    def do_step(self):
+        f, tol = self.f, self.tol
         fails = 0
-        while True:  # controlled_runge_kutta::try_step until success (max_step_checker: 500)
+        while True:  # controlled_runge_kutta::try_step until success (max_step_checker: 500 failures)
+            x, t, dt, k1 = self.x, self.t, self.dt, self.k1
             ks = [k1]
             for s in range(6):
                 xt = 1.0 * x
@@ -163,36 +168,51 @@ def integrate_dense(f, x0, t0, dt0, tol, t_out, max_steps=100000):
                     if b != 0.0:
                         xt = xt + (dt * b) * ks[j]
                 ks.append(f(xt, t + dt * _A[s]))
-            x_new, k7 = xt, ks[6]
             err_vec = sum((dt * dc) * kk for dc, kk in zip(_DC, ks) if dc != 0.0)
-            err = float(np.max(np.abs(err_vec) / (tol + tol * (np.abs(x) + abs(dt) * np.abs(k1)))))
+            with np.errstate(invalid="ignore", divide="ignore"):
+                err = float(np.max(np.abs(err_vec) / (tol + tol * (np.abs(x) + abs(dt) * np.abs(k1)))))
             if err > 1.0:
-                dt *= max(0.9 * err ** (-1 / 3), 0.2)
+                self.dt = dt * max(0.9 * err ** (-1 / 3), 0.2)
                 fails += 1
                 if fails >= 500:
-                    return out
+                    return False
                 continue
             break
-        x_old, k_old, t_old = x, k1, t
-        x, k1, t = x_new, k7, t + dt
+        self.x_old, self.k_old, self.t_old, self.ks = x, k1, t, ks
+        self.x, self.k1, self.t = xt, ks[6], t + dt
         if err < 0.5:
-            dt *= 0.9 * max(5.0**-5, err) ** (-1 / 5)
+            self.dt = dt * 0.9 * max(5.0**-5, err) ** (-1 / 5)
+        return True
+
+    def dense(self, tq):  # Hairer-Norsett-Wanner I, p. 191 as coded in runge_kutta_dopri5.hpp:229-275
+        h = self.t - self.t_old
+        th = (tq - self.t_old) / h
+        X1 = 5.0 * (2558722523.0 - 31403016.0 * th) / 11282082432.0
+        X3 = 100.0 * (882725551.0 - 15701508.0 * th) / 32700410799.0
+        X4 = 25.0 * (443332067.0 - 31403016.0 * th) / 1880347072.0
+        X5 = 32805.0 * (23143187.0 - 3489224.0 * th) / 199316789632.0
+        X6 = 55.0 * (29972135.0 - 7076736.0 * th) / 822651844.0
+        X7 = 10.0 * (7414447.0 - 829305.0 * th) / 29380423.0
+        A, Bc, Cc, D = th * th * (3 - 2 * th), th * th * (th - 1), th * th * (th - 1) ** 2, th * (th - 1) ** 2
+        ks = self.ks
+        return (self.x_old + h * (A * _C[0] - Cc * X1 + D) * self.k_old + h * (A * _C[2] + Cc * X3) * ks[2]
+                + h * (A * _C[3] - Cc * X4) * ks[3] + h * (A * _C[4] + Cc * X5) * ks[4]
+                + h * (A * _C[5] - Cc * X6) * ks[5] + h * (Bc + Cc * X7) * ks[6])
+
+
+def integrate_dense(f, x0, t0, dt0, tol, t_out, max_steps=100000):
+    """Stepped until every t_out has been passed; states at t_out (NaN rows where the solve gave up)."""
+    st = DenseDopri5(f, x0, t0, dt0, tol)
+    out = np.full((len(t_out), len(x0)), np.nan)
+    k_out, steps = 0, 0
+    while st.t <= t_out[-1]:
+        if not st.do_step():
+            break
         steps += 1
         if steps > max_steps:
-            return out
-        while k_out < len(t_out) and t > t_out[k_out]:  # dense output (Hairer-Norsett-Wanner I, p. 191)
-            h = t - t_old
-            th = (t_out[k_out] - t_old) / h
-            X1 = 5.0 * (2558722523.0 - 31403016.0 * th) / 11282082432.0
-            X3 = 100.0 * (882725551.0 - 15701508.0 * th) / 32700410799.0
-            X4 = 25.0 * (443332067.0 - 31403016.0 * th) / 1880347072.0
-            X5 = 32805.0 * (23143187.0 - 3489224.0 * th) / 199316789632.0
-            X6 = 55.0 * (29972135.0 - 7076736.0 * th) / 822651844.0
-            X7 = 10.0 * (7414447.0 - 829305.0 * th) / 29380423.0
-            A, Bc, Cc, D = th * th * (3 - 2 * th), th * th * (th - 1), th * th * (th - 1) ** 2, th * (th - 1) ** 2
-            out[k_out] = (x_old + h * (A * _C[0] - Cc * X1 + D) * k_old + h * (A * _C[2] + Cc * X3) * ks[2]
-                          + h * (A * _C[3] - Cc * X4) * ks[3] + h * (A * _C[4] + Cc * X5) * ks[4]
-                          + h * (A * _C[5] - Cc * X6) * ks[5] + h * (Bc + Cc * X7) * k7)
+            break
+        while k_out < len(t_out) and st.t > t_out[k_out]:
+            out[k_out] = st.dense(t_out[k_out])
             k_out += 1
     return out
 
@@ -263,6 +283,202 @@ def solve_forward_row(m: Model, theta, t_lat):
     return tab
 
 
+# ---- forward + reverse shock pair: src/dynamics/reverse-shock.tpp:11-591 (unmagnetised shells) ------------------------
+def _compression(Gamma_rel):  # compute_4vel_jump(gamma_rel, sigma = 0): shock.cpp:90-138, shock-physics.h:40-66
+    ad = adiabatic_idx(Gamma_rel)
+    u_down = math.sqrt(max((Gamma_rel - 1) * (ad - 1) ** 2 / (-ad * (ad - 2) * (Gamma_rel - 1) + 2), 0.0))
+    u_up = math.sqrt((1 + u_down**2) * max((Gamma_rel - 1) * (Gamma_rel + 1), 0.0)) + u_down * Gamma_rel
+    return u_up / u_down if u_down != 0 else 4 * Gamma_rel
+
+
+def _rel_Gamma(g1, g2):  # shock-physics.h:192-204
+    u1u2 = math.sqrt(max((g1 - 1) * (g1 + 1) * (g2 - 1) * (g2 + 1), 0.0))
+    den = g1 * g2 - 1 + u1u2
+    return 1.0 if den <= 0 else 1 + (g1 - g2) ** 2 / den
+
+
+def _sound_speed(G):  # shock-physics.h:75-78
+    ad = adiabatic_idx(G)
+    return math.sqrt(max(ad * (ad - 1) * (G - 1) / (1 + (G - 1) * ad), 0.0)) * C
+
+
+def _smoothstep(e0, e1, x):  # reverse-shock.tpp:11-20
+    t = min(max((x - e0) / (e1 - e0), 0.0), 1.0)
+    return t * t * (3.0 - 2.0 * t)
+
+
+def solve_pair_row(m: Model, rvs_eps_B, theta, T0, t_lat):
+    """(forward table, reverse table, injection_idx) of one row: grid_solve_shock_pair (reverse-shock.tpp:511-591).
+    State: Gamma, x4, x3, m2, m3, U2_th, U3_th, r, t_comv, eps4, m4 (reverse-shock.hpp:29-45 without theta)."""
+    iG, iX4, iX3, iM2, iM3, iU2, iU3, iR, iT, iE4, iM4 = range(11)
+    n = len(t_lat)
+    G4 = m.Gamma0_of(theta)
+    deps0 = m.eps_k_of(theta) / T0
+    dm0 = deps0 / (G4 * C * C)
+    u4 = math.sqrt(G4 * G4 - 1) * C
+    cs4 = _sound_speed(G4)
+    beta4 = math.sqrt((G4 - 1) * (G4 + 1)) / G4
+    eps_e_rad = m.eps_e if m.radiative else 0.0
+
+    def init_state(t0):  # set_init_state: reverse-shock.tpp:314-357
+        x = np.zeros(11)
+        x[iR] = beta4 * C * t0 * G4 * G4 * (1 + beta4)
+        x[iT] = x[iR] / math.sqrt((G4 - 1) * (G4 + 1)) / C
+        dt = min(t0, T0)
+        x[iE4], x[iM4] = deps0 * dt, dm0 * dt
+        x[iX4] = G4 * t0 * beta4 * C if t0 < T0 else G4 * T0 * beta4 * C + cs4 * (t0 - T0) * G4
+        x[iM2] = simpson_logspace(lambda u: m.rho(math.exp(u)) * math.exp(u) ** 3, x[iR])
+        mj = dm0 * T0
+        x[iG] = G4 / (1 + x[iM2] / mj) if (mj > 0 and x[iM2] > 0) else G4
+        ad = adiabatic_idx(x[iG])
+        cool = 3 * (ad - 1)
+        x[iU2] = (1 - eps_e_rad) * (x[iG] - 1) * C * C * simpson_logspace(
+            lambda u: m.rho(math.exp(u)) * math.exp(u) ** 3 * (math.exp(u) / x[iR]) ** cool, x[iR])
+        G34 = _rel_Gamma(G4, x[iG])
+        if G34 > 1 and x[iM4] > 0 and x[iX4] > 0:
+            x[iX3] = x[iX4] * 1e-8
+            x[iM3] = x[iM4] * _compression(G34) * x[iX3] / x[iX4]
+            x[iU3] = (G34 - 1) * x[iM3] * C * C
+        return x
+
+    def rhs(xr, t):  # FRShockEqn::operator(): reverse-shock.tpp:252-294 and the rate terms :62-250
+        Gm = min(max(xr[iG], 1.0), G4)
+        m4 = xr[iM4]
+        m3 = min(max(xr[iM3], 0.0), max(m4, 0.0))
+        x3, U3 = max(xr[iX3], 0.0), max(xr[iU3], 0.0)
+        x4, m2, U2, r, tc = xr[iX4], xr[iM2], xr[iU2], xr[iR], xr[iT]
+        d = np.zeros(11)
+        u3 = math.sqrt((Gm - 1) * (Gm + 1))
+        dr, dtc = u3 * (Gm + u3) * C, Gm + u3
+        d[iR], d[iT] = dr, dtc
+        rho = m.rho(r)
+        dm2 = r * r * rho * dr
+        d[iM2] = dm2
+        w = _smoothstep(T0 * 1.5, T0 * 0.5, t)
+        deps4, dm4 = (w * deps0, w * dm0) if w > 1e-6 else (0.0, 0.0)
+        d[iE4], d[iM4] = deps4, dm4
+        G34 = _rel_Gamma(G4, Gm)
+        comp = _compression(G34)
+        f = min(dm4 / dm0, 1.0) if (dm0 > 0 and dm4 > 0) else 0.0
+        se4 = cs4 * dtc
+        dx4 = f * u4 + (1 - f) * se4 if f > 1e-6 else se4
+        d[iX4] = dx4
+        se3 = _sound_speed(G34) * dtc
+        dx3 = se3
+        remaining = max(m4 - m3, 0.0)
+        if not (m4 <= 0):
+            cw = f + (1.0 - f) * remaining / m4
+            if not (cw < 1e-6):
+                pen = Gm * comp / G4 - 1
+                if not (pen <= 0):
+                    beta3 = math.sqrt((Gm - 1) * (Gm + 1)) / Gm
+                    dx3dt = (G4 - Gm) * (G4 + Gm) * (1 + beta3) * C / (G4 * G4 * (beta3 + beta4) * pen)
+                    crossing = abs(dx3dt * Gm)
+                    if pen < 1:
+                        cs = _sound_speed(G34)
+                        crossing = min(crossing, math.sqrt(cs * cs / (C * C)) * C * dtc)
+                    dx3 = cw * crossing + (1.0 - cw) * se3
+        d[iX3] = dx3
+        dm3 = 0.0
+        if not (m4 <= 0) and not (remaining <= 0 and f < 1e-6):
+            dm3dt = (f * m4 + (1.0 - f) * remaining) * comp / x4 * dx3
+            if f > 1e-6:
+                cap = _smoothstep(0, 1.0, m3 / m4)
+                dm3 = (1.0 - cap) * dm3dt + cap * min(dm3dt, dm4)
+            else:
+                dm3 = dm3dt
+        d[iM3] = dm3
+        ad2, ad3 = adiabatic_idx(Gm), adiabatic_idx(G34)
+        eps_rad = radiative_efficiency(m, tc, Gm, (Gm - 1) * 4 * Gm * rho * C * C)
+        dlnv2 = 2 * dr / r + (dx4 / x4 if x4 > 0 else 0.0)
+        dU2 = (1 - eps_rad) * dm2 * (Gm - 1) * C * C - (ad2 - 1) * dlnv2 * U2
+        dlnv3 = 2 * dr / r + (dx3 / x3 if x3 > 0 else 0.0)
+        dU3 = dm3 * (G34 - 1) * C * C - (ad3 - 1) * dlnv3 * U3
+        d[iU2], d[iU3] = dU2, dU3
+        Ge = lambda ad: (ad * Gm * Gm - ad + 1) / Gm          # noqa: E731  compute_effective_Gamma
+        dGe = lambda ad: (ad * Gm * Gm + ad - 1) / (Gm * Gm)  # noqa: E731
+        a = (Gm - 1) * C * C * dm2 + (Gm - G4) * C * C * dm3 + Ge(ad2) * dU2 + Ge(ad3) * dU3
+        b = (m2 + m3) * C * C + dGe(ad2) * U2 + dGe(ad3) * U3
+        q = -a / b if b != 0 else math.nan
+        d[iG] = q if (b != 0 and math.isfinite(q)) else 0.0
+        return d
+
+    def complete(x, t):  # crossing_complete: reverse-shock.tpp:49-60
+        return not (x[iM3] < 0.999 * x[iM4]) and not (_smoothstep(T0 * 1.5, T0 * 0.5, t) > 1e-6)
+
+    t0 = min(t_lat[0], 0.01 * SEC, 0.1 * estimate_t_dec(m, theta))
+    x0 = init_state(t0)
+    blank = lambda: dict(t_comv=np.zeros(n), r=np.zeros(n), Gamma=np.ones(n), Gamma_th=np.ones(n), B=np.zeros(n), N_p=np.zeros(n))  # noqa: E731
+    F, R = blank(), blank()
+    if x0[iG] <= 1.03:  # RS_Gamma_limit: stopping shock
+        for tb in (F, R):
+            tb["t_comv"][:], tb["r"][:] = x0[iT], x0[iR]
+        return F, R, n
+    st = DenseDopri5(rhs, x0, t0, 1e-9 * t0, m.rtol)
+    crossing, pending, inj, t_cross, t_start = True, False, n, 0.0, t0
+    cross = {}
+    k, steps = 0, 0
+
+    def save(k, x):  # save_fwd_shock_state + save_rvs_shock_state: forward-shock.tpp:151-173, reverse-shock.tpp:403-426
+        comp2 = _compression(_rel_Gamma(1.0, x[iG]))
+        Gth2 = x[iU2] / (x[iM2] * C * C) + 1 if x[iM2] != 0 else 1.0
+        F["t_comv"][k], F["r"][k], F["Gamma"][k], F["Gamma_th"][k] = x[iT], x[iR], x[iG], Gth2
+        F["B"][k] = math.sqrt(8 * PI * m.eps_B * (Gth2 - 1) * m.rho(x[iR]) * comp2 * C * C)
+        F["N_p"][k] = x[iM2] / MP
+        if k <= inj:
+            comp34 = _compression(_rel_Gamma(G4, x[iG]))
+            rho4 = x[iM4] / (x[iR] * x[iR] * x[iX4])
+            Gth3 = x[iU3] / (x[iM3] * C * C) + 1 if x[iM3] != 0 else 1.0
+            if Gth3 < 1 + 1e-6:
+                Gth3 = 1.0
+            B3 = math.sqrt(8 * PI * rvs_eps_B * (Gth3 - 1) * rho4 * comp34 * C * C)
+        else:
+            comp = cross["V3"] / (x[iR] * x[iR] * x[iX3])
+            Gth3 = x[iU3] / (x[iM3] * C * C) + 1 if x[iM3] != 0 else 1.0
+            B3 = math.sqrt(8 * PI * rvs_eps_B * (Gth3 - 1) * cross["rho3"] * comp * C * C)
+        R["t_comv"][k], R["r"][k], R["Gamma"][k], R["Gamma_th"][k], R["B"][k], R["N_p"][k] = x[iT], x[iR], x[iG], Gth3, B3, x[iM3] / MP
+
+    while st.t <= t_lat[-1]:
+        if not st.do_step():
+            break
+        steps += 1
+        if steps > 100000 or st.t + st.dt == st.t:
+            break
+        if crossing and complete(st.x, st.t):  # locate_crossing_time: reverse-shock.tpp:482-495
+            lo, hi = t_start, st.t
+            for _ in range(100):
+                if not ((hi - lo) > 1e-12 * hi):
+                    break
+                mid = 0.5 * (lo + hi)
+                if complete(st.dense(mid), mid):
+                    hi = mid
+                else:
+                    lo = mid
+            xc = st.dense(hi)
+            t_cross = hi
+            rho4 = xc[iM4] / (xc[iR] * xc[iR] * xc[iX4])  # save_cross_state: reverse-shock.tpp:298-312
+            cross = dict(V3=xc[iR] * xc[iR] * xc[iX3], rho3=rho4 * _compression(_rel_Gamma(G4, xc[iG])))
+            crossing, pending = False, True
+        t_start = st.t
+        while k < n and st.t > t_lat[k]:
+            x = st.dense(t_lat[k])
+            if pending and t_lat[k] >= t_cross:
+                inj, pending = (k if k > 0 else 1), False
+            save(k, x)
+            k += 1
+    # reverse_shock_early_extrap: reverse-shock.tpp:428-467
+    cut = next((q for q in range(n) if R["Gamma_th"][q] > 1 + 1e-6), n)
+    if not (cut == 0 or cut >= n - 2 or cut >= inj):
+        l2r = math.log2(R["r"][cut])
+        dl = math.log2(R["r"][cut + 2]) - l2r
+        for key, off in (("Gamma_th", 1.0), ("B", 0.0), ("N_p", 0.0)):
+            l0 = math.log2(R[key][cut] - off)
+            slope = (math.log2(R[key][cut + 2] - off) - l0) / dl
+            for q in range(cut):
+                R[key][q] = off + 2.0 ** (l0 + slope * (math.log2(R["r"][q]) - l2r))
+    return F, R, inj
+
+
 # ---- synchrotron electrons and photons: src/radiation/synchrotron.cpp:45-408, smooth-power-law-syn.cpp:26-166 ------
 _KS = 3 * E / (4 * PI * ME * C)
 
@@ -274,12 +490,15 @@ def _softplus2(x):  # src/util/fast-math.h:179-185
     return np.where(x > 20, x, np.where(x < -20, 0.0, mid))
 
 
-def photon_tables(m: Model, tab):
-    """Per-cell spectral coefficients (generate_syn_electrons + generate_syn_photons + SmoothPowerLawSyn::build)."""
-    B, r, Gth, Np, tc, p = tab["B"], tab["r"], tab["Gamma_th"], tab["N_p"], tab["t_comv"], m.p
+def photon_tables(m: Model, tab, rad=None, inj=None):
+    """Per-cell spectral coefficients (generate_syn_electrons + generate_syn_photons + SmoothPowerLawSyn::build).
+    `rad` = (eps_e, eps_B, p, xi_e) of the shock (default: the forward shock's); cells k >= inj are relic cells whose
+    gamma_c / gamma_M cool adiabatically from the crossing cell inj-1 (synchrotron.cpp:190-195, synchrotron.h:187-201)."""
+    eps_e, _eps_B, p, xi_e = rad if rad is not None else (m.eps_e, m.eps_B, m.p, m.xi_e)
+    B, r, Gth, Np, tc = tab["B"], tab["r"], tab["Gamma_th"], tab["N_p"], tab["t_comv"]
     with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
         gM = np.where(B == 0, np.inf, np.sqrt(6 * PI * E / SIGMA_T / B))
-        gave = m.eps_e * (Gth - 1) * (MP / ME) / m.xi_e
+        gave = eps_e * (Gth - 1) * (MP / ME) / xi_e
         if p > 2:
             gm = (p - 2) / (p - 1) * gave + 1
         else:  # 1 < p < 2 (p == 2 root-finding is not restated)
@@ -287,10 +506,14 @@ def photon_tables(m: Model, tab):
         fsyn = (gm - 1) / gm
         if p > 3:
             fsyn = np.exp2((p - 1) / 2 * np.log2(fsyn))
-        Ne = Np * m.xi_e * fsyn
+        Ne = Np * xi_e * fsyn
         col = Ne / (r * r)
         gbar = (6 * PI * ME * C / SIGMA_T) / (B * B * tc)
         gc = (gbar + np.sqrt(gbar * gbar + 4)) / 2
+        if inj is not None and 0 < inj < len(B):  # relic cells: cool_after_crossing from cell inj - 1
+            f_ad = (gm[inj:] - 1) / (gm[inj - 1] - 1)
+            gc = np.concatenate([gc[:inj], (gc[inj - 1] - 1) * f_ad + 1])
+            gM = np.concatenate([gM[:inj], (gM[inj - 1] - 1) * f_ad + 1])
         I_peak = B * ((PI / 4) * 0.92 * math.sqrt(3.0) * E**3 / (ME * C * C)) * col / (4 * PI)
         freq = lambda g: np.where((B == 0) | ~np.isfinite(g), 0.0, _KS * B * g * g)  # noqa: E731
         # compute_syn_gamma_a: synchrotron.cpp:212-246 (no inverse Compton: every ic factor is 1)
@@ -334,12 +557,13 @@ def photon_tables(m: Model, tab):
         thin_fast = np.where(l2a < l2c, (l2a - l2c) / 3, np.where(l2a < l2m, -0.5 * (l2a - l2c),
                              -0.5 * (l2m - l2c) - 0.5 * p * (l2a - l2m)))
         c["thick_norm"] = np.where(l2m < l2c, thin_slow, thin_fast) - thick_sharp
+    c["p"] = p
     return c
 
 
 def log2_I_nu(m: Model, c, l2nu):
     """SmoothPowerLawSyn::compute_log2_I_nu (smooth-power-law-syn.cpp:26-46,80-92,159-166); arrays broadcast."""
-    smooth_thick = (3.44 * m.p - 1.41) / LN2
+    smooth_thick = (3.44 * c["p"] - 1.41) / LN2
     x_far = 1.5 * math.log2(20.0 / smooth_thick)
     with np.errstate(over="ignore", invalid="ignore"):
         thin = ((l2nu - c["lo"]) / 3.0 - _softplus2(c["d_lo"] * (l2nu - c["lo"])) / c["s_lo"]
@@ -355,17 +579,30 @@ def log2_I_nu(m: Model, c, l2nu):
 
 # ---- observer: src/core/observer.cpp:17-37,143-205,439-454, observer.h:355-445 -------------------------------------
 def flux_density_grid(p, theta, phi, t_rows, reps, phi_mirrored, n_phi_eff, t_obs, nu_obs):
-    """F_nu[n_nu, n_t] (erg cm^-2 s^-1 Hz^-1) of one forward-shock model on the GIVEN grid: theta[N_theta],
-    phi[N_phi], t_rows[n_reps, N_t] (engine-frame lattice of each representative row, code units), reps."""
+    """F_nu[n_nu, n_t] (erg cm^-2 s^-1 Hz^-1) of one model on the GIVEN grid: theta[N_theta], phi[N_phi],
+    t_rows[n_reps, N_t] (engine-frame lattice of each representative row, code units), reps.
+    Forward-shock model: returns the forward synchrotron flux.  With a reverse shock (has_rvs): returns
+    (forward, reverse); one EAT geometry serves both (pybind/pymodel.h:943-950)."""
     m = Model(p)
     theta, phi = np.asarray(theta, float), np.asarray(phi, float)
     n_th = theta.size
-    tabs = [solve_forward_row(m, theta[j0], t_rows[r]) for r, j0 in enumerate(reps)]
-    coefs = [photon_tables(m, tb) for tb in tabs]
+    has_rvs = bool(np.asarray(p["has_rvs"]).reshape(-1)[0])
+    shocks = []  # per shock: (tables per rep, coefficient tables per rep)
+    if has_rvs:
+        rv = np.asarray(p["rvs"]).reshape(-1)[0]
+        rad_r = tuple(float(rv[k]) for k in ("eps_e", "eps_B", "p", "xi_e"))
+        T0 = float(np.asarray(p["duration"]).reshape(-1)[0]) * SEC
+        rows = [solve_pair_row(m, rad_r[1], theta[j0], T0, t_rows[r]) for r, j0 in enumerate(reps)]
+        tabs = [r[0] for r in rows]
+        shocks.append((tabs, [photon_tables(m, tb) for tb in tabs]))
+        shocks.append(([r[1] for r in rows], [photon_tables(m, r[1], rad_r, r[2]) for r in rows]))
+    else:
+        tabs = [solve_forward_row(m, theta[j0], t_rows[r]) for r, j0 in enumerate(reps)]
+        shocks.append((tabs, [photon_tables(m, tb) for tb in tabs]))
     rep_of = np.searchsorted(np.asarray(reps), np.arange(n_th), side="right") - 1
     l2t_obs = np.log2(np.asarray(t_obs, float) * SEC)
     l2nu = np.log2(np.asarray(nu_obs, float) * HZ) + math.log2(1 + m.z)
-    F = np.zeros((l2nu.size, l2t_obs.size))
+    F = [np.zeros((l2nu.size, l2t_obs.size)) for _ in shocks]
     cos_o, sin_o = math.cos(m.theta_v), math.sin(m.theta_v)
     last = n_phi_eff - 1
     for i in range(n_phi_eff):
@@ -378,23 +615,25 @@ def flux_density_grid(p, theta, phi, t_rows, reps, phi_mirrored, n_phi_eff, t_ob
         else:
             dphi = 0.5 * (phi[min(i + 1, last)] - phi[max(i - 1, 0)])
         for j in range(n_th):
-            tb, cf = tabs[rep_of[j]], coefs[rep_of[j]]
+            tb = tabs[rep_of[j]]
             t_eng = np.asarray(t_rows[rep_of[j]], float)
             cos_v = math.sin(theta[j]) * math.cos(phi[i]) * sin_o + math.cos(theta[j]) * cos_o
             c_lo = math.cos(theta[j]) if j == 0 else math.cos(0.5 * (theta[j - 1] + theta[j]))
             c_hi = math.cos(theta[j]) if j == n_th - 1 else math.cos(0.5 * (theta[j] + theta[j + 1]))
             dOmega = abs((c_hi - c_lo) * dphi)
             Gm, r = tb["Gamma"], tb["r"]
-            with np.errstate(divide="ignore", invalid="ignore"):
+            with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
                 l2dop = -np.log2(Gm - np.sqrt((Gm - 1) * (Gm + 1)) * cos_v)
                 l2t = np.log2(t_eng * (1 + m.z) + (1 - cos_v) / C * (1 + m.z) * r)
                 l2geom = (np.log2(np.float64(dOmega)) + 2 * np.log2(r)) + 3 * l2dop
-                L = log2_I_nu(m, cf, l2nu[:, None] - l2dop[None, :]) + l2geom[None, :]  # [n_nu, N_t]
                 # iterate_to: t_row[k] <= x < t_row[k+1] (observer.h:309-313,405-433)
                 k = np.searchsorted(l2t, l2t_obs, side="right") - 1
                 ok = (k >= 0) & (k <= l2t.size - 2)
                 kk = np.clip(k, 0, l2t.size - 2)
-                slope = (L[:, kk + 1] - L[:, kk]) / (l2t[kk + 1] - l2t[kk])[None, :]
-                val = np.exp2(L[:, kk] + (l2t_obs - l2t[kk])[None, :] * slope)
-            F += np.where(ok[None, :] & np.isfinite(slope), val, 0.0)
-    return F * ((1 + m.z) / (m.d_L * m.d_L)) / FLUX_DEN_CGS
+                for si, (_tabs, coefs) in enumerate(shocks):
+                    L = log2_I_nu(m, coefs[rep_of[j]], l2nu[:, None] - l2dop[None, :]) + l2geom[None, :]  # [n_nu, N_t]
+                    slope = (L[:, kk + 1] - L[:, kk]) / (l2t[kk + 1] - l2t[kk])[None, :]
+                    val = np.exp2(L[:, kk] + (l2t_obs - l2t[kk])[None, :] * slope)
+                    F[si] += np.where(ok[None, :] & np.isfinite(slope), val, 0.0)
+    scale = ((1 + m.z) / (m.d_L * m.d_L)) / FLUX_DEN_CGS
+    return tuple(f * scale for f in F) if has_rvs else F[0] * scale

@@ -37,6 +37,33 @@ def test_restatement_matches_reference(name):
     assert err < 1e-8, err
 
 
+@pytest.mark.parametrize("name", ["C3_wind_thick", "config5_truth", "thin_ism_offaxis"])
+def test_restatement_pair_matches_reference(name):
+    """Forward + reverse shock (the config-5 / C3 path): pair ODE with crossing detection, shock-table
+    completion, early-time extrapolation, relic-cell cooling, both spectra through one EAT geometry."""
+    from oracle import restatement
+
+    ref = _ref()
+    if name == "C3_wind_thick":
+        p, t, nu = configs.C3()
+        t = t[::5]
+    elif name == "config5_truth":
+        p, t, nu = configs.make(rvs=(0.1, 1e-2, 2.5), duration=100.0), np.logspace(2.5, 6.5, 14), np.array([1e9, 4.84e14, 1e18])
+    else:
+        p = configs.make(E_iso=3e52, Gamma0=120.0, n_ism=0.1, theta_obs=0.05, rvs=(0.05, 3e-3, 2.2), duration=1.0)
+        t, nu = np.logspace(2, 7, 14), np.array([1e9, 1e14, 1e17])
+    d = ref.details(p, float(t[0]), float(t[-1]))
+    info = d["info"]
+    Ff, Fr = restatement.flux_density_grid(p, d["theta"], d["phi"], d["t_rows"], d["reps"], bool(info["phi_mirrored"]),
+                                           int(info["n_phi_eff"]), t, nu)
+    R = ref.flux_density_grid(p, t, nu)[0]
+    for F, comp in ((Ff, 1), (Fr, 3)):
+        b = R[comp]
+        m = b > 1e-3 * b.max(axis=-1, keepdims=True)
+        err = np.max(np.abs(F[m] - b[m]) / b[m])
+        assert err < 1e-7, (name, comp, err)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["C1", "gauss_offaxis"])
 def test_gpu_matches_restatement_on_its_own_grid(name):
@@ -58,3 +85,21 @@ def test_gpu_matches_restatement_on_its_own_grid(name):
     Gf = eng.flux_density_grid(p, t, nu)[0, 1]
     m = F > 1e-3 * F.max(axis=-1, keepdims=True)
     assert np.max(np.abs(Gf[m] - F[m]) / F[m]) < 1e-8
+
+
+@pytest.mark.gpu
+def test_gpu_pair_matches_restatement_on_its_own_grid():
+    """Config-5 shape (FS+RS tophat): GPU against the numpy restatement on the GPU's own grid."""
+    from oracle import restatement
+    from vegasafterglow_b200.engine import Engine
+
+    eng = Engine(0)
+    p, t, nu = configs.make(rvs=(0.1, 1e-2, 2.5), duration=100.0), np.logspace(2.5, 6.5, 14), np.array([1e9, 4.84e14, 1e18])
+    d = eng.details(p, float(t[0]), float(t[-1]))
+    info = d["info"]
+    Ff, Fr = restatement.flux_density_grid(p, d["theta"], d["phi"], d["t_rows"], d["reps"], bool(info["phi_mirrored"]),
+                                           int(info["n_phi_eff"]), t, nu)
+    G = eng.flux_density_grid(p, t, nu)[0]
+    for F, comp in ((Ff, 1), (Fr, 3)):
+        m = F > 1e-3 * F.max(axis=-1, keepdims=True)
+        assert np.max(np.abs(G[comp][m] - F[m]) / F[m]) < 1e-7, comp
