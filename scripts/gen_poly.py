@@ -31,13 +31,13 @@ def horner(c, x):
 
 ln2 = np.log(ld(2))
 # exp2 on [-0.5, 0.5]
-for deg in (11, 12):
+for deg in (9, 10, 11, 12):
     c = cheb_fit(lambda f: np.exp(f * ln2), ld(-0.5), ld(0.5), deg)
     xs = np.linspace(-0.5, 0.5, 200001).astype(ld)
     cd = c.astype(np.float64)
     err = np.max(np.abs(horner(cd.astype(ld), xs) / np.exp(xs * ln2) - 1))
     print("exp2 deg", deg, "max rel err", float(err))
-    if deg == 12:
+    if deg == 10:  # the degree vag_math.cuh uses (VAG_EXP2_DEG)
         print("EXP2 = {" + ", ".join(float(v).hex() for v in cd) + "};")
 # log2(m) = s * q(s^2), s=(m-1)/(m+1), m in [sqrt(.5), sqrt(2)) -> z = s^2 in [0, 0.02944]
 smax = (np.sqrt(ld(2)) - 1) / (np.sqrt(ld(2)) + 1)
