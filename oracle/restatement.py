@@ -3,13 +3,16 @@ for forward-shock synchrotron models: blas
 electrons and photons, equal-arrival-time-surface flux integration.  It shares no code with the product
 (`vegasafterglow_b200/csrc`): different language, different structure (row-vectorised numpy, scalar dopri5).
 
-Scope: TophatJet / GaussianJet / PowerLawJet, ISM / Wind(k_m = 2), forward shock, no inverse Compton, no
-spreading, axisymmetric.  The adaptive (phi, theta, t) grid (row a1) is an INPUT here -- taken from the
-reference's own `details()` tables -- so that this file stays small enough to audit; the grid stage is pinned
-separately, directly against the reference's Coord (tests/test_hostemu_parity.py::test_stage_tables).
+Scope: TophatJet / GaussianJet / PowerLawJet, ISM / Wind(k_m = 2), forward shock and forward + reverse shock
+(unmagnetised), no inverse Compton, no spreading, axisymmetric.  `flux_density_grid` takes the adaptive
+(phi, theta, t) grid as an input (e.g. the reference's own `details()` tables), which isolates the physics stages;
+`auto_grid` restates the grid builder (row a1) and `model_flux` chains the two into the whole path.
 
-Pinned by tests/test_restatement.py: flux of BASELINE configs C1 (tophat) and C2 (Gaussian off-axis) against the
-unmodified reference (oracle/_ref) to <= 1e-8.  Citations are `path:line` in the reference repository.
+Pinned by tests/test_restatement.py against the unmodified reference (oracle/_ref): physics stages on the
+reference's grid <= 2e-10 (C1, Gaussian off-axis, power-law/wind, C3, config-5 truth model, thin shell); restated
+grid = identical node counts / symmetry groups, nodes to the quadrature-noise level (2e-11 structured jets, 2e-6
+tophat); whole path 2.6e-7 (C1), 1e-11 (C2), 4e-9 (C3), 5e-13 (power-law/wind).  Citations are `path:line` in the
+reference repository.
 """
 from __future__ import annotations
 
@@ -637,3 +640,323 @@ def flux_density_grid(p, theta, phi, t_rows, reps, phi_mirrored, n_phi_eff, t_ob
                     F[si] += np.where(ok[None, :] & np.isfinite(slope), val, 0.0)
     scale = ((1 + m.z) / (m.d_L * m.d_L)) / FLUX_DEN_CGS
     return tuple(f * scale for f in F) if has_rvs else F[0] * scale
+
+
+# =====================================================================================================================
+# Row a1: the adaptive (phi, theta, t) grid -- auto_grid and its callees (src/core/grid-refinement.h:40-706,
+# src/core/grid-refinement.cpp:140-197, Coord::detect_symmetry src/core/mesh.h:120-185) for the typed jets,
+# isotropic media, axisymmetric, non-spreading models.
+# =====================================================================================================================
+THETA_MIN = 1e-6          # defaults::grid::theta_min
+N_SAMPLES = 200           # defaults::sampling::theta_samples
+
+
+def _linspace_at(a, b, n, i):  # xt::linspace element (xbuilder.hpp:199-222,460-468): a + step i, last forced to b
+    step = (b - a) / max(1.0, float(n - 1))
+    return b if (n > 1 and i == n - 1) else a + step * float(i)
+
+
+def _structure_weight(G):  # grid-refinement.h:11-13
+    return G * math.sqrt(max((G - 1) * G, 0.0))
+
+
+def _beta(G):
+    return math.sqrt((G - 1) * (G + 1)) / G
+
+
+def find_jet_jumps(m: Model):  # grid-refinement.h:40-86
+    n_scan, lo, hi = 512, THETA_MIN, PI / 2
+    dth = (hi - lo) / (n_scan - 1)
+    if m.Gamma0_of(hi) >= GAMMA_CUT:
+        return [hi]
+    jumps, prev_th, prev_G = [], lo, m.Gamma0_of(lo)
+    for j in range(1, n_scan):
+        cur_th = lo + dth * float(j)
+        cur_G = m.Gamma0_of(cur_th)
+        if prev_G >= GAMMA_CUT or cur_G >= GAMMA_CUT:
+            scale = max(prev_G - 1, cur_G - 1)
+            if scale > 0 and abs(cur_G - prev_G) > 0.5 * scale:
+                a, b = prev_th, cur_th
+                while b - a > 1e-9:
+                    mid = 0.5 * (a + b)
+                    Gm = m.Gamma0_of(mid)
+                    if abs(Gm - prev_G) < abs(Gm - cur_G):
+                        a = mid
+                    else:
+                        b = mid
+                jumps.append(a if prev_G > cur_G else b)
+        prev_th, prev_G = cur_th, cur_G
+    return jumps
+
+
+def find_theta_range(m: Model):  # grid-refinement.h:88-111
+    lo, hi = THETA_MIN, PI / 2
+    step = (hi - lo) / 512
+    th_max, th_min = hi, lo
+    th = hi
+    while th >= lo:
+        if m.Gamma0_of(th) >= GAMMA_CUT:
+            th_max = th
+            break
+        th -= step
+    th = lo
+    while th <= hi:
+        if m.Gamma0_of(th) >= GAMMA_CUT:
+            th_min = th
+            break
+        th += step
+    return th_min, th_max
+
+
+def inverse_cdf_sampling(pdf, lo, hi, num, log_sample, midpoint):  # grid-refinement.h:137-189
+    if log_sample:
+        a, b = math.log10(lo), math.log10(hi)
+        x_i = [10.0 ** _linspace_at(a, b, N_SAMPLES, i) for i in range(N_SAMPLES)]
+    else:
+        x_i = [_linspace_at(lo, hi, N_SAMPLES, i) for i in range(N_SAMPLES)]
+    cdf = [0.0] * N_SAMPLES
+    st = DenseDopri5(lambda _x, t: np.array([pdf(t)]), [0.0], lo, (hi - lo) / 1e3, 1e-6)
+    k, steps = 1, 0
+    while st.t <= hi:
+        if not st.do_step():
+            break
+        steps += 1
+        if steps > 100000:
+            break
+        while k < N_SAMPLES and st.t > x_i[k]:
+            cdf[k] = float(st.dense(x_i[k])[0])
+            k += 1
+    c0, c1 = cdf[0], cdf[-1]
+    out = []
+    for q in range(num):
+        target = c0 + (c1 - c0) * (q + 0.5) / num if midpoint else _linspace_at(c0, c1, num, q)
+        j = 0
+        while j < N_SAMPLES and not (target <= cdf[j]):
+            j += 1
+        if j >= N_SAMPLES:
+            out.append(0.0)
+        elif j == 0:
+            out.append(x_i[0])
+        else:
+            den = cdf[j] - cdf[j - 1]
+            out.append(x_i[j - 1] + (x_i[j] - x_i[j - 1]) / den * (target - cdf[j - 1]) if den > 0 else x_i[j - 1])
+    return out
+
+
+def adaptive_theta_grid(m: Model, th_min, th_max, base_pts, theta_v, theta_resol):  # grid-refinement.h:199-291
+    scan, ext = 100, th_max - th_min
+    peak_w, G_peak, s_sum, last_bright, G_v = 0.0, 1.0, 0.0, 0, 1.0
+    for i in range(scan + 1):
+        th = th_min + ext * i / scan
+        Gm = m.Gamma0_of(th)
+        w = _structure_weight(Gm)
+        s_sum += w
+        if w > peak_w:
+            peak_w, G_peak, last_bright = w, Gm, i
+        elif w > 0.01 * peak_w:
+            last_bright = i
+        dth = th - theta_v
+        G_v = max(G_v, Gm / math.sqrt(1.0 + Gm * Gm * dth * dth))
+    floor_w = 0.25 * peak_w
+    cdf_est = (s_sum / scan + floor_w) * ext
+    th_bright = th_min + ext * last_bright / scan
+    G_peak = max(G_peak, G_v)
+    dop_alpha = 12.0 * math.sqrt(peak_w / max(_structure_weight(G_v), 1.0))
+    Gp2, Gv2 = G_peak * G_peak, G_v * G_v
+    beam = lambda dec, coeff, off: int(max(0.0, dec - off) * theta_resol * coeff)  # noqa: E731
+    core_pts = beam(math.log10(max(1.0, G_peak * (th_bright - th_min))), 55.0, 1.0)
+    view_pts = beam(math.log10(max(1.0, G_v * max(theta_v - th_min, th_max - theta_v))), 25.0, 0.0) if theta_v * G_peak > 3.0 else 0
+    total = base_pts + core_pts + view_pts
+    cal = lambda n, c: (float(n) / base_pts * cdf_est / c) if (n > 0 and c > 0) else 0.0  # noqa: E731
+    core_w = cal(core_pts, 0.5 * math.log((1.0 + Gp2 * th_max * th_max) / (1.0 + Gp2 * th_min * th_min)))
+    vl, vr = theta_v - th_min, th_max - theta_v
+    view_w = cal(view_pts, 0.5 * (math.log(1.0 + Gv2 * vl * vl) + math.log(1.0 + Gv2 * vr * vr)))
+
+    def pdf(th):
+        Gm = m.Gamma0_of(th)
+        b = _beta(Gm)
+        dop = (1 - b) / (1 - b * math.cos(th - theta_v))
+        d = th - theta_v
+        return (core_w * Gp2 * th / (1.0 + Gp2 * th * th) + view_w * Gv2 * abs(d) / (1.0 + Gv2 * d * d)
+                + (1 + dop_alpha * dop) * _structure_weight(Gm) + floor_w)
+
+    return inverse_cdf_sampling(pdf, th_min, th_max, total, True, False)
+
+
+def adaptive_phi_grid(m: Model, phi_num, theta_v, theta, phi_max, boost_cap):  # grid-refinement.h:295-360
+    if theta_v == 0:
+        return [_linspace_at(0.0, 2 * PI, phi_num, i) for i in range(phi_num)]
+    n = len(theta)
+    half = phi_max < 2 * PI
+    dcos, beta, sw, ct, st = [], [], [], [], []
+    for it in range(n):
+        left = 0.0 if it == 0 else 0.5 * (theta[it - 1] + theta[it])
+        right = theta[it] if it == n - 1 else 0.5 * (theta[it] + theta[it + 1])
+        dcos.append(abs(math.cos(left) - math.cos(right)))
+        Gm = m.Gamma0_of(theta[it])
+        beta.append(_beta(Gm))
+        sw.append(_structure_weight(Gm))
+        ct.append(math.cos(theta[it]))
+        st.append(math.sin(theta[it]))
+    cos_tv, sin_tv = math.cos(theta_v), math.sin(theta_v)
+
+    def weight(phi):
+        cp, w = math.cos(phi), 0.0
+        for it in range(n):
+            ca = ct[it] * cos_tv + st[it] * sin_tv * cp
+            w += (1 - beta[it]) / (1 - beta[it] * ca) * sw[it] * dcos[it]
+        return w
+
+    A = [weight(phi_max * float(s) / 100) for s in range(101)]
+    peak, tot = 0.0, 0.0
+    for a in A:
+        peak = max(peak, a)
+        tot += a
+    floor_w = 0.05 * peak
+    if boost_cap > 0 and peak > 0:
+        conc = (peak + floor_w) / (tot / 101 + floor_w)
+        phi_num = int(float(phi_num) * min(max(conc / 5, 1.0), boost_cap))
+    return inverse_cdf_sampling(lambda ph: weight(ph) + floor_w, 0, phi_max, phi_num, False, half)
+
+
+def _band_lattice(ts, t_end, b_lo, b_hi, n, factor):  # logspace_with_band_refinement: grid-refinement.h:533-569
+    b_lo, b_hi = max(b_lo, ts), min(b_hi, t_end)
+    if not (b_hi > b_lo) or n < 8:
+        la, lb = math.log10(ts), math.log10(t_end)
+        return [10.0 ** _linspace_at(la, lb, n, i) for i in range(n)]
+    l0, l1, l2, l3 = math.log10(ts), math.log10(b_lo), math.log10(b_hi), math.log10(t_end)
+    w1, w2, w3 = l1 - l0, factor * (l2 - l1), l3 - l2
+    segs = n - 1
+    rnd = lambda v: int(math.floor(v + 0.5)) if v >= 0 else -int(math.floor(-v + 0.5))  # noqa: E731  std::round
+    n1 = min(rnd(float(segs) * w1 / (w1 + w2 + w3)), segs - 2)
+    n3 = min(rnd(float(segs) * w3 / (w1 + w2 + w3)), segs - 1 - n1 - 1)
+    n2 = segs - n1 - n3
+    g = [10.0 ** (l0 + (l1 - l0) * float(k) / float(n1)) for k in range(n1)]
+    g += [10.0 ** (l1 + (l2 - l1) * float(k) / float(n2)) for k in range(n2)]
+    g += [10.0 ** ((l2 + (l3 - l2) * float(k) / float(n3)) if n3 > 0 else l3) for k in range(n3 + 1)]
+    return g
+
+
+def _cross_lattice(t_start, t_end, t_refine, t_num, base_num):  # grid-refinement.cpp:166-197
+    t_refine = min(max(t_refine, t_start), t_end)
+    if t_refine <= t_start or t_refine >= t_end:
+        la, lb = math.log10(t_start), math.log10(t_end)
+        return [10.0 ** _linspace_at(la, lb, t_num, i) for i in range(t_num)]
+    n_post = int(float(base_num) * math.log10(t_end / t_refine) / math.log10(t_end / t_start))
+    n_post = max(n_post, 2)
+    if n_post >= t_num:
+        n_post = t_num // 2
+    n_pre = t_num + 1 - n_post
+    la, lb = math.log10(t_start), math.log10(t_refine)
+    g = [10.0 ** _linspace_at(la, lb, n_pre, k) for k in range(n_pre)]
+    la, lb = math.log10(t_refine), math.log10(t_end)
+    g += [10.0 ** _linspace_at(la, lb, n_post, k) for k in range(1, n_post)]
+    return g[:t_num]
+
+
+def auto_grid(p, t_obs_min, t_obs_max):
+    """auto_grid (grid-refinement.h:638-706): theta[N_theta], phi[N_phi], reps, t_rows[n_reps][N_t] (code units),
+    phi_mirrored, n_phi_eff for one axisymmetric, non-spreading typed-jet model; t_obs in seconds."""
+    m = Model(p)
+    g = lambda k: float(np.asarray(p[k]).reshape(-1)[0])  # noqa: E731
+    is_rvs = bool(g("has_rvs"))
+    phi_res = g("phi_resol") if g("phi_resol") > 0 else 0.06
+    th_res = g("theta_resol") if g("theta_resol") > 0 else (0.2 if is_rvs else 0.15)
+    t_res = g("t_resol") if g("t_resol") > 0 else (10.0 if is_rvs else 6.0)
+    T0 = g("duration") * SEC
+    tv = m.theta_v
+    t_min, t_max = t_obs_min * SEC, t_obs_max * SEC
+    jumps = find_jet_jumps(m)
+    inner, outer = find_theta_range(m)
+    for j in jumps:
+        outer = max(outer, j)
+    th_min, th_max = max(THETA_MIN, inner), min(outer, PI / 2)
+    theta_num = 36 + int((th_max - th_min) * 180 / PI * th_res)
+    base = adaptive_theta_grid(m, th_min, th_max, theta_num, tv, th_res)
+    # jump_refinement_grid (grid-refinement.cpp:140-164) + merge_grids (grid-refinement.h:362-393)
+    tight = (th_max - th_min) / len(base) / 8
+    feat = []
+    for jt in jumps:
+        if jt >= PI / 2 - 0.01:
+            continue
+        if jt - tight >= th_min:
+            feat.append(jt - tight)
+        if jt + tight <= th_max:
+            feat.append(jt + tight)
+        if th_min <= jt <= th_max:
+            feat.append(jt)
+    feat = sorted(set(feat))
+    theta, i, j = [], 0, 0
+    add = lambda v: theta.append(v) if (not theta or theta[-1] != v) else None  # noqa: E731
+    while i < len(base) and j < len(feat):
+        if base[i] <= feat[j]:
+            add(base[i])
+            i += 1
+            if base[i - 1] == feat[j]:
+                j += 1
+        else:
+            add(feat[j])
+            j += 1
+    for v in base[i:]:
+        add(v)
+    for v in feat[j:]:
+        add(v)
+    n_th = len(theta)
+    # phi grid (grid-refinement.h:664-693)
+    phi_base = max(int(360 * phi_res), 1)
+    mirror = tv != 0 and phi_base > 4
+    if mirror:
+        phi = adaptive_phi_grid(m, (phi_base + 1) // 2, tv, theta, PI, 5.0)
+    else:
+        boost = math.sqrt(max(m.Gamma0_of(tv) * math.sin(tv) / (2 * PI), 1.0))
+        phi_num = min(max(int(phi_base * boost), 1), phi_base * 5)
+        if phi_num <= 2:
+            phi = [_linspace_at(0.0, 2 * PI, phi_num, i) for i in range(phi_num)]
+        else:
+            phi = adaptive_phi_grid(m, phi_num, tv, theta, 2 * PI, 0.0)
+        if len(phi) >= 2:
+            shift = 0.5 * (phi[1] - phi[0])
+            phi = [v + shift for v in phi]
+    n_phi_eff = 1 if tv == 0 else len(phi)
+    # detect_symmetry (mesh.h:120-185)
+    reps = [0] + [j for j in range(1, n_th) if m.eps_k_of(theta[j - 1]) != m.eps_k_of(theta[j])
+                  or m.Gamma0_of(theta[j - 1]) != m.Gamma0_of(theta[j])]
+    # build_time_grid (grid-refinement.h:471-636) with phi_size = 1
+    t_end = 1.01 * t_max / (1 + m.z)
+    cos_tv, sin_tv, cos_p0 = math.cos(tv), math.sin(tv), math.cos(phi[0])
+    t_dec = {r: estimate_t_dec(m, theta[r]) for r in reps}
+    min_raw = min_guard = min_cut = t_end
+    max_ref, td, ri = 0.0, 0.0, -1
+    for j in range(n_th):
+        if ri + 1 < len(reps) and reps[ri + 1] == j:
+            ri += 1
+            td = t_dec[reps[ri]]
+        b = _beta(m.Gamma0_of(theta[j]))
+        cos_a = math.cos(theta[j]) * cos_tv + math.sin(theta[j]) * sin_tv * cos_p0
+        ts = 0.99 * t_min * (1 - b) / (1 - cos_a * b) / (1 + m.z)
+        cut = min(0.01 * td, 1e-2 * SEC)
+        if is_rvs:
+            cut = min(cut, 0.01 * T0)
+            max_ref = max(max_ref, 10.0 * max(td, T0))
+        min_raw, min_guard, min_cut = min(min_raw, ts), min(min_guard, max(ts, cut)), min(min_cut, cut)
+    has_early = min_raw < min_cut
+    n_base = int(max(math.log10(t_end / min_guard), 1.0) * t_res)
+    extra = int(1.0 * math.log10(min(max_ref, t_end) / min_guard) * t_res) if (is_rvs and max_ref > min_guard) else 0
+    n_tot = n_base + extra
+    t_rows = []
+    for r in reps:
+        if is_rvs:
+            lat = _cross_lattice(min_guard, t_end, 10 * max(t_dec[r], T0), n_tot, n_base)
+        else:
+            lat = _band_lattice(min_guard, t_end, t_dec[r] / 3, 3 * t_dec[r], n_tot, 3.0)
+        t_rows.append(([min_raw] if has_early else []) + lat)
+    return dict(theta=np.array(theta), phi=np.array(phi), reps=np.array(reps), t_rows=np.array(t_rows),
+                phi_mirrored=mirror, n_phi_eff=n_phi_eff)
+
+
+def model_flux(p, t_obs, nu_obs):
+    """The whole path (rows a1-a6, a9) restated: grid, dynamics, radiation, EATS.  Returns the forward
+    synchrotron flux [n_nu, n_t], or (forward, reverse) with a reverse shock."""
+    t_obs = np.asarray(t_obs, float)
+    g = auto_grid(p, float(t_obs.min()), float(t_obs.max()))
+    return flux_density_grid(p, g["theta"], g["phi"], g["t_rows"], g["reps"], g["phi_mirrored"], g["n_phi_eff"], t_obs, nu_obs)

@@ -64,6 +64,55 @@ def test_restatement_pair_matches_reference(name):
         assert err < 1e-7, (name, comp, err)
 
 
+def _full_cases():
+    return {
+        "C1": (configs.C1()[0], configs.C1()[1][::4], configs.C1()[2]),
+        "C2": (configs.C2()[0], configs.C2()[1][::10], configs.C2()[2][::3]),
+        "C3": (configs.C3()[0], configs.C3()[1][::5], configs.C3()[2]),
+        "powerlaw_wind": (configs.make(jet="powerlaw", medium="wind", theta_obs=0.15, k_e=2.5, k_g=1.5),
+                          np.logspace(2.5, 7.5, 16), np.array([1e9, 1e14, 1e17])),
+    }
+
+
+@pytest.mark.parametrize("name", ["C1", "C2", "C3", "powerlaw_wind"])
+def test_restated_grid_and_full_path_match_reference(name):
+    """Row a1 restated as well (auto_grid): identical node counts / symmetry groups / mirroring, nodes to the
+    quadrature-noise level, and the whole restated path (grid + physics) within the 1e-6 parity bar."""
+    from oracle import restatement
+
+    ref = _ref()
+    p, t, nu = _full_cases()[name]
+    g = restatement.auto_grid(p, float(t[0]), float(t[-1]))
+    d = ref.details(p, float(t[0]), float(t[-1]))
+    assert g["theta"].shape == d["theta"].shape and g["phi"].shape == d["phi"].shape and g["t_rows"].shape == d["t_rows"].shape
+    assert np.array_equal(g["reps"], d["reps"])
+    assert bool(g["phi_mirrored"]) == bool(d["info"]["phi_mirrored"]) and g["n_phi_eff"] == int(d["info"]["n_phi_eff"])
+    np.testing.assert_allclose(g["theta"], d["theta"], rtol=1e-5)  # tophat grids carry ~1e-6 of quadrature noise
+    np.testing.assert_allclose(g["phi"], d["phi"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(g["t_rows"], d["t_rows"], rtol=1e-8)
+    F = restatement.model_flux(p, t, nu)
+    R = ref.flux_density_grid(p, t, nu)[0]
+    for f, comp in (zip(F, (1, 3)) if isinstance(F, tuple) else ((F, 1),)):
+        b = R[comp]
+        m = b > 1e-3 * b.max(axis=-1, keepdims=True)
+        assert np.max(np.abs(f[m] - b[m]) / b[m]) < 1e-6, (name, comp)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["C1", "C2", "C3", "powerlaw_wind"])
+def test_gpu_matches_full_restatement(name):
+    """GPU against the fully restated path (its own grid builder included)."""
+    from oracle import restatement
+    from vegasafterglow_b200.engine import Engine
+
+    p, t, nu = _full_cases()[name]
+    F = restatement.model_flux(p, t, nu)
+    G = Engine(0).flux_density_grid(p, t, nu)[0]
+    for f, comp in (zip(F, (1, 3)) if isinstance(F, tuple) else ((F, 1),)):
+        m = f > 1e-3 * f.max(axis=-1, keepdims=True)
+        assert np.max(np.abs(G[comp][m] - f[m]) / f[m]) < 2e-6, (name, comp)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["C1", "gauss_offaxis"])
 def test_gpu_matches_restatement_on_its_own_grid(name):
