@@ -136,6 +136,21 @@ def test_full_size_batch_properties(engine):
         assert_parity(fs, g, "4096-walker sample")
 
 
+def test_bench_size_batch_is_batch_size_independent(engine):
+    # the bench workload's size: 16384 forward-shock models per call.  The launch geometry changes with the batch
+    # (k_grid 8 / 16 / 32 lanes per model, k_dynamics 8 / 32 rows per warp, EATS row split), the arithmetic of a
+    # model does not: a strided sample evaluated on its own reproduces its rows of the big batch.
+    n = 16384
+    t, nu = configs.C1()[1:]
+    P = configs.random_draw(n, seed=1000)
+    f, st = engine.flux_density_grid(P, t, nu, return_status=True)
+    assert (st == 0).all() and np.isfinite(f).all() and (f[:, 0] > 0).all()
+    idx = np.arange(0, n, 331)
+    np.testing.assert_allclose(engine.flux_density_grid(P[idx], t, nu), f[idx], rtol=1e-13)
+    mid = engine.flux_density_grid(P[:2048], t, nu)  # 16 lanes per model in k_grid, 32 rows per warp in k_dynamics
+    np.testing.assert_allclose(mid, f[:2048], rtol=1e-13)
+
+
 def test_error_conventions(engine):
     p, t, nu = configs.C1()
     with pytest.raises(ValueError, match="ascending"):
