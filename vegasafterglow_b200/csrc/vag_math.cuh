@@ -179,13 +179,19 @@ VAG_HD double dlog2_nc(double x) {
 // 81 rows centred at x_i = -20 + i/2, degree 7 in u = 2 (x - x_i) in [-1/2, 1/2]; the function is
 // analytic with its nearest singularities at x = +-i pi/ln 2 (|Im| = 4.53), so the Chebyshev
 // interpolant converges like 36^-n: truncation < 5e-13 absolute (tests/test_host_logic.py checks it).
-// A row is 8 doubles = 64 B, read as four 16-byte shared-memory loads.
+// Layout: four planes of 16-byte coefficient pairs, plane j = (c_2j, c_2j+1) of every row, row r at pair index
+// r + (r >> 3).  A spectrum point's rows advance by a near-constant stride from one lattice node (thread) to the
+// next, typically 1-4 rows; with the skew the eight threads of a quarter warp then read eight distinct 16-byte
+// bank groups for every stride in {1, 2, 4, 8} (the row-major 64-byte rows this replaces offered two bank groups
+// per load: 237 M of 449 M shared-load wavefronts of k_eats were bank-conflict replays, L1 data pipe 74 %).
 // The table is generated on the host in long double (build_softplus_lut) and staged in shared memory.
 // ---------------------------------------------------------------------------------------------
 constexpr int SPL_ROWS = 81;
 constexpr int SPL_DEG = 7;
-constexpr int SPL_STRIDE = 8;  // doubles per row
-constexpr int SPL_DOUBLES = SPL_ROWS * SPL_STRIDE;
+constexpr int SPL_PLANE = 192;  // doubles per plane: 96 pair slots >= 81 + (80 >> 3) + 1, a multiple of 128 B
+constexpr int SPL_DOUBLES = ((SPL_DEG + 1) / 2) * SPL_PLANE;
+// index (in doubles) of monomial coefficient q of `row`
+VAG_HD constexpr int spl_index(int row, int q) { return (q >> 1) * SPL_PLANE + ((row + (row >> 3)) << 1) + (q & 1); }
 
 inline void build_softplus_lut(double* lut) {
     constexpr int n = SPL_DEG + 1;
@@ -220,7 +226,7 @@ inline void build_softplus_lut(double* lut) {
         // t = 2 u  (u = 2 (x - xc) in [-1/2, 1/2])
         long double scale = 1;
         for (int q = 0; q < n; ++q) {
-            lut[row * SPL_STRIDE + q] = (double)(mono[q] * scale);
+            lut[spl_index(row, q)] = (double)(mono[q] * scale);
             scale *= 2;
         }
     }
@@ -237,8 +243,8 @@ VAG_HD double log2_softplus_lut(const double* __restrict__ lut, double x) {
     row = imin(imax(row, 0), SPL_ROWS - 1);                        // a NaN argument must not index outside the table
     const double u = y - (t - magic);                              // [-1/2, 1/2]
 #if defined(__CUDA_ARCH__)
-    const double2* c2 = reinterpret_cast<const double2*>(lut) + row * (SPL_STRIDE / 2);
-    const double2 c01 = c2[0], c23 = c2[1], c45 = c2[2], c67 = c2[3];
+    const double2* c2 = reinterpret_cast<const double2*>(lut) + (row + (row >> 3));
+    const double2 c01 = c2[0], c23 = c2[SPL_PLANE / 2], c45 = c2[SPL_PLANE], c67 = c2[3 * SPL_PLANE / 2];
     double p = fma(c67.y, u, c67.x);
     p = fma(p, u, c45.y);
     p = fma(p, u, c45.x);
@@ -247,9 +253,8 @@ VAG_HD double log2_softplus_lut(const double* __restrict__ lut, double x) {
     p = fma(p, u, c01.y);
     p = fma(p, u, c01.x);
 #else
-    const double* c = lut + row * SPL_STRIDE;
-    double p = c[SPL_DEG];
-    for (int j = SPL_DEG - 1; j >= 0; --j) p = fma(p, u, c[j]);
+    double p = lut[spl_index(row, SPL_DEG)];
+    for (int j = SPL_DEG - 1; j >= 0; --j) p = fma(p, u, lut[spl_index(row, j)]);
 #endif
     return p;
 }
