@@ -220,7 +220,7 @@ void eats_emulate(const BatchWs& w, int mi, int which, const EatsRequest& rq0, d
             } else {
                 for (int l = 0; l < nl; ++l)
                     for (int ii = 0; ii < rq.ni; ++ii)
-                        out[(size_t)(l0 + l) * rq.n_t_obs + i0 + ii] = flux_scale(M, acc[l * EATS_T_BLOCK + ii]);
+                        out[(size_t)(l0 + l) * rq.n_t_obs + i0 + ii] = flux_scale(M, acc[l * rq.acc_stride + ii]);
             }
         }
     }
@@ -244,6 +244,7 @@ int run_flux(const vag_params* params, size_t n, const double* t, size_t n_t, co
     rq.lg2_t_obs = lg2t.data();
     rq.lg2_nu_obs = lg2nu.data();
     rq.t_obs_lin = tl.data();
+    rq.acc_stride = eats_acc_stride((int)n_t);
     const size_t comp = series ? n_t : n_nu * n_t;
     double nu_range[2] = {*std::min_element(lg2nu.begin(), lg2nu.end()), *std::max_element(lg2nu.begin(), lg2nu.end())};
     run_ic_tables(hb, nu_range);

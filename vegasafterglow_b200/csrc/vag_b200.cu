@@ -332,8 +332,9 @@ __global__ void __launch_bounds__(128, EATS_MIN_BLOCKS) k_eats(BatchWs w, EatsRe
     const int n_t = M.h->n_t;
     const int erows = M.h->n_theta * M.h->n_phi_eff;
     const bool series = rq0.series != 0;
-    double* acc = smem + SPL_DOUBLES;  // [nu_tile][EATS_T_BLOCK]
-    EatsShared sh = eats_carve(acc + nu_tile * EATS_T_BLOCK, max_n_t, series, row_chunk, nu_tile);
+    double* acc = smem + SPL_DOUBLES;  // [nu_tile][acc_stride]
+    const int acc_stride = rq0.acc_stride;
+    EatsShared sh = eats_carve(acc + nu_tile * acc_stride, max_n_t, series, row_chunk, nu_tile);
     EatsRequest rq = rq0;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int comp = which == 0 ? VAG_C_FWD_SYNC : which == 1 ? VAG_C_RVS_SYNC : which == 2 ? VAG_C_FWD_SSC : VAG_C_RVS_SSC;
@@ -349,7 +350,7 @@ __global__ void __launch_bounds__(128, EATS_MIN_BLOCKS) k_eats(BatchWs w, EatsRe
         for (int i0 = 0; i0 < rq.n_t_obs; i0 += EATS_T_BLOCK) {
             rq.i0 = i0;
             rq.ni = imin(EATS_T_BLOCK, rq.n_t_obs - i0);
-            for (int a = tid; a < nu_tile * EATS_T_BLOCK; a += nthr) acc[a] = 0.0;
+            for (int a = tid; a < nu_tile * acc_stride; a += nthr) acc[a] = 0.0;
             for (int q0 = split * rpp; q0 < erows; q0 += n_split * rpp) {
                 const int nrows = imin(rpp, erows - q0);
                 sh.rowg = rowg + q0;
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(128, EATS_MIN_BLOCKS) k_eats(BatchWs w, EatsRe
             // accumulator columns are thread-owned (ii == tid mod nthr): no barrier needed here
             for (int ii = tid; ii < rq.ni; ii += nthr) {
                 for (int l = 0; l < nl; ++l) {
-                    const double v = flux_scale(M, acc[l * EATS_T_BLOCK + ii]);
+                    const double v = flux_scale(M, acc[l * acc_stride + ii]);
                     double* p = series ? (dst + i0 + ii) : (dst + (size_t)(l0 + l) * rq.n_t_obs + i0 + ii);
                     if (n_split == 1)
                         *p = v;
@@ -714,10 +715,11 @@ int run_flux(vag_context* ctx, const vag_params* d_params, size_t n, const Reque
         const int nu_tile = rq_in.series ? 1 : (int)std::min<size_t>(EATS_NU_TILE, n_nu);
         auto smem_bytes = [&](int rc_) {
             return sizeof(double) *
-                   (nu_tile * EATS_T_BLOCK + eats_shared_doubles(max_n_t, rq_in.series, rc_, nu_tile) + SPL_DOUBLES);
+                   (nu_tile * eats_acc_stride((int)n_t) + eats_shared_doubles(max_n_t, rq_in.series, rc_, nu_tile) + SPL_DOUBLES);
         };
-        // fewer staged rows per pass while that buys residency: 8 CTAs / SM need <= 28 KB each
-        while (row_chunk > 4 && smem_bytes(row_chunk) > 28 * 1024) --row_chunk;
+        // fewer staged rows per pass while that buys residency: 8 CTAs / SM need <= 27 KB each (227 KB per SM,
+        // 1 KB per CTA reserved by the system)
+        while (row_chunk > 4 && smem_bytes(row_chunk) > 27 * 1024) --row_chunk;
         while (row_chunk > 1 && smem_bytes(row_chunk) > budget) --row_chunk;
         if (smem_bytes(row_chunk) > budget)
             return fail(VAG_ERR_CAPACITY, "time lattice too long for the EATS shared-memory stage");
@@ -738,6 +740,7 @@ int run_flux(vag_context* ctx, const vag_params* d_params, size_t n, const Reque
         rq.lg2_t_obs = lg2_t;
         rq.lg2_nu_obs = lg2_nu;
         rq.t_obs_lin = t_lin;
+        rq.acc_stride = eats_acc_stride((int)n_t);
         const dim3 eg((unsigned)n, (unsigned)n_split, 2);
         k_eats<0><<<eg, 128, sb, s>>>(w, rq, d_out, n_split, row_chunk, max_n_t, nu_tile);
         ctx->launches++;

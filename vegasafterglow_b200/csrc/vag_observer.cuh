@@ -221,9 +221,12 @@ struct EatsRequest {
     const double* lg2_nu_obs;  // [n_nu]     log2(nu * unit::Hz)   (without the 1+z shift)
     const double* t_obs_lin;   // [n_t_obs]  t * unit::sec
     int i0, ni;                // block of observation points handled by the current pass
+    int acc_stride;            // accumulator columns per frequency: eats_acc_stride(n_t_obs)
 };
 
 constexpr int EATS_T_BLOCK = 256;   // observation points accumulated per pass
+// accumulator columns actually staged: short requests (100 epochs) do not pay for 256 columns of shared memory
+VAG_HD int eats_acc_stride(int n_t_obs) { return n_t_obs >= EATS_T_BLOCK ? EATS_T_BLOCK : ((n_t_obs + 31) & ~31); }
 
 // row_chunk <= EATS_ROW_CHUNK rows are staged per pass (the host lowers it when n_t is large)
 VAG_HD size_t eats_shared_doubles(int n_t, bool series, int row_chunk, int nu_tile) {
@@ -314,7 +317,7 @@ VAG_HD void eats_phase1(const EatsModel& M, const EatsRequest& rq, const EatsSha
 }
 
 // phase 2 (grid): thread <-> observation time; accumulates the chunk's rows into acc[l][idx]
-// acc layout: [nu_tile][EATS_T_BLOCK] (thread-owned columns, no atomics).  NLC = compile-time number of
+// acc layout: [nu_tile][rq.acc_stride] (thread-owned columns, no atomics).  NLC = compile-time number of
 // frequencies of the tile: their NLC interpolation exponentials are evaluated as one interleaved batch.
 // exp2 arguments are clamped to [-1000, 1020]: below, the reference's term is < 1e-301 of anything it is
 // added to (it underflows there); above, it would have overflowed.
@@ -349,7 +352,7 @@ VAG_HD void eats_phase2_grid_n(const EatsModel& M, const EatsRequest& rq, const 
             for (int l = 0; l < NLC; ++l) sum[l] += fin[l] ? val[l] : 0.0;
         }
 #pragma unroll
-        for (int l = 0; l < NLC; ++l) acc[l * EATS_T_BLOCK + ii] += sum[l];
+        for (int l = 0; l < NLC; ++l) acc[l * rq.acc_stride + ii] += sum[l];
     }
 }
 VAG_HD void eats_phase2_grid(const EatsModel& M, const EatsRequest& rq, const EatsShared& sh, int nrows, int nl,
