@@ -294,20 +294,47 @@ def main():
         def step_ll(self=sl):
             self.eng.chi2_series_dev(self.d_pl.data_ptr(), n_ll, *[a.data_ptr() for a in self.d_arr], ts.size,
                                      self.d_chi2.data_ptr(), self.d_st_ll.data_ptr(), self.stream.cuda_stream)
-            if world > 1:  # the only inter-GPU traffic of the path: gather of float64[n] log-likelihoods
-                with torch.cuda.stream(self.stream):
-                    dist.all_gather_into_tensor(gathered, self.d_chi2)
         sl.step_ll = step_ll
 
-    # with a collective in the step, keep one batch in flight per rank (NCCL ops must be issued in the
-    # same order on every rank)
-    S_ll = 1 if world > 1 else S
+    # The only inter-GPU traffic of the path is the gather of float64[n] log-likelihoods after every step.  NCCL
+    # operations must be issued in the same order on every rank, so the worker threads (one per in-flight batch)
+    # never call the collective themselves: they record an event when their step is enqueued, and THIS thread
+    # issues the all-gathers in step order on a separate communication stream that waits on those events.
+    S_ll = S
+    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
 
     def run_ll(k):
+        if world == 1:
+            def worker(si):
+                for _ in range(si, k, S_ll):
+                    slots[si].step_ll()
+            list(pool.map(worker, range(min(S_ll, k))))
+            return
+        import threading
+        enqueued = [threading.Event() for _ in range(k)]
+        gather_issued = [threading.Event() for _ in range(k)]
+        ev_done = [torch.cuda.Event() for _ in range(k)]
+        ev_gathered = [torch.cuda.Event() for _ in range(k)]
+
         def worker(si):
-            for _ in range(si, k, S_ll):
+            for i in range(si, k, S_ll):
+                if i >= S_ll:  # this slot's chi2 vector is free once the gather of its previous step has run
+                    gather_issued[i - S_ll].wait()
+                    slots[si].stream.wait_event(ev_gathered[i - S_ll])
                 slots[si].step_ll()
-        list(pool.map(worker, range(min(S_ll, k))))
+                ev_done[i].record(slots[si].stream)
+                enqueued[i].set()
+
+        futs = [pool.submit(worker, si) for si in range(min(S_ll, k))]
+        for i in range(k):
+            enqueued[i].wait()
+            comm_stream.wait_event(ev_done[i])
+            with torch.cuda.stream(comm_stream):
+                dist.all_gather_into_tensor(gathered, slots[i % S_ll].d_chi2)
+            ev_gathered[i].record(comm_stream)
+            gather_issued[i].set()
+        for f in futs:
+            f.result()
 
     run_ll(args.warmup * S_ll)
     barrier()
@@ -316,10 +343,12 @@ def main():
     la.record(main)
     for sl in slots:
         sl.stream.wait_event(la)
+    if comm_stream is not None:
+        comm_stream.wait_event(la)
     run_ll(args.steps)
-    for sl in slots:
+    for st_ in [sl.stream for sl in slots] + ([comm_stream] if comm_stream is not None else []):
         e = torch.cuda.Event()
-        e.record(sl.stream)
+        e.record(st_)
         main.wait_event(e)
     lb.record(main)
     barrier()
