@@ -234,14 +234,13 @@ inline void build_softplus_lut(double* lut) {
 
 // src/util/fast-math.h:179-185 (log2_softplus) through the table
 VAG_HD double log2_softplus_lut(const double* __restrict__ lut, double x) {
-    if (x > 20.0) return x;
+    if (!(x <= 20.0)) return x;  // also a NaN argument: it must not reach the table index
     if (x < -20.0) return 0.0;
-    const double y = fma(x, 2.0, 40.0);  // [0, 80]
-    const double magic = 6755399441055744.0;
-    const double t = y + magic;
-    int row = (int)(uint32_t)(double_to_bits(t) & 0xFFFFFFFFull);  // round-to-nearest integer of y
-    row = imin(imax(row, 0), SPL_ROWS - 1);                        // a NaN argument must not index outside the table
-    const double u = y - (t - magic);                              // [-1/2, 1/2]
+    // row = round(2 x + 40) in [0, 80], read off the low word of 2 x + (40 + 1.5 * 2^52); u = 2 x + 40 - row
+    const double magic40 = 6755399441055744.0 + 40.0;
+    const double t = fma(x, 2.0, magic40);
+    const int row = (int)(uint32_t)(double_to_bits(t) & 0xFFFFFFFFull);
+    const double u = fma(x, 2.0, magic40 - t);  // magic40 - t = 40 - row exactly; u in [-1/2, 1/2]
 #if defined(__CUDA_ARCH__)
     const double2* c2 = reinterpret_cast<const double2*>(lut) + (row + (row >> 3));
     const double2 c01 = c2[0], c23 = c2[SPL_PLANE / 2], c45 = c2[SPL_PLANE], c67 = c2[3 * SPL_PLANE / 2];
