@@ -56,6 +56,30 @@ def test_fresh_draws_against_reference(engine, kw, n):
           f"{np.median(model_errors(g['flux_alt'], g['flux'])):.2e}")
 
 
+@pytest.mark.parametrize("n_t,n_nu", [(1, 1), (33, 2), (257, 3), (300, 9), (513, 1)])
+def test_observation_block_shapes_against_reference(engine, n_t, n_nu):
+    # k_eats accumulates <= 256 observation times and <= 8 frequencies per pass and sizes its accumulator
+    # columns by the request: exercise the partial / multiple blocks and frequency tiles (grid and series form)
+    from oracle import ref
+
+    if not ref.available() or not ref.available("alt"):
+        pytest.skip("oracle/_ref not present")
+    P = np.concatenate([configs.random_draw(3, seed=7), configs.random_draw(3, seed=8, rvs=True)])
+    t = np.logspace(1.5, 7.5, n_t) if n_t > 1 else np.array([3.0e4])
+    nu = np.logspace(9, 18, n_nu) if n_nu > 1 else np.array([4.84e14])
+    g = {"flux": ref.flux_density_grid(P, t, nu, n_threads=ref.hardware_threads())}
+    with ref.use_variant("alt"):
+        g["flux_alt"] = ref.flux_density_grid(P, t, nu, n_threads=ref.hardware_threads())
+    f, st = engine.flux_density_grid(P, t, nu, return_status=True)
+    assert (st == 0).all()
+    assert_parity(f, g, f"grid {n_t}x{n_nu}")
+    ts, nus = np.repeat(t, nu.size), np.tile(nu, t.size)
+    fs = engine.flux_density_series(P, ts, nus)
+    for c in (0, 1, 3):
+        np.testing.assert_allclose(fs[:, c].reshape(P.size, t.size, nu.size).transpose(0, 2, 1), f[:, c], rtol=1e-11,
+                                   atol=0)
+
+
 def test_series_equals_grid(engine):
     p, t, nu = configs.C3()
     fg = engine.flux_density_grid(p, t, nu)
