@@ -126,10 +126,12 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": config_dict(args, 1) | {"batch_per_gpu": n, "global_batch": n},
+        # the config is the GPU arm's (same workload, metric and unit); what one reference step actually processed
+        # is a bounded sample of it, stated in cpu_baseline.sample
+        "dtype": "f64", "data": "synthetic", "config": config_dict(args, args.gpus),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference",
-                         "sample": f"{n} parameter sets per step x {args.steps} steps, std::thread over the unmodified "
-                                   f"reference (oracle/ref_driver.cpp), {cores} threads"},
+                         "sample": f"first {n} parameter sets of the {args.batch}-set batch per step x {args.steps} steps, "
+                                   f"std::thread over the unmodified reference (oracle/ref_driver.cpp), {cores} threads"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
