@@ -255,10 +255,17 @@ VAG_HD void inverse_cdf_sampling(const Par& par, const Pdf& pdf, double lo, doub
         }
     }
     const double c0 = cdf_i[0], c1 = cdf_i[n_samp - 1];
+    // first j with target <= cdf_i[j].  A lane visits its queries in ascending q, hence (c1 >= c0) ascending target, and
+    // every sample below the previous hit has already failed the test for a smaller target: the scan resumes there
+    // instead of restarting at 0 (same result as the reference's scan from 0 for any cdf_i, monotone or not).
+    int j_resume = 0;
+    double target_prev = -kInf;
     par.for_each(num, [&](int q) {
         const double target = midpoint ? (c0 + (c1 - c0) * ((double)q + 0.5) / (double)num) : linspace_at(c0, c1, num, q);
-        int j = 0;
+        int j = (target >= target_prev) ? j_resume : 0;
         while (j < n_samp && !(target <= cdf_i[j])) ++j;
+        j_resume = j;
+        target_prev = target;
         double xo = 0;
         if (j < n_samp) {
             if (j == 0) {
