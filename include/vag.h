@@ -230,6 +230,11 @@ int vag_last_stage_ms(vag_context* ctx, float ms[8]);
 int vag_last_launch_count(vag_context* ctx);
 /* dependent-free DFMA throughput of the device in TFLOP/s (FP64 roofline denominator) */
 int vag_measure_fp64_peak(vag_context* ctx, double* tflops);
+/* Device self-test of the libm-exact functions the grid kernel evaluates (csrc/vag_libm.cuh):
+ * out[i] = fn(x[i]) with fn 0 exp, 1 exp2, 2 log, 3 log2, 4 log10, 5 pow(x[i], y[i]), 6 sin, 7 cos; host buffers.
+ * The results must equal the host libm's bit for bit (the reference's theta / phi grids depend on it,
+ * src/core/grid-refinement.h:137-189); y is NULL except for pow. */
+int vag_selftest_libm(vag_context* ctx, int fn, const double* x, const double* y, double* out, size_t n);
 
 #ifdef __cplusplus
 }

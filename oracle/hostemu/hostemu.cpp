@@ -8,6 +8,7 @@
 #include <cstring>
 #include <vector>
 
+#include "../../vegasafterglow_b200/csrc/vag_libm.cuh"
 #include "../../vegasafterglow_b200/csrc/vag_pipeline.cuh"
 
 using namespace vag;
@@ -327,6 +328,28 @@ int vagemu_details(const vag_params* p, double t_min, double t_max, vag_grid_inf
     if (inj_idx) std::memcpy(inj_idx, w.inj_idx, sizeof(int) * h.n_reps);
     if (coef_fwd) std::memcpy(coef_fwd, w.coef_fwd, sizeof(double) * cells * PH_NCOEF);
     if (coef_rvs && p->has_rvs) std::memcpy(coef_rvs, w.coef_rvs, sizeof(double) * cells * PH_NCOEF);
+    return 0;
+}
+
+// gl:: functions of vag_libm.cuh (use_ref = 0) or the live libm they restate (use_ref = 1), elementwise.
+// fn: 0 exp, 1 exp2, 2 log, 3 log2, 4 log10, 5 pow(x, y), 6 sin, 7 cos
+int vagemu_libm_eval(int fn, const double* x, const double* y, double* out, size_t n, int use_ref) {
+    for (size_t i = 0; i < n; ++i) {
+        const double a = x[i], b = y ? y[i] : 0.0;
+        double r;
+        switch (fn) {
+            case 0: r = use_ref ? std::exp(a) : gl::exp(a); break;
+            case 1: r = use_ref ? std::exp2(a) : gl::exp2(a); break;
+            case 2: r = use_ref ? std::log(a) : gl::log(a); break;
+            case 3: r = use_ref ? std::log2(a) : gl::log2(a); break;
+            case 4: r = use_ref ? std::log10(a) : gl::log10(a); break;
+            case 5: r = use_ref ? std::pow(a, b) : gl::pow(a, b); break;
+            case 6: r = use_ref ? std::sin(a) : gl::sin(a); break;
+            case 7: r = use_ref ? std::cos(a) : gl::cos(a); break;
+            default: return -1;
+        }
+        out[i] = r;
+    }
     return 0;
 }
 

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "../../include/vag.h"
+#include "vag_libm.cuh"
 #include "vag_pipeline.cuh"
 
 using namespace vag;
@@ -407,6 +408,26 @@ __global__ void k_nan_capacity(BatchWs w, double* out, size_t comp_sz_total) {
     const int mi = blockIdx.x;
     if (!(w.status[mi] & VAG_ST_CAPACITY)) return;
     for (size_t i = threadIdx.x; i < comp_sz_total; i += blockDim.x) out[(size_t)mi * comp_sz_total + i] = NAN;
+}
+
+// Self-test of vag_libm.cuh on the device: out[i] = gl::fn(x[i] [, y[i]]) (fn as in vag_selftest_libm, include/vag.h)
+__global__ void k_libm_selftest(int fn, const double* __restrict__ x, const double* __restrict__ y, double* __restrict__ out,
+                                size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double a = x[i], b = y ? y[i] : 0.0;
+        double r = 0;
+        switch (fn) {
+            case 0: r = gl::exp(a); break;
+            case 1: r = gl::exp2(a); break;
+            case 2: r = gl::log(a); break;
+            case 3: r = gl::log2(a); break;
+            case 4: r = gl::log10(a); break;
+            case 5: r = gl::pow(a, b); break;
+            case 6: r = gl::sin(a); break;
+            case 7: r = gl::cos(a); break;
+        }
+        out[i] = r;
+    }
 }
 
 // FP64 FMA throughput probe (roofline denominator for the ODE / radiation / EATS kernels, which are
@@ -972,6 +993,24 @@ int vag_measure_fp64_peak(vag_context* ctx, double* tflops) {
     cudaEventDestroy(a);
     cudaEventDestroy(b);
     *tflops = best;
+    return VAG_OK;
+}
+
+int vag_selftest_libm(vag_context* ctx, int fn, const double* x, const double* y, double* out, size_t n) {
+    if (fn < 0 || fn > 7) return fail(VAG_ERR_INVALID, "vag_selftest_libm: fn must be 0..7");
+    if ((fn == 5) != (y != nullptr)) return fail(VAG_ERR_INVALID, "vag_selftest_libm: y is required for pow only");
+    if (n == 0) return VAG_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->io_aux.ensure(3 * n * sizeof(double)));
+    double* d_x = static_cast<double*>(ctx->io_aux.p);
+    double* d_y = d_x + n;
+    double* d_o = d_y + n;
+    CK(cudaMemcpyAsync(d_x, x, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (y) CK(cudaMemcpyAsync(d_y, y, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    k_libm_selftest<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(fn, d_x, y ? d_y : nullptr, d_o, n);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d_o, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return VAG_OK;
 }
 

@@ -148,6 +148,17 @@ class Engine:
         _lib.check(self._lib.vag_measure_fp64_peak(self._h, C.byref(v)))
         return float(v.value)
 
+    LIBM_FUNCS = ("exp", "exp2", "log", "log2", "log10", "pow", "sin", "cos")
+
+    def selftest_libm(self, fn, x, y=None):
+        """Device evaluation of one libm-exact function of csrc/vag_libm.cuh (include/vag.h vag_selftest_libm)."""
+        x = _f64(x).reshape(-1)
+        out = np.empty_like(x)
+        yv = None if y is None else _f64(y).reshape(-1)
+        _lib.check(self._lib.vag_selftest_libm(self._h, self.LIBM_FUNCS.index(fn), x.ctypes.data,
+                                               None if yv is None else yv.ctypes.data, out.ctypes.data, x.size))
+        return out
+
     def last_launch_count(self):
         return int(self._lib.vag_last_launch_count(self._h))
 
