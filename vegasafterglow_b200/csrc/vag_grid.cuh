@@ -113,16 +113,37 @@ VAG_HD size_t grid_work_doubles(int cap_theta, int cap_phi) {
     return (size_t)6 * cap_theta + 2 * (GRID_NSCAN + 7) + 2 * dflt::theta_samples + cap_phi + 32;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// BIT-EXACT SECTION.  Everything from here to estimate_t_dec determines, or is determined by, the step
+// positions of the reference's adaptive CDF quadratures (theta grid, then the phi grid whose pdf sums over
+// the theta nodes).  Those quadratures are chaotic in the last bit (vag_libm.cuh header), so this section
+// reproduces the REFERENCE BUILD's arithmetic operation by operation: the instruction sequence g++ emits for
+// src/core/grid-refinement.h under the reference's flags (CMakeLists.txt:10-16: -O3 -ffp-contract=fast
+// -freciprocal-math on an FMA target), read off oracle/_ref/libvagref.so.  What that means concretely:
+//   * a product feeding a sum is ONE fma exactly where gcc fused it (first product of an a*b + c*d pair), and
+//     two roundings everywhere else -- written with gl::mul / gl::add / gl::fma, which no compiler re-contracts;
+//   * a division by a compile-time constant is a multiplication by its rounded reciprocal (x / 100 -> x * 0.01,
+//     the dense-output constants of Boost's dopri5), divisions by variables are true divisions;
+//   * libm calls go through gl:: (the host libm's own algorithms and tables).
+// oracle/hostemu runs the same source on the host; tests/test_grid_exact.py demands bit-equal theta / phi nodes
+// against the unmodified reference there, and the -m gpu tier demands bit-equal nodes between device and host.
+// ---------------------------------------------------------------------------------------------------
 VAG_HD double structure_weight(double Gamma) {  // grid-refinement.h:11-13
-    return Gamma * sqrt(vmax((Gamma - 1) * Gamma, 0.0));
+    const double w0 = gl::mul(gl::sub(Gamma, 1.0), Gamma);
+    const double s = (0.0 > w0) ? 0.0 : gl::sqrt(w0);
+    return gl::mul(Gamma, s);
+}
+// physics::relativistic::gamma_to_beta (src/core/physics.h:36-40) as compiled
+VAG_HD double gamma_to_beta_x(double Gamma) {
+    return gl::div(gl::sqrt(gl::mul(gl::add(Gamma, 1.0), gl::sub(Gamma, 1.0))), Gamma);
 }
 
 // xt::linspace(a, b, n)[i] (external/xtensor/generators/xbuilder.hpp:199-222,460-468):
-// a + step*i with the last element forced to b.
+// fma(i, step, a) with the last element forced to b.
 VAG_HD double linspace_at(double a, double b, int n, int i) {
-    const double step = (b - a) / fmax(1.0, (double)(n - 1));
+    const double step = gl::div(gl::sub(b, a), fmax(1.0, (double)(n - 1)));
     if (n > 1 && i == n - 1) return b;
-    return a + step * (double)i;
+    return gl::fma((double)i, step, a);
 }
 
 // ---- find_jet_jumps: grid-refinement.h:40-86 -------------------------------------------------
@@ -130,14 +151,14 @@ template <class Par>
 VAG_HD int find_jet_jumps(const Par& par, const ModelCfg& m, double gamma_cut, double* jumps, int cap, double* G) {
     constexpr int n_scan = 512;
     constexpr double eps = dflt::binary_search_eps;
-    const double theta_lo = dflt::theta_min;
-    const double theta_hi = con::pi / 2;
-    const double dtheta = (theta_hi - theta_lo) / (n_scan - 1);
+    constexpr double theta_lo = dflt::theta_min;
+    constexpr double theta_hi = con::pi / 2;
+    constexpr double dtheta = (theta_hi - theta_lo) / (n_scan - 1);
     if (jet_Gamma0(m, theta_hi) >= gamma_cut) {
         jumps[0] = theta_hi;
         return 1;
     }
-    par.for_each(n_scan, [&](int j) { G[j] = jet_Gamma0(m, j == 0 ? theta_lo : theta_lo + dtheta * (double)j); });
+    par.for_each(n_scan, [&](int j) { G[j] = jet_Gamma0(m, j == 0 ? theta_lo : gl::fma((double)j, dtheta, theta_lo)); });
     // The walk's jump test at node j reads only G[j-1] and G[j]: the candidates are found with an
     // order-preserving parallel search, each hit is then refined exactly as the sequential walk does.
     int n = 0;
@@ -149,8 +170,8 @@ VAG_HD int find_jet_jumps(const Par& par, const ModelCfg& m, double gamma_cut, d
         return scale > 0 && dG > 0.5 * scale;
     };
     for (int j = par.first_true(1, n_scan, is_jump); j < n_scan; j = par.first_true(j + 1, n_scan, is_jump)) {
-        const double prev_th = (j - 1 == 0) ? theta_lo : theta_lo + dtheta * (double)(j - 1);
-        const double cur_th = theta_lo + dtheta * (double)j;
+        const double prev_th = (j - 1 == 0) ? theta_lo : gl::fma((double)(j - 1), dtheta, theta_lo);
+        const double cur_th = gl::fma((double)j, dtheta, theta_lo);
         const double prev_G = G[j - 1], cur_G = G[j];
         double lo = prev_th, hi = cur_th;
         while (hi - lo > eps) {
@@ -197,48 +218,141 @@ VAG_HD void find_theta_range(const Par& par, const ModelCfg& m, double gamma_cut
     }
 }
 
+// ---- the scalar quadrature stepper of inverse_CFD_sampling ----------------------------------------
+// Boost.odeint's dense_output_runge_kutta<controlled_runge_kutta<runge_kutta_dopri5<double>>> driving
+// dx/dt = pdf(t) (the state never enters the right-hand side), as g++ compiled it into inverse_CFD_sampling:
+//   stage abscissae   fma(a_i, dt, t) for a = 1/5, 3/10, 4/5, 8/9 and t + dt for the last two
+//   new state         x + (dt c1) k1 + (dt c3) k3 + (dt c4) k4 + (dt c5) k5 + (dt c6) k6 as one fma chain, left to right
+//   error             ((dt dc3) k3 rounded) then the fma chain dc1 k1, dc4 k4, dc5 k5, dc6 k6, dc7 k7
+//   error norm        |e| / fma(eps, fma(|dt|, |k1|, |x|), eps)           (controlled_runge_kutta.hpp:64-90)
+//   rejected          dt = max(0.9 pow(err, -1/3), 0.2) dt                (:114-129)
+//   accepted          t += dt;  err < 0.5:  dt *= (err > 5^-5) ? 0.9 pow(err, -1/5) : 4.5   (:131-153)
+//   dense output      Hairer's continuous extension with the reciprocal-constant weights below (dopri5.hpp:229-275)
+// VARIANT: g++ compiled the stepper twice.  Inlined into the theta-grid sampler (VARIANT = 0) the unused stage
+// states were eliminated, so dt * a2 has one use and fuses into the first stage abscissa, and the error-norm scale is
+// fma(|dt|, |k1|, |x|).  The phi-grid sampler (VARIANT = 1) calls the out-of-line do_step, which keeps the stage states:
+// dt * b21 (= dt * a2) is shared with them, hence rounded before it is added to t, and the scale is |x| + (|dt| |k1|
+// rounded).  Everything else is identical.
+template <int VARIANT>
+struct CdfQuad {
+    double x, k1, t, dt;           // current state, FSAL derivative, time, next step size
+    double xo, ko, to;             // state / derivative / time at the start of the last accepted step
+    double k3, k4, k5, k6;         // stages of the last accepted step
+    bool deriv_ready;
+    static constexpr double a2 = 1.0 / 5, a3 = 3.0 / 10, a4 = 4.0 / 5, a5 = 8.0 / 9;
+    static constexpr double c1 = 35.0 / 384, c3 = 500.0 / 1113, c4 = 125.0 / 192, c5 = -2187.0 / 6784, c6 = 11.0 / 84;
+    static constexpr double dc1 = c1 - 5179.0 / 57600, dc3 = c3 - 7571.0 / 16695, dc4 = c4 - 393.0 / 640,
+                            dc5 = c5 - (-92097.0 / 339200), dc6 = c6 - 187.0 / 2100, dc7 = -1.0 / 40;
+
+    VAG_HD void initialize(double t0, double dt0) {
+        x = 0;
+        t = to = t0;
+        dt = dt0;
+        deriv_ready = false;
+    }
+    // abscissa of stage s = 0..5 (k2 .. k7) of an attempt from (t, dt)
+    VAG_HD static double stage_time(double t, double dt, int s) {
+        const double a = (s == 0) ? a2 : (s == 1) ? a3 : (s == 2) ? a4 : a5;
+        if (VARIANT == 1 && s == 0) return gl::add(gl::mul(a2, dt), t);
+        return s < 4 ? gl::fma(a, dt, t) : gl::add(dt, t);
+    }
+    // one attempt with the six stage values kk[0..5] = pdf(stage_time(t, dt, s)); true = accepted
+    VAG_HD bool try_step(const double* kk, double eps) {
+        const double K3 = kk[1], K4 = kk[2], K5 = kk[3], K6 = kk[4], K7 = kk[5];
+        double xn = gl::fma(gl::mul(dt, c1), k1, x);
+        xn = gl::fma(gl::mul(dt, c3), K3, xn);
+        xn = gl::fma(gl::mul(dt, c4), K4, xn);
+        xn = gl::fma(gl::mul(dt, c5), K5, xn);
+        xn = gl::fma(gl::mul(dt, c6), K6, xn);
+        double e = gl::mul(gl::mul(dt, dc3), K3);
+        e = gl::fma(gl::mul(dt, dc1), k1, e);
+        e = gl::fma(gl::mul(dt, dc4), K4, e);
+        e = gl::fma(gl::mul(dt, dc5), K5, e);
+        e = gl::fma(gl::mul(dt, dc6), K6, e);
+        e = gl::fma(gl::mul(dt, dc7), K7, e);
+        const double scale = (VARIANT == 1) ? gl::add(fabs(x), gl::mul(fabs(dt), fabs(k1))) : gl::fma(fabs(dt), fabs(k1), fabs(x));
+        const double den = gl::fma(eps, scale, eps);
+        const double err = fabs(gl::div(fabs(e), den));
+        if (err > 1.0) {
+            dt = gl::mul(vmax(0.2, gl::mul(gl::pow(err, -1.0 / 3.0), 0.9)), dt);
+            return false;
+        }
+        xo = x;
+        ko = k1;
+        to = t;
+        k3 = K3;
+        k4 = K4;
+        k5 = K5;
+        k6 = K6;
+        x = xn;
+        k1 = K7;
+        t = gl::add(dt, t);
+        if (err < 0.5) dt = gl::mul(dt, (err > 0.00032) ? gl::mul(gl::pow(err, -1.0 / 5.0), 0.9) : 4.5);
+        return true;
+    }
+    // dense output at tq inside the last accepted step
+    VAG_HD double calc_state(double tq) const {
+        constexpr double b1 = c1, b3 = c3, b4 = c4, b5 = c5, b6 = c6;
+        const double h = gl::sub(t, to);
+        const double th = gl::div(gl::sub(tq, to), h);
+        const double X1 = gl::mul(gl::mul(gl::fnma(31403016.0, th, 2558722523.0), 5.0), 1.0 / 11282082432.0);
+        const double X3 = gl::mul(gl::mul(gl::fnma(15701508.0, th, 882725551.0), 100.0), 1.0 / 32700410799.0);
+        const double X4 = gl::mul(gl::mul(gl::fnma(31403016.0, th, 443332067.0), 25.0), 1.0 / 1880347072.0);
+        const double X5 = gl::mul(gl::mul(gl::fnma(3489224.0, th, 23143187.0), 32805.0), 1.0 / 199316789632.0);
+        const double X6 = gl::mul(gl::mul(gl::fnma(7076736.0, th, 29972135.0), 55.0), 1.0 / 822651844.0);
+        const double X7 = gl::mul(gl::mul(gl::fnma(829305.0, th, 7414447.0), 10.0), 1.0 / 29380423.0);
+        const double thm1 = gl::sub(th, 1.0);
+        const double thsq = gl::mul(th, th);
+        const double A = gl::mul(gl::fnma(2.0, th, 3.0), thsq);
+        const double B = gl::mul(thsq, thm1);
+        const double C = gl::mul(B, thm1);
+        const double D0 = gl::mul(thm1, th);
+        double w1 = gl::fms(A, b1, gl::mul(X1, C));
+        w1 = gl::fma(D0, thm1, w1);
+        const double w3 = gl::fma(A, b3, gl::mul(X3, C));
+        const double w4 = gl::fms(A, b4, gl::mul(X4, C));
+        const double w5 = gl::fma(A, b5, gl::mul(X5, C));
+        const double w6 = gl::fms(A, b6, gl::mul(X6, C));
+        const double w7 = gl::fma(C, X7, B);
+        double r = gl::fma(gl::mul(w1, h), ko, xo);
+        r = gl::fma(gl::mul(w3, h), k3, r);
+        r = gl::fma(gl::mul(w4, h), k4, r);
+        r = gl::fma(gl::mul(w5, h), k5, r);
+        r = gl::fma(gl::mul(w6, h), k6, r);
+        r = gl::fma(gl::mul(w7, h), k1, r);
+        return r;
+    }
+};
+
 // ---- inverse_CFD_sampling: grid-refinement.h:137-189 -----------------------------------------
 // pdf(x) functor; writes num nodes to x_out.  x_i / cdf_i: n_samp doubles each, kk: 8 doubles.
-template <class Par, class Pdf>
+template <int VARIANT, class Par, class Pdf>
 VAG_HD void inverse_cdf_sampling(const Par& par, const Pdf& pdf, double lo, double hi, int num, bool log_sample,
                                  bool midpoint, double* x_out, double* x_i, double* cdf_i, double* kk) {
     constexpr int n_samp = dflt::theta_samples;
     constexpr double rtol = dflt::ode_rtol;
     {
-        const double a = log_sample ? log10(lo) : lo, b = log_sample ? log10(hi) : hi;
+        const double a = log_sample ? gl::log10(lo) : lo, b = log_sample ? gl::log10(hi) : hi;
         par.for_each(n_samp, [&](int i) {
             const double v = linspace_at(a, b, n_samp, i);
-            x_i[i] = log_sample ? pow(10.0, v) : v;
+            x_i[i] = log_sample ? gl::pow(10.0, v) : v;
             cdf_i[i] = 0;
         });
     }
-    // Stage values are produced in parallel into kk[0..5] before every attempt; the stepper then
-    // consumes them in call order.  (The pdf ignores the state: dxdt = pdf(t).)
-    struct Sys {
-        const double* kk;
-        int next;
-        VAG_HD void operator()(const double* /*x*/, double* dxdt, double /*t*/) { dxdt[0] = kk[next++]; }
-    } sys{kk, 0};
-
-    Dopri5<1> st;
-    const double x0 = 0;
-    st.initialize(&x0, lo, (hi - lo) / 1e3, rtol);
+    CdfQuad<VARIANT> st;
+    st.initialize(lo, gl::mul(gl::sub(hi, lo), 1.0 / 1e3));
     int k = 1;
     for (int steps = 0; st.t <= hi;) {
         if (!st.deriv_ready) {
-            kk[0] = pdf(st.t);
-            sys.next = 0;
+            st.k1 = pdf(st.t);
+            st.deriv_ready = true;
         }
-        st.begin_step(sys);
         bool ok = false;
         for (int fails = 0; fails < 500; ++fails) {
             const double t0 = st.t, dt = st.dt;
-            par.for_each(6, [&](int s) {
-                const double a = (s == 0) ? 1.0 / 5 : (s == 1) ? 3.0 / 10 : (s == 2) ? 4.0 / 5 : (s == 3) ? 8.0 / 9 : 1.0;
-                kk[s] = pdf(s < 4 ? t0 + dt * a : t0 + dt);
-            });
-            sys.next = 0;
-            if (st.try_step(sys)) {
+            // the six stage evaluations of an attempt are independent (a pure quadrature): one lane each
+            par.for_each(6, [&](int s) { kk[s] = pdf(CdfQuad<VARIANT>::stage_time(t0, dt, s)); });
+            if (st.try_step(kk, rtol)) {
                 ok = true;
                 break;
             }
@@ -250,7 +364,7 @@ VAG_HD void inverse_cdf_sampling(const Par& par, const Pdf& pdf, double lo, doub
         while (k + m < n_samp && st.t > x_i[k + m]) ++m;
         if (m > 0) {
             const int k0 = k;
-            par.for_each(m, [&](int i) { st.calc_state(x_i[k0 + i], &cdf_i[k0 + i]); });
+            par.for_each(m, [&](int i) { cdf_i[k0 + i] = st.calc_state(x_i[k0 + i]); });
             k += m;
         }
     }
@@ -261,7 +375,9 @@ VAG_HD void inverse_cdf_sampling(const Par& par, const Pdf& pdf, double lo, doub
     int j_resume = 0;
     double target_prev = -kInf;
     par.for_each(num, [&](int q) {
-        const double target = midpoint ? (c0 + (c1 - c0) * ((double)q + 0.5) / (double)num) : linspace_at(c0, c1, num, q);
+        // midpoint quantiles: front + (back - front) * (q + 0.5) / num, evaluated lazily by xtensor per element
+        const double target = midpoint ? gl::add(c0, gl::div(gl::mul(gl::sub(c1, c0), gl::add((double)q, 0.5)), (double)num))
+                                       : linspace_at(c0, c1, num, q);
         int j = (target >= target_prev) ? j_resume : 0;
         while (j < n_samp && !(target <= cdf_i[j])) ++j;
         j_resume = j;
@@ -271,10 +387,10 @@ VAG_HD void inverse_cdf_sampling(const Par& par, const Pdf& pdf, double lo, doub
             if (j == 0) {
                 xo = x_i[0];
             } else {
-                const double denom = cdf_i[j] - cdf_i[j - 1];
+                const double denom = gl::sub(cdf_i[j], cdf_i[j - 1]);
                 if (denom > 0) {
-                    const double slope = (x_i[j] - x_i[j - 1]) / denom;
-                    xo = x_i[j - 1] + slope * (target - cdf_i[j - 1]);
+                    const double slope = gl::div(gl::sub(x_i[j], x_i[j - 1]), denom);
+                    xo = gl::fma(slope, gl::sub(target, cdf_i[j - 1]), x_i[j - 1]);
                 } else {
                     xo = x_i[j - 1];
                 }
@@ -287,16 +403,18 @@ VAG_HD void inverse_cdf_sampling(const Par& par, const Pdf& pdf, double lo, doub
 // ---- adaptive_theta_grid: grid-refinement.h:199-291 ------------------------------------------
 struct ThetaPdf {
     const ModelCfg& m;
-    double theta_v, core_weight, view_weight, Gamma_peak_sq, Gamma_v_sq, doppler_alpha, floor_weight;
+    double theta_v, cw_Gpsq, vw_Gvsq, Gamma_peak_sq, Gamma_v_sq, doppler_alpha, floor_weight;
     VAG_HD double operator()(double theta) const {
-        const double Gamma = jet_Gamma0(m, theta);
-        const double beta = gamma_to_beta(Gamma);
-        const double doppler = (1 - beta) / (1 - beta * cos(theta - theta_v));
+        const double Gamma = jet_Gamma0<true>(m, theta);
+        const double dtheta = gl::sub(theta, theta_v);
+        const double beta = gamma_to_beta_x(Gamma);
+        const double c = gl::cos(dtheta);
+        const double doppler = gl::div(gl::sub(1.0, beta), gl::fnma(c, beta, 1.0));
         const double structure = structure_weight(Gamma);
-        const double dtheta = theta - theta_v;
-        return core_weight * Gamma_peak_sq * theta / (1.0 + Gamma_peak_sq * theta * theta) +
-               view_weight * Gamma_v_sq * fabs(dtheta) / (1.0 + Gamma_v_sq * dtheta * dtheta) +
-               (1 + doppler_alpha * doppler) * structure + floor_weight;
+        const double a1 = gl::fma(doppler, doppler_alpha, 1.0);
+        const double core = gl::div(gl::mul(cw_Gpsq, theta), gl::fma(gl::mul(Gamma_peak_sq, theta), theta, 1.0));
+        const double view = gl::div(gl::mul(vw_Gvsq, fabs(dtheta)), gl::fma(gl::mul(dtheta, Gamma_v_sq), dtheta, 1.0));
+        return gl::add(gl::fma(a1, structure, gl::add(view, core)), floor_weight);
     }
 };
 
@@ -307,62 +425,80 @@ VAG_HD int adaptive_theta_grid(const Par& par, const ModelCfg& m, double theta_m
                                double* samp, double* kk) {
     constexpr double core_beam_coeff = 55.0, view_beam_coeff = 25.0, doppler_alpha0 = 12.0, floor_fraction = 0.25;
     constexpr int scan_pts = 100;
-    const double theta_extent = theta_max - theta_min;
+    const double theta_extent = gl::sub(theta_max, theta_min);
     double peak_weight = 0, Gamma_peak = 1.0, struct_sum = 0, Gamma_v = 1.0;
     int last_bright = 0;
     par.for_each(scan_pts + 1, [&](int i) {
-        const double theta = theta_min + theta_extent * i / scan_pts;
+        const double theta = gl::fma(gl::mul((double)i, theta_extent), 0.01, theta_min);
         const double Gamma = jet_Gamma0(m, theta);
-        const double dth = theta - theta_v;
+        const double dth = gl::sub(theta, theta_v);
         A[i] = Gamma;
-        B[i] = Gamma / sqrt(1.0 + Gamma * Gamma * dth * dth);
+        B[i] = gl::div(Gamma, gl::sqrt(gl::fma(gl::mul(gl::mul(Gamma, Gamma), dth), dth, 1.0)));
     });
     for (int i = 0; i <= scan_pts; ++i) {
         const double Gamma = A[i];
         const double w = structure_weight(Gamma);
-        struct_sum += w;
+        struct_sum = gl::add(struct_sum, w);
         if (w > peak_weight) {
             peak_weight = w;
             Gamma_peak = Gamma;
             last_bright = i;
-        } else if (w > 0.01 * peak_weight) {
+        } else if (w > gl::mul(peak_weight, 0.01)) {
             last_bright = i;
         }
         Gamma_v = vmax(Gamma_v, B[i]);
     }
-    const double floor_weight = floor_fraction * peak_weight;
-    const double CDF_est = (struct_sum / scan_pts + floor_weight) * theta_extent;
-    const double theta_bright = theta_min + theta_extent * last_bright / scan_pts;
+    const double floor_weight = gl::mul(floor_fraction, peak_weight);
+    const double CDF_est = gl::mul(theta_extent, gl::fma(struct_sum, 0.01, floor_weight));
+    const double theta_bright = gl::fma(gl::mul((double)last_bright, theta_extent), 0.01, theta_min);
 
     Gamma_peak = vmax(Gamma_peak, Gamma_v);
-    const double doppler_alpha = doppler_alpha0 * sqrt(peak_weight / vmax(structure_weight(Gamma_v), 1.0));
+    const double sw_v = structure_weight(Gamma_v);
+    const double doppler_alpha = gl::mul(gl::sqrt((1.0 > sw_v) ? peak_weight : gl::div(peak_weight, sw_v)), doppler_alpha0);
 
-    const double Gamma_peak_sq = Gamma_peak * Gamma_peak;
-    const double Gamma_v_sq = Gamma_v * Gamma_v;
+    const double Gamma_peak_sq = gl::mul(Gamma_peak, Gamma_peak);
+    const double Gamma_v_sq = gl::mul(Gamma_v, Gamma_v);
     // compute_beam_pts(log_decades, coeff, offset) = size_t(max(0, log_decades - offset) * resol * coeff)
-    const long long core_beam_pts = (long long)(vmax(0.0, log10(vmax(1.0, Gamma_peak * (theta_bright - theta_min))) - 1.0) *
-                                                theta_resol * core_beam_coeff);
-    const long long view_beam_pts =
-        (theta_v * Gamma_peak > 3.0)
-            ? (long long)(vmax(0.0, log10(vmax(1.0, Gamma_v * vmax(theta_v - theta_min, theta_max - theta_v))) - 0.0) *
-                          theta_resol * view_beam_coeff)
-            : 0;
+    auto decades = [&](double arg, double offset) {  // max(0, log10(max(1, arg)) - offset)
+        if (!(arg > 1.0)) return 0.0;
+        const double d = gl::sub(gl::log10(arg), offset);
+        return (d > 0.0) ? d : 0.0;
+    };
+    const double core_real =
+        gl::mul(gl::mul(decades(gl::mul(gl::sub(theta_bright, theta_min), Gamma_peak), 1.0), theta_resol), core_beam_coeff);
+    const long long core_beam_pts = (long long)core_real;
+    const double theta_v_left = gl::sub(theta_v, theta_min);
+    const double theta_v_right = gl::sub(theta_max, theta_v);
+    double view_real = 0;
+    long long view_beam_pts = 0;
+    if (gl::mul(theta_v, Gamma_peak) > 3.0) {
+        view_real = gl::mul(gl::mul(decades(gl::mul(vmax(theta_v_left, theta_v_right), Gamma_v), 0.0), theta_resol), view_beam_coeff);
+        view_beam_pts = (long long)view_real;
+    }
     const long long total_pts = base_pts + core_beam_pts + view_beam_pts;
     if (total_pts > cap) return -(int)total_pts;
 
     auto calibrate = [&](long long n_pts, double beam_cdf) -> double {
-        return (n_pts > 0 && beam_cdf > 0) ? (double)n_pts / base_pts * CDF_est / beam_cdf : 0.0;
+        return (n_pts > 0 && beam_cdf > 0) ? gl::div(gl::mul(gl::div((double)n_pts, (double)base_pts), CDF_est), beam_cdf) : 0.0;
     };
-    const double core_weight = calibrate(core_beam_pts, 0.5 * log((1.0 + Gamma_peak_sq * theta_max * theta_max) /
-                                                                  (1.0 + Gamma_peak_sq * theta_min * theta_min)));
-    const double theta_v_left = theta_v - theta_min;
-    const double theta_v_right = theta_max - theta_v;
-    const double view_weight = calibrate(view_beam_pts, 0.5 * (log(1.0 + Gamma_v_sq * theta_v_left * theta_v_left) +
-                                                              log(1.0 + Gamma_v_sq * theta_v_right * theta_v_right)));
+    const double core_cdf = gl::mul(
+        gl::log(gl::div(gl::fma(gl::mul(theta_max, Gamma_peak_sq), theta_max, 1.0), gl::fma(gl::mul(theta_min, Gamma_peak_sq), theta_min, 1.0))),
+        0.5);
+    const double core_weight = calibrate(core_beam_pts, core_cdf);
+    const double view_cdf = gl::mul(gl::add(gl::log(gl::fma(gl::mul(Gamma_v_sq, theta_v_right), theta_v_right, 1.0)),
+                                            gl::log(gl::fma(gl::mul(theta_v_left, Gamma_v_sq), theta_v_left, 1.0))),
+                                    0.5);
+    const double view_weight = calibrate(view_beam_pts, view_cdf);
 
-    const ThetaPdf pdf{m, theta_v, core_weight, view_weight, Gamma_peak_sq, Gamma_v_sq, doppler_alpha, floor_weight};
-    inverse_cdf_sampling(par, pdf, theta_min, theta_max, (int)total_pts, /*log=*/true, /*midpoint=*/false, out, samp,
-                         samp + dflt::theta_samples, kk);
+    const ThetaPdf pdf{m,          theta_v,      gl::mul(Gamma_peak_sq, core_weight), gl::mul(Gamma_v_sq, view_weight), Gamma_peak_sq,
+                       Gamma_v_sq, doppler_alpha, floor_weight};
+    // an Ejecta's profile is a std::function call the optimiser cannot see through: the stage states stay alive (VARIANT 1)
+    if (m.ejecta)
+        inverse_cdf_sampling<1>(par, pdf, theta_min, theta_max, (int)total_pts, /*log=*/true, /*midpoint=*/false, out, samp,
+                                samp + dflt::theta_samples, kk);
+    else
+        inverse_cdf_sampling<0>(par, pdf, theta_min, theta_max, (int)total_pts, /*log=*/true, /*midpoint=*/false, out, samp,
+                                samp + dflt::theta_samples, kk);
     return (int)total_pts;
 }
 
@@ -370,7 +506,7 @@ VAG_HD int adaptive_theta_grid(const Par& par, const ModelCfg& m, double theta_m
 VAG_HD int jump_refinement_grid(const double* jumps, int n_jumps, double theta_min, double theta_max,
                                 double avg_spacing, double* pts) {
     int n = 0;
-    const double tight = avg_spacing / 8;
+    const double tight = avg_spacing * 0.125;
     for (int idx = 0; idx < n_jumps; ++idx) {
         const double jt = jumps[idx];
         if (jt >= con::pi / 2 - 0.01) continue;
@@ -422,20 +558,21 @@ VAG_HD int merge_grids(const double* a, int na, const double* b, int nb, double*
 // pdf: every typed jet is phi-independent, so the hoisted values are the ones the reference
 // recomputes inside phi_weight on every call.
 struct PhiPdf {
-    const double *beta, *sw, *dcos, *ct, *st;
+    const double *beta, *sw, *dcos, *ct_ctv, *st_stv;  // beta, structure weight, dcos, cos(theta), sin_tv sin(theta)
     int n_theta;
-    double cos_tv, sin_tv, floor_weight;
+    double cos_tv, floor_weight;
     VAG_HD double weight(double phi) const {
-        const double cos_phi = cos(phi);
+        const double cos_phi = gl::cos(phi);
         double w = 0;
         for (int it = 0; it < n_theta; ++it) {
-            const double cos_alpha = ct[it] * cos_tv + st[it] * sin_tv * cos_phi;
-            const double a = (1 - beta[it]) / (1 - beta[it] * cos_alpha);
-            w += a * sw[it] * dcos[it];
+            // cos_alpha = fma(cos_tv, cos(theta), (sin_tv sin(theta)) cos_phi);  a = (1 - beta) / fnma(cos_alpha, beta, 1)
+            const double cos_alpha = gl::fma(cos_tv, ct_ctv[it], gl::mul(st_stv[it], cos_phi));
+            const double a = gl::div(gl::sub(1.0, beta[it]), gl::fnma(cos_alpha, beta[it], 1.0));
+            w = gl::fma(gl::mul(sw[it], a), dcos[it], w);
         }
         return w;
     }
-    VAG_HD double operator()(double phi) const { return weight(phi) + floor_weight; }
+    VAG_HD double operator()(double phi) const { return gl::add(weight(phi), floor_weight); }
 };
 
 // scratch: per-theta arrays pt[5*n_theta], A[>=101], samples [2*theta_samples], kk[8]
@@ -451,38 +588,39 @@ VAG_HD int adaptive_phi_grid(const Par& par, const ModelCfg& m, int phi_num, dou
     const bool half_range = phi_max < 2 * con::pi;
     double* beta = pt;
     double* sw = beta + n_theta;
-    double* ct = sw + n_theta;
-    double* st = ct + n_theta;
+    double* ct = sw + n_theta;      // cos(theta)
+    double* st = ct + n_theta;      // sin_tv * sin(theta)
     double* dcos_arr = st + n_theta;
+    const double cos_tv = gl::cos(theta_v), sin_tv = gl::sin(theta_v);
     par.for_each(n_theta, [&](int it) {
         const double left = (it == 0) ? 0.0 : 0.5 * (theta[it - 1] + theta[it]);
         const double right = (it == n_theta - 1) ? theta[it] : 0.5 * (theta[it] + theta[it + 1]);
-        dcos_arr[it] = fabs(cos(left) - cos(right));
+        dcos_arr[it] = fabs(gl::sub(gl::cos(left), gl::cos(right)));
         const double Gamma = jet_Gamma0(m, theta[it]);
-        beta[it] = gamma_to_beta(Gamma);
+        beta[it] = gamma_to_beta_x(Gamma);
         sw[it] = structure_weight(Gamma);
-        ct[it] = cos(theta[it]);
-        st[it] = sin(theta[it]);
+        ct[it] = gl::cos(theta[it]);
+        st[it] = gl::mul(sin_tv, gl::sin(theta[it]));
     });
-    PhiPdf pdf{beta, sw, dcos_arr, ct, st, n_theta, cos(theta_v), sin(theta_v), 0.0};
+    PhiPdf pdf{beta, sw, dcos_arr, ct, st, n_theta, cos_tv, 0.0};
 
     constexpr int scan_pts = 100;
-    par.for_each(scan_pts + 1, [&](int s) { A[s] = pdf.weight(phi_max * (double)s / scan_pts); });
+    par.for_each(scan_pts + 1, [&](int s) { A[s] = pdf.weight(gl::mul(gl::mul(phi_max, (double)s), 0.01)); });
     double peak_weight = 0, sum_weight = 0;
     for (int s = 0; s <= scan_pts; ++s) {
         peak_weight = vmax(peak_weight, A[s]);
-        sum_weight += A[s];
+        sum_weight = gl::add(sum_weight, A[s]);
     }
-    const double floor_weight = 0.05 * peak_weight;
+    const double floor_weight = gl::mul(0.05, peak_weight);
     if (self_boost_cap > 0 && peak_weight > 0) {
-        const double mean_pdf = sum_weight / (scan_pts + 1) + floor_weight;
-        const double concentration = (peak_weight + floor_weight) / mean_pdf;
-        const double boost = vclamp(concentration / 5, 1.0, self_boost_cap);
-        phi_num = (int)(long long)((double)phi_num * boost);
+        const double mean_pdf = gl::fma(sum_weight, 1.0 / (scan_pts + 1), floor_weight);
+        const double concentration = gl::div(gl::add(peak_weight, floor_weight), mean_pdf);
+        const double boost = vclamp(gl::mul(concentration, 0.2), 1.0, self_boost_cap);
+        phi_num = (int)(long long)gl::mul((double)phi_num, boost);
     }
     if (phi_num > cap) return -phi_num;
     pdf.floor_weight = floor_weight;
-    inverse_cdf_sampling(par, pdf, 0, phi_max, phi_num, /*log=*/false, /*midpoint=*/half_range, out, samp,
+    inverse_cdf_sampling<1>(par, pdf, 0, phi_max, phi_num, /*log=*/false, /*midpoint=*/half_range, out, samp,
                          samp + dflt::theta_samples, kk);
     return phi_num;
 }

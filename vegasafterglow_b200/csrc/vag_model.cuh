@@ -8,6 +8,7 @@
 
 #include "../../include/vag.h"
 #include "vag_common.cuh"
+#include "vag_libm.cuh"
 
 namespace vag {
 
@@ -23,6 +24,8 @@ struct ModelCfg {
     // jet
     int jet_type;
     double theta_c, eps_k0, Gamma0, k_e, k_g, gauss_norm, T0;
+    int ejecta;           // the reference builds this jet as an `Ejecta` of std::function profiles (pymodel.cpp:47-146)
+    double gauss_spread;  // math::gaussian: -2 theta_c^2 (jet.h:376-379)
     double theta_w, E_iso, E_iso_w, Gamma0_w, sigma0;  // Ejecta-family profiles work on E_iso [erg] heights
     int has_magnetar;
     double mag_L, mag_t0, mag_q;
@@ -68,6 +71,8 @@ VAG_HD ModelCfg make_cfg(const vag_params& p) {
     m.k_e = p.k_e;
     m.k_g = p.k_g;
     m.gauss_norm = -1 / (2 * p.theta_c * p.theta_c);  // jet.h:141
+    m.ejecta = (p.jet_type >= VAG_JET_TWO_COMPONENT || p.sigma0 > 0 || p.has_magnetar) ? 1 : 0;
+    m.gauss_spread = -2 * p.theta_c * p.theta_c;
     m.T0 = p.duration * unit::sec;
     m.theta_w = p.theta_w;
     m.E_iso = p.E_iso;
@@ -118,43 +123,76 @@ VAG_HD ModelCfg make_cfg(const vag_params& p) {
 }
 
 // ---- jet profiles (phi-independent for every typed variant) --------------------------------
+// Spelled out in contraction-proof operations (vag_libm.cuh) with the host libm's exp / exp2 / log2: the grid
+// builder's CDF quadrature needs the profile bit-identical to the reference build's (vag_grid.cuh), and every
+// other caller is served by the same values.  Operation order = the reference build's instruction sequence
+// (jet.h:116,175-177,243-245 as compiled: Gaussian Gamma0 is one fma, the power law keeps its true divisions).
+// RECIP: where g++ inlined PowerLawJet::Gamma0 several times into one function (the theta-grid sampler's seven stage
+// evaluations), -freciprocal-math turned theta / theta_c into theta * (1 / theta_c); single call sites divide.
+template <bool RECIP = false>
+VAG_HD double jet_powlaw(const ModelCfg& m, double theta, double k) {  // fast_pow(theta / theta_c, k) (fast-math.h:147-149)
+    const double ratio = RECIP ? gl::mul(theta, gl::div(1.0, m.theta_c)) : gl::div(theta, m.theta_c);
+    return gl::exp2(gl::mul(gl::log2(ratio), k));
+}
+template <bool RECIP = false>
 VAG_HD double jet_Gamma0(const ModelCfg& m, double theta) {
     switch (m.jet_type) {
+        // the Ejecta forms (a magnetar or sigma0 > 0 turns a typed jet into math::*_plus_one profiles, pymodel.cpp:47-95):
+        // (Gamma0 - 1) + 1 is not always Gamma0, and math::gaussian divides by -2 theta_c^2 where GaussianJet multiplies
         case VAG_JET_TOPHAT:
+            if (m.ejecta) return gl::add(theta < m.theta_c ? gl::sub(m.Gamma0, 1.0) : 0.0, 1.0);  // jet.h:360-367
             return theta < m.theta_c ? m.Gamma0 : 1;  // jet.h:116
         case VAG_JET_GAUSSIAN:
-            return (m.Gamma0 - 1) * fast_exp(theta * theta * m.gauss_norm) + 1;  // jet.h:175-177
-        case VAG_JET_POWERLAW:
-            return (m.Gamma0 - 1) / (1 + fast_pow(theta / m.theta_c, m.k_g)) + 1;  // jet.h:243-245
+            if (m.ejecta)  // jet.h:376-384
+                return gl::fma(gl::exp(gl::div(gl::mul(theta, theta), m.gauss_spread)), gl::sub(m.Gamma0, 1.0), 1.0);
+            return gl::fma(gl::sub(m.Gamma0, 1.0), gl::exp(gl::mul(gl::mul(theta, theta), m.gauss_norm)), 1.0);  // jet.h:175-177
+        case VAG_JET_POWERLAW:  // jet.h:243-245, 395-401
+            if (m.ejecta) return gl::add(gl::div(gl::sub(m.Gamma0, 1.0), gl::add(jet_powlaw<false>(m, theta, m.k_g), 1.0)), 1.0);
+            return gl::add(gl::div(gl::sub(m.Gamma0, 1.0), gl::add(jet_powlaw<RECIP>(m, theta, m.k_g), 1.0)), 1.0);
         // Ejecta family: Gamma0 = profile(Gamma0 - 1, ...) + 1 (math::*_plus_one, jet.h:403-470)
         case VAG_JET_TWO_COMPONENT:
-            return ((theta <= m.theta_c) ? (m.Gamma0 - 1) : (theta <= m.theta_w) ? (m.Gamma0_w - 1) : 0.) + 1;
+            return gl::add((theta <= m.theta_c) ? gl::sub(m.Gamma0, 1.0) : (theta <= m.theta_w) ? gl::sub(m.Gamma0_w, 1.0) : 0., 1.0);
         case VAG_JET_STEP_POWERLAW:
-            return ((theta <= m.theta_c) ? (m.Gamma0 - 1) : (m.Gamma0_w - 1) * fast_pow(theta / m.theta_c, -m.k_g)) + 1;
+            return gl::add((theta <= m.theta_c) ? gl::sub(m.Gamma0, 1.0)
+                                                : gl::mul(gl::sub(m.Gamma0_w, 1.0), jet_powlaw(m, theta, -m.k_g)), 1.0);
         default:  // VAG_JET_POWERLAW_WING
-            return ((theta <= m.theta_c) ? 0. : (m.Gamma0_w - 1) * fast_pow(theta / m.theta_c, -m.k_g)) + 1;
+            return gl::add((theta <= m.theta_c) ? 0. : gl::mul(gl::sub(m.Gamma0_w, 1.0), jet_powlaw(m, theta, -m.k_g)), 1.0);
     }
 }
 
 VAG_HD double jet_eps_k(const ModelCfg& m, double theta) {
+    if (m.ejecta) {
+        // Ejecta: E_iso(theta) [erg] (math::* profile, jet.h:360-470) * (unit::erg / 4 pi)  (convert_unit_jet, pymodel.cpp:188-211)
+        double E;
+        switch (m.jet_type) {
+            case VAG_JET_TOPHAT:
+                E = theta < m.theta_c ? m.E_iso : 0.;
+                break;
+            case VAG_JET_GAUSSIAN:
+                E = gl::mul(m.E_iso, gl::exp(gl::div(gl::mul(theta, theta), m.gauss_spread)));
+                break;
+            case VAG_JET_POWERLAW:
+                E = gl::div(m.E_iso, gl::add(jet_powlaw(m, theta, m.k_e), 1.0));
+                break;
+            case VAG_JET_TWO_COMPONENT:
+                E = (theta <= m.theta_c) ? m.E_iso : (theta <= m.theta_w) ? m.E_iso_w : 0.;
+                break;
+            case VAG_JET_STEP_POWERLAW:
+                E = (theta <= m.theta_c) ? m.E_iso : gl::mul(m.E_iso_w, jet_powlaw(m, theta, -m.k_e));
+                break;
+            default:
+                E = (theta <= m.theta_c) ? 0. : gl::mul(m.E_iso_w, jet_powlaw(m, theta, -m.k_e));
+                break;
+        }
+        return gl::mul(E, unit::erg / (4 * con::pi));
+    }
     switch (m.jet_type) {
         case VAG_JET_TOPHAT:
             return theta < m.theta_c ? m.eps_k0 : 0;  // jet.h:107
         case VAG_JET_GAUSSIAN:
-            return m.eps_k0 * fast_exp(theta * theta * m.gauss_norm);  // jet.h:164-166
-        case VAG_JET_POWERLAW:
-            return m.eps_k0 / (1 + fast_pow(theta / m.theta_c, m.k_e));  // jet.h:232-234
-        default: {
-            // Ejecta family: E_iso(theta) [erg] * (unit::erg / 4 pi)  (convert_unit_jet, pymodel.cpp:188-211)
-            double E;
-            if (m.jet_type == VAG_JET_TWO_COMPONENT)
-                E = (theta <= m.theta_c) ? m.E_iso : (theta <= m.theta_w) ? m.E_iso_w : 0.;
-            else if (m.jet_type == VAG_JET_STEP_POWERLAW)
-                E = (theta <= m.theta_c) ? m.E_iso : m.E_iso_w * fast_pow(theta / m.theta_c, -m.k_e);
-            else
-                E = (theta <= m.theta_c) ? 0. : m.E_iso_w * fast_pow(theta / m.theta_c, -m.k_e);
-            return E * (unit::erg / (4 * con::pi));
-        }
+            return gl::mul(m.eps_k0, gl::exp(gl::mul(gl::mul(theta, theta), m.gauss_norm)));  // jet.h:164-166
+        default:  // VAG_JET_POWERLAW
+            return gl::div(m.eps_k0, gl::add(jet_powlaw(m, theta, m.k_e), 1.0));  // jet.h:232-234
     }
 }
 
