@@ -83,6 +83,17 @@ def main():
     P3 = configs.random_draw(8, seed=34, jet="step_powerlaw", rvs=True, theta_obs_max=0.2)
     P3["E_iso_w"], P3["Gamma0_w"], P3["k_e"], P3["k_g"] = P3["E_iso"] * 0.3, np.maximum(P3["Gamma0"] * 0.5, 5.0), 3.0, 1.5
     save("batch_rs_step_powerlaw", P3, t, nu)
+    # PowerLawWing (pybind/pymodel.cpp:131-146, math::powerlaw_wing jet.h:403-416): a hollow core, the wing carries
+    # E_iso_w / Gamma0_w; forward shock and forward + reverse shock, on and off axis
+    rw = np.random.default_rng(61)
+    PW = configs.random_draw(16, seed=60, jet="powerlaw_wing", theta_obs_max=0.4)
+    PW["has_rvs"][8:] = 1
+    PW["rvs"][8:] = PW["fwd"][8:]
+    PW["duration"][8:] = 10 ** rw.uniform(0, 3, 8)
+    PW["theta_c"] = rw.uniform(0.03, 0.15, 16)
+    PW["E_iso_w"], PW["Gamma0_w"] = 10 ** rw.uniform(50, 53, 16), 10 ** rw.uniform(1.0, 2.5, 16)
+    PW["k_e"], PW["k_g"] = rw.uniform(1.5, 4.5, 16), rw.uniform(1.0, 3.0, 16)
+    save("batch_mixed_powerlaw_wing", PW, t, nu)
     P4 = configs.random_draw(16, seed=35, rvs=True)
     P4["sigma0"] = 10 ** np.random.default_rng(36).uniform(-2, 1, 16)
     save("batch_rs_magnetized_tophat", P4, t, nu)

@@ -36,66 +36,42 @@ def model_errors(a, b, comp=0, floor=1e-2):
     return out
 
 
-# Parity bar (BASELINE.json north_star): max relative flux error <= 1e-6 in FP64.
+# Parity bar (BASELINE.json north_star): max relative flux error <= 1e-6 in FP64, per model, no tail allowance.
 #
-# What "identical to the reference" can mean here is limited by the reference itself: its adaptive
-# theta grid is the inverse CDF of a dopri5 quadrature (src/core/grid-refinement.h:137-189,199-291)
-# whose pdf contains the Doppler term (1-beta)/(1-beta cos) -- a cancellation that amplifies last-bit
-# differences by ~Gamma^2 -- and whose step-size controller is driven by that noise.  Two builds of
-# the SAME unmodified source (oracle/Makefile: libvagref.so vs libvagref_alt.so, FMA/xsimd on vs off)
-# therefore differ by a heavy-tailed amount: median ~1e-7, max 5.8e-5 over 256 seeded tophat draws
-# (DESIGN.md section 6).  Every later stage (time lattice, ODE, radiation, EATS) reproduces the
-# reference to <= 1e-9 given the same grid.  Fixtures carry both reference builds, and the rule is:
-#   * per model:  err <= max(1e-6, SPREAD_FACTOR x that model's reference-vs-reference spread);
-#   * heavy tail: in batches of >= 16 models at most TAIL_FRACTION of the models (>= 1) may miss the
-#     per-model rule, and then only up to max(TAIL_CAP, SPREAD_FACTOR x the batch's largest spread);
-#   * batches of >= 16 models must have a median error <= MEDIAN_RTOL.
+# The reference's (theta, phi) grid is the inverse CDF of adaptive dopri5 quadratures (src/core/grid-refinement.h:
+# 137-189,199-360) that amplify a one-ulp difference anywhere upstream of a step position into ~1e-8 in the nodes:
+# two builds of the SAME unmodified source (oracle/Makefile: libvagref.so vs libvagref_alt.so, FMA / xsimd on vs off)
+# differ by up to 5.8e-5 in a tophat flux and 2.6e-3 in a structured reverse shock (the `flux_alt` planes of the
+# fixtures record it).  The grid kernel therefore reproduces the reference build's arithmetic bit for bit
+# (csrc/vag_libm.cuh, csrc/vag_grid.cuh; tests/test_grid_exact.py demands 0 ulps on the nodes), and every later stage
+# (time lattice, ODE, radiation, EATS) is smooth: round 2's GPU errors are <= 5e-7 on every fixture outside CHAOTIC
+# (profiles/parity_r02.json), median ~1e-12.
 FLUX_RTOL = 1e-6
-SPREAD_FACTOR = 4.0
-TAIL_FRACTION = 0.02
-TAIL_CAP = 1e-5
-MEDIAN_RTOL = 1e-8
+MEDIAN_RTOL = 1e-9
 
 
 def assert_parity(flux, g, what):
     for comp in (0, 1, 2, 3, 4):
         err = model_errors(flux, g["flux"], comp)
-        spread = model_errors(g["flux_alt"], g["flux"], comp)
-        tol = np.maximum(FLUX_RTOL, SPREAD_FACTOR * spread)
-        bad = np.nonzero(err > tol)[0]
-        n = err.size
-        allowed = max(1, int(np.ceil(TAIL_FRACTION * n))) if n >= 16 else 0
-        assert bad.size <= allowed, (f"{what} comp {comp}: models {bad.tolist()} exceed tolerance: err={err[bad]}, "
-                                     f"tol={tol[bad]}")
-        cap = max(TAIL_CAP, SPREAD_FACTOR * float(spread.max()))
-        assert err.max() <= max(cap, float(tol.max())), f"{what} comp {comp}: max err {err.max():.3e} > cap {cap:.3e}"
-        if n >= 16 and np.any(g["flux"][:, comp] > 0):
+        bad = np.nonzero(err > FLUX_RTOL)[0]
+        assert bad.size == 0, f"{what} comp {comp}: models {bad.tolist()} exceed {FLUX_RTOL}: err={err[bad]}"
+        if err.size >= 16 and np.any(g["flux"][:, comp] > 0):
             assert np.median(err) <= MEDIAN_RTOL, f"{what} comp {comp}: median err {np.median(err):.3e}"
     return model_errors(flux, g["flux"], 0)
 
 
-# Configurations the reference itself only reproduces to ~1e-3 between builds: structured-jet
-# reverse shocks (chaotic wing rows, tests/python/test_golden.py:95) and magnetised shells (the
-# sigma > 0 jump conditions are tolerance-sensitive: "reverse-shock flux vs a deep reference converges as
-# 9.4e-3 / 1.0e-4 / 5.4e-5 at rtol 1e-6 / 1e-7 / 1e-8", src/dynamics/reverse-shock.tpp:529-537).  They are
-# held to the reference's OWN golden acceptance contract |a-b| <= 2e-3 |b| + 1e-2 peak
-# (tests/python/golden/regenerate.py:29-30) plus a median bar that shows the typical model is still
-# reproduced far below it.
-#
-# Spreading jets join the list for a different reason: a `structured` model gives every theta row its
-# own time lattice (build_time_grid, grid-refinement.h:612-619), so a row starts to contribute at its own
-# first observer-time node and the flux is a DISCONTINUOUS function of the theta grid at those onsets.  The
-# GPU theta grid differs from the reference's by the quadrature noise described above (~1e-4 in the nodes
-# for the occasional model); for that model the bins next to a row onset move by ~5e-3 while all other
-# bins stay <= 1e-4 (measured: 15 of 16 models of batch_fs_spreading_tophat <= 1.2e-6, one at 6.8e-3 in two
-# isolated time bins).  The host emulation, which shares glibc's libm with the reference, reproduces the same
-# fixtures to <= 1e-8.
-CHAOTIC = ("golden_gauss_ism_rs", "batch_rs_magnetized_tophat", "series_rs_gauss", "batch_rs_step_powerlaw",
-           "batch_fs_spreading_tophat", "batch_fs_spreading_gauss", "batch_fs_spreading_powerlaw_wind",
-           "batch_rs_spreading_tophat", "batch_ssc_spreading_tophat")
+# Configurations whose SHOCK-PAIR ODE is itself chaotic in the last bit (not the grid: their device grids equal the
+# reference's bit for bit): a magnetar-fed forward shock inside the pair system (the injection term drives the step
+# controller through the crossing, src/dynamics/reverse-shock.tpp:75-77,231-233) and magnetised shells ("reverse-shock
+# flux vs a deep reference converges as 9.4e-3 / 1.0e-4 / 5.4e-5 at rtol 1e-6 / 1e-7 / 1e-8",
+# src/dynamics/reverse-shock.tpp:529-537).  The host build of the very same source, with glibc's libm and gcc's
+# contractions, misses the reference by 2.6e-4 / 6.2e-4 on them, and the reference's own two builds differ by 3.2e-4 /
+# 1.3e-4.  They are held to the reference's OWN golden acceptance contract |a-b| <= 2e-3 |b| + 1e-2 peak
+# (tests/python/golden/regenerate.py:29-30) plus a median bar showing that the typical model is reproduced to 1e-6.
+CHAOTIC = ("batch_rs_magnetar_tophat", "batch_rs_magnetized_tophat")
 
 
-def assert_reference_contract(flux, g, what, median_rtol=1e-4):
+def assert_reference_contract(flux, g, what):
     ref = g["flux"]
     for comp in (0, 1, 2, 3, 4):
         for i in range(ref.shape[0]):
@@ -105,4 +81,6 @@ def assert_reference_contract(flux, g, what, median_rtol=1e-4):
                 continue
             assert np.all(np.abs(a - b) <= 2e-3 * np.abs(b) + 1e-2 * b.max()), (what, comp, i)
     if ref.shape[0] >= 8:
-        assert np.median(model_errors(flux, ref, 0)) <= median_rtol, what
+        # typical model: within the bar, or within twice the reference's own typical cross-build deviation
+        spread = np.median(model_errors(g["flux_alt"], ref, 0))
+        assert np.median(model_errors(flux, ref, 0)) <= max(FLUX_RTOL, 2 * spread), what
