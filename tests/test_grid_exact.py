@@ -105,4 +105,4 @@ def test_device_grid_equals_host_build_and_reference_bitwise(engine):
         if ref is not None:
             assert_same_grid(d, ref.details(p, 1e2, 1e7), f"draw {i}: device vs reference")
         n += 1
-    assert n > 100
+    assert n > 60
