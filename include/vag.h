@@ -29,8 +29,9 @@ enum {
     VAG_ERR_INVALID = 1, /* argument validation failed: mirrors AFTERGLOW_REQUIRE -> ValueError
                             (pybind/error_handling.h:31-69) */
     VAG_ERR_CUDA = 2,    /* CUDA runtime error / no device                                       */
-    VAG_ERR_UNSUPPORTED = 3, /* a switch of the reference that this path does not implement yet
-                                (jet spreading, axisymmetric=False, Ejecta/Medium callbacks, k_m != 2)               */
+    VAG_ERR_UNSUPPORTED = 3, /* a switch of the reference that this path does not implement:
+                                axisymmetric=False together with spreading=True; Python-callable
+                                Ejecta / Medium profiles cannot be expressed in vag_params at all   */
     VAG_ERR_CAPACITY = 4     /* a per-model grid exceeded the compiled capacity                  */
 };
 
@@ -68,11 +69,12 @@ typedef struct vag_radiation {
 
 /* One parameter set = everything Model.__init__ receives (pybind/pybind.cpp:384-422,
  * pybind/pymodel.h:613-649) for the typed jet/medium variants. */
-typedef struct vag_params {
+typedef struct vag_params { /* 320 bytes, mirrored by vegasafterglow_b200/abi.py PARAMS_DTYPE */
     /* jet: TophatJet/GaussianJet/PowerLawJet(theta_c, E_iso, Gamma0[, k_e, k_g], spreading,
-     * duration)  pybind/pymodel.cpp:47-95 */
+     * duration)  pybind/pymodel.cpp:47-95; two-component / step-power-law / power-law-wing :97-146 */
     int32_t jet_type;
-    int32_t spreading; /* must be 0 (VAG_ERR_UNSUPPORTED otherwise) */
+    int32_t spreading; /* spreading=True of the jet factories: lateral spreading (forward-shock models) and
+                          Symmetry::structured lattices; not together with axisymmetric = 0 */
     double theta_c, E_iso, Gamma0, k_e, k_g, duration;
     double theta_w, E_iso_w, Gamma0_w; /* wing of the two-component / step-power-law / power-law-wing jets */
     double sigma0;                     /* ejecta magnetisation (constant; the reference expresses it through
@@ -159,6 +161,29 @@ int vag_chi2_series(vag_context* ctx, const vag_params* params, size_t n_models,
                     const double* lnF_obs, const double* sigma_ln, const double* w, size_t n, double* chi2,
                     int32_t* status);
 
+/* One band-integrated data set of the likelihood (VegasAfterglow/fitting/fitter.py BandObs, :525-531): observed
+ * band fluxes [erg cm^-2 s^-1] at ascending epochs t[n], compared with Model.flux(t, nu_min, nu_max, num_nu). */
+typedef struct vag_band_obs {
+    const double* t;        /* [n] seconds, ascending                                   */
+    const double* lnF_obs;  /* [n] ln(observed band flux)                               */
+    const double* sigma_ln; /* [n] err / flux                                           */
+    const double* w;        /* [n] weights                                              */
+    size_t n;
+    double nu_min, nu_max;  /* Hz                                                        */
+    size_t num_nu;          /* frequency nodes of the Boole quadrature (>= 2)            */
+} vag_band_obs;
+
+/* Replaces Fitter._evaluate (fitter.py:503-533) for a batch: chi2[i] = sum over the point data (as vag_chi2_series;
+ * n_points may be 0) + sum over every band data set of w ((lnF_obs - ln max(F_band, 1e-300)) / sigma_ln)^2.
+ * A non-finite sum, or a model whose ODE hit Boost's 500-rejection limit (VAG_ST_ODE_FAIL500 -- an exception in the
+ * reference, logL = -inf in its samplers, samplers.py:63-70), gives chi2 = +inf.  status[i] = OR over all terms. */
+int vag_chi2(vag_context* ctx, const vag_params* params, size_t n_models, const double* t, const double* nu,
+             const double* lnF_obs, const double* sigma_ln, const double* w, size_t n_points, const vag_band_obs* bands,
+             size_t n_bands, double* chi2, int32_t* status);
+
+/* ok[i] = 1 where vag_params_validate accepts params[i], else 0 (no error is raised for rejected sets). */
+int vag_params_validate_batch(const vag_params* params, size_t n, int32_t* ok);
+
 /* ------------------------------------------------------------------------------------------- */
 /* batched model evaluation, DEVICE buffers (no copies; asynchronous on `stream`)               */
 /* ------------------------------------------------------------------------------------------- */
@@ -230,6 +255,10 @@ int vag_last_stage_ms(vag_context* ctx, float ms[8]);
 int vag_last_launch_count(vag_context* ctx);
 /* dependent-free DFMA throughput of the device in TFLOP/s (FP64 roofline denominator) */
 int vag_measure_fp64_peak(vag_context* ctx, double* tflops);
+/* Test hook: lower the shock ODE's accepted-step limit (defaults::solver::max_ode_steps = 100000 -> VAG_ST_ODE_STEP_CAP,
+ * forward-shock.tpp:196-200) and / or the consecutive-rejection limit (Boost's 500 -> VAG_ST_ODE_FAIL500) so that the failure
+ * semantics can be exercised; 0 restores the reference value. */
+int vag_debug_set_ode_limits(vag_context* ctx, int max_steps, int max_fails);
 /* Device self-test of the libm-exact functions the grid kernel evaluates (csrc/vag_libm.cuh):
  * out[i] = fn(x[i]) with fn 0 exp, 1 exp2, 2 log, 3 log2, 4 log10, 5 pow(x[i], y[i]), 6 sin, 7 cos; host buffers.
  * The results must equal the host libm's bit for bit (the reference's theta / phi grids depend on it,

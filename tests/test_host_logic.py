@@ -66,6 +66,10 @@ def test_pybind_mirror_error_conventions():
     pp = np.frombuffer(mm.params_bytes, dtype=abi.PARAMS_DTYPE)[0]
     assert pp["jet_type"] == abi.JET_TWO_COMPONENT and pp["theta_w"] == 0.3 and pp["Gamma0_w"] == 50
     m = va.Model(va.TophatJet(0.1, 1e52, 300), va.ISM(1), obs, rad)
+    # Model.resolutions (pybind/pybind.cpp:453): the defaults in effect, or what was passed
+    assert m.resolutions == (0.06, 0.15, 6.0)
+    assert va.Model(va.TophatJet(0.1, 1e52, 300), va.ISM(1), obs, rad, rvs_rad=rad).resolutions == (0.06, 0.2, 10.0)
+    assert va.Model(va.TophatJet(0.1, 1e52, 300), va.ISM(1), obs, rad, resolutions=(0.1, 0.3, 8)).resolutions == (0.1, 0.3, 8.0)
     with pytest.raises(ValueError, match="same size"):
         m.flux_density(np.array([1.0, 2.0]), np.array([1e9]))
     with pytest.raises(ValueError, match="non-empty"):
@@ -79,6 +83,56 @@ def test_partition_covers_everything():
             assert blocks[0][0] == 0 and blocks[-1][1] == n
             assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
             assert max(b[1] - b[0] for b in blocks) <= -(-n // world) if n else True
+
+
+def test_cost_balanced_assignment_of_a_mixed_ensemble():
+    # a tophat walker is one ODE row and one phi row, a structured off-axis walker ~50 x ~15 of
+    # them.  The cost proxy must see that, and the serpentine deal must level it: max / min per-rank cost <= 1.15.
+    P = np.concatenate([configs.random_draw(3072, seed=1, rvs=True),
+                        configs.random_draw(1024, seed=2, rvs=True, jet="gaussian", theta_obs_max=0.4)])
+    P = P[np.random.default_rng(0).permutation(P.size)]
+    cost = parallel.cost_proxy(P, 1e2, 1e7)
+    g = P["jet_type"] == abi.JET_GAUSSIAN
+    assert np.median(cost[g]) > 10 * np.median(cost[~g])
+    for world in (2, 4, 8):
+        sets = parallel.balanced_assignment(cost, world)
+        assert sorted(np.concatenate(sets).tolist()) == list(range(P.size))
+        per = np.array([cost[s].sum() for s in sets])
+        assert per.max() / per.min() <= 1.15, (world, per)
+        contiguous = np.array([cost[slice(*parallel.partition(P.size, world, r))].sum() for r in range(world)])
+        assert per.max() <= contiguous.max()
+
+
+def test_invalid_walkers_are_masked_before_the_split():
+    # a walker the model constructor rejects (theta_w <= theta_c is routine in MCMC) must not change what any
+    # rank sends into the collective.  The mask is pure host code on the full ensemble.
+    from vegasafterglow_b200.engine import Engine
+
+    P = configs.random_draw(9, seed=4)
+    P["theta_c"][3] = -0.1
+    P["fwd"]["eps_e"][7] = 2.0
+    ok = Engine.valid_mask(P)
+    assert ok.tolist() == [True, True, True, False, True, True, True, False, True]
+    seen = []
+
+    def evaluate(block):
+        seen.append(len(block))
+        return np.arange(len(block), dtype=float)
+
+    chi2 = parallel.partitioned_chi2(None, P, np.array([1e3, 1e5]), None, None, None, None, evaluate=evaluate, valid=ok)
+    assert seen == [7] and np.isinf(chi2[[3, 7]]).all() and np.isfinite(np.delete(chi2, [3, 7])).all()
+
+
+def test_band_observation_record():
+    b = fitting.band_obs(t=[2e4, 1e3], flux=[2e-12, 1e-12], err=[2e-13, 2e-13], nu_min=7.25e16, nu_max=2.4e18, num_points=9,
+                         weights=[2.0, 1.0])
+    np.testing.assert_array_equal(b["t"], [1e3, 2e4])
+    np.testing.assert_allclose(b["lnF_obs"], np.log([1e-12, 2e-12]))
+    np.testing.assert_allclose(b["sigma_ln"], [0.2, 0.1])
+    np.testing.assert_array_equal(b["w"], [1.0, 2.0])  # band weights are NOT normalised (fitter.py:362-373)
+    assert (b["nu_min"], b["nu_max"], b["num_nu"]) == (7.25e16, 2.4e18, 9)
+    with pytest.raises(ValueError, match="positive"):
+        fitting.band_obs([1.0], [0.0], [1.0], 1e9, 1e10)
 
 
 def test_likelihood_parameter_mapping():
@@ -112,6 +166,14 @@ _GLOO_WORKER = textwrap.dedent("""
     chi2 = parallel.partitioned_chi2(None, P, ts, nus, lnF, sig, w, evaluate=host_eval)
     full = host_eval(P)
     assert chi2.shape == (7,) and np.array_equal(chi2, full), (chi2, full)
+    chi2c = parallel.partitioned_chi2(None, P, ts, nus, lnF, sig, w, evaluate=host_eval, balance=False)
+    assert np.array_equal(chi2c, full)
+    # a rejected walker on ONE rank's share: masked on every rank before the split, one collective of one shape
+    from vegasafterglow_b200.engine import Engine
+    Q = P.copy(); Q["theta_c"][5] = -1.0
+    ok = Engine.valid_mask(Q)
+    chi2m = parallel.partitioned_chi2(None, Q, ts, nus, lnF, sig, w, evaluate=host_eval, valid=ok)
+    assert np.isinf(chi2m[5]) and np.array_equal(np.delete(chi2m, 5), np.delete(full, 5))
     lo, hi = parallel.partition(7, 2, dist.get_rank())
     assert (lo, hi) == ((0, 4) if dist.get_rank() == 0 else (4, 7))
     dist.destroy_process_group()

@@ -78,6 +78,15 @@ GRID_INFO_DTYPE = np.dtype(
     align=True,
 )
 
+
+
+class BandObs(C.Structure):
+    """``vag_band_obs`` (include/vag.h): one band-integrated data set of the likelihood."""
+
+    _fields_ = [("t", C.c_void_p), ("lnF_obs", C.c_void_p), ("sigma_ln", C.c_void_p), ("w", C.c_void_p), ("n", C.c_size_t),
+                ("nu_min", C.c_double), ("nu_max", C.c_double), ("num_nu", C.c_size_t)]
+
+
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
 

@@ -311,7 +311,7 @@ __global__ void k_band_reduce(const double* __restrict__ F, const double* __rest
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(128, EATS_MIN_BLOCKS) k_eats(BatchWs w, EatsRequest rq0, double* __restrict__ out, int n_split,
-                                                 int row_chunk, int max_n_t, int nu_tile) {
+                                                 int row_chunk, int max_n_t, int nu_tile, size_t split_stride) {
     extern __shared__ __align__(16) double smem[];
     const int mi = blockIdx.x;
     const int split = blockIdx.y;
@@ -340,7 +340,9 @@ __global__ void __launch_bounds__(128, EATS_MIN_BLOCKS) k_eats(BatchWs w, EatsRe
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int comp = which == 0 ? VAG_C_FWD_SYNC : which == 1 ? VAG_C_RVS_SYNC : which == 2 ? VAG_C_FWD_SSC : VAG_C_RVS_SSC;
     const size_t comp_sz = series ? (size_t)rq.n_t_obs : (size_t)rq.n_nu * rq.n_t_obs;
-    double* dst = out + ((size_t)mi * VAG_NCOMP + comp) * comp_sz;
+    // row-split batches (n_split > 1, small batches): each split owns a slab of `out` (= the partial buffer) and
+    // k_sum_splits adds the slabs in split order -- deterministic, unlike an atomicAdd into one cell
+    double* dst = out + (size_t)split * split_stride + ((size_t)mi * VAG_NCOMP + comp) * comp_sz;
     const int n_nu_tiles = series ? 1 : (rq.n_nu + nu_tile - 1) / nu_tile;
     const RowGeom* rowg = w.rowgeom + (size_t)mi * w.max_erows;
     // rows per pass: this model's lattice may be shorter than the batch maximum the buffers are sized for
@@ -368,15 +370,21 @@ __global__ void __launch_bounds__(128, EATS_MIN_BLOCKS) k_eats(BatchWs w, EatsRe
                 for (int l = 0; l < nl; ++l) {
                     const double v = flux_scale(M, acc[l * acc_stride + ii]);
                     double* p = series ? (dst + i0 + ii) : (dst + (size_t)(l0 + l) * rq.n_t_obs + i0 + ii);
-                    if (n_split == 1)
-                        *p = v;
-                    else
-                        atomicAdd(p, v);
+                    *p = v;
                 }
             }
             __syncthreads();
         }
     }
+}
+
+// out[e] = sum over the row splits, in split order
+__global__ void k_sum_splits(double* __restrict__ out, const double* __restrict__ part, int n_split, size_t elems) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= elems) return;
+    double s = 0;
+    for (int q = 0; q < n_split; ++q) s += part[(size_t)q * elems + e];
+    out[e] = s;
 }
 
 // total = sum of the present components (PyFlux::calc_total, pybind/pymodel.cpp:350-364)
@@ -390,8 +398,12 @@ __global__ void k_total(double* out, size_t n_models, size_t comp_sz) {
 }
 
 // K4: one warp per model; chi2 over the series total (fitter.py:497-501)
+// A model whose ODE exhausted Boost's 500 consecutive step rejections is an exception in the reference
+// (max_step_checker.hpp:99-106) that the samplers turn into logL = -inf (samplers.py:63-70): chi2 = +inf here.
+// accumulate: add to chi2[] (band terms after the point term, fitter.py:525-531).
 __global__ void k_chi2(const double* __restrict__ flux, size_t n_models, int n, const double* __restrict__ lnF,
-                       const double* __restrict__ sigma_ln, const double* __restrict__ wgt, double* chi2) {
+                       const double* __restrict__ sigma_ln, const double* __restrict__ wgt, double* chi2,
+                       const int* __restrict__ status, int accumulate) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= (int)n_models) return;
@@ -400,7 +412,16 @@ __global__ void k_chi2(const double* __restrict__ flux, size_t n_models, int n, 
     for (int i = lane; i < n; i += 32) s += chi2_term(lnF[i], F[i], sigma_ln[i], wgt[i]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) chi2[warp] = isfinite(s) ? s : kInf;
+    if (lane == 0) {
+        if (accumulate) s += chi2[warp];
+        const bool fatal = status && (status[warp] & VAG_ST_ODE_FAIL500);
+        chi2[warp] = (isfinite(s) && !fatal) ? s : kInf;
+    }
+}
+
+__global__ void k_or_status(int32_t* acc, const int32_t* __restrict__ st, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) acc[i] |= st[i];
 }
 
 __global__ void k_nan_capacity(BatchWs w, double* out, size_t comp_sz_total) {
@@ -486,10 +507,12 @@ struct DevBuf {
 struct vag_context {
     int device = 0;
     cudaStream_t stream = nullptr;
-    DevBuf model_buf, row_buf, cell_buf, obs_buf, io_params, io_t, io_nu, io_out, io_status, io_aux, ic_buf, lut_buf, sp_buf, geom_buf;
+    DevBuf model_buf, row_buf, cell_buf, obs_buf, io_params, io_t, io_nu, io_out, io_status, io_aux, ic_buf, lut_buf, sp_buf, geom_buf, io_w, io_obs, io_chi2, split_buf;
     int* h_totals = nullptr;        // pinned
     long long* h_cells = nullptr;   // pinned
-    int cap_theta = 384, cap_phi = 128;
+    int cap_theta = 384, cap_phi = 128;            // capacities of the batch in flight (host calls derive them per batch)
+    int dbg_max_ode_steps = 0, dbg_max_ode_fails = 0;
+    int user_cap_theta = 384, user_cap_phi = 128;  // vag_set_capacity: what the *_dev entry points run with
     bool profiling = false;
     int out_mode = VAG_OUT_DENSE;
     cudaEvent_t ev[8] = {};
@@ -528,6 +551,11 @@ void caps_for(const vag_params* p, size_t n, int& cap_theta, int& cap_phi) {
     }
 }
 
+constexpr size_t EATS_SMEM_BUDGET = 200 * 1024;  // dynamic shared memory k_eats may ask for
+// models per pipeline pass: k_rowgeom / k_rowcos / k_dop_extrema index the model with gridDim.y (<= 65535), and the
+// per-model workspaces of a pass stay below a few GB; larger batches are processed in consecutive passes
+constexpr size_t MAX_MODELS_PER_PASS = 32768;
+
 struct Request {
     bool series;
     const double* d_t;
@@ -539,6 +567,8 @@ struct Request {
 int setup_models(vag_context* ctx, BatchWs& w, const vag_params* d_params, size_t n) {
     w = BatchWs{};
     w.n_models = (int)n;
+    w.dbg_max_ode_steps = ctx->dbg_max_ode_steps;
+    w.dbg_max_ode_fails = ctx->dbg_max_ode_fails;
     w.cap_theta = ctx->cap_theta;
     w.cap_phi = ctx->cap_phi;
     w.work_per_model = grid_work_doubles(w.cap_theta, w.cap_phi);
@@ -691,11 +721,9 @@ int run_front(vag_context* ctx, BatchWs& w, const vag_params* d_params, size_t n
     return VAG_OK;
 }
 
-int run_flux(vag_context* ctx, const vag_params* d_params, size_t n, const Request& rq_in, double* d_out,
-             int32_t* d_status, const double* d_lnF, const double* d_sig, const double* d_w, double* d_chi2,
-             cudaStream_t s) {
-    if (n == 0) return VAG_OK;
-    ctx->launches = 0;
+int run_flux_pass(vag_context* ctx, const vag_params* d_params, size_t n, const Request& rq_in, double* d_out,
+                  int32_t* d_status, const double* d_lnF, const double* d_sig, const double* d_w, double* d_chi2,
+                  cudaStream_t s) {
     const size_t n_t = rq_in.n_t, n_nu = rq_in.n_nu;
     // observation arrays
     CK(ctx->obs_buf.ensure(sizeof(double) * (2 * n_t + n_nu + 8)));
@@ -731,7 +759,7 @@ int run_flux(vag_context* ctx, const vag_params* d_params, size_t n, const Reque
     const int max_erows = std::max(totals[TOT_MAX_EROWS], 1);
     if (totals[TOT_ROWS] > 0) {
         // shared-memory budget -> rows staged per pass
-        const size_t budget = 200 * 1024;
+        const size_t budget = EATS_SMEM_BUDGET;
         int row_chunk = EATS_ROW_CHUNK;
         const int nu_tile = rq_in.series ? 1 : (int)std::min<size_t>(EATS_NU_TILE, n_nu);
         auto smem_bytes = [&](int rc_) {
@@ -750,10 +778,7 @@ int run_flux(vag_context* ctx, const vag_params* d_params, size_t n, const Reque
         const size_t target_ctas = (size_t)ctx->sm_count * 2;
         if (n * 2 < target_ctas) n_split = (int)std::min<size_t>(chunks, (target_ctas + n * 2 - 1) / (n * 2));
         n_split = std::max(n_split, 1);
-        const size_t sb = smem_bytes(row_chunk);
-        CK(cudaFuncSetAttribute(k_eats<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
-        CK(cudaFuncSetAttribute(k_eats<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
-        CK(cudaFuncSetAttribute(k_eats<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
+        const size_t sb = smem_bytes(row_chunk);  // <= EATS_SMEM_BUDGET, the opt-in limit set once in vag_create
         EatsRequest rq{};
         rq.series = rq_in.series ? 1 : 0;
         rq.n_t_obs = (int)n_t;
@@ -763,12 +788,23 @@ int run_flux(vag_context* ctx, const vag_params* d_params, size_t n, const Reque
         rq.t_obs_lin = t_lin;
         rq.acc_stride = eats_acc_stride((int)n_t);
         const dim3 eg((unsigned)n, (unsigned)n_split, 2);
-        k_eats<0><<<eg, 128, sb, s>>>(w, rq, d_out, n_split, row_chunk, max_n_t, nu_tile);
+        const size_t elems = n * VAG_NCOMP * comp_sz;
+        double* eats_out = d_out;
+        if (n_split > 1) {
+            CK(ctx->split_buf.ensure(sizeof(double) * elems * n_split));
+            eats_out = static_cast<double*>(ctx->split_buf.p);
+            CK(cudaMemsetAsync(eats_out, 0, sizeof(double) * elems * n_split, s));
+        }
+        k_eats<0><<<eg, 128, sb, s>>>(w, rq, eats_out, n_split, row_chunk, max_n_t, nu_tile, elems);
         ctx->launches++;
         if (w.any_ssc) {
-            k_eats<1><<<eg, 128, sb, s>>>(w, rq, d_out, n_split, row_chunk, max_n_t, nu_tile);
-            k_eats<2><<<eg, 128, sb, s>>>(w, rq, d_out, n_split, row_chunk, max_n_t, nu_tile);
+            k_eats<1><<<eg, 128, sb, s>>>(w, rq, eats_out, n_split, row_chunk, max_n_t, nu_tile, elems);
+            k_eats<2><<<eg, 128, sb, s>>>(w, rq, eats_out, n_split, row_chunk, max_n_t, nu_tile, elems);
             ctx->launches += 2;
+        }
+        if (n_split > 1) {
+            k_sum_splits<<<(unsigned)((elems + 255) / 256), 256, 0, s>>>(d_out, eats_out, n_split, elems);
+            ctx->launches++;
         }
     }
     mark(ctx, 4, s);
@@ -776,13 +812,15 @@ int run_flux(vag_context* ctx, const vag_params* d_params, size_t n, const Reque
         const size_t tot = n * comp_sz;
         k_total<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_out, n, comp_sz);
         ctx->launches++;
-        if (totals[TOT_STATUS_OR] & VAG_ST_CAPACITY) {
+        // the SSC lattices can overflow later than the grid (k_ic_spectrum sets the bit after k_scan read the OR):
+        // with ssc shocks in the batch the kernel runs unconditionally and tests each model's bit on the device
+        if ((totals[TOT_STATUS_OR] & VAG_ST_CAPACITY) || w.any_ssc) {
             k_nan_capacity<<<(unsigned)n, 128, 0, s>>>(w, d_out, VAG_NCOMP * comp_sz);
             ctx->launches++;
         }
     }
     if (d_chi2) {
-        k_chi2<<<(unsigned)((n * 32 + 127) / 128), 128, 0, s>>>(d_out, n, (int)n_t, d_lnF, d_sig, d_w, d_chi2);
+        k_chi2<<<(unsigned)((n * 32 + 127) / 128), 128, 0, s>>>(d_out, n, (int)n_t, d_lnF, d_sig, d_w, d_chi2, w.status, 0);
         ctx->launches++;
     }
     mark(ctx, 5, s);
@@ -791,6 +829,19 @@ int run_flux(vag_context* ctx, const vag_params* d_params, size_t n, const Reque
     if (ctx->profiling) {
         CK(cudaStreamSynchronize(s));
         for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
+    }
+    return VAG_OK;
+}
+
+int run_flux(vag_context* ctx, const vag_params* d_params, size_t n, const Request& rq, double* d_out, int32_t* d_status,
+             const double* d_lnF, const double* d_sig, const double* d_w, double* d_chi2, cudaStream_t s) {
+    ctx->launches = 0;
+    const size_t comp_sz = rq.series ? rq.n_t : rq.n_nu * rq.n_t;
+    for (size_t lo = 0; lo < n; lo += MAX_MODELS_PER_PASS) {
+        const size_t m = std::min(MAX_MODELS_PER_PASS, n - lo);
+        if (int rc = run_flux_pass(ctx, d_params + lo, m, rq, d_out + lo * VAG_NCOMP * comp_sz, d_status ? d_status + lo : nullptr,
+                                   d_lnF, d_sig, d_w, d_chi2 ? d_chi2 + lo : nullptr, s))
+            return rc;
     }
     return VAG_OK;
 }
@@ -927,6 +978,11 @@ int vag_create(int device, vag_context** out) {
     cudaFuncSetCacheConfig(k_grid<16>, cudaFuncCachePreferL1);
     cudaFuncSetCacheConfig(k_grid<32>, cudaFuncCachePreferL1);
     cudaFuncSetAttribute(k_dynamics<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    // per-function process state: set once, to the largest request run_flux can make (not per call, where two contexts
+    // with different request shapes would race on it)
+    CK(cudaFuncSetAttribute(k_eats<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EATS_SMEM_BUDGET));
+    CK(cudaFuncSetAttribute(k_eats<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EATS_SMEM_BUDGET));
+    CK(cudaFuncSetAttribute(k_eats<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EATS_SMEM_BUDGET));
     *out = c;
     return VAG_OK;
 }
@@ -936,7 +992,8 @@ void vag_destroy(vag_context* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->model_buf, &c->row_buf, &c->cell_buf, &c->obs_buf, &c->io_params, &c->io_t, &c->io_nu,
-                      &c->io_out, &c->io_status, &c->io_aux, &c->ic_buf, &c->lut_buf, &c->sp_buf, &c->geom_buf})
+                      &c->io_out, &c->io_status, &c->io_aux, &c->ic_buf, &c->lut_buf, &c->sp_buf, &c->geom_buf, &c->io_w, &c->io_obs,
+                      &c->io_chi2, &c->split_buf})
         b->release();
     if (c->h_totals) cudaFreeHost(c->h_totals);
     if (c->h_cells) cudaFreeHost(c->h_cells);
@@ -967,8 +1024,15 @@ int vag_set_output_mode(vag_context* ctx, int mode) {
 }
 int vag_set_capacity(vag_context* ctx, int cap_theta, int cap_phi) {
     if (cap_theta < 40 || cap_phi < 2) return fail(VAG_ERR_INVALID, "capacity too small");
-    ctx->cap_theta = cap_theta;
-    ctx->cap_phi = cap_phi;
+    ctx->cap_theta = ctx->user_cap_theta = cap_theta;
+    ctx->cap_phi = ctx->user_cap_phi = cap_phi;
+    return VAG_OK;
+}
+
+int vag_debug_set_ode_limits(vag_context* ctx, int max_steps, int max_fails) {
+    if (!ctx) return fail(VAG_ERR_INVALID, "ctx is NULL");
+    ctx->dbg_max_ode_steps = max_steps > 0 ? max_steps : 0;
+    ctx->dbg_max_ode_fails = max_fails > 0 ? max_fails : 0;
     return VAG_OK;
 }
 
@@ -1021,6 +1085,8 @@ int vag_flux_density_grid_dev(vag_context* ctx, const vag_params* d_params, size
     if (!ctx) return fail(VAG_ERR_INVALID, "ctx is NULL");
     if (n_t == 0) return fail(VAG_ERR_INVALID, "time array must be non-empty");
     if (n_nu == 0) return fail(VAG_ERR_INVALID, "frequency array must be non-empty");
+    ctx->cap_theta = ctx->user_cap_theta;  // host-buffer calls in between may have run with tighter per-batch capacities
+    ctx->cap_phi = ctx->user_cap_phi;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     Request rq{false, d_t, d_nu, n_t, n_nu};
@@ -1031,6 +1097,8 @@ int vag_flux_density_series_dev(vag_context* ctx, const vag_params* d_params, si
                                 const double* d_nu, size_t n, double* d_out, int32_t* d_status, void* stream) {
     if (!ctx) return fail(VAG_ERR_INVALID, "ctx is NULL");
     if (n == 0) return fail(VAG_ERR_INVALID, "time array must be non-empty");
+    ctx->cap_theta = ctx->user_cap_theta;  // host-buffer calls in between may have run with tighter per-batch capacities
+    ctx->cap_phi = ctx->user_cap_phi;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     Request rq{true, d_t, d_nu, n, n};
@@ -1042,6 +1110,8 @@ int vag_chi2_series_dev(vag_context* ctx, const vag_params* d_params, size_t n_m
                         size_t n, double* d_chi2, int32_t* d_status, void* stream) {
     if (!ctx) return fail(VAG_ERR_INVALID, "ctx is NULL");
     if (n == 0) return fail(VAG_ERR_INVALID, "time array must be non-empty");
+    ctx->cap_theta = ctx->user_cap_theta;  // host-buffer calls in between may have run with tighter per-batch capacities
+    ctx->cap_phi = ctx->user_cap_phi;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     CK(ctx->io_out.ensure(sizeof(double) * n_models * VAG_NCOMP * n));
@@ -1062,6 +1132,11 @@ static int host_prepare(vag_context* ctx, const vag_params* params, size_t n_mod
                     "time and frequency arrays must have the same size\nIf you intend to get grid-like output, use "
                     "the generic `flux_density_grid` instead");
     if (!check_ascending(t, n_t)) return fail(VAG_ERR_INVALID, "time array must be in ascending order");
+    // log10(t_end / t_start) sizes the time lattice: a zero, negative or non-finite epoch / frequency has no meaning
+    for (size_t i = 0; i < n_t; ++i)
+        if (!finite_pos(t[i])) return fail(VAG_ERR_INVALID, "observation times must be finite and > 0");
+    for (size_t i = 0; i < n_nu; ++i)
+        if (!finite_pos(nu[i])) return fail(VAG_ERR_INVALID, "observation frequencies must be finite and > 0");
     for (size_t i = 0; i < n_models; ++i)
         if (int rc = vag_params_validate(&params[i])) return rc;
     CK(cudaSetDevice(ctx->device));
@@ -1148,68 +1223,173 @@ int vag_flux_density_series(vag_context* ctx, const vag_params* params, size_t n
     return VAG_OK;
 }
 
-// Replaces PyModel::flux (pybind/pymodel.cpp:391-410): band-integrated flux over [nu_min, nu_max]
-int vag_flux_band(vag_context* ctx, const vag_params* params, size_t n_models, const double* t, size_t n_t,
-                  double nu_min, double nu_max, size_t num_nu, double* out, int32_t* status) {
-    if (!(nu_min > 0)) return fail(VAG_ERR_INVALID, "nu_min must be positive");
-    if (!(nu_max > nu_min)) return fail(VAG_ERR_INVALID, "nu_max must be greater than nu_min");
+// Frequency grid (code units) and quadrature weights of PyModel::flux (pybind/pymodel.cpp:391-410): xt::logspace of the
+// unit-scaled bounds, Boole's rule in ln(nu) with 3/8 / Simpson / trapezoid remainders (src/core/quadrature.h:138-191),
+// times the Jacobian nu and the code-unit -> Hz factor, so that sum_i F_nu[cgs](nu_i) w_i is erg cm^-2 s^-1.
+static int band_grid(double nu_min, double nu_max, size_t num_nu, std::vector<double>& nu, std::vector<double>& wgt) {
+    if (!(nu_min > 0) || !std::isfinite(nu_min)) return fail(VAG_ERR_INVALID, "nu_min must be positive");
+    if (!(nu_max > nu_min) || !std::isfinite(nu_max)) return fail(VAG_ERR_INVALID, "nu_max must be greater than nu_min");
     if (num_nu < 2) return fail(VAG_ERR_INVALID, "num_nu must be at least 2");
-    // frequency grid in code units exactly as the reference builds it (xt::logspace of the
-    // unit-scaled bounds) and its Boole weights (src/core/quadrature.h:138-191)
-    std::vector<double> nu(num_nu), wgt(num_nu, 0.0);
-    {
-        const double a = std::log10(nu_min * unit::Hz), b = std::log10(nu_max * unit::Hz);
-        for (size_t i = 0; i < num_nu; ++i) nu[i] = std::pow(10.0, linspace_at(a, b, (int)num_nu, (int)i));
-        const double h = std::log(nu[1] / nu[0]);
-        const double cb = 2.0 * h / 45.0;
-        size_t j = 0;
-        for (; j + 4 < num_nu; j += 4) {
-            wgt[j] += cb * 7;
-            wgt[j + 1] += cb * 32;
-            wgt[j + 2] += cb * 12;
-            wgt[j + 3] += cb * 32;
-            wgt[j + 4] += cb * 7;
-        }
-        const size_t remaining = num_nu - 1 - j;
-        if (remaining == 3) {
-            const double c38 = 3.0 * h / 8.0;
-            wgt[j] += c38;
-            wgt[j + 1] += c38 * 3;
-            wgt[j + 2] += c38 * 3;
-            wgt[j + 3] += c38;
-        } else if (remaining == 2) {
-            const double c13 = h / 3.0;
-            wgt[j] += c13;
-            wgt[j + 1] += c13 * 4;
-            wgt[j + 2] += c13;
-        } else if (remaining == 1) {
-            wgt[j] += 0.5 * h;
-            wgt[j + 1] += 0.5 * h;
-        }
-        // Jacobian, and code-unit frequency -> Hz so that sum(F_nu[cgs] * w) is erg cm^-2 s^-1
-        // (the reference divides the code-unit sum by unit::flux_cgs, pymodel.cpp:404)
-        for (size_t i = 0; i < num_nu; ++i) wgt[i] = wgt[i] * nu[i] / unit::Hz;
+    nu.assign(num_nu, 0.0);
+    wgt.assign(num_nu, 0.0);
+    const double a = std::log10(nu_min * unit::Hz), b = std::log10(nu_max * unit::Hz);
+    const double step = (b - a) / std::fmax(1.0, (double)(num_nu - 1));
+    for (size_t i = 0; i < num_nu; ++i) nu[i] = std::pow(10.0, (i == num_nu - 1) ? b : a + step * (double)i);
+    const double h = std::log(nu[1] / nu[0]);
+    const double cb = 2.0 * h / 45.0;
+    size_t j = 0;
+    for (; j + 4 < num_nu; j += 4) {
+        wgt[j] += cb * 7;
+        wgt[j + 1] += cb * 32;
+        wgt[j + 2] += cb * 12;
+        wgt[j + 3] += cb * 32;
+        wgt[j + 4] += cb * 7;
     }
-    if (int rc = host_prepare(ctx, params, n_models, t, n_t, nu.data(), num_nu, false)) return rc;
-    if (n_models == 0) return VAG_OK;
-    cudaStream_t s = ctx->stream;
+    const size_t remaining = num_nu - 1 - j;
+    if (remaining == 3) {
+        const double c38 = 3.0 * h / 8.0;
+        wgt[j] += c38;
+        wgt[j + 1] += c38 * 3;
+        wgt[j + 2] += c38 * 3;
+        wgt[j + 3] += c38;
+    } else if (remaining == 2) {
+        const double c13 = h / 3.0;
+        wgt[j] += c13;
+        wgt[j + 1] += c13 * 4;
+        wgt[j + 2] += c13;
+    } else if (remaining == 1) {
+        wgt[j] += 0.5 * h;
+        wgt[j + 1] += 0.5 * h;
+    }
+    for (size_t i = 0; i < num_nu; ++i) wgt[i] = wgt[i] * nu[i] / unit::Hz;
+    return VAG_OK;
+}
+
+// Band-integrated flux of a batch whose parameters are already on the device: grid evaluation on the band's
+// frequency nodes, then the weighted sum over frequency.  *d_band -> [n_models][VAG_NCOMP][n_t] inside io_out.
+static int run_band(vag_context* ctx, size_t n_models, const double* t, size_t n_t, double nu_min, double nu_max,
+                    size_t num_nu, double** d_band, cudaStream_t s) {
+    std::vector<double> nu, wgt;
+    if (int rc = band_grid(nu_min, nu_max, num_nu, nu, wgt)) return rc;
+    if (!check_ascending(t, n_t)) return fail(VAG_ERR_INVALID, "time array must be in ascending order");
+    for (size_t i = 0; i < n_t; ++i)
+        if (!finite_pos(t[i])) return fail(VAG_ERR_INVALID, "observation times must be finite and > 0");
+    CK(ctx->io_t.ensure(sizeof(double) * n_t));
+    CK(ctx->io_nu.ensure(sizeof(double) * num_nu));
+    CK(ctx->io_w.ensure(sizeof(double) * num_nu));
     const size_t grid_elems = n_models * VAG_NCOMP * num_nu * n_t;
     CK(ctx->io_out.ensure(sizeof(double) * (grid_elems + n_models * VAG_NCOMP * n_t)));
-    CK(ctx->io_aux.ensure(sizeof(double) * num_nu));
+    // (the previous pass over these staging buffers has completed on this stream; pageable copies are staged by the runtime)
+    CK(cudaMemcpyAsync(ctx->io_t.p, t, sizeof(double) * n_t, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->io_nu.p, nu.data(), sizeof(double) * num_nu, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->io_w.p, wgt.data(), sizeof(double) * num_nu, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));  // nu / wgt are locals
     double* d_grid = static_cast<double*>(ctx->io_out.p);
-    double* d_band = d_grid + grid_elems;
-    CK(cudaMemcpyAsync(ctx->io_aux.p, wgt.data(), sizeof(double) * num_nu, cudaMemcpyHostToDevice, s));
+    *d_band = d_grid + grid_elems;
     Request rq{false, static_cast<double*>(ctx->io_t.p), static_cast<double*>(ctx->io_nu.p), n_t, num_nu, true};
     if (int rc = run_flux(ctx, static_cast<vag_params*>(ctx->io_params.p), n_models, rq, d_grid,
                           static_cast<int32_t*>(ctx->io_status.p), nullptr, nullptr, nullptr, nullptr, s))
         return rc;
     const size_t n_mc = n_models * VAG_NCOMP;
-    k_band_reduce<<<(unsigned)((n_mc * n_t + 255) / 256), 256, 0, s>>>(d_grid, static_cast<double*>(ctx->io_aux.p), d_band,
+    k_band_reduce<<<(unsigned)((n_mc * n_t + 255) / 256), 256, 0, s>>>(d_grid, static_cast<double*>(ctx->io_w.p), *d_band,
                                                                      n_mc, (int)num_nu, (int)n_t);
     ctx->launches++;
-    CK(cudaMemcpyAsync(out, d_band, sizeof(double) * n_mc * n_t, cudaMemcpyDeviceToHost, s));
+    CK(cudaGetLastError());
+    return VAG_OK;
+}
+
+// Replaces PyModel::flux (pybind/pymodel.cpp:391-410): band-integrated flux over [nu_min, nu_max]
+int vag_flux_band(vag_context* ctx, const vag_params* params, size_t n_models, const double* t, size_t n_t,
+                  double nu_min, double nu_max, size_t num_nu, double* out, int32_t* status) {
+    std::vector<double> nu, wgt;
+    if (int rc = band_grid(nu_min, nu_max, num_nu, nu, wgt)) return rc;
+    if (int rc = host_prepare(ctx, params, n_models, t, n_t, nu.data(), num_nu, false)) return rc;
+    if (n_models == 0) return VAG_OK;
+    cudaStream_t s = ctx->stream;
+    double* d_band = nullptr;
+    if (int rc = run_band(ctx, n_models, t, n_t, nu_min, nu_max, num_nu, &d_band, s)) return rc;
+    CK(cudaMemcpyAsync(out, d_band, sizeof(double) * n_models * VAG_NCOMP * n_t, cudaMemcpyDeviceToHost, s));
     if (status) CK(cudaMemcpyAsync(status, ctx->io_status.p, sizeof(int32_t) * n_models, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    return VAG_OK;
+}
+
+// Replaces Fitter._evaluate (VegasAfterglow/fitting/fitter.py:503-533) for a batch of parameter sets: the chi-squared of the
+// point data (flux_density series) plus one term per band-integrated data set (Model.flux), all in ln-flux space.
+int vag_chi2(vag_context* ctx, const vag_params* params, size_t n_models, const double* t, const double* nu,
+             const double* lnF_obs, const double* sigma_ln, const double* w, size_t n_points, const vag_band_obs* bands,
+             size_t n_bands, double* chi2, int32_t* status) {
+    if (!ctx || !chi2) return fail(VAG_ERR_INVALID, "NULL argument");
+    if (n_points && (!t || !nu || !lnF_obs || !sigma_ln || !w)) return fail(VAG_ERR_INVALID, "point data arrays must not be NULL");
+    if (n_bands && !bands) return fail(VAG_ERR_INVALID, "bands is NULL");
+    if (n_points == 0 && n_bands == 0) return fail(VAG_ERR_INVALID, "no data: n_points and n_bands are both 0");
+    for (size_t b = 0; b < n_bands; ++b) {
+        const vag_band_obs& B = bands[b];
+        if (B.n == 0 || !B.t || !B.lnF_obs || !B.sigma_ln || !B.w) return fail(VAG_ERR_INVALID, "band data arrays must be non-empty");
+        std::vector<double> gnu, gw;
+        if (int rc = band_grid(B.nu_min, B.nu_max, B.num_nu, gnu, gw)) return rc;
+    }
+    // validation + upload of the parameters (and of the point request when there is one)
+    const double one = 1.0;
+    if (int rc = n_points ? host_prepare(ctx, params, n_models, t, n_points, nu, n_points, true)
+                          : host_prepare(ctx, params, n_models, bands[0].t, bands[0].n, &one, 1, false))
+        return rc;
+    if (n_models == 0) return VAG_OK;
+    cudaStream_t s = ctx->stream;
+    size_t max_obs = n_points;
+    for (size_t b = 0; b < n_bands; ++b) max_obs = std::max(max_obs, bands[b].n);
+    CK(ctx->io_obs.ensure(sizeof(double) * 3 * max_obs));
+    CK(ctx->io_chi2.ensure(sizeof(double) * n_models + sizeof(int32_t) * n_models));
+    double* d_lnF = static_cast<double*>(ctx->io_obs.p);
+    double* d_sig = d_lnF + max_obs;
+    double* d_w = d_sig + max_obs;
+    double* d_chi2 = static_cast<double*>(ctx->io_chi2.p);
+    int32_t* d_stat_or = reinterpret_cast<int32_t*>(d_chi2 + n_models);
+    CK(cudaMemsetAsync(d_chi2, 0, sizeof(double) * n_models, s));
+    CK(cudaMemsetAsync(d_stat_or, 0, sizeof(int32_t) * n_models, s));
+    int launches = 0;
+    auto upload = [&](const double* a, const double* b_, const double* c, size_t n) -> int {
+        CK(cudaMemcpyAsync(d_lnF, a, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d_sig, b_, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d_w, c, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+        return VAG_OK;
+    };
+    const unsigned cg = (unsigned)((n_models * 32 + 127) / 128);
+    if (n_points) {
+        if (int rc = upload(lnF_obs, sigma_ln, w, n_points)) return rc;
+        CK(ctx->io_out.ensure(sizeof(double) * n_models * VAG_NCOMP * n_points));
+        Request rq{true, static_cast<double*>(ctx->io_t.p), static_cast<double*>(ctx->io_nu.p), n_points, n_points};
+        if (int rc = run_flux(ctx, static_cast<vag_params*>(ctx->io_params.p), n_models, rq, static_cast<double*>(ctx->io_out.p),
+                              static_cast<int32_t*>(ctx->io_status.p), nullptr, nullptr, nullptr, nullptr, s))
+            return rc;
+        k_chi2<<<cg, 128, 0, s>>>(static_cast<double*>(ctx->io_out.p), n_models, (int)n_points, d_lnF, d_sig, d_w, d_chi2,
+                                  static_cast<int32_t*>(ctx->io_status.p), 1);
+        k_or_status<<<(unsigned)((n_models + 255) / 256), 256, 0, s>>>(d_stat_or, static_cast<int32_t*>(ctx->io_status.p), n_models);
+        launches += ctx->launches + 2;
+    }
+    for (size_t b = 0; b < n_bands; ++b) {
+        const vag_band_obs& B = bands[b];
+        double* d_band = nullptr;
+        if (int rc = run_band(ctx, n_models, B.t, B.n, B.nu_min, B.nu_max, B.num_nu, &d_band, s)) return rc;
+        if (int rc = upload(B.lnF_obs, B.sigma_ln, B.w, B.n)) return rc;
+        k_chi2<<<cg, 128, 0, s>>>(d_band, n_models, (int)B.n, d_lnF, d_sig, d_w, d_chi2, static_cast<int32_t*>(ctx->io_status.p), 1);
+        k_or_status<<<(unsigned)((n_models + 255) / 256), 256, 0, s>>>(d_stat_or, static_cast<int32_t*>(ctx->io_status.p), n_models);
+        launches += ctx->launches + 2;
+        CK(cudaStreamSynchronize(s));  // the observation staging buffers are reused by the next band
+    }
+    ctx->launches = launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(chi2, d_chi2, sizeof(double) * n_models, cudaMemcpyDeviceToHost, s));
+    if (status) CK(cudaMemcpyAsync(status, d_stat_or, sizeof(int32_t) * n_models, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return VAG_OK;
+}
+
+// per-parameter-set validation of a batch: ok[i] = 1 where vag_params_validate accepts params[i] (a sampler masks the
+// rejected walkers to logL = -inf the way the reference maps the constructor's exception, samplers.py:63-70)
+int vag_params_validate_batch(const vag_params* params, size_t n, int32_t* ok) {
+    if ((!params || !ok) && n) return fail(VAG_ERR_INVALID, "NULL argument");
+    for (size_t i = 0; i < n; ++i) ok[i] = vag_params_validate(&params[i]) == VAG_OK ? 1 : 0;
     return VAG_OK;
 }
 

@@ -45,6 +45,7 @@ struct ModelCfg {
     int has_rvs;
     // numerics
     double phi_resol, theta_resol, t_resol, rtol;
+    int max_ode_steps, max_ode_fails;  // defaults::solver::max_ode_steps, Boost's 500 (vag_debug_set_ode_limits lowers them in tests)
 };
 
 VAG_HD RadCfg make_rad(const vag_radiation& r, int radiative) {
@@ -119,6 +120,8 @@ VAG_HD ModelCfg make_cfg(const vag_params& p) {
     m.theta_resol = p.theta_resol > 0 ? p.theta_resol : (r ? dflt::rvs_theta_resolution : dflt::theta_resolution);
     m.t_resol = p.t_resol > 0 ? p.t_resol : (r ? dflt::rvs_time_resolution : dflt::time_resolution);
     m.rtol = p.rtol > 0 ? p.rtol : dflt::dynamics_rtol;
+    m.max_ode_steps = dflt::max_ode_steps;
+    m.max_ode_fails = 500;
     return m;
 }
 

@@ -25,6 +25,7 @@ enum { TOT_ROWS = 0, TOT_MAX_NT, TOT_MAX_NTHETA, TOT_MAX_EROWS, TOT_STATUS_OR, T
 
 struct BatchWs {
     int n_models;
+    int dbg_max_ode_steps, dbg_max_ode_fails;  // > 0: override the ODE step / consecutive-rejection limits (tests)
     int cap_theta, cap_phi;
     size_t work_per_model;  // doubles
     const vag_params* params;
@@ -80,6 +81,8 @@ struct BatchWs {
 template <class Par>
 VAG_HD void k0_grid_body(const Par& par, const BatchWs& w, int mi, double t_obs_min, double t_obs_max) {
     ModelCfg cfg = make_cfg(w.params[mi]);
+    if (w.dbg_max_ode_steps > 0) cfg.max_ode_steps = w.dbg_max_ode_steps;
+    if (w.dbg_max_ode_fails > 0) cfg.max_ode_fails = w.dbg_max_ode_fails;
     w.cfg[mi] = cfg;
     GridSlab s;
     s.theta = w.theta + (size_t)mi * w.cap_theta;

@@ -390,14 +390,14 @@ VAG_HD int solve_fwd_row(const ModelCfg& m, double theta, double theta_s, double
     st.begin_step(eqn);
     while (st.t <= t_back) {
         if (!st.try_step(eqn)) {
-            if (++fails >= 500) {
+            if (++fails >= m.max_ode_fails) {
                 status |= VAG_ST_ODE_FAIL500;
                 break;
             }
             continue;
         }
         fails = 0;
-        if (++steps > dflt::max_ode_steps) {
+        if (++steps > m.max_ode_steps) {
             status |= VAG_ST_ODE_STEP_CAP;
             break;
         }
@@ -767,14 +767,14 @@ VAG_HD int solve_pair_row(const ModelCfg& m, double theta, double t_dec, const d
     st.begin(eqn);
     while (st.t <= t_back) {
         if (!st.try_step(eqn)) {
-            if (++fails >= 500) {
+            if (++fails >= m.max_ode_fails) {
                 status |= VAG_ST_ODE_FAIL500;
                 break;
             }
             continue;
         }
         fails = 0;
-        if (++steps > dflt::max_ode_steps) {
+        if (++steps > m.max_ode_steps) {
             status |= VAG_ST_ODE_STEP_CAP;
             break;
         }

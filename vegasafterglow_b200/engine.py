@@ -110,6 +110,43 @@ class Engine:
                                              chi2.ctypes.data, st.ctypes.data))
         return (chi2, st) if return_status else chi2
 
+    def chi2(self, params, points=None, bands=(), return_status=False):
+        """Batched ``Fitter._evaluate`` (fitter.py:503-533) -> chi2[n_models]: the point-data term (``points`` =
+        (t, nu, lnF_obs, sigma_ln, w), times ascending, or None) plus one term per band-integrated data set
+        (``bands``: dicts with t, lnF_obs, sigma_ln, w, nu_min, nu_max, num_nu -- ``Model.flux`` on each).
+        +inf where the sum is not finite or the model's ODE failed (include/vag.h vag_chi2)."""
+        p = self._params(params)
+        keep = []  # the arrays must outlive the call
+        if points is not None:
+            pt = [_f64(a).reshape(-1) for a in points]
+            if len(pt) != 5 or len({a.size for a in pt}) != 1:
+                raise ValueError("points must be (t, nu, lnF_obs, sigma_ln, w) of one size")
+            n_pt = pt[0].size
+        else:
+            pt, n_pt = [np.zeros(0)] * 5, 0
+        arr = (abi.BandObs * max(len(bands), 1))()
+        for i, b in enumerate(bands):
+            cols = [_f64(b[k]).reshape(-1) for k in ("t", "lnF_obs", "sigma_ln", "w")]
+            if len({a.size for a in cols}) != 1:
+                raise ValueError("band arrays t, lnF_obs, sigma_ln, w must have the same size")
+            keep.append(cols)
+            arr[i] = abi.BandObs(cols[0].ctypes.data, cols[1].ctypes.data, cols[2].ctypes.data, cols[3].ctypes.data,
+                                 cols[0].size, float(b["nu_min"]), float(b["nu_max"]), int(b["num_nu"]))
+        out = np.empty(p.size)
+        st = np.zeros(p.size, dtype=np.int32)
+        _lib.check(self._lib.vag_chi2(self._h, p.ctypes.data, p.size, *[a.ctypes.data if n_pt else None for a in pt], n_pt,
+                                      C.cast(arr, C.c_void_p) if len(bands) else None, len(bands), out.ctypes.data,
+                                      st.ctypes.data))
+        return (out, st) if return_status else out
+
+    @staticmethod
+    def valid_mask(params):
+        """bool[n]: which parameter sets pass the constructor checks of the reference (vag_params_validate_batch)."""
+        p = np.ascontiguousarray(params, dtype=abi.PARAMS_DTYPE).reshape(-1)
+        ok = np.zeros(p.size, dtype=np.int32)
+        _lib.check(_lib.load().vag_params_validate_batch(p.ctypes.data, p.size, ok.ctypes.data))
+        return ok.astype(bool)
+
     # ---- device buffers (raw pointers) ---------------------------------------------------------
     def flux_density_grid_dev(self, d_params, n_models, d_t, n_t, d_nu, n_nu, d_out, d_status=0, stream=0):
         _lib.check(self._lib.vag_flux_density_grid_dev(self._h, d_params, n_models, d_t, n_t, d_nu, n_nu, d_out,
@@ -133,6 +170,10 @@ class Engine:
         """True: host-buffer calls skip the planes of components no model of the batch has (vag.h VAG_OUT_PRESENT)."""
         _lib.check(self._lib.vag_set_output_mode(self._h, 1 if present_only else 0))
         self._present_only = bool(present_only)
+
+    def debug_set_ode_limits(self, max_steps=0, max_fails=0):
+        """Test hook (include/vag.h vag_debug_set_ode_limits): 0 restores the reference limits."""
+        _lib.check(self._lib.vag_debug_set_ode_limits(self._h, int(max_steps), int(max_fails)))
 
     def set_profiling(self, on=True):
         _lib.check(self._lib.vag_set_profiling(self._h, 1 if on else 0))

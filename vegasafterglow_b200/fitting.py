@@ -42,6 +42,18 @@ def consolidate_data(t, nu, flux, err, weights=None):
     return t, nu, np.log(flux), err / flux, w
 
 
+def band_obs(t, flux, err, nu_min, nu_max, num_points=5, weights=None):
+    """One band-integrated data set in the form ``Engine.chi2`` takes (fitter.py BandObs + :525-531: ln flux,
+    relative error, weights as given -- the reference normalises only the point-data weights)."""
+    t, flux, err = (np.asarray(a, dtype=np.float64).reshape(-1) for a in (t, flux, err))
+    w = np.ones_like(t) if weights is None else np.asarray(weights, dtype=np.float64).reshape(-1)
+    if np.any(flux <= 0) or np.any(err <= 0):
+        raise ValueError("the log-flux likelihood requires strictly positive fluxes and errors")
+    order = np.argsort(t, kind="stable")
+    return {"t": t[order], "lnF_obs": np.log(flux[order]), "sigma_ln": err[order] / flux[order], "w": w[order],
+            "nu_min": float(nu_min), "nu_max": float(nu_max), "num_nu": int(num_points)}
+
+
 class BatchedLikelihood:
     """``log_prob_batch(samples[n, ndim]) -> logp[n]`` on the GPU.
 
@@ -52,7 +64,7 @@ class BatchedLikelihood:
 
     def __init__(self, engine, template, names: Sequence[str], log_scale: Sequence[bool], t, nu, flux, err,
                  weights=None, lower=None, upper=None, log_prior: Optional[Callable] = None,
-                 log_likelihood_fn: Callable = lambda chi2: -0.5 * chi2, distributed: bool = False):
+                 log_likelihood_fn: Callable = lambda chi2: -0.5 * chi2, distributed: bool = False, bands=()):
         self.engine = engine
         self.template = np.ascontiguousarray(template, dtype=abi.PARAMS_DTYPE).reshape(-1)[:1].copy()
         self.names = list(names)
@@ -60,7 +72,14 @@ class BatchedLikelihood:
         for n in self.names:
             if n not in _FIELDS:
                 raise ValueError(f"unknown parameter '{n}' (supported: {sorted(_FIELDS)})")
-        self.t, self.nu, self.lnF, self.sig, self.w = consolidate_data(t, nu, flux, err, weights)
+        if len(np.atleast_1d(t)):
+            self.t, self.nu, self.lnF, self.sig, self.w = consolidate_data(t, nu, flux, err, weights)
+        else:
+            self.t = self.nu = self.lnF = self.sig = self.w = np.zeros(0)
+        # band-integrated data sets (Fitter.add_flux -> BandObs; fitter.py:525-531 evaluates Model.flux on each)
+        self.bands = [band_obs(**b) for b in bands]
+        if not self.t.size and not self.bands:
+            raise ValueError("no data")
         self.lower = None if lower is None else np.asarray(lower, dtype=np.float64)
         self.upper = None if upper is None else np.asarray(upper, dtype=np.float64)
         self.log_prior = log_prior
@@ -79,13 +98,30 @@ class BatchedLikelihood:
                 P[path[0]][path[1]] = col
         return P
 
+    def _evaluate(self, P: np.ndarray) -> np.ndarray:
+        if not self.bands:
+            return self.engine.chi2_series(P, self.t, self.nu, self.lnF, self.sig, self.w)
+        pts = (self.t, self.nu, self.lnF, self.sig, self.w) if self.t.size else None
+        return self.engine.chi2(P, pts, self.bands)
+
     def chi2(self, samples: np.ndarray) -> np.ndarray:
+        """chi2 of every sample; +inf for a sample the model constructor rejects (the reference maps that exception to
+        logL = -inf, samplers.py:63-70).  The validity mask is computed from the parameters alone, identically on every
+        rank, BEFORE the ensemble is split: a rejected walker can therefore never desynchronise the collective."""
+        from .engine import Engine
+
         P = self.to_params(samples)
+        ok = Engine.valid_mask(P)
         if self.distributed:
             from . import parallel
 
-            return parallel.partitioned_chi2(self.engine, P, self.t, self.nu, self.lnF, self.sig, self.w)
-        return self.engine.chi2_series(P, self.t, self.nu, self.lnF, self.sig, self.w)
+            tt = self.t if self.t.size else np.concatenate([b["t"] for b in self.bands])
+            return parallel.partitioned_chi2(self.engine, P, tt, self.nu, self.lnF, self.sig, self.w, evaluate=self._evaluate,
+                                             valid=ok)
+        out = np.full(P.size, np.inf)
+        if ok.any():
+            out[ok] = self._evaluate(P[ok])
+        return out
 
     def __call__(self, samples: np.ndarray) -> np.ndarray:
         samples = np.atleast_2d(np.asarray(samples, dtype=np.float64))
@@ -98,15 +134,7 @@ class BatchedLikelihood:
         logp = np.full(n, -np.inf)
         idx = np.nonzero(in_bounds)[0]
         if idx.size:
-            try:
-                chi2 = self.chi2(samples[idx])
-            except ValueError:
-                # a walker outside the model's validity range (the reference maps the exception
-                # of that walker to -inf, samplers.py:63-70): fall back to per-walker validation
-                chi2 = np.full(idx.size, np.inf)
-                ok = np.array([self._valid(samples[i:i + 1]) for i in idx])
-                if ok.any():
-                    chi2[ok] = self.chi2(samples[idx[ok]])
+            chi2 = self.chi2(samples[idx])
             ll = np.where(np.isfinite(chi2), self.log_likelihood_fn(chi2), -np.inf)
             ll[~np.isfinite(ll)] = -np.inf
             if self.log_prior is not None:
@@ -114,8 +142,3 @@ class BatchedLikelihood:
             logp[idx] = ll
         return logp
 
-    def _valid(self, sample):
-        from . import _lib
-
-        p = self.to_params(sample)
-        return _lib.load().vag_params_validate(p.ctypes.data) == abi.VAG_OK

@@ -501,6 +501,16 @@ PYBIND11_MODULE(VegasAfterglowC_b200, m) {
         .def_property_readonly("fwd_rad", [](const Model& mdl) { return mdl.fwd_; })
         .def_property_readonly("rvs_rad", [](const Model& mdl) { return mdl.rvs_; })
         .def_property_readonly("rtol", [](const Model& mdl) { return mdl.params().rtol; })
+        // PyModel::get_resolutions (pybind/pybind.cpp:453, pymodel.h:750): the values in effect, i.e. an omitted
+        // `resolutions` reads back as the defaults the constructor selected (pymodel.h:633-640)
+        .def_property_readonly("resolutions",
+                               [](const Model& mdl) {
+                                   const vag_params& p = mdl.params();
+                                   const bool r = p.has_rvs != 0;
+                                   return std::make_tuple(p.phi_resol > 0 ? p.phi_resol : 0.06,
+                                                          p.theta_resol > 0 ? p.theta_resol : (r ? 0.2 : 0.15),
+                                                          p.t_resol > 0 ? p.t_resol : (r ? 10.0 : 6.0));
+                               })
         .def_property_readonly("axisymmetric", [](const Model& mdl) { return mdl.params().axisymmetric != 0; })
         .def_property_readonly("radiative_fireball", [](const Model& mdl) { return mdl.params().radiative_fireball != 0; })
         .def_property_readonly("params_bytes",
