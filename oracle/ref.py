@@ -55,14 +55,26 @@ def lib():
     return _libs[_variant]
 
 
+_pymod = None
+
+
 def pymodule():
-    """The reference's own pybind11 module (Model, TophatJet, ...) built from its sources."""
+    """The reference's own pybind11 module (Model, TophatJet, ...) built from its sources.  Loaded once per process
+    (pybind11 registers its types globally): a copy imported as ``VegasAfterglow.VegasAfterglowC`` is reused."""
+    global _pymod
+    import sys
+
+    if _pymod is None:
+        _pymod = sys.modules.get("VegasAfterglow.VegasAfterglowC")
+    if _pymod is not None:
+        return _pymod
     cands = glob.glob(os.path.join(_REF_DIR, "VegasAfterglowC*.so"))
     if not cands:
         raise RuntimeError("oracle/_ref/VegasAfterglowC*.so missing: run `make -C oracle`")
     spec = importlib.util.spec_from_file_location("VegasAfterglowC", cands[0])
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
+    _pymod = mod
     return mod
 
 

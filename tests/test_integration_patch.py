@@ -104,8 +104,11 @@ def refpkg(tmp_path_factory):
     sys.path.insert(0, str(base))
     for k in [k for k in sys.modules if k == "VegasAfterglow" or k.startswith("VegasAfterglow.")]:
         del sys.modules[k]
+    if ref._pymod is not None:  # the pybind module may be loaded only once per process: reuse an earlier load
+        sys.modules["VegasAfterglow.VegasAfterglowC"] = ref._pymod
     import VegasAfterglow.fitting as fitting_mod
 
+    ref._pymod = sys.modules["VegasAfterglow.VegasAfterglowC"]
     yield fitting_mod
     sys.path.remove(str(base))
     for k, v in saved.items():
