@@ -243,14 +243,23 @@ int vag_details_photons(vag_context* ctx, const vag_params* p, double t_min, dou
  * untouched there.  This mirrors the reference's FluxDict, whose absent components are empty
  * arrays that are never materialised (pybind/pymodel.h:361-383), and saves 3/5 of the device-to-host
  * traffic of a forward-shock synchrotron batch.  VAG_C_TOTAL and VAG_C_FWD_SYNC are always present. */
-enum { VAG_OUT_DENSE = 0, VAG_OUT_PRESENT = 1 };
+enum { VAG_OUT_DENSE = 0, VAG_OUT_PRESENT = 1, VAG_OUT_PRESENT_ALIAS_TOTAL = 2 };
 int vag_set_output_mode(vag_context* ctx, int mode);
+/* VAG_OUT_PRESENT_ALIAS_TOTAL: as VAG_OUT_PRESENT, and when exactly ONE emission component exists in the whole batch
+ * (e.g. forward-shock synchrotron only) the `total` plane -- which is then that component bit for bit -- is not
+ * transferred either: vag_last_total_alias() returns the component index (VAG_C_*) whose plane holds the total of the
+ * most recent host-buffer call, or -1 when `total` was written.  (The pybind mirror hands the same array out twice.) */
+int vag_last_total_alias(vag_context* ctx);
 
 /* per-stage device time of the most recent batched call on this context, milliseconds:
  * [0]=grid (K0) [1]=dynamics (K1) [2]=radiation (K2) [3]=EATS flux (K3) [4]=likelihood (K4)
  * Only filled when vag_set_profiling(ctx, 1) was called (adds event records + one sync). */
 int vag_set_profiling(vag_context* ctx, int enable);
 int vag_last_stage_ms(vag_context* ctx, float ms[8]);
+/* Work counters of the most recent profiled pass (the denominators of bench.py's roofline entries): [0] forward-only ODE
+ * rows, [1] forward+reverse ODE rows, [2] shock-table cells x shocks, [3] EATS cells (shocks x n_phi_eff x n_theta x n_t),
+ * [4] EATS rows, [5] theta-quadrature attempts, [6] phi-quadrature attempts x n_theta, [7] sum of n_theta. */
+int vag_last_work(vag_context* ctx, double work[8]);
 /* number of kernel launches issued by the most recent batched call */
 int vag_last_launch_count(vag_context* ctx);
 /* dependent-free DFMA throughput of the device in TFLOP/s (FP64 roofline denominator) */

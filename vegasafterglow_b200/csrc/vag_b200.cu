@@ -419,6 +419,24 @@ __global__ void k_chi2(const double* __restrict__ flux, size_t n_models, int n, 
     }
 }
 
+// Work counters of a batch (profiling only): [0] forward-only ODE rows, [1] pair ODE rows, [2] shock-table cells x shocks,
+// [3] EATS cells = sum_models shocks n_phi_eff n_theta n_t, [4] EATS rows = sum shocks n_phi_eff n_theta,
+// [5] theta-quadrature attempts, [6] phi-quadrature attempts x n_theta, [7] sum n_theta
+__global__ void k_work(BatchWs w, double* out) {
+    const int mi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mi >= w.n_models) return;
+    const GridHeader& h = w.hdr[mi];
+    const ModelCfg& c = w.cfg[mi];
+    const double S = c.has_rvs ? 2.0 : 1.0;
+    atomicAdd(out + (c.has_rvs ? 1 : 0), (double)h.n_reps);
+    atomicAdd(out + 2, S * h.n_reps * (double)h.n_t);
+    atomicAdd(out + 3, S * h.n_phi_eff * (double)h.n_theta * h.n_t);
+    atomicAdd(out + 4, S * h.n_phi_eff * (double)h.n_theta);
+    atomicAdd(out + 5, (double)h.quad_attempts_theta);
+    atomicAdd(out + 6, (double)h.quad_attempts_phi * h.n_theta);
+    atomicAdd(out + 7, (double)h.n_theta);
+}
+
 __global__ void k_or_status(int32_t* acc, const int32_t* __restrict__ st, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) acc[i] |= st[i];
@@ -515,8 +533,11 @@ struct vag_context {
     int user_cap_theta = 384, user_cap_phi = 128;  // vag_set_capacity: what the *_dev entry points run with
     bool profiling = false;
     int out_mode = VAG_OUT_DENSE;
+    int total_alias = -1;  // VAG_OUT_PRESENT_ALIAS_TOTAL: component plane the last host call's `total` equals, or -1
     cudaEvent_t ev[8] = {};
     float stage_ms[8] = {};
+    double work[8] = {};   // k_work counters of the last profiled pass
+    DevBuf work_buf;
     int launches = 0;
     int sm_count = 148;
 };
@@ -772,11 +793,18 @@ int run_flux_pass(vag_context* ctx, const vag_params* d_params, size_t n, const 
         while (row_chunk > 1 && smem_bytes(row_chunk) > budget) --row_chunk;
         if (smem_bytes(row_chunk) > budget)
             return fail(VAG_ERR_CAPACITY, "time lattice too long for the EATS shared-memory stage");
-        // row-split so that small batches still fill the 148 SMs
+        // Row split: a (model, shock) whose rows do not fit one pass is cut into up to `chunks` CTAs, as many as it takes to
+        // put ~2 waves of CTAs (8 resident per SM) on the device.  Tophat-on-axis batches of thousands of models need
+        // none; a few hundred structured off-axis or SSC models (hundreds of rows each, BASELINE.json configs 2 and 4)
+        // would otherwise run as one long CTA per model on a mostly idle device.  The splits write disjoint slabs that
+        // k_sum_splits adds in a fixed order (deterministic).
         const int chunks = (max_erows + row_chunk - 1) / row_chunk;
-        int n_split = 1;
-        const size_t target_ctas = (size_t)ctx->sm_count * 2;
-        if (n * 2 < target_ctas) n_split = (int)std::min<size_t>(chunks, (target_ctas + n * 2 - 1) / (n * 2));
+        const int n_shock = totals[TOT_ANY_PAIR] ? 2 : 1;
+        const size_t target_ctas = (size_t)ctx->sm_count * EATS_MIN_BLOCKS * 2;
+        const size_t have = n * (size_t)n_shock;
+        int n_split = (have < target_ctas) ? (int)std::min<size_t>(chunks, (target_ctas + have - 1) / have) : 1;
+        const size_t slab_bytes = sizeof(double) * n * VAG_NCOMP * comp_sz;
+        while (n_split > 1 && slab_bytes * n_split > ((size_t)1 << 30)) --n_split;  // <= 1 GiB of slabs
         n_split = std::max(n_split, 1);
         const size_t sb = smem_bytes(row_chunk);  // <= EATS_SMEM_BUDGET, the opt-in limit set once in vag_create
         EatsRequest rq{};
@@ -787,7 +815,7 @@ int run_flux_pass(vag_context* ctx, const vag_params* d_params, size_t n, const 
         rq.lg2_nu_obs = lg2_nu;
         rq.t_obs_lin = t_lin;
         rq.acc_stride = eats_acc_stride((int)n_t);
-        const dim3 eg((unsigned)n, (unsigned)n_split, 2);
+        const dim3 eg((unsigned)n, (unsigned)n_split, (unsigned)n_shock);  // no reverse shock in the batch: no z = 1 CTAs
         const size_t elems = n * VAG_NCOMP * comp_sz;
         double* eats_out = d_out;
         if (n_split > 1) {
@@ -827,6 +855,10 @@ int run_flux_pass(vag_context* ctx, const vag_params* d_params, size_t n, const 
     if (d_status) CK(cudaMemcpyAsync(d_status, w.status, sizeof(int) * n, cudaMemcpyDeviceToDevice, s));
     CK(cudaGetLastError());
     if (ctx->profiling) {
+        CK(ctx->work_buf.ensure(sizeof(double) * 8));
+        CK(cudaMemsetAsync(ctx->work_buf.p, 0, sizeof(double) * 8, s));
+        k_work<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(w, static_cast<double*>(ctx->work_buf.p));
+        CK(cudaMemcpyAsync(ctx->work, ctx->work_buf.p, sizeof(double) * 8, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&ctx->stage_ms[i], ctx->ev[i], ctx->ev[i + 1]);
     }
@@ -993,7 +1025,7 @@ void vag_destroy(vag_context* c) {
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->model_buf, &c->row_buf, &c->cell_buf, &c->obs_buf, &c->io_params, &c->io_t, &c->io_nu,
                       &c->io_out, &c->io_status, &c->io_aux, &c->ic_buf, &c->lut_buf, &c->sp_buf, &c->geom_buf, &c->io_w, &c->io_obs,
-                      &c->io_chi2, &c->split_buf})
+                      &c->io_chi2, &c->split_buf, &c->work_buf})
         b->release();
     if (c->h_totals) cudaFreeHost(c->h_totals);
     if (c->h_cells) cudaFreeHost(c->h_cells);
@@ -1012,16 +1044,22 @@ int vag_last_stage_ms(vag_context* ctx, float ms[8]) {
     return VAG_OK;
 }
 int vag_last_launch_count(vag_context* ctx) { return ctx->launches; }
+int vag_last_work(vag_context* ctx, double work[8]) {
+    for (int i = 0; i < 8; ++i) work[i] = ctx->work[i];
+    return VAG_OK;
+}
 int vag_synchronize(vag_context* ctx) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     return VAG_OK;
 }
 int vag_set_output_mode(vag_context* ctx, int mode) {
-    if (mode != VAG_OUT_DENSE && mode != VAG_OUT_PRESENT) return fail(VAG_ERR_INVALID, "unknown output mode");
+    if (mode != VAG_OUT_DENSE && mode != VAG_OUT_PRESENT && mode != VAG_OUT_PRESENT_ALIAS_TOTAL)
+        return fail(VAG_ERR_INVALID, "unknown output mode");
     ctx->out_mode = mode;
     return VAG_OK;
 }
+int vag_last_total_alias(vag_context* ctx) { return ctx ? ctx->total_alias : -1; }
 int vag_set_capacity(vag_context* ctx, int cap_theta, int cap_phi) {
     if (cap_theta < 40 || cap_phi < 2) return fail(VAG_ERR_INVALID, "capacity too small");
     ctx->cap_theta = ctx->user_cap_theta = cap_theta;
@@ -1169,6 +1207,20 @@ static int copy_out(vag_context* ctx, const vag_params* params, size_t n_models,
         if (params[i].has_rvs) {
             present[VAG_C_RVS_SYNC] = true;
             if (params[i].rvs.ssc) present[VAG_C_RVS_SSC] = true;
+        }
+    }
+    // exactly one emission component in the whole batch: `total` is that component, bit for bit -- do not ship it twice
+    ctx->total_alias = -1;
+    if (ctx->out_mode == VAG_OUT_PRESENT_ALIAS_TOTAL) {
+        int n_present = 0, which = -1;
+        for (int c = 1; c < VAG_NCOMP; ++c)
+            if (present[c]) {
+                ++n_present;
+                which = c;
+            }
+        if (n_present == 1) {
+            present[VAG_C_TOTAL] = false;
+            ctx->total_alias = which;
         }
     }
     const char* src = static_cast<const char*>(ctx->io_out.p);

@@ -32,6 +32,7 @@ struct GridHeader {
     double t_end, min_t_start, min_t_early;
     int spreading, structured;
     double theta_s;  // jet_spreading_edge (spreading models)
+    int quad_attempts_theta, quad_attempts_phi;  // dopri5 attempts of the two CDF quadratures (work counters)
 };
 
 // Slab of per-model arrays (capacities fixed per batch by the host).
@@ -326,9 +327,10 @@ struct CdfQuad {
 
 // ---- inverse_CFD_sampling: grid-refinement.h:137-189 -----------------------------------------
 // pdf(x) functor; writes num nodes to x_out.  x_i / cdf_i: n_samp doubles each, kk: 8 doubles.
+// Returns the number of quadrature attempts (6 pdf evaluations each): the work counter behind bench.py's K0 roofline entry.
 template <int VARIANT, class Par, class Pdf>
-VAG_HD void inverse_cdf_sampling(const Par& par, const Pdf& pdf, double lo, double hi, int num, bool log_sample,
-                                 bool midpoint, double* x_out, double* x_i, double* cdf_i, double* kk) {
+VAG_HD int inverse_cdf_sampling(const Par& par, const Pdf& pdf, double lo, double hi, int num, bool log_sample,
+                                bool midpoint, double* x_out, double* x_i, double* cdf_i, double* kk) {
     constexpr int n_samp = dflt::theta_samples;
     constexpr double rtol = dflt::ode_rtol;
     {
@@ -341,7 +343,7 @@ VAG_HD void inverse_cdf_sampling(const Par& par, const Pdf& pdf, double lo, doub
     }
     CdfQuad<VARIANT> st;
     st.initialize(lo, gl::mul(gl::sub(hi, lo), 1.0 / 1e3));
-    int k = 1;
+    int k = 1, attempts = 0;
     for (int steps = 0; st.t <= hi;) {
         if (!st.deriv_ready) {
             st.k1 = pdf(st.t);
@@ -352,6 +354,7 @@ VAG_HD void inverse_cdf_sampling(const Par& par, const Pdf& pdf, double lo, doub
             const double t0 = st.t, dt = st.dt;
             // the six stage evaluations of an attempt are independent (a pure quadrature): one lane each
             par.for_each(6, [&](int s) { kk[s] = pdf(CdfQuad<VARIANT>::stage_time(t0, dt, s)); });
+            ++attempts;
             if (st.try_step(kk, rtol)) {
                 ok = true;
                 break;
@@ -398,6 +401,7 @@ VAG_HD void inverse_cdf_sampling(const Par& par, const Pdf& pdf, double lo, doub
         }
         x_out[q] = xo;
     });
+    return attempts;
 }
 
 // ---- adaptive_theta_grid: grid-refinement.h:199-291 ------------------------------------------
@@ -422,7 +426,7 @@ struct ThetaPdf {
 template <class Par>
 VAG_HD int adaptive_theta_grid(const Par& par, const ModelCfg& m, double theta_min, double theta_max, int base_pts,
                                double theta_v, double theta_resol, double* out, int cap, double* A, double* B,
-                               double* samp, double* kk) {
+                               double* samp, double* kk, int* attempts = nullptr) {
     constexpr double core_beam_coeff = 55.0, view_beam_coeff = 25.0, doppler_alpha0 = 12.0, floor_fraction = 0.25;
     constexpr int scan_pts = 100;
     const double theta_extent = gl::sub(theta_max, theta_min);
@@ -493,12 +497,14 @@ VAG_HD int adaptive_theta_grid(const Par& par, const ModelCfg& m, double theta_m
     const ThetaPdf pdf{m,          theta_v,      gl::mul(Gamma_peak_sq, core_weight), gl::mul(Gamma_v_sq, view_weight), Gamma_peak_sq,
                        Gamma_v_sq, doppler_alpha, floor_weight};
     // an Ejecta's profile is a std::function call the optimiser cannot see through: the stage states stay alive (VARIANT 1)
+    int na;
     if (m.ejecta)
-        inverse_cdf_sampling<1>(par, pdf, theta_min, theta_max, (int)total_pts, /*log=*/true, /*midpoint=*/false, out, samp,
-                                samp + dflt::theta_samples, kk);
+        na = inverse_cdf_sampling<1>(par, pdf, theta_min, theta_max, (int)total_pts, /*log=*/true, /*midpoint=*/false, out, samp,
+                                     samp + dflt::theta_samples, kk);
     else
-        inverse_cdf_sampling<0>(par, pdf, theta_min, theta_max, (int)total_pts, /*log=*/true, /*midpoint=*/false, out, samp,
-                                samp + dflt::theta_samples, kk);
+        na = inverse_cdf_sampling<0>(par, pdf, theta_min, theta_max, (int)total_pts, /*log=*/true, /*midpoint=*/false, out, samp,
+                                     samp + dflt::theta_samples, kk);
+    if (attempts) *attempts = na;
     return (int)total_pts;
 }
 
@@ -579,7 +585,7 @@ struct PhiPdf {
 template <class Par>
 VAG_HD int adaptive_phi_grid(const Par& par, const ModelCfg& m, int phi_num, double theta_v, const double* theta,
                              int n_theta, bool is_axisymmetric, double phi_max, double self_boost_cap, double* out,
-                             int cap, double* pt, double* A, double* samp, double* kk) {
+                             int cap, double* pt, double* A, double* samp, double* kk, int* attempts = nullptr) {
     if (theta_v == 0 && is_axisymmetric) {
         if (phi_num > cap) return -phi_num;
         par.for_each(phi_num, [&](int i) { out[i] = linspace_at(0., 2 * con::pi, phi_num, i); });
@@ -620,8 +626,9 @@ VAG_HD int adaptive_phi_grid(const Par& par, const ModelCfg& m, int phi_num, dou
     }
     if (phi_num > cap) return -phi_num;
     pdf.floor_weight = floor_weight;
-    inverse_cdf_sampling<1>(par, pdf, 0, phi_max, phi_num, /*log=*/false, /*midpoint=*/half_range, out, samp,
-                         samp + dflt::theta_samples, kk);
+    const int na = inverse_cdf_sampling<1>(par, pdf, 0, phi_max, phi_num, /*log=*/false, /*midpoint=*/half_range, out, samp,
+                                           samp + dflt::theta_samples, kk);
+    if (attempts) *attempts = na;
     return phi_num;
 }
 
@@ -775,8 +782,9 @@ VAG_HD void build_grid(const Par& par, const ModelCfg& m, double t_obs_min, doub
     const int theta_num =
         dflt::min_theta_points + (int)(long long)((theta_max - theta_min) * 180 / con::pi * m.theta_resol);
 
+    h.quad_attempts_theta = h.quad_attempts_phi = 0;
     const int n_base = adaptive_theta_grid(par, m, theta_min, theta_max, theta_num, theta_view, m.theta_resol,
-                                           base_theta, s.cap_theta, A, B, samp, kk);
+                                           base_theta, s.cap_theta, A, B, samp, kk, &h.quad_attempts_theta);
     if (n_base < 0) return fail_capacity();
     const double avg_spacing = (theta_max - theta_min) / n_base;
     double feat[3 * JUMP_CAP];
@@ -794,7 +802,7 @@ VAG_HD void build_grid(const Par& par, const ModelCfg& m, double t_obs_min, doub
     if (mirror_phi) {
         const int n_half = (phi_base + 1) / 2;
         n_phi = adaptive_phi_grid(par, m, n_half, theta_view, s.theta, n_theta, axis, con::pi, 5.0, s.phi, s.cap_phi, pt,
-                                  A, samp, kk);
+                                  A, samp, kk, &h.quad_attempts_phi);
         h.phi_mirrored = 1;
     } else {
         const double doppler_sharpness = jet_Gamma0(m, theta_view) * sin(theta_view);
@@ -810,7 +818,7 @@ VAG_HD void build_grid(const Par& par, const ModelCfg& m, double t_obs_min, doub
                 n_phi = -n_phi;
         } else {
             n_phi = adaptive_phi_grid(par, m, (int)phi_num, theta_view, s.theta, n_theta, axis, 2 * con::pi, 0.0, s.phi,
-                                      s.cap_phi, pt, A, samp, kk);
+                                      s.cap_phi, pt, A, samp, kk, &h.quad_attempts_phi);
         }
         if (n_phi >= 2) {
             const double shift = 0.5 * (s.phi[1] - s.phi[0]);

@@ -166,10 +166,15 @@ class Engine:
     def set_capacity(self, cap_theta, cap_phi):
         _lib.check(self._lib.vag_set_capacity(self._h, int(cap_theta), int(cap_phi)))
 
-    def set_output_mode(self, present_only: bool):
-        """True: host-buffer calls skip the planes of components no model of the batch has (vag.h VAG_OUT_PRESENT)."""
-        _lib.check(self._lib.vag_set_output_mode(self._h, 1 if present_only else 0))
+    def set_output_mode(self, present_only: bool, alias_total: bool = False):
+        """True: host-buffer calls skip the planes of components no model of the batch has (vag.h VAG_OUT_PRESENT);
+        alias_total: additionally skip `total` when it equals the batch's only component (``last_total_alias()``)."""
+        _lib.check(self._lib.vag_set_output_mode(self._h, (2 if alias_total else 1) if present_only else 0))
         self._present_only = bool(present_only)
+
+    def last_total_alias(self):
+        """Index into ``abi.COMPONENTS`` of the plane that holds `total` after the last host call, or -1."""
+        return int(self._lib.vag_last_total_alias(self._h))
 
     def debug_set_ode_limits(self, max_steps=0, max_fails=0):
         """Test hook (include/vag.h vag_debug_set_ode_limits): 0 restores the reference limits."""
@@ -183,6 +188,13 @@ class Engine:
         self._lib.vag_last_stage_ms(self._h, ms)
         names = ("grid", "dynamics", "radiation", "eats", "finish")
         return {k: float(ms[i]) for i, k in enumerate(names)}
+
+    def last_work(self):
+        """Work counters of the last profiled pass (include/vag.h vag_last_work)."""
+        w = (C.c_double * 8)()
+        self._lib.vag_last_work(self._h, w)
+        names = ("rows_fwd", "rows_pair", "cells", "eats_cells", "eats_rows", "quad_attempts_theta", "quad_phi_evals", "sum_n_theta")
+        return {k: float(w[i]) for i, k in enumerate(names)}
 
     def measure_fp64_peak(self):
         v = C.c_double()
