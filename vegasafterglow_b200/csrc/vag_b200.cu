@@ -353,7 +353,10 @@ __global__ void __launch_bounds__(128, EATS_MIN_BLOCKS) k_eats(BatchWs w, EatsRe
         for (int i0 = 0; i0 < rq.n_t_obs; i0 += EATS_T_BLOCK) {
             rq.i0 = i0;
             rq.ni = imin(EATS_T_BLOCK, rq.n_t_obs - i0);
-            for (int a = tid; a < nu_tile * acc_stride; a += nthr) acc[a] = 0.0;
+            // zeroed by the thread that accumulates into and finally reads the column (ii == tid mod nthr): no barrier is
+            // needed even when this split has no pass to run (compute-sanitizer racecheck, profiles/r02_sanitize.txt)
+            for (int ii = tid; ii < rq.ni; ii += nthr)
+                for (int l = 0; l < nu_tile; ++l) acc[l * acc_stride + ii] = 0.0;
             for (int q0 = split * rpp; q0 < erows; q0 += n_split * rpp) {
                 const int nrows = imin(rpp, erows - q0);
                 sh.rowg = rowg + q0;
