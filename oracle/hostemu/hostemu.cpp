@@ -90,6 +90,7 @@ void run_front(HostBatch& hb, const vag_params* params, size_t n, double t_min, 
     w.any_ssc = 0;
     for (size_t i = 0; i < n; ++i) w.any_ssc |= (params[i].fwd.ssc || (params[i].has_rvs && params[i].rvs.ssc)) ? 1 : 0;
     for (size_t i = 0; i < n; ++i) k0c_rowmap_body(w, (int)i);
+    for (int r = 0; r < rows; ++r) k1_lattice_body(w, r, 0, 1);
     for (int r = 0; r < rows; ++r) {
         double col[K1_COL_DOUBLES];
         if (w.cfg[w.row_model[r]].has_rvs)

@@ -19,6 +19,7 @@ int main(int argc, char** argv) {
         HostBatch hb;
         g_step_stats = StepStats{};
         run_front(hb, &P[i], 1, t_min, t_max);
-        printf("%zu %d %d %ld %ld\n", i, hb.w.hdr[0].n_t, hb.w.totals[TOT_ROWS], g_step_stats.attempts, g_step_stats.rejects);
+        printf("%zu %d %d %ld %ld %ld %ld\n", i, hb.w.hdr[0].n_t, hb.w.totals[TOT_ROWS], g_step_stats.attempts, g_step_stats.rejects,
+               g_step_stats.attempts_s, g_step_stats.rejects_s);
     }
 }

@@ -143,6 +143,12 @@ __global__ void k_rowmap(BatchWs w) {
 // (conflict-free: a lane only ever touches its own column).
 // PAIR selects the rows a launch integrates (forward+reverse pairs with the shared-memory stepper, or
 // forward-only rows with the register-resident one, which needs no shared memory).
+// K1a: one warp per unique ODE row builds its time lattice (n_t independent pow(10, .) evaluations)
+__global__ void __launch_bounds__(128) k_lattice(BatchWs w, int n_rows) {
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (row < n_rows) k1_lattice_body(w, row, threadIdx.x & 31, 32);
+}
+
 template <bool PAIR>
 __global__ void __launch_bounds__(32) k_dynamics(BatchWs w, int n_rows, int lanes) {
     __shared__ double s_col[PAIR ? K1_COL_DOUBLES * 32 : 1];
@@ -713,7 +719,8 @@ int run_front(vag_context* ctx, BatchWs& w, const vag_params* d_params, size_t n
     if (rows > 0) {
         k_rowmap<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(w);
         k_rowgeom<<<dim3((unsigned)((w.max_erows + 127) / 128), (unsigned)n), 128, 0, s>>>(w);
-        ctx->launches++;
+        k_lattice<<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(w, rows);
+        ctx->launches += 2;
         mark(ctx, 1, s);
         {
             // rows per warp: up to one warp per scheduler before warps are filled up

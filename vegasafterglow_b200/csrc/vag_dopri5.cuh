@@ -24,13 +24,17 @@ namespace vag {
 
 #if defined(VAG_INSTRUMENT) && !defined(__CUDA_ARCH__)
 // host-only analysis hook (scripts/step_stats.cpp): attempts / rejections of the current row
-struct StepStats { long attempts = 0, rejects = 0; };
+struct StepStats { long attempts = 0, rejects = 0, attempts_s = 0, rejects_s = 0; };
 inline StepStats g_step_stats;
 #define VAG_COUNT_ATTEMPT() (++g_step_stats.attempts)
 #define VAG_COUNT_REJECT() (++g_step_stats.rejects)
+#define VAG_COUNT_ATTEMPT_S() (++g_step_stats.attempts_s)
+#define VAG_COUNT_REJECT_S() (++g_step_stats.rejects_s)
 #else
 #define VAG_COUNT_ATTEMPT() ((void)0)
 #define VAG_COUNT_REJECT() ((void)0)
+#define VAG_COUNT_ATTEMPT_S() ((void)0)
+#define VAG_COUNT_REJECT_S() ((void)0)
 #endif
 
 // err^p of the step-size controller (err finite and > 0 at both call sites): exp2(p log2 err) with the
@@ -296,7 +300,7 @@ struct Dopri5S {
         constexpr double c1 = 35.0 / 384, c3 = 500.0 / 1113, c4 = 125.0 / 192, c5 = -2187.0 / 6784, c6 = 11.0 / 84;
         constexpr double dc1 = c1 - 5179.0 / 57600, dc3 = c3 - 7571.0 / 16695, dc4 = c4 - 393.0 / 640,
                          dc5 = c5 - (-92097.0 / 339200), dc6 = c6 - 187.0 / 2100, dc7 = -1.0 / 40;
-        VAG_COUNT_ATTEMPT();
+        VAG_COUNT_ATTEMPT_S();
         double xt[N];
 #pragma unroll 1
         for (int s = 0; s < 6; ++s) {
@@ -329,7 +333,7 @@ struct Dopri5S {
             err = vmax(err, fabs(r));
         }
         if (err > 1.0) {
-            VAG_COUNT_REJECT();
+            VAG_COUNT_REJECT_S();
             dt *= vmax(0.9 * ctrl_pow<false>(err, -1.0 / 3.0), 0.2);
             return false;
         }

@@ -677,14 +677,16 @@ VAG_HD double estimate_t_dec(const ModelCfg& m, double theta) {
 // ---- time lattice: grid-refinement.h:516-581, grid-refinement.cpp:166-197 ---------------------
 VAG_HD double logspace_at(double la, double lb, int n, int i) { return pow(10.0, linspace_at(la, lb, n, i)); }
 
+// The lattice builders fill grid[idx] for idx = tid, tid + nthr, ... (tid = 0, nthr = 1: the whole row): every node is
+// an independent expression of the segment bounds, so a warp builds a row's lattice in parallel (k_lattice).
 // logspace_with_band_refinement(ts, t_end, b_lo, b_hi, n, factor) -> grid[n]
 VAG_HD void logspace_with_band_refinement(double ts, double t_end, double b_lo, double b_hi, int n, double factor,
-                                          double* grid) {
+                                          double* grid, int tid = 0, int nthr = 1) {
     b_lo = vmax(b_lo, ts);
     b_hi = vmin(b_hi, t_end);
     if (!(b_hi > b_lo) || n < 8) {
         const double la = log10(ts), lb = log10(t_end);
-        for (int i = 0; i < n; ++i) grid[i] = logspace_at(la, lb, n, i);
+        for (int i = tid; i < n; i += nthr) grid[i] = logspace_at(la, lb, n, i);
         return;
     }
     const double l0 = log10(ts), l1 = log10(b_lo), l2 = log10(b_hi), l3 = log10(t_end);
@@ -695,20 +697,27 @@ VAG_HD void logspace_with_band_refinement(double ts, double t_end, double b_lo, 
     n1 = n1 < segs - 2 ? n1 : segs - 2;
     n3 = n3 < segs - 1 - n1 - 1 ? n3 : segs - 1 - n1 - 1;
     const long long n2 = segs - n1 - n3;
-    int idx = 0;
-    for (long long k = 0; k < n1; ++k) grid[idx++] = pow(10.0, l0 + (l1 - l0) * (double)k / (double)n1);
-    for (long long k = 0; k < n2; ++k) grid[idx++] = pow(10.0, l1 + (l2 - l1) * (double)k / (double)n2);
-    for (long long k = 0; k <= n3; ++k)
-        grid[idx++] = pow(10.0, (n3 > 0) ? l2 + (l3 - l2) * (double)k / (double)n3 : l3);
+    for (long long idx = tid; idx < n1 + n2 + n3 + 1; idx += nthr) {
+        double v;
+        if (idx < n1) {
+            v = pow(10.0, l0 + (l1 - l0) * (double)idx / (double)n1);
+        } else if (idx < n1 + n2) {
+            v = pow(10.0, l1 + (l2 - l1) * (double)(idx - n1) / (double)n2);
+        } else {
+            const long long k = idx - n1 - n2;
+            v = pow(10.0, (n3 > 0) ? l2 + (l3 - l2) * (double)k / (double)n3 : l3);
+        }
+        grid[idx] = v;
+    }
 }
 
 // logspace_with_cross_refinement(t_start, t_end, t_refine, t_num, base_t_num) -> grid[t_num]
 VAG_HD void logspace_with_cross_refinement(double t_start, double t_end, double t_refine, int t_num, int base_t_num,
-                                           double* grid) {
+                                           double* grid, int tid = 0, int nthr = 1) {
     t_refine = vclamp(t_refine, t_start, t_end);
     if (t_refine <= t_start || t_refine >= t_end) {
         const double la = log10(t_start), lb = log10(t_end);
-        for (int i = 0; i < t_num; ++i) grid[i] = logspace_at(la, lb, t_num, i);
+        for (int i = tid; i < t_num; i += nthr) grid[i] = logspace_at(la, lb, t_num, i);
         return;
     }
     const double log_total = log10(t_end / t_start);
@@ -717,15 +726,17 @@ VAG_HD void logspace_with_cross_refinement(double t_start, double t_end, double 
     if (n_post < 2) n_post = 2;
     if (n_post >= t_num) n_post = t_num / 2;
     const long long n_pre = t_num + 1 - n_post;
-    for (int i = 0; i < t_num; ++i) grid[i] = 0;
-    int idx = 0;
-    {
-        const double la = log10(t_start), lb = log10(t_refine);
-        for (long long k = 0; k < n_pre; ++k) grid[idx++] = logspace_at(la, lb, (int)n_pre, (int)k);
-    }
-    {
-        const double la = log10(t_refine), lb = log10(t_end);
-        for (long long k = 1; k < n_post && idx < t_num; ++k) grid[idx++] = logspace_at(la, lb, (int)n_post, (int)k);
+    const double la0 = log10(t_start), lb0 = log10(t_refine), lb1 = log10(t_end);
+    // nodes [0, n_pre): first segment; then k = 1 .. n_post - 1 of the second while the array has room; the rest stay 0
+    for (long long idx = tid; idx < t_num; idx += nthr) {
+        double v = 0;
+        if (idx < n_pre) {
+            v = logspace_at(la0, lb0, (int)n_pre, (int)idx);
+        } else {
+            const long long k = idx - n_pre + 1;
+            if (k < n_post) v = logspace_at(lb0, lb1, (int)n_post, (int)k);
+        }
+        grid[idx] = v;
     }
 }
 
@@ -734,16 +745,16 @@ VAG_HD void logspace_with_cross_refinement(double t_start, double t_end, double 
 // row its own (build_time_grid, grid-refinement.h:612-619): row_start = max(t_raw, cut),
 // row_early = 0.99 min(t_raw, cut), left by build_grid in the model's scratch slab.
 VAG_HD void build_row_lattice(const GridHeader& h, double t_dec, double T0, double row_start, double row_early,
-                              double* t_row) {
+                              double* t_row, int tid = 0, int nthr = 1) {
     double* grid = t_row + (h.has_early ? 1 : 0);
     const double ts = h.structured ? row_start : h.min_t_start;
     if (h.is_rvs) {
         const double t_cross_limit = vmax(t_dec, T0);
-        logspace_with_cross_refinement(ts, h.t_end, 10 * t_cross_limit, h.t_num_tot, h.t_num_base, grid);
+        logspace_with_cross_refinement(ts, h.t_end, 10 * t_cross_limit, h.t_num_tot, h.t_num_base, grid, tid, nthr);
     } else {
-        logspace_with_band_refinement(ts, h.t_end, t_dec / 3, 3 * t_dec, h.t_num_tot, 3.0, grid);
+        logspace_with_band_refinement(ts, h.t_end, t_dec / 3, 3 * t_dec, h.t_num_tot, 3.0, grid, tid, nthr);
     }
-    if (h.has_early) t_row[0] = h.structured ? row_early : h.min_t_early;
+    if (h.has_early && tid == 0) t_row[0] = h.structured ? row_early : h.min_t_early;
 }
 
 // ---- auto_grid: grid-refinement.h:638-706 (axisymmetric, typed jets) --------------------------

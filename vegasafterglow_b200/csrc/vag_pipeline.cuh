@@ -173,6 +173,31 @@ VAG_HD RawRow raw_row(const BatchWs& w, long long off) {
 
 // K1: sequential part of one row -- time lattice + dopri5 integration, raw node states only
 constexpr int K1_COL_DOUBLES = Dopri5S<FREqn::N>::kDoublesPerThread;  // stage-vector column of one row
+// K1a: engine-time lattice of one unique row, nodes strided over (tid, nthr) (every node is an independent pow(10, .))
+VAG_HD void k1_lattice_body(const BatchWs& w, int row, int tid, int nthr) {
+    const int mi = w.row_model[row];
+    const int r = w.row_rep[row];
+    const GridHeader& h = w.hdr[mi];
+    const ModelCfg& cfg = w.cfg[mi];
+    const long long off = w.cell_off[mi] + (long long)r * h.n_t;
+    const double t_dec = w.t_dec[(size_t)mi * w.cap_theta + r];
+    // per-row lattice bounds of a structured model: work[j] and work[cap_theta + j] (build_grid)
+    const double* work = w.work + (size_t)mi * w.work_per_model;
+    build_row_lattice(h, t_dec, cfg.T0, h.structured ? work[r] : 0.0, h.structured ? work[w.cap_theta + r] : 0.0,
+                      w.t_rows + off, tid, nthr);
+    // grid-refinement.h:633-635: every thread re-reads the nodes it wrote itself (and thread 0 the early point)
+    bool finite = true;
+    for (int k = tid + (h.has_early ? 1 : 0); k < h.n_t; k += nthr) finite = finite && isfinite(w.t_rows[off + k]);
+    if (tid == 0 && h.has_early) finite = finite && isfinite(w.t_rows[off]);
+    if (!finite) {
+#if defined(__CUDA_ARCH__)
+        atomicOr(&w.status[mi], VAG_ST_GRID_NONFINITE);
+#else
+        w.status[mi] |= VAG_ST_GRID_NONFINITE;
+#endif
+    }
+}
+
 template <bool PAIR>
 VAG_HD void k1_dynamics_body(const BatchWs& w, int row, double* col, int col_stride) {
     const int mi = w.row_model[row];
@@ -180,16 +205,10 @@ VAG_HD void k1_dynamics_body(const BatchWs& w, int row, double* col, int col_str
     const GridHeader& h = w.hdr[mi];
     const ModelCfg& cfg = w.cfg[mi];
     const long long off = w.cell_off[mi] + (long long)r * h.n_t;
-    double* t_row = w.t_rows + off;
+    double* t_row = w.t_rows + off;  // written by k1_lattice_body
     const double t_dec = w.t_dec[(size_t)mi * w.cap_theta + r];
     const double theta = w.theta[(size_t)mi * w.cap_theta + w.reps[(size_t)mi * w.cap_theta + r]];
-    // per-row lattice bounds of a structured model: work[j] and work[cap_theta + j] (build_grid)
-    const double* work = w.work + (size_t)mi * w.work_per_model;
-    build_row_lattice(h, t_dec, cfg.T0, h.structured ? work[r] : 0.0, h.structured ? work[w.cap_theta + r] : 0.0, t_row);
-    int st = 0;
-    bool finite = true;
-    for (int k = 0; k < h.n_t; ++k) finite = finite && isfinite(t_row[k]);
-    if (!finite) st |= VAG_ST_GRID_NONFINITE;
+    int st = 0;  // (a non-finite lattice node was flagged by k1_lattice_body)
     const ShockRow sf = shock_row(w.fwd, off);
     const RawRow raw = raw_row(w, off);
     RowDyn rd;
