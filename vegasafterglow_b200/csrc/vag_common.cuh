@@ -124,6 +124,13 @@ VAG_HD double vsqrt(double x) {
 VAG_HD double vdiv(double a, double b) { return a / b; }
 VAG_HD double vsqrt(double x) { return sqrt(x); }
 #endif
+// Pins a value as computed HERE: the compiler otherwise sinks an expensive operand of a select into a conditional
+// block, and the branch ends the basic block the caller wants in one piece (device only; no code is emitted).
+#if defined(__CUDA_ARCH__)
+#define VAG_KEEP(x) asm volatile("" : "+d"(x))
+#else
+#define VAG_KEEP(x) ((void)0)
+#endif
 VAG_HD double adiabatic_idx_fast(double gamma) { return 4.0 / 3.0 + vdiv(1.0, 3 * gamma); }  // gamma >= 1
 
 }  // namespace vag

@@ -306,13 +306,20 @@ struct Dopri5S {
         for (int s = 0; s < 6; ++s) {
 #pragma unroll
             for (int i = 0; i < N; ++i) xt[i] = 1.0 * x[i];
-#pragma unroll 1
-            for (int j = 0; j <= s; ++j) {
+            // All six tableau columns as straight-line code, the absent ones (zero above the diagonal, and k2 in the
+            // 5th-order row) deselected: a rolled j loop cuts the stage into basic blocks of one column each, and
+            // with one warp per scheduler the N independent accumulations only overlap inside a block.  The
+            // deselected term is never added (a stale slot may hold anything), so the sum is the reference's.
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
                 const double b = VAG_DPB[s][j];
-                if (b == 0) continue;  // k2 does not enter the 5th-order solution
+                const bool use = b != 0;
                 const double db = dt * b;
 #pragma unroll
-                for (int i = 0; i < N; ++i) xt[i] = xt[i] + db * K(j, i);
+                for (int i = 0; i < N; ++i) {
+                    const double v = xt[i] + db * K(j, i);
+                    xt[i] = use ? v : xt[i];
+                }
             }
             double kk[N];
             sys(xt, kk, t + dt * VAG_DPA[s]);

@@ -459,6 +459,7 @@ struct FREqn {
     const ModelCfg& m;
     double Gamma4, deps0_dt, dm0_dt, u4, theta0;
     double cs4, beta4;  // compute_sound_speed(Gamma4), gamma_to_beta(Gamma4): row constants of the RHS
+    int mode;           // right-hand side of this row: 0 rhs_general, 1 / 2 rhs_fast without / with radiative losses
     // crossing state: reverse-shock.hpp:66-70
     double u_x, r_x, B3_ordered_x, V3_comv_x, rho3_x;
     enum { iG = 0, iX4, iX3, iM2, iM3, iU2, iU3, iR, iT, iE4, iM4, N };
@@ -473,6 +474,8 @@ struct FREqn {
         cs4 = compute_sound_speed(Gamma4);
         beta4 = gamma_to_beta(Gamma4);
         u_x = r_x = B3_ordered_x = V3_comv_x = rho3_x = 0;
+        // cold ejecta without energy injection in an ISM / Wind(k = 2) medium: the branch-free right-hand side
+        mode = (m.has_magnetar || m.wind_generic || m.sigma0 > 0) ? 0 : (m.fwd.eps_e_rad != 0 ? 2 : 1);
     }
 
     VAG_HD double injection_efficiency(double dm4) const {  // reverse-shock.tpp:42-47
@@ -491,7 +494,181 @@ struct FREqn {
     VAG_HD bool crossing_complete(const double* x, double t) const { return crossing_complete_m(x[iM3], x[iM4], t); }
 
     // FRShockEqn::operator(): reverse-shock.tpp:252-294 (+ the rate terms :62-250)
+    // Rows of unmagnetised ejecta without energy injection (mode 1 / 2) evaluate rhs_fast, ONE basic block of
+    // straight-line code; whenever an operand leaves the range its branch-free arithmetic is valid for (or the shell
+    // turns out magnetised) it reports false and the evaluation is repeated by rhs_general, which keeps the IEEE
+    // operators and the branches of the reference.
     VAG_HD void operator()(const double* xr, double* d, double t) const {
+        if (mode == 2) {
+            if (rhs_fast<true>(xr, d, t)) return;
+        } else if (mode == 1) {
+            if (rhs_fast<false>(xr, d, t)) return;
+        }
+        rhs_general(xr, d, t);
+    }
+
+    // The same right-hand side as rhs_general for sigma = 0, no injection, ISM / Wind(k = 2): every condition is a
+    // select, every division / square root the branch-free faithful form on an operand checked to be positive, normal
+    // and finite (`ok`).  Measured on the B200 (profiles/r02c_*): blocks of > 100 instructions retire at ~80 stall
+    // samples per instruction, the 20-60 instruction blocks the branches of rhs_general leave at 200-400 -- with one
+    // warp per scheduler only a long block lets the independent chains of this function overlap.
+    template <bool RAD>
+    VAG_HD bool rhs_fast(const double* xr, double* d, double t) const {
+        const double Gamma = vclamp(xr[iG], 1.0, Gamma4);
+        const double m4 = xr[iM4];
+        const double m3 = vclamp(xr[iM3], 0.0, vmax(m4, 0.0));
+        const double x3 = vmax(xr[iX3], 0.0);
+        const double U3 = vmax(xr[iU3], 0.0);
+        const double x4 = xr[iX4], m2 = xr[iM2], U2 = xr[iU2], r = xr[iR], t_comv = xr[iT], eps4 = xr[iE4];
+        bool ok = r > 1e-150 && r < 1e150;
+
+        const double u3 = vsqrt((Gamma - 1) * (Gamma + 1));
+        const double dr = u3 * (Gamma + u3) * con::c;
+        const double dtc = Gamma + u3;
+        d[iR] = dr;
+        d[iT] = dtc;
+        // medium_rho: ISM medium.h:58, Wind(k = 2) medium.h:107-109
+        const double rho_wind = vdiv(m.wind_A, m.wind_r02 + r * r) + m.rho_ism;
+        const double rho = (m.medium_type == VAG_MEDIUM_ISM) ? m.rho_ism : rho_wind;
+        const double dm2 = r * r * rho * dr;
+        d[iM2] = dm2;
+
+        const double inject_w = smoothstep(m.T0 * 1.5, m.T0 * 0.5, t);
+        const bool inj_on = inject_w > 1e-6;
+        const double deps4 = inj_on ? inject_w * deps0_dt : 0.0;
+        const double dm4 = inj_on ? inject_w * dm0_dt : 0.0;
+        d[iE4] = deps4;
+        d[iM4] = dm4;
+
+        // compute_rel_Gamma (shock-physics.h:192-204)
+        double Gamma34;
+        {
+            const double u1u2 = vsqrt(vmax((Gamma4 - 1) * (Gamma4 + 1) * (Gamma - 1) * (Gamma + 1), 0.0));
+            const double dg = Gamma4 - Gamma;
+            const double denom = Gamma4 * Gamma - 1 + u1u2;
+            const bool degenerate = denom <= 0;
+            const double g = 1 + vdiv(dg * dg, degenerate ? 1.0 : denom);
+            Gamma34 = degenerate ? 1.0 : g;
+        }
+        const double ad2 = adiabatic_idx_fast(Gamma);
+        const double ad34 = adiabatic_idx_fast(Gamma34);
+        const double cs34 = compute_sound_speed_ad(Gamma34, ad34);
+        const double cs34_dtc = cs34 * dtc;
+        const double dlnv_r = vdiv(2 * dr, r);
+        // shell_sigma: the general path when the shell is (or becomes) magnetised
+        {
+            const double den = Gamma4 * m4 * con::c2;
+            const bool den_ok = den > 1e-290 && den < 1e290;
+            const double sigma = vdiv(eps4, den_ok ? den : 1.0) - 1;
+            ok = ok && den_ok && !(sigma > con::sigma_cut);
+        }
+        const double comp_ratio = compute_4vel_jump_ad(Gamma34, 0.0, ad34);
+
+        // injection_efficiency
+        const bool inj_eff = dm0_dt > 0 && dm4 > 0;
+        double f_inj = vmin(vdiv(dm4, inj_eff ? dm0_dt : 1.0), 1.0);
+        VAG_KEEP(f_inj);
+        const double f = inj_eff ? f_inj : 0.0;
+        const double sound4 = cs4 * dtc;
+        const double dx4 = (f > 1e-6) ? f * u4 + (1 - f) * sound4 : sound4;
+        d[iX4] = dx4;
+
+        double eps_rad = 0;
+        if (RAD) {  // radiative_efficiency (shock-physics.h:247-288), ordinary operand range only
+            const RadCfg& rad = m.fwd;
+            const double e_th = (Gamma - 1) * 4 * Gamma * rho * con::c2;
+            const double gamma_m = rad.gamma_m_coeff * (Gamma - 1) + 1;
+            const double den = e_th * t_comv;
+            const bool den_ok = den > 1e-100 && den < 1e100;
+            ok = ok && den_ok;
+            const double gamma_bar = vdiv(rad.gamma_c_coeff, den_ok ? den : 1.0);
+            const double gamma_c = 0.5 * (gamma_bar + vsqrt(gamma_bar * gamma_bar + 4));
+            const double ratio = vdiv(gamma_m, gamma_c);
+            const bool slow_cooling = ratio < 1 && rad.p > 2;
+            const bool ratio_ok = ratio > 1e-300;
+            double pw = dexp2_nc(vmax((rad.p - 2) * dlog2_nc((slow_cooling && ratio_ok) ? ratio : 0.5), -1000.0));
+            VAG_KEEP(pw);
+            eps_rad = slow_cooling ? rad.eps_e_rad * (ratio_ok ? pw : 0.0) : rad.eps_e_rad;
+        }
+
+        // compute_dx3_dt
+        const double remaining = vmax(m4 - m3, 0.0);
+        const bool has_shell = !(m4 <= 0);
+        const double m4_s = has_shell ? m4 : 1.0;
+        const double crossing_w = f + vdiv((1.0 - f) * remaining, m4_s);
+        const double penetration = vdiv(Gamma * comp_ratio, Gamma4) - 1;
+        const bool crossing_on = has_shell && !(crossing_w < 1e-6) && !(penetration <= 0);
+        double dx3;
+        {
+            const double pen_s = crossing_on ? penetration : 1.0;
+            const double beta3 = vdiv(u3, Gamma);
+            const double dx3dt = vdiv((Gamma4 - Gamma) * (Gamma4 + Gamma) * (1 + beta3) * con::c,
+                                      Gamma4 * Gamma4 * (beta3 + beta4) * pen_s);
+            double crossing = fabs(dx3dt * Gamma);
+            // v_ms of rhs_general with sigma = 0: va2 = 0, sqrt(0 + cs2 (1 - 0)) c
+            const double cs2 = cs34 * cs34 / (con::c * con::c);
+            const double v_ms = vsqrt(cs2) * con::c;
+            crossing = (penetration < 1) ? vmin(crossing, v_ms * dtc) : crossing;
+            dx3 = crossing_on ? crossing_w * crossing + (1.0 - crossing_w) * cs34_dtc : cs34_dtc;
+        }
+        d[iX3] = dx3;
+
+        // compute_dm3_dt
+        double dm3;
+        {
+            const bool feeding = has_shell && !(remaining <= 0 && f < 1e-6);
+            const double eff_mass = f * m4 + (1.0 - f) * remaining;
+            const bool x4_ok = x4 > 1e-290 && x4 < 1e290;
+            ok = ok && x4_ok;
+            const double column_den3 = vdiv(eff_mass * comp_ratio, x4_ok ? x4 : 1.0);
+            const double dm3dt = column_den3 * dx3;
+            const double ratio = vdiv(m3, m4_s);
+            const double cap_w = smoothstep(0, 1.0, ratio);
+            const double capped_rate = vmin(dm3dt, dm4);
+            const double injected = (1.0 - cap_w) * dm3dt + cap_w * capped_rate;
+            dm3 = feeding ? ((f > 1e-6) ? injected : dm3dt) : 0.;
+        }
+        d[iM3] = dm3;
+
+        // compute_dU2_dt
+        double dU2;
+        {
+            const double shock_heating = dm2 * (Gamma - 1) * con::c2;
+            const double x4_s = (x4 > 0) ? x4 : 1.0;
+            const double dlnvdt = dlnv_r + ((x4 > 0) ? vdiv(dx4, x4_s) : 0.0);
+            const double adiabatic_cooling = -(ad2 - 1) * dlnvdt * U2;
+            dU2 = (1 - eps_rad) * shock_heating + adiabatic_cooling;
+        }
+        d[iU2] = dU2;
+        // compute_dU3_dt
+        double dU3;
+        {
+            const double x3_s = (x3 > 0) ? x3 : 1.0;
+            const double dlnvdt = dlnv_r + ((x3 > 0) ? vdiv(dx3, x3_s) : 0.0);
+            const double adiabatic_cooling = -(ad34 - 1) * dlnvdt * U3;
+            const double shock_heating = dm3 * (Gamma34 - 1) * con::c2;
+            dU3 = shock_heating + adiabatic_cooling;
+        }
+        d[iU3] = dU3;
+
+        // compute_dGamma_dt
+        {
+            const double Gamma_eff2 = compute_effective_Gamma(ad2, Gamma);
+            const double Gamma_eff3 = compute_effective_Gamma(ad34, Gamma);
+            const double dGamma_eff2 = compute_effective_Gamma_dGamma(ad2, Gamma);
+            const double dGamma_eff3 = compute_effective_Gamma_dGamma(ad34, Gamma);
+            const double a = (Gamma - 1) * con::c2 * dm2 + (Gamma - Gamma4) * con::c2 * dm3 + Gamma_eff2 * dU2 +
+                             Gamma_eff3 * dU3;
+            const double b = (m2 + m3) * con::c2 + dGamma_eff2 * U2 + dGamma_eff3 * U3;
+            const bool b_ok = b > 1e-290 && b < 1e290;
+            const double q = vdiv(-a, b_ok ? b : 1.0);
+            ok = ok && b_ok && fabs(q) < kInf;
+            d[iG] = q;
+        }
+        return ok;
+    }
+
+    VAG_HD void rhs_general(const double* xr, double* d, double t) const {
         // projection onto the physical domain
         const double Gamma = vclamp(xr[iG], 1.0, Gamma4);
         const double m4 = xr[iM4];
