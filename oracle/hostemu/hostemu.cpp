@@ -233,18 +233,24 @@ int run_flux(const vag_params* params, size_t n, const double* t, size_t n_t, co
     HostBatch hb;
     const double t_min = *std::min_element(t, t + n_t), t_max = *std::max_element(t, t + n_t);
     run_front(hb, params, n, t_min, t_max);
-    std::vector<double> lg2t(n_t), tl(n_t), lg2nu(n_nu);
+    std::vector<double> lg2t(n_t), tl(n_t), lg2nu(n_nu), nul(n_nu), nu23(n_nu);
     for (size_t i = 0; i < n_t; ++i) {
         tl[i] = t[i] * unit::sec;
         lg2t[i] = std::log2(tl[i]);
     }
-    for (size_t i = 0; i < n_nu; ++i) lg2nu[i] = std::log2(nu[i] * unit::Hz);
+    for (size_t i = 0; i < n_nu; ++i) {
+        nul[i] = nu[i] * unit::Hz;
+        lg2nu[i] = std::log2(nul[i]);
+        nu23[i] = std::exp2((2. / 3) * lg2nu[i]);
+    }
     EatsRequest rq{};
     rq.series = series ? 1 : 0;
     rq.n_t_obs = (int)n_t;
     rq.n_nu = (int)n_nu;
     rq.lg2_t_obs = lg2t.data();
     rq.lg2_nu_obs = lg2nu.data();
+    rq.nu_obs_lin = nul.data();
+    rq.nu23_obs = nu23.data();
     rq.t_obs_lin = tl.data();
     rq.acc_stride = eats_acc_stride((int)n_t);
     const size_t comp = series ? n_t : n_nu * n_t;

@@ -286,14 +286,21 @@ __global__ void __launch_bounds__(128) k_ic_spectrum(BatchWs w, int n_rows, int 
 
 // observation request pre-pass: log2 of the (unit-scaled) times and frequencies
 __global__ void k_prep_obs(const double* __restrict__ t, int n_t, const double* __restrict__ nu, int n_nu,
-                           double* lg2_t, double* t_lin, double* lg2_nu, int nu_in_code_units) {
+                           double* lg2_t, double* t_lin, double* lg2_nu, double* nu_lin, double* nu23,
+                           int nu_in_code_units) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_t) {
         const double tl = t[i] * unit::sec;
         t_lin[i] = tl;
         lg2_t[i] = log2(tl);
     }
-    if (i < n_nu) lg2_nu[i] = log2(nu_in_code_units ? nu[i] : nu[i] * unit::Hz);
+    if (i < n_nu) {
+        const double v = nu_in_code_units ? nu[i] : nu[i] * unit::Hz;
+        const double l = log2(v);
+        lg2_nu[i] = l;
+        nu_lin[i] = v;
+        nu23[i] = exp2((2. / 3) * l);
+    }
 }
 
 // Observer::flux (src/core/observer.h:555-567): band[m][c][j] = sum_i F[m][c][i][j] * w[i]
@@ -757,15 +764,17 @@ int run_flux_pass(vag_context* ctx, const vag_params* d_params, size_t n, const 
                   cudaStream_t s) {
     const size_t n_t = rq_in.n_t, n_nu = rq_in.n_nu;
     // observation arrays
-    CK(ctx->obs_buf.ensure(sizeof(double) * (2 * n_t + n_nu + 8)));
+    CK(ctx->obs_buf.ensure(sizeof(double) * (2 * n_t + 3 * n_nu + 8)));
     double* lg2_t = static_cast<double*>(ctx->obs_buf.p);
     double* t_lin = lg2_t + n_t;
     double* lg2_nu = t_lin + n_t;
-    double* nu_range = lg2_nu + n_nu;
+    double* nu_lin = lg2_nu + n_nu;
+    double* nu23 = nu_lin + n_nu;
+    double* nu_range = nu23 + n_nu;
     {
         const size_t m = std::max(n_t, n_nu);
         k_prep_obs<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(rq_in.d_t, (int)n_t, rq_in.d_nu, (int)n_nu, lg2_t, t_lin,
-                                                              lg2_nu, rq_in.nu_code_units ? 1 : 0);
+                                                              lg2_nu, nu_lin, nu23, rq_in.nu_code_units ? 1 : 0);
         ctx->launches++;
     }
     BatchWs w;
@@ -823,6 +832,8 @@ int run_flux_pass(vag_context* ctx, const vag_params* d_params, size_t n, const 
         rq.n_nu = (int)n_nu;
         rq.lg2_t_obs = lg2_t;
         rq.lg2_nu_obs = lg2_nu;
+        rq.nu_obs_lin = nu_lin;
+        rq.nu23_obs = nu23;
         rq.t_obs_lin = t_lin;
         rq.acc_stride = eats_acc_stride((int)n_t);
         const dim3 eg((unsigned)n, (unsigned)n_split, (unsigned)n_shock);  // no reverse shock in the batch: no z = 1 CTAs

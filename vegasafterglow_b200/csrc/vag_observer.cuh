@@ -112,12 +112,13 @@ VAG_HD double node_time(const EatsModel& M, const RowGeom& g, int n_t, int k) {
 
 // log2 grids of one node: finalize_log_grids (observer.cpp:439-454) on the pre-logged geometry path, or on
 // the linear dOmega r^2 of a spreading jet (observer.cpp:131-139)
+// dop_lin = Gamma - u cos(v) = 2^-lg2_dop, the linear quantity the log was taken of
 VAG_HD void node_logs(const EatsModel& M, const RowGeom& g, int n_t, int k, double& lg2_t, double& lg2_dop,
-                      double& lg2_geom) {
+                      double& lg2_geom, double& dop_lin) {
     const long o = (long)g.rep * n_t + k;
     if (M.spreading) {
         const double cos_v = spread_cos_v(M, g, o);
-        const double dop_lin = M.Gamma[o] - M.geo_u[o] * cos_v;
+        dop_lin = M.Gamma[o] - M.geo_u[o] * cos_v;
         const double time = (M.t_rows[o] + (1 - cos_v) * M.r[o] / con::c) * M.one_plus_z;
         const double dOmega = fabs(M.geo_dcos[o] * g.lg2_dOmega);
         lg2_dop = -rlog2(dop_lin);
@@ -125,7 +126,7 @@ VAG_HD void node_logs(const EatsModel& M, const RowGeom& g, int n_t, int k, doub
         lg2_geom = rlog2(dOmega * M.r[o] * M.r[o]) + 3.0 * lg2_dop;
         return;
     }
-    const double dop_lin = M.Gamma[o] - M.geo_u[o] * g.cos_v;
+    dop_lin = M.Gamma[o] - M.geo_u[o] * g.cos_v;
     const double time = M.t_rows[o] * M.one_plus_z + g.t_coeff * M.r[o];
     lg2_dop = -rlog2(dop_lin);
     lg2_t = rlog2(time);
@@ -219,6 +220,8 @@ struct EatsRequest {
     int n_t_obs, n_nu;     // series: n_nu == n_t_obs (per-point frequencies)
     const double* lg2_t_obs;   // [n_t_obs]  log2(t * unit::sec)
     const double* lg2_nu_obs;  // [n_nu]     log2(nu * unit::Hz)   (without the 1+z shift)
+    const double* nu_obs_lin;  // [n_nu]     nu * unit::Hz
+    const double* nu23_obs;    // [n_nu]     (nu * unit::Hz)^(2/3) = exp2(2/3 lg2_nu_obs)
     const double* t_obs_lin;   // [n_t_obs]  t * unit::sec
     int i0, ni;                // block of observation points handled by the current pass
     int acc_stride;            // accumulator columns per frequency: eats_acc_stride(n_t_obs)
@@ -283,8 +286,8 @@ VAG_HD void eats_phase1(const EatsModel& M, const EatsRequest& rq, const EatsSha
     for (int it = tid; it < nrows * n_t; it += nthr) {
         const int r = it / n_t, k = it - r * n_t;
         const RowGeom g = sh.rowg[r];
-        double lt, ld, lg;
-        node_logs(M, g, n_t, k, lt, ld, lg);
+        double lt, ld, lg, dop_lin;
+        node_logs(M, g, n_t, k, lt, ld, lg, dop_lin);
         sh.lg2t[it] = lt;
         if (rq.series) {
             sh.lg2dop[it] = ld;
@@ -301,9 +304,15 @@ VAG_HD void eats_phase1(const EatsModel& M, const EatsRequest& rq, const EatsSha
                     const double* base = M.coef + ((long)g.rep * n_t + k);
                     const long stride = M.coef_stride;
                     const SynCoefRegs cr = load_syn_coefs([&](int c) { return base[c * stride]; });
+                    // The two exponentials of a spectrum point factor into a cell part and a frequency part (comoving
+                    // nu' = nu_obs (1 + z) dop_lin):  (nu' / nu_m)^(2/3) = x23_cell nu_obs^(2/3),  nu' / nu_M = cut_cell nu_obs.
+                    // One exp2 per cell serves the whole tile instead of two per frequency.
+                    const double x23_cell = rexp2((-2. / 3) * (ld + cr.log2_nu_m - lg2_1pz));
+                    const double cut_cell = con::log2e * cr.inv_nu_M * (M.one_plus_z * dop_lin);
                     for (int l = 0; l < nl; ++l) {
                         const double lg2_nu_src = rq.lg2_nu_obs[l0 + l] + lg2_1pz;
-                        bv[l] = photon_log2_I_nu_fast(cr, M.sp_lut, M.smooth_thick, M.log2_x_far, lg2_nu_src - ld) + lg;
+                        bv[l] = photon_log2_I_nu_tile(cr, M.sp_lut, M.smooth_thick, M.log2_x_far, lg2_nu_src - ld,
+                                                      x23_cell * rq.nu23_obs[l0 + l], cut_cell * rq.nu_obs_lin[l0 + l]) + lg;
                     }
                 } else {
                     for (int l = 0; l < nl; ++l) {

@@ -320,6 +320,23 @@ VAG_HD double photon_log2_I_nu_fast(const SynCoefRegs& c, const double* __restri
     return spec - con::log2e * c.inv_nu_M * rexp2(log2_nu);
 }
 
+// photon_log2_I_nu_fast with the two exponentials of the point supplied by the caller: x23 = 2^(2/3 log2_x) and
+// cut = log2(e) 2^log2_nu / nu_M.  A frequency tile of one cell shares them up to a per-frequency factor
+// (eats_phase1), so they cost one multiplication each instead of one exp2 each (identities; <= 2 ulp per factor).
+VAG_HD double photon_log2_I_nu_tile(const SynCoefRegs& c, const double* __restrict__ sp_lut, double smooth_thick,
+                                    double log2_x_far, double log2_nu, double x23, double cut) {
+    const double dlo = log2_nu - c.log2_nu_lo;
+    const double thin = dlo * (1.0 / 3.0) - log2_softplus_lut(sp_lut, c.diff_lo * dlo) * c.inv_smooth_lo -
+                        log2_softplus_lut(sp_lut, c.diff_hi * (log2_nu - c.log2_nu_hi)) * c.inv_smooth_hi;
+    const double log2_x = log2_nu - c.log2_nu_m;
+    double thick = 2.5 * log2_x;
+    if (!(log2_x > log2_x_far)) thick += log2_softplus_lut(sp_lut, -0.5 * log2_x - smooth_thick * x23);
+    const double b = thick + c.log2_thick_norm;
+    const double smooth = thin - log2_softplus_lut(sp_lut, c.s_a * (thin - b)) * c.inv_s_a;
+    const double spec = c.log2_I_max + (c.inv_smooth_lo + smooth);
+    return (log2_nu - c.log2_nu_M < -20) ? spec : spec - cut;
+}
+
 // One cell of K2: shock state -> photon coefficients.  For relic cells (k >= injection_idx,
 // synchrotron.h:187-201) the injection-time cell k_inj-1 is re-derived from its shock state
 // instead of being read from a neighbour's output, so every cell is independent.

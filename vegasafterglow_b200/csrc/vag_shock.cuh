@@ -254,16 +254,87 @@ template <bool INJ, bool SPREAD>
 struct FwdEqnT {
     const ModelCfg& m;
     double m_jet0, theta0, dOmega0, theta_s;
+    int mode;  // 0: rhs_general; 1 / 2: rhs_fast without / with radiative losses (ISM or Wind(k = 2), no injection, no spreading)
     enum { iG = 0, iM2 = 1, iU = 2, iR = 3, iT = 4, iTh = 5, iE = SPREAD ? 6 : 5, N = 5 + (INJ ? 1 : 0) + (SPREAD ? 1 : 0) };
 
     VAG_HD FwdEqnT(const ModelCfg& m_, double theta, double theta_s_) : m(m_), theta0(theta), theta_s(theta_s_) {
         m_jet0 = jet_eps_k(m, theta) / jet_Gamma0(m, theta) / con::c2;  // forward-shock.tpp:20
         m_jet0 /= 1 + m.sigma0;                                          // :21-23
         dOmega0 = 1 - cos(theta);                                        // :18
+        mode = (INJ || SPREAD || m.wind_generic) ? 0 : (m.fwd.eps_e_rad != 0 ? 2 : 1);
     }
 
-    // ForwardShockEqn::operator(): forward-shock.tpp:27-118
+    // ForwardShockEqn::operator(): forward-shock.tpp:27-118.  As for the shock pair (FREqn), rows without injection
+    // and spreading evaluate the branch-free rhs_fast -- one basic block per stage, so that the independent chains of
+    // the right-hand side overlap with one warp per scheduler -- and repeat the evaluation with rhs_general whenever
+    // an operand leaves the range that arithmetic is valid for.
     VAG_HD void operator()(const double* x, double* d, double t) const {
+        if (!INJ && !SPREAD) {
+            if (mode == 2) {
+                if (rhs_fast<true>(x, d)) return;
+            } else if (mode == 1) {
+                if (rhs_fast<false>(x, d)) return;
+            }
+        }
+        rhs_general(x, d, t);
+    }
+
+    template <bool RAD>
+    VAG_HD bool rhs_fast(const double* x, double* d) const {
+        const double Gamma = x[iG], r = x[iR];
+        const double u2 = (Gamma - 1) * (Gamma + 1);
+        bool ok = u2 >= 0 && r > 1e-150 && r < 1e150;  // Gamma < 1 must give NaN as in the reference: general path
+        const double u = vsqrt(u2 >= 0 ? u2 : 1.0);
+        const double dr = u * (Gamma + u) * con::c;
+        d[iR] = dr;
+        d[iT] = Gamma + u;
+        const double rho_wind = vdiv(m.wind_A, m.wind_r02 + r * r) + m.rho_ism;  // medium.h:107-109
+        const double rho = (m.medium_type == VAG_MEDIUM_ISM) ? m.rho_ism : rho_wind;
+        const double dm2 = r * r * rho * dr;
+        d[iM2] = dm2;
+        double eps_rad = 0;
+        if (RAD) {  // radiative_efficiency (shock-physics.h:247-288), ordinary operand range only
+            const RadCfg& rad = m.fwd;
+            const double e_th = (Gamma - 1) * 4 * Gamma * rho * con::c2;
+            const double gamma_m = rad.gamma_m_coeff * (Gamma - 1) + 1;
+            const double den = e_th * x[iT];
+            const bool den_ok = den > 1e-100 && den < 1e100;
+            ok = ok && den_ok;
+            const double gamma_bar = vdiv(rad.gamma_c_coeff, den_ok ? den : 1.0);
+            const double gamma_c = 0.5 * (gamma_bar + vsqrt(gamma_bar * gamma_bar + 4));
+            const double ratio = vdiv(gamma_m, gamma_c);
+            const bool slow_cooling = ratio < 1 && rad.p > 2;
+            const bool ratio_ok = ratio > 1e-300;
+            double pw = dexp2_nc(vmax((rad.p - 2) * dlog2_nc((slow_cooling && ratio_ok) ? ratio : 0.5), -1000.0));
+            VAG_KEEP(pw);
+            eps_rad = slow_cooling ? rad.eps_e_rad * (ratio_ok ? pw : 0.0) : rad.eps_e_rad;
+        }
+        const double ad_idx = adiabatic_idx_fast(Gamma);
+        const double dlnV_r = vdiv(3 * dr, r);
+        double dG;
+        {
+            const double Gamma2 = Gamma * Gamma;
+            const double Gamma_eff = vdiv(ad_idx * (Gamma2 - 1) + 1, Gamma);
+            const double dGamma_eff = vdiv(ad_idx * (Gamma2 + 1) - 1, Gamma2);
+            const double U = x[iU];
+            const double a1 = -(Gamma - 1) * (Gamma_eff + 1) * con::c2 * dm2;
+            const double a2 = (ad_idx - 1) * Gamma_eff * U * dlnV_r;
+            const double b1 = (m_jet0 + x[iM2]) * con::c2;
+            const double b2 = (dGamma_eff + vdiv(Gamma_eff * (ad_idx - 1), Gamma)) * U;
+            const double b = b1 + b2;
+            const bool b_ok = b > 1e-290 && b < 1e290;
+            dG = vdiv(a1 + a2, b_ok ? b : 1.0);
+            ok = ok && b_ok && fabs(dG) < kInf;
+            d[iG] = dG;
+        }
+        {
+            const double dlnVdt = dlnV_r - vdiv(dG, Gamma);
+            d[iU] = (1 - eps_rad) * (Gamma - 1) * con::c2 * dm2 - (ad_idx - 1) * dlnVdt * x[iU];
+        }
+        return ok;
+    }
+
+    VAG_HD void rhs_general(const double* x, double* d, double t) const {
         const double Gamma = x[iG];
         const double deps = INJ ? jet_deps_dt(m, theta0, t) : 0.0;
         if (INJ) d[INJ ? iE : 0] = deps;
@@ -387,6 +458,7 @@ VAG_HD int solve_fwd_row(const ModelCfg& m, double theta, double theta_s, double
     st.initialize(x, t0, 0.01 * t0, m.rtol);
     const double t_back = t[n_t - 1];
     int k = 0, status = 0, fails = 0, steps = 0;
+    double t_next = t[0];
     st.begin_step(eqn);
     while (st.t <= t_back) {
         if (!st.try_step(eqn)) {
@@ -401,12 +473,13 @@ VAG_HD int solve_fwd_row(const ModelCfg& m, double theta, double theta_s, double
             status |= VAG_ST_ODE_STEP_CAP;
             break;
         }
-        while (k < n_t && st.t > t[k]) {
-            st.calc_state(t[k], x);
+        while (st.t > t_next) {  // t_next = t[k], +inf behind the last node: fetched when k advances, not per step
+            st.calc_state(t_next, x);
 #pragma unroll
             for (int c = 0; c < 5; ++c) raw.c[c][k] = x[c];
             if (SPREAD) raw.theta[k] = x[SPREAD ? Eqn::iTh : 0];
             ++k;
+            t_next = k < n_t ? t[k] : kInf;
         }
         st.t_old = st.t;  // dense_output_runge_kutta::do_step: the next step starts here
     }
@@ -941,6 +1014,7 @@ VAG_HD int solve_pair_row(const ModelCfg& m, double theta, double t_dec, const d
     double t_step_start = t0;
     const double t_back = t[n_t - 1];
     int status = 0, fails = 0, steps = 0;
+    double t_next = k < n_t ? t[k] : kInf;
     st.begin(eqn);
     while (st.t <= t_back) {
         if (!st.try_step(eqn)) {
@@ -985,15 +1059,16 @@ VAG_HD int solve_pair_row(const ModelCfg& m, double theta, double t_dec, const d
             injection_idx_pending = true;
         }
         t_step_start = st.t;
-        while (k < n_t && st.t > t[k]) {
-            st.calc_state(t[k], x);
-            if (injection_idx_pending && t[k] >= t_cross) {
+        while (st.t > t_next) {  // t_next = t[k], +inf behind the last node: fetched when k advances, not per step
+            st.calc_state(t_next, x);
+            if (injection_idx_pending && t_next >= t_cross) {
                 injection_idx = k > 0 ? k : 1;
                 injection_idx_pending = false;
             }
 #pragma unroll
             for (int c = 0; c < FREqn::N; ++c) raw.c[c][k] = x[c];
             ++k;
+            t_next = k < n_t ? t[k] : kInf;
         }
         st.advance();
     }
