@@ -251,6 +251,13 @@ int vag_set_output_mode(vag_context* ctx, int mode);
  * most recent host-buffer call, or -1 when `total` was written.  (The pybind mirror hands the same array out twice.) */
 int vag_last_total_alias(vag_context* ctx);
 
+/* Series requests (vag_flux_density_series, vag_chi2*) whose points share at most 8 distinct frequencies -- multi-band
+ * light curves -- are evaluated "banded": the boundary luminosities of every lattice node are staged once per band and
+ * a point interpolates its band's column, instead of every point evaluating both bracketing spectra itself (the
+ * evaluation points are those of Observer::specific_flux_series, src/core/observer.h:494-520; results agree to
+ * rounding).  mode 0 (default): chosen per request by cost; 1: never; 2: whenever the request has <= 8 frequencies. */
+int vag_set_series_mode(vag_context* ctx, int mode);
+
 /* per-stage device time of the most recent batched call on this context, milliseconds:
  * [0]=grid (K0) [1]=dynamics (K1) [2]=radiation (K2) [3]=EATS flux (K3) [4]=likelihood (K4)
  * Only filled when vag_set_profiling(ctx, 1) was called (adds event records + one sync). */

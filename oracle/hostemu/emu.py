@@ -47,7 +47,9 @@ def flux_density_grid(params, t, nu):
     return out, st
 
 
-def flux_density_series(params, t, nu):
+def flux_density_series(params, t, nu, series_mode=0):
+    """series_mode as vag_set_series_mode (include/vag.h): 0 auto, 1 per-point spectra, 2 banded whenever possible."""
+    lib().vagemu_set_series_mode(C.c_int(int(series_mode)))
     p, pp = _params(params)
     t = np.ascontiguousarray(t, dtype=np.float64)
     nu = np.ascontiguousarray(nu, dtype=np.float64)

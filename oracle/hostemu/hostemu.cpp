@@ -183,10 +183,11 @@ void eats_emulate(const BatchWs& w, int mi, int which, const EatsRequest& rq0, d
     const int n_t = h.n_t;
     const int erows = h.n_theta * h.n_phi_eff;
     const bool series = rq0.series != 0;
-    const int nu_tile = series ? 1 : std::min(EATS_NU_TILE, rq0.n_nu);
-    std::vector<double> smem(eats_shared_doubles(n_t, series, EATS_ROW_CHUNK, nu_tile) + 8);
+    const bool banded = rq0.n_bands > 0;
+    const int nu_tile = series ? (banded ? rq0.n_bands : 1) : std::min(EATS_NU_TILE, rq0.n_nu);
+    std::vector<double> smem(eats_shared_doubles(n_t, series && !banded, EATS_ROW_CHUNK, nu_tile) + 8);
     std::vector<double> acc(EATS_NU_TILE * EATS_T_BLOCK);
-    EatsShared sh = eats_carve(smem.data(), n_t, series, EATS_ROW_CHUNK, nu_tile);
+    EatsShared sh = eats_carve(smem.data(), n_t, series && !banded, EATS_ROW_CHUNK, nu_tile);
     std::vector<RowGeom> rowg(erows);
     for (int q = 0; q < erows; ++q) rowg[q] = row_geometry(M, q / h.n_theta, q % h.n_theta);
     const int rows_per_pass = eats_rows_per_pass(n_t, EATS_ROW_CHUNK, NTHR);
@@ -194,7 +195,7 @@ void eats_emulate(const BatchWs& w, int mi, int which, const EatsRequest& rq0, d
     const int n_nu_tiles = series ? 1 : (rq.n_nu + nu_tile - 1) / nu_tile;
     for (int tile = 0; tile < n_nu_tiles; ++tile) {
         const int l0 = tile * nu_tile;
-        const int nl = series ? 1 : std::min(nu_tile, rq.n_nu - l0);
+        const int nl = series ? (banded ? rq.n_bands : 1) : std::min(nu_tile, rq.n_nu - l0);
         for (int i0 = 0; i0 < rq.n_t_obs; i0 += EATS_T_BLOCK) {
             rq.i0 = i0;
             rq.ni = std::min(EATS_T_BLOCK, rq.n_t_obs - i0);
@@ -208,7 +209,9 @@ void eats_emulate(const BatchWs& w, int mi, int which, const EatsRequest& rq0, d
                     if (M.mode == 2) eats_phase1<2>(M, rq, sh, nrows, l0, nl, tid, NTHR);
                 }
                 for (int tid = 0; tid < NTHR; ++tid) {
-                    if (!series) {
+                    if (banded) {
+                        eats_phase2_banded(M, rq, sh, nrows, acc.data(), tid, NTHR);
+                    } else if (!series) {
                         eats_phase2_grid(M, rq, sh, nrows, nl, acc.data(), tid, NTHR);
                     } else {
                         if (M.mode == 0) eats_phase2_series<0>(M, rq, sh, nrows, acc.data(), tid, NTHR);
@@ -227,6 +230,8 @@ void eats_emulate(const BatchWs& w, int mi, int which, const EatsRequest& rq0, d
         }
     }
 }
+
+int g_series_mode = 0;  // as vag_set_series_mode (include/vag.h)
 
 int run_flux(const vag_params* params, size_t n, const double* t, size_t n_t, const double* nu, size_t n_nu,
              bool series, double* out, int32_t* status) {
@@ -253,6 +258,37 @@ int run_flux(const vag_params* params, size_t n, const double* t, size_t n_t, co
     rq.nu23_obs = nu23.data();
     rq.t_obs_lin = tl.data();
     rq.acc_stride = eats_acc_stride((int)n_t);
+    // banded series (vag_b200.cu run_flux_pass / k_series_bands): distinct frequencies in order of first appearance
+    std::vector<int> band_of(n_t, 0);
+    std::vector<double> b_lg2, b_lin, b_23;
+    if (series && g_series_mode != 1) {
+        bool ok = true;
+        for (size_t i = 0; i < n_nu && ok; ++i) {
+            int q = -1;
+            for (size_t b = 0; b < b_lg2.size(); ++b)
+                if (b_lg2[b] == lg2nu[i]) q = (int)b;
+            if (q < 0) {
+                if ((int)b_lg2.size() >= EATS_NU_TILE || !(lg2nu[i] == lg2nu[i])) {
+                    ok = false;
+                    break;
+                }
+                q = (int)b_lg2.size();
+                b_lg2.push_back(lg2nu[i]);
+                b_lin.push_back(nul[i]);
+                b_23.push_back(nu23[i]);
+            }
+            band_of[i] = q;
+        }
+        int max_n_t = 1;
+        for (size_t mi = 0; mi < n; ++mi) max_n_t = std::max(max_n_t, hb.w.hdr[mi].n_t);
+        if (ok && !b_lg2.empty() && (g_series_mode == 2 || b_lg2.size() * (size_t)max_n_t <= 6 * n_t)) {
+            rq.n_bands = (int)b_lg2.size();
+            rq.band_of = band_of.data();
+            rq.lg2_nu_obs = b_lg2.data();
+            rq.nu_obs_lin = b_lin.data();
+            rq.nu23_obs = b_23.data();
+        }
+    }
     const size_t comp = series ? n_t : n_nu * n_t;
     double nu_range[2] = {*std::min_element(lg2nu.begin(), lg2nu.end()), *std::max_element(lg2nu.begin(), lg2nu.end())};
     run_ic_tables(hb, nu_range);
@@ -275,6 +311,7 @@ int run_flux(const vag_params* params, size_t n, const double* t, size_t n_t, co
 }  // namespace
 
 extern "C" {
+void vagemu_set_series_mode(int mode) { g_series_mode = mode; }
 
 // max |log2_softplus_lut - log2(1 + 2^x)| over n points of [-20, 20] (reference in long double)
 double vagemu_softplus_lut_maxerr(int n) {

@@ -87,6 +87,42 @@ def test_series_equals_grid(engine):
         np.testing.assert_allclose(fs[0, c].reshape(t.size, nu.size).T, fg[0, c], rtol=1e-12)
 
 
+def test_banded_series_equals_per_point_series(engine):
+    # vag_set_series_mode: 1 = per-point spectra, 2 = banded (<= 8 distinct frequencies); same evaluation points, so
+    # the two agree to rounding -- forward + reverse shock batch, SSC batch, and a 9-frequency request that cannot band
+    ts = np.sort(np.logspace(2.3, 6.8, 60) * (1 + 0.01 * np.arange(60) % 0.05))
+    nus = np.tile([1e9, 5e9, 4.84e14, 1e17, 1e18], 12)
+    nus9 = np.tile(np.logspace(9, 18, 9), 7)[:60]
+    for P in (configs.random_draw(64, seed=77, rvs=True),
+              configs.random_draw(8, seed=78, jet="gaussian", theta_obs_max=0.3, ssc=True)):
+        try:
+            engine.set_series_mode(1)
+            f1, st1 = engine.flux_density_series(P, ts, nus, return_status=True)
+            g1 = engine.flux_density_series(P, ts, nus9)
+            engine.set_series_mode(2)
+            f2, st2 = engine.flux_density_series(P, ts, nus, return_status=True)
+            g2 = engine.flux_density_series(P, ts, nus9)
+        finally:
+            engine.set_series_mode(0)
+        assert (st1 == 0).all() and (st2 == 0).all()
+        assert (f1[:, 0] > 0).all()
+        np.testing.assert_allclose(f2, f1, rtol=1e-11)
+        np.testing.assert_array_equal(g1, g2)
+    # and against the unmodified reference, banded
+    from oracle import ref
+    if ref.available():
+        P = configs.random_draw(16, seed=79, rvs=True)
+        engine.set_series_mode(2)
+        try:
+            f = engine.flux_density_series(P, ts, nus)
+        finally:
+            engine.set_series_mode(0)
+        r = ref.flux_density_series(P, ts, nus)
+        for c in (1, 3):
+            m = r[:, c] > 1e-2 * r[:, c].max(axis=-1, keepdims=True)
+            assert np.max(np.abs(f[:, c][m] - r[:, c][m]) / r[:, c][m]) < 1e-6
+
+
 def test_exact_invariants(engine):
     # tests/python/test_physics_invariants.py:37-105
     p, t, nu = configs.C3()

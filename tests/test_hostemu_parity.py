@@ -59,6 +59,24 @@ def test_series_equals_grid():
     np.testing.assert_allclose(fs[0, 0].reshape(t.size, nu.size).T, fg[0, 0], rtol=1e-12)
 
 
+def test_banded_series_equals_per_point_series():
+    # multi-band light curve (5 bands x 12 epochs, each band on its own epochs): the banded evaluation (boundary
+    # luminosities staged per band) and the per-point one evaluate the same spectra at the same nodes
+    p, _, _ = configs.C3()
+    nus = np.tile([1e9, 5e9, 4.84e14, 1e17, 1e18], 12)
+    ts = np.sort(np.logspace(2.3, 6.8, 60) * (1 + 0.01 * np.arange(60) % 0.05))
+    f1, st1 = emu.flux_density_series(p, ts, nus, series_mode=1)
+    f2, st2 = emu.flux_density_series(p, ts, nus, series_mode=2)
+    assert (st1 == 0).all() and (st2 == 0).all()
+    assert (f1[0, 0] > 0).all()
+    np.testing.assert_allclose(f2, f1, rtol=1e-12)
+    # nine distinct frequencies: not a banded request, mode 2 falls back to per-point spectra (identical bits)
+    nus9 = np.tile(np.logspace(9, 18, 9), 7)[:60]
+    g1, _ = emu.flux_density_series(p, ts, nus9, series_mode=1)
+    g2, _ = emu.flux_density_series(p, ts, nus9, series_mode=2)
+    np.testing.assert_array_equal(g1, g2)
+
+
 def test_distance_scaling_and_total():
     # F ~ 1/d_L^2 to 1e-9 and total == sum of parts to 1e-12 (test_physics_invariants.py:37-60)
     p, t, nu = configs.C3()

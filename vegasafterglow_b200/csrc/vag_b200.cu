@@ -303,6 +303,51 @@ __global__ void k_prep_obs(const double* __restrict__ t, int n_t, const double* 
     }
 }
 
+// Distinct frequencies of a series request (one CTA).  out_n = their number, or EATS_NU_TILE + 1 when there are more
+// (or a NaN); band_of[i] = index of point i's frequency in the list; the list is kept as log2 / linear / ^(2/3).
+// The list grows in order of first appearance: each round appends the unmatched point of lowest index.
+__global__ void __launch_bounds__(1024) k_series_bands(const double* __restrict__ lg2_nu, const double* __restrict__ nu_lin,
+                                                        const double* __restrict__ nu23, int n, int* band_of, double* b_lg2,
+                                                        double* b_lin, double* b_23, int* out_n) {
+    __shared__ double s_u[EATS_NU_TILE + 1];
+    __shared__ int s_cnt, s_cand;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const double v = i < n ? lg2_nu[i] : 0.0;
+        int mine = -1;
+        for (;;) {
+            const int cnt = s_cnt;
+            if (mine < 0)
+                for (int q = 0; q < cnt; ++q)
+                    if (s_u[q] == v) mine = q;
+            __syncthreads();
+            if (threadIdx.x == 0) s_cand = 0x7fffffff;
+            __syncthreads();
+            if (i < n && mine < 0) atomicMin(&s_cand, i);
+            __syncthreads();
+            const int cand = s_cand;
+            if (cand == 0x7fffffff) break;
+            if (cnt >= EATS_NU_TILE) {  // a ninth value (or a NaN, which matches nothing): not a banded request
+                if (threadIdx.x == 0) *out_n = EATS_NU_TILE + 1;
+                return;
+            }
+            if (threadIdx.x == 0) {
+                s_u[cnt] = lg2_nu[cand];
+                b_lg2[cnt] = lg2_nu[cand];
+                b_lin[cnt] = nu_lin[cand];
+                b_23[cnt] = nu23[cand];
+                s_cnt = cnt + 1;
+            }
+            __syncthreads();
+        }
+        if (i < n) band_of[i] = mine;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out_n = s_cnt;
+}
+
 // Observer::flux (src/core/observer.h:555-567): band[m][c][j] = sum_i F[m][c][i][j] * w[i]
 __global__ void k_band_reduce(const double* __restrict__ F, const double* __restrict__ wgt, double* __restrict__ out,
                               size_t n_mc, int n_nu, int n_t) {
@@ -346,9 +391,11 @@ __global__ void __launch_bounds__(128, EATS_MIN_BLOCKS) k_eats(BatchWs w, EatsRe
     const int n_t = M.h->n_t;
     const int erows = M.h->n_theta * M.h->n_phi_eff;
     const bool series = rq0.series != 0;
-    double* acc = smem + SPL_DOUBLES;  // [nu_tile][acc_stride]
+    const bool banded = rq0.n_bands > 0;  // series points read a (node, band) tile staged as in grid mode
+    double* acc = smem + SPL_DOUBLES;     // [acc_cols][acc_stride]
     const int acc_stride = rq0.acc_stride;
-    EatsShared sh = eats_carve(acc + nu_tile * acc_stride, max_n_t, series, row_chunk, nu_tile);
+    const int acc_cols = series ? 1 : nu_tile;
+    EatsShared sh = eats_carve(acc + acc_cols * acc_stride, max_n_t, series && !banded, row_chunk, nu_tile);
     EatsRequest rq = rq0;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int comp = which == 0 ? VAG_C_FWD_SYNC : which == 1 ? VAG_C_RVS_SYNC : which == 2 ? VAG_C_FWD_SSC : VAG_C_RVS_SSC;
@@ -362,28 +409,30 @@ __global__ void __launch_bounds__(128, EATS_MIN_BLOCKS) k_eats(BatchWs w, EatsRe
     const int rpp = eats_rows_per_pass(n_t, row_chunk, nthr);
     for (int tile = 0; tile < n_nu_tiles; ++tile) {
         const int l0 = tile * nu_tile;
-        const int nl = series ? 1 : imin(nu_tile, rq.n_nu - l0);
+        const int nl = series ? (banded ? rq.n_bands : 1) : imin(nu_tile, rq.n_nu - l0);
         for (int i0 = 0; i0 < rq.n_t_obs; i0 += EATS_T_BLOCK) {
             rq.i0 = i0;
             rq.ni = imin(EATS_T_BLOCK, rq.n_t_obs - i0);
             // zeroed by the thread that accumulates into and finally reads the column (ii == tid mod nthr): no barrier is
             // needed even when this split has no pass to run (compute-sanitizer racecheck, profiles/r02_sanitize.txt)
             for (int ii = tid; ii < rq.ni; ii += nthr)
-                for (int l = 0; l < nu_tile; ++l) acc[l * acc_stride + ii] = 0.0;
+                for (int l = 0; l < acc_cols; ++l) acc[l * acc_stride + ii] = 0.0;
             for (int q0 = split * rpp; q0 < erows; q0 += n_split * rpp) {
                 const int nrows = imin(rpp, erows - q0);
                 sh.rowg = rowg + q0;
                 __syncthreads();  // previous pass finished reading the staged rows (and the table is loaded)
                 eats_phase1<MODE>(M, rq, sh, nrows, l0, nl, tid, nthr);
                 __syncthreads();
-                if (series)
+                if (banded)
+                    eats_phase2_banded(M, rq, sh, nrows, acc, tid, nthr);
+                else if (series)
                     eats_phase2_series<MODE>(M, rq, sh, nrows, acc, tid, nthr);
                 else
                     eats_phase2_grid(M, rq, sh, nrows, nl, acc, tid, nthr);
             }
             // accumulator columns are thread-owned (ii == tid mod nthr): no barrier needed here
             for (int ii = tid; ii < rq.ni; ii += nthr) {
-                for (int l = 0; l < nl; ++l) {
+                for (int l = 0; l < (series ? 1 : nl); ++l) {
                     const double v = flux_scale(M, acc[l * acc_stride + ii]);
                     double* p = series ? (dst + i0 + ii) : (dst + (size_t)(l0 + l) * rq.n_t_obs + i0 + ii);
                     *p = v;
@@ -544,6 +593,8 @@ struct vag_context {
     DevBuf model_buf, row_buf, cell_buf, obs_buf, io_params, io_t, io_nu, io_out, io_status, io_aux, ic_buf, lut_buf, sp_buf, geom_buf, io_w, io_obs, io_chi2, split_buf;
     int* h_totals = nullptr;        // pinned
     long long* h_cells = nullptr;   // pinned
+    int* h_bands = nullptr;         // pinned: distinct frequencies of the series request in flight
+    int series_mode = 0;            // vag_set_series_mode: 0 auto, 1 per-point spectra always, 2 banded whenever possible
     int cap_theta = 384, cap_phi = 128;            // capacities of the batch in flight (host calls derive them per batch)
     int dbg_max_ode_steps = 0, dbg_max_ode_fails = 0;
     int user_cap_theta = 384, user_cap_phi = 128;  // vag_set_capacity: what the *_dev entry points run with
@@ -764,17 +815,29 @@ int run_flux_pass(vag_context* ctx, const vag_params* d_params, size_t n, const 
                   cudaStream_t s) {
     const size_t n_t = rq_in.n_t, n_nu = rq_in.n_nu;
     // observation arrays
-    CK(ctx->obs_buf.ensure(sizeof(double) * (2 * n_t + 3 * n_nu + 8)));
+    CK(ctx->obs_buf.ensure(sizeof(double) * (2 * n_t + 3 * n_nu + 8 + 3 * EATS_NU_TILE) + sizeof(int) * (n_t + 2)));
     double* lg2_t = static_cast<double*>(ctx->obs_buf.p);
     double* t_lin = lg2_t + n_t;
     double* lg2_nu = t_lin + n_t;
     double* nu_lin = lg2_nu + n_nu;
     double* nu23 = nu_lin + n_nu;
     double* nu_range = nu23 + n_nu;
+    double* band_lg2 = nu_range + 8;
+    double* band_lin = band_lg2 + EATS_NU_TILE;
+    double* band_23 = band_lin + EATS_NU_TILE;
+    int* band_of = reinterpret_cast<int*>(band_23 + EATS_NU_TILE);
+    int* d_n_bands = band_of + n_t;
     {
         const size_t m = std::max(n_t, n_nu);
         k_prep_obs<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(rq_in.d_t, (int)n_t, rq_in.d_nu, (int)n_nu, lg2_t, t_lin,
                                                               lg2_nu, nu_lin, nu23, rq_in.nu_code_units ? 1 : 0);
+        ctx->launches++;
+    }
+    *ctx->h_bands = 0;
+    if (rq_in.series && ctx->series_mode != 1) {
+        // distinct frequencies of the request; the count reaches the host with run_front's synchronisation
+        k_series_bands<<<1, 1024, 0, s>>>(lg2_nu, nu_lin, nu23, (int)n_nu, band_of, band_lg2, band_lin, band_23, d_n_bands);
+        CK(cudaMemcpyAsync(ctx->h_bands, d_n_bands, sizeof(int), cudaMemcpyDeviceToHost, s));
         ctx->launches++;
     }
     BatchWs w;
@@ -801,10 +864,18 @@ int run_flux_pass(vag_context* ctx, const vag_params* d_params, size_t n, const 
         // shared-memory budget -> rows staged per pass
         const size_t budget = EATS_SMEM_BUDGET;
         int row_chunk = EATS_ROW_CHUNK;
-        const int nu_tile = rq_in.series ? 1 : (int)std::min<size_t>(EATS_NU_TILE, n_nu);
+        // Banded series: the boundary luminosities of every (node, band) are staged once per row instead of two spectra
+        // per (point, row).  Per row that is at most n_bands * n_t tile evaluations (typically ~half: nodes outside the
+        // observation window are skipped) against 2 * n_points full ones, each ~2x dearer (coefficient loads, two
+        // reciprocals and two exp2 per point): taken while it is the smaller bill.
+        const int n_bands_req = rq_in.series ? *ctx->h_bands : 0;
+        const bool banded = n_bands_req >= 1 && n_bands_req <= EATS_NU_TILE &&
+                            (ctx->series_mode == 2 || (size_t)n_bands_req * max_n_t <= 6 * n_t);
+        const int nu_tile = rq_in.series ? (banded ? n_bands_req : 1) : (int)std::min<size_t>(EATS_NU_TILE, n_nu);
+        const int acc_cols = rq_in.series ? 1 : nu_tile;
         auto smem_bytes = [&](int rc_) {
-            return sizeof(double) *
-                   (nu_tile * eats_acc_stride((int)n_t) + eats_shared_doubles(max_n_t, rq_in.series, rc_, nu_tile) + SPL_DOUBLES);
+            return sizeof(double) * (acc_cols * eats_acc_stride((int)n_t) +
+                                     eats_shared_doubles(max_n_t, rq_in.series && !banded, rc_, nu_tile) + SPL_DOUBLES);
         };
         // fewer staged rows per pass while that buys residency: 8 CTAs / SM need <= 27 KB each (227 KB per SM,
         // 1 KB per CTA reserved by the system)
@@ -831,9 +902,11 @@ int run_flux_pass(vag_context* ctx, const vag_params* d_params, size_t n, const 
         rq.n_t_obs = (int)n_t;
         rq.n_nu = (int)n_nu;
         rq.lg2_t_obs = lg2_t;
-        rq.lg2_nu_obs = lg2_nu;
-        rq.nu_obs_lin = nu_lin;
-        rq.nu23_obs = nu23;
+        rq.lg2_nu_obs = banded ? band_lg2 : lg2_nu;
+        rq.nu_obs_lin = banded ? band_lin : nu_lin;
+        rq.nu23_obs = banded ? band_23 : nu23;
+        rq.n_bands = banded ? n_bands_req : 0;
+        rq.band_of = band_of;
         rq.t_obs_lin = t_lin;
         rq.acc_stride = eats_acc_stride((int)n_t);
         const dim3 eg((unsigned)n, (unsigned)n_split, (unsigned)n_shock);  // no reverse shock in the batch: no z = 1 CTAs
@@ -1018,6 +1091,7 @@ int vag_create(int device, vag_context** out) {
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaMallocHost(&c->h_totals, sizeof(int) * TOT_N));
     CK(cudaMallocHost(&c->h_cells, sizeof(long long)));
+    CK(cudaMallocHost(&c->h_bands, sizeof(int)));
     for (auto& ev : c->ev) CK(cudaEventCreate(&ev));
     {
         std::vector<double> lut(SPL_DOUBLES);
@@ -1050,6 +1124,7 @@ void vag_destroy(vag_context* c) {
         b->release();
     if (c->h_totals) cudaFreeHost(c->h_totals);
     if (c->h_cells) cudaFreeHost(c->h_cells);
+    if (c->h_bands) cudaFreeHost(c->h_bands);
     for (auto& ev : c->ev)
         if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c->stream);
@@ -1081,6 +1156,11 @@ int vag_set_output_mode(vag_context* ctx, int mode) {
     return VAG_OK;
 }
 int vag_last_total_alias(vag_context* ctx) { return ctx ? ctx->total_alias : -1; }
+int vag_set_series_mode(vag_context* ctx, int mode) {
+    if (mode < 0 || mode > 2) return fail(VAG_ERR_INVALID, "unknown series mode");
+    ctx->series_mode = mode;
+    return VAG_OK;
+}
 int vag_set_capacity(vag_context* ctx, int cap_theta, int cap_phi) {
     if (cap_theta < 40 || cap_phi < 2) return fail(VAG_ERR_INVALID, "capacity too small");
     ctx->cap_theta = ctx->user_cap_theta = cap_theta;

@@ -224,6 +224,12 @@ struct EatsRequest {
     const double* nu23_obs;    // [n_nu]     (nu * unit::Hz)^(2/3) = exp2(2/3 lg2_nu_obs)
     const double* t_obs_lin;   // [n_t_obs]  t * unit::sec
     int i0, ni;                // block of observation points handled by the current pass
+    // Banded series (n_bands > 0): the points of a series request share <= EATS_NU_TILE distinct frequencies.  The
+    // boundary luminosities are then staged per (node, band) exactly as in grid mode -- lg2_nu_obs / nu_obs_lin /
+    // nu23_obs hold the n_bands distinct frequencies -- and a point reads the column band_of[i] of its two
+    // bracketing nodes instead of evaluating both spectra itself (same evaluation points as observer.h:494-520).
+    int n_bands;
+    const int* band_of;        // [n_t_obs] band index of every point
     int acc_stride;            // accumulator columns per frequency: eats_acc_stride(n_t_obs)
 };
 
@@ -289,7 +295,7 @@ VAG_HD void eats_phase1(const EatsModel& M, const EatsRequest& rq, const EatsSha
         double lt, ld, lg, dop_lin;
         node_logs(M, g, n_t, k, lt, ld, lg, dop_lin);
         sh.lg2t[it] = lt;
-        if (rq.series) {
+        if (rq.series && rq.n_bands == 0) {
             sh.lg2dop[it] = ld;
             sh.lg2geo[it] = lg;
         } else {
@@ -398,6 +404,27 @@ VAG_HD void eats_phase2_series(const EatsModel& M, const EatsRequest& rq, const 
             const double lo = cell_log2_I_nu<MODE>(M, rep, n_t, k, lg2_nu - sh.lg2dop[ro + k]) + sh.lg2geo[ro + k];
             const double hi = cell_log2_I_nu<MODE>(M, rep, n_t, k + 1, lg2_nu - sh.lg2dop[ro + k + 1]) + sh.lg2geo[ro + k + 1];
             sum += interp_contrib(lo, hi, t_row[k], t_row[k + 1], x);
+        }
+        acc[ii] += sum;
+    }
+}
+
+// phase 2 (banded series): thread <-> data point; the interval is located with the series rule and the two boundary
+// luminosities of the point's band come from the staged tile
+VAG_HD void eats_phase2_banded(const EatsModel& M, const EatsRequest& rq, const EatsShared& sh, int nrows, double* acc,
+                               int tid, int nthr) {
+    const int n_t = M.h->n_t;
+    for (int ii = tid; ii < rq.ni; ii += nthr) {
+        const int s = rq.i0 + ii;
+        const double x = rq.lg2_t_obs[s];
+        const int b = rq.band_of[s];
+        double sum = 0;
+        for (int r = 0; r < nrows; ++r) {
+            const double* t_row = sh.lg2t + (size_t)r * n_t;
+            const int k = find_interval(t_row, n_t, x, true);
+            if (k < 0) continue;
+            const double* bv = sh.bv + ((size_t)r * n_t + k) * sh.nu_tile + b;
+            sum += interp_contrib(bv[0], bv[sh.nu_tile], t_row[k], t_row[k + 1], x);
         }
         acc[ii] += sum;
     }

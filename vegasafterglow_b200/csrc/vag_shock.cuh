@@ -458,7 +458,8 @@ VAG_HD int solve_fwd_row(const ModelCfg& m, double theta, double theta_s, double
     st.initialize(x, t0, 0.01 * t0, m.rtol);
     const double t_back = t[n_t - 1];
     int k = 0, status = 0, fails = 0, steps = 0;
-    double t_next = t[0];
+    // the next two lattice nodes ride in registers (+inf behind the last one): the loop test never waits for a load
+    double t_next = t[0], t_next2 = 1 < n_t ? t[1] : kInf;
     st.begin_step(eqn);
     while (st.t <= t_back) {
         if (!st.try_step(eqn)) {
@@ -473,13 +474,14 @@ VAG_HD int solve_fwd_row(const ModelCfg& m, double theta, double theta_s, double
             status |= VAG_ST_ODE_STEP_CAP;
             break;
         }
-        while (st.t > t_next) {  // t_next = t[k], +inf behind the last node: fetched when k advances, not per step
+        while (st.t > t_next) {  // t_next = t[k]
             st.calc_state(t_next, x);
 #pragma unroll
             for (int c = 0; c < 5; ++c) raw.c[c][k] = x[c];
             if (SPREAD) raw.theta[k] = x[SPREAD ? Eqn::iTh : 0];
             ++k;
-            t_next = k < n_t ? t[k] : kInf;
+            t_next = t_next2;
+            t_next2 = k + 1 < n_t ? t[k + 1] : kInf;
         }
         st.t_old = st.t;  // dense_output_runge_kutta::do_step: the next step starts here
     }
@@ -1014,7 +1016,8 @@ VAG_HD int solve_pair_row(const ModelCfg& m, double theta, double t_dec, const d
     double t_step_start = t0;
     const double t_back = t[n_t - 1];
     int status = 0, fails = 0, steps = 0;
-    double t_next = k < n_t ? t[k] : kInf;
+    // the next two lattice nodes ride in registers (+inf behind the last one): the loop test never waits for a load
+    double t_next = k < n_t ? t[k] : kInf, t_next2 = k + 1 < n_t ? t[k + 1] : kInf;
     st.begin(eqn);
     while (st.t <= t_back) {
         if (!st.try_step(eqn)) {
@@ -1059,7 +1062,7 @@ VAG_HD int solve_pair_row(const ModelCfg& m, double theta, double t_dec, const d
             injection_idx_pending = true;
         }
         t_step_start = st.t;
-        while (st.t > t_next) {  // t_next = t[k], +inf behind the last node: fetched when k advances, not per step
+        while (st.t > t_next) {  // t_next = t[k]
             st.calc_state(t_next, x);
             if (injection_idx_pending && t_next >= t_cross) {
                 injection_idx = k > 0 ? k : 1;
@@ -1068,7 +1071,8 @@ VAG_HD int solve_pair_row(const ModelCfg& m, double theta, double t_dec, const d
 #pragma unroll
             for (int c = 0; c < FREqn::N; ++c) raw.c[c][k] = x[c];
             ++k;
-            t_next = k < n_t ? t[k] : kInf;
+            t_next = t_next2;
+            t_next2 = k + 1 < n_t ? t[k + 1] : kInf;
         }
         st.advance();
     }

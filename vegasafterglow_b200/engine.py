@@ -172,6 +172,11 @@ class Engine:
         _lib.check(self._lib.vag_set_output_mode(self._h, (2 if alias_total else 1) if present_only else 0))
         self._present_only = bool(present_only)
 
+    def set_series_mode(self, mode: int):
+        """Evaluation of series requests with <= 8 distinct frequencies (vag.h vag_set_series_mode): 0 auto (default),
+        1 per-point spectra always, 2 banded whenever possible."""
+        _lib.check(self._lib.vag_set_series_mode(self._h, int(mode)))
+
     def last_total_alias(self):
         """Index into ``abi.COMPONENTS`` of the plane that holds `total` after the last host call, or -1."""
         return int(self._lib.vag_last_total_alias(self._h))
