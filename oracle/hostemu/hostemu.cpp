@@ -281,7 +281,7 @@ int run_flux(const vag_params* params, size_t n, const double* t, size_t n_t, co
         }
         int max_n_t = 1;
         for (size_t mi = 0; mi < n; ++mi) max_n_t = std::max(max_n_t, hb.w.hdr[mi].n_t);
-        if (ok && !b_lg2.empty() && (g_series_mode == 2 || b_lg2.size() * (size_t)max_n_t <= 6 * n_t)) {
+        if (ok && !b_lg2.empty() && (g_series_mode == 2 || b_lg2.size() * (size_t)max_n_t <= 3 * n_t)) {
             rq.n_bands = (int)b_lg2.size();
             rq.band_of = band_of.data();
             rq.lg2_nu_obs = b_lg2.data();

@@ -33,8 +33,11 @@ static_assert(sizeof(vag_params) == 320, "vag_params layout must match vegasafte
 // K0: G lanes per model (vag_grid.cuh GroupPar), 32 / G models per warp, 4 warps per CTA.  Narrow groups
 // share the scalar instruction stream between more models (throughput, large batches); wide groups
 // finish one model sooner (latency, small batches).
+#ifndef GRID_MIN_BLOCKS
+#define GRID_MIN_BLOCKS 4
+#endif
 template <int G>
-__global__ void __launch_bounds__(128, 4) k_grid(BatchWs w, const double* __restrict__ t_obs, int n_t_obs) {
+__global__ void __launch_bounds__(128, GRID_MIN_BLOCKS) k_grid(BatchWs w, const double* __restrict__ t_obs, int n_t_obs) {
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int mi = gt / G;
     if (mi >= w.n_models) return;  // whole groups exit together
@@ -865,12 +868,12 @@ int run_flux_pass(vag_context* ctx, const vag_params* d_params, size_t n, const 
         const size_t budget = EATS_SMEM_BUDGET;
         int row_chunk = EATS_ROW_CHUNK;
         // Banded series: the boundary luminosities of every (node, band) are staged once per row instead of two spectra
-        // per (point, row).  Per row that is at most n_bands * n_t tile evaluations (typically ~half: nodes outside the
-        // observation window are skipped) against 2 * n_points full ones, each ~2x dearer (coefficient loads, two
-        // reciprocals and two exp2 per point): taken while it is the smaller bill.
+        // per (point, row): n_bands * n_t tile evaluations against 2 * n_points per-point ones.  Measured on the
+        // config-5 batch (5 bands, ~100-node lattices, scripts/series_ab.py): 3.18 ms banded, flat in the number of
+        // points, against 1.97 ms per 100 points -- the break-even is n_bands * n_t ~ 3 n_points.
         const int n_bands_req = rq_in.series ? *ctx->h_bands : 0;
         const bool banded = n_bands_req >= 1 && n_bands_req <= EATS_NU_TILE &&
-                            (ctx->series_mode == 2 || (size_t)n_bands_req * max_n_t <= 6 * n_t);
+                            (ctx->series_mode == 2 || (size_t)n_bands_req * max_n_t <= 3 * n_t);
         const int nu_tile = rq_in.series ? (banded ? n_bands_req : 1) : (int)std::min<size_t>(EATS_NU_TILE, n_nu);
         const int acc_cols = rq_in.series ? 1 : nu_tile;
         auto smem_bytes = [&](int rc_) {
