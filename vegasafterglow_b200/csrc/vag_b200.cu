@@ -1102,6 +1102,19 @@ int vag_create(int device, vag_context** out) {
         CK(c->sp_buf.ensure(sizeof(double) * SPL_DOUBLES));
         CK(cudaMemcpy(c->sp_buf.p, lut.data(), sizeof(double) * SPL_DOUBLES, cudaMemcpyHostToDevice));
     }
+    {
+        // node sequences of find_theta_range (vag_grid.cuh ThetaWalk): plain IEEE running sums, identical on host and
+        // device; uploaded once per device
+        static std::mutex mu;
+        static bool done[256] = {};
+        std::lock_guard<std::mutex> lk(mu);
+        if (device < 256 && !done[device]) {
+            ThetaWalk tw;
+            build_theta_walk(tw);
+            CK(cudaMemcpyToSymbol(g_theta_walk, &tw, sizeof(tw)));
+            done[device] = true;
+        }
+    }
     // k_grid spills its scratch to local memory: prefer L1.  k_dynamics keeps its dopri5 stage vectors
     // in shared memory (23 KB per 32-row CTA): give it the full carve-out so several CTAs share an SM.
     cudaFuncSetCacheConfig(k_grid<8>, cudaFuncCachePreferL1);

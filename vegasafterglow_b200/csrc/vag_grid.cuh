@@ -194,28 +194,56 @@ VAG_HD int find_jet_jumps(const Par& par, const ModelCfg& m, double gamma_cut, d
 // The reference walks th -= step / th += step with early exit; the node sequence (a running sum,
 // so not j*step) is generated in uniform code, the profile evaluated at all nodes in parallel,
 // and the first hit taken in walk order.
-template <class Par>
-VAG_HD void find_theta_range(const Par& par, const ModelCfg& m, double gamma_cut, double& theta_min, double& theta_max,
-                             double* TH, double* G) {
+// The two node sequences are running sums of compile-time constants -- the same 513 + 513 doubles for every model --
+// so they are generated ONCE (ThetaWalk: on the device by k_init_tables at vag_create, on the host at first use) by the
+// reference's own loop; a per-model copy cost every model a 1026-long dependent DADD chain and 8 KB of scratch writes.
+struct ThetaWalk {
+    double down[GRID_NSCAN + 7], up[GRID_NSCAN + 7];
+    int n_down, n_up;
+};
+VAG_HD void build_theta_walk(ThetaWalk& w) {
     constexpr int n_scan = 512;
     const double theta_lo = dflt::theta_min;
     const double theta_hi = con::pi / 2;
-    theta_max = theta_hi;
-    theta_min = theta_lo;
     const double step = (theta_hi - theta_lo) / n_scan;
     int n = 0;
-    for (double th = theta_hi; th >= theta_lo && n < GRID_NSCAN + 6; th -= step) TH[n++] = th;
-    par.for_each(n, [&](int j) { G[j] = jet_Gamma0(m, TH[j]); });
-    {
-        const int j = par.first_true(0, n, [&](int q) { return G[q] >= gamma_cut; });
-        if (j < n) theta_max = TH[j];
-    }
+    for (double th = theta_hi; th >= theta_lo && n < GRID_NSCAN + 6; th -= step) w.down[n++] = th;
+    w.n_down = n;
     n = 0;
-    for (double th = theta_lo; th <= theta_hi && n < GRID_NSCAN + 6; th += step) TH[n++] = th;
-    par.for_each(n, [&](int j) { G[j] = jet_Gamma0(m, TH[j]); });
+    for (double th = theta_lo; th <= theta_hi && n < GRID_NSCAN + 6; th += step) w.up[n++] = th;
+    w.n_up = n;
+}
+#if defined(__CUDACC__)
+__device__ ThetaWalk g_theta_walk;
+#endif
+VAG_HD const ThetaWalk& theta_walk() {
+#if defined(__CUDA_ARCH__)
+    return g_theta_walk;
+#else
+    static const ThetaWalk w = [] {
+        ThetaWalk t;
+        build_theta_walk(t);
+        return t;
+    }();
+    return w;
+#endif
+}
+// The profile is evaluated inside the order-preserving first-hit search (G lanes per round, stop at the first round
+// with a hit -- the reference's early exit): an on-axis core ends the upward walk in its first round.
+template <class Par>
+VAG_HD void find_theta_range(const Par& par, const ModelCfg& m, double gamma_cut, double& theta_min, double& theta_max) {
+    const ThetaWalk& tw = theta_walk();
+    theta_max = con::pi / 2;
+    theta_min = dflt::theta_min;
     {
-        const int j = par.first_true(0, n, [&](int q) { return G[q] >= gamma_cut; });
-        if (j < n) theta_min = TH[j];
+        const int n = tw.n_down;
+        const int j = par.first_true(0, n, [&](int q) { return jet_Gamma0(m, tw.down[q]) >= gamma_cut; });
+        if (j < n) theta_max = tw.down[j];
+    }
+    {
+        const int n = tw.n_up;
+        const int j = par.first_true(0, n, [&](int q) { return jet_Gamma0(m, tw.up[q]) >= gamma_cut; });
+        if (j < n) theta_min = tw.up[j];
     }
 }
 
@@ -363,8 +391,9 @@ VAG_HD int inverse_cdf_sampling(const Par& par, const Pdf& pdf, double lo, doubl
         if (!ok) break;
         if (++steps > dflt::max_ode_steps) break;
         // dense output for every sample abscissa the accepted step passed
-        int m = 0;
-        while (k + m < n_samp && st.t > x_i[k + m]) ++m;
+        // m = number of sample abscissae the step passed: first q >= k with !(st.t > x_i[q]), searched G at a time
+        const double t_now = st.t;
+        const int m = par.first_true(k, n_samp, [&](int q) { return !(t_now > x_i[q]); }) - k;
         if (m > 0) {
             const int k0 = k;
             par.for_each(m, [&](int i) { cdf_i[k0 + i] = st.calc_state(x_i[k0 + i]); });
@@ -382,7 +411,25 @@ VAG_HD int inverse_cdf_sampling(const Par& par, const Pdf& pdf, double lo, doubl
         const double target = midpoint ? gl::add(c0, gl::div(gl::mul(gl::sub(c1, c0), gl::add((double)q, 0.5)), (double)num))
                                        : linspace_at(c0, c1, num, q);
         int j = (target >= target_prev) ? j_resume : 0;
-        while (j < n_samp && !(target <= cdf_i[j])) ++j;
+        for (;;) {  // the sequential scan, four candidates per round: independent loads, tests in scan order
+            const int last = n_samp - 1;
+            const double c0 = cdf_i[imin(j, last)], c1 = cdf_i[imin(j + 1, last)], c2 = cdf_i[imin(j + 2, last)],
+                         c3 = cdf_i[imin(j + 3, last)];
+            if (!(j < n_samp) || target <= c0) break;
+            if (!(j + 1 < n_samp) || target <= c1) {
+                j += 1;
+                break;
+            }
+            if (!(j + 2 < n_samp) || target <= c2) {
+                j += 2;
+                break;
+            }
+            if (!(j + 3 < n_samp) || target <= c3) {
+                j += 3;
+                break;
+            }
+            j += 4;
+        }
         j_resume = j;
         target_prev = target;
         double xo = 0;
@@ -785,7 +832,7 @@ VAG_HD void build_grid(const Par& par, const ModelCfg& m, double t_obs_min, doub
     const int n_jumps = find_jet_jumps(par, m, con::Gamma_cut, jumps, JUMP_CAP, A);
     if (n_jumps < 0) return fail_capacity();
     double inner_edge, outer_edge;
-    find_theta_range(par, m, con::Gamma_cut, inner_edge, outer_edge, A, B);
+    find_theta_range(par, m, con::Gamma_cut, inner_edge, outer_edge);
     for (int i = 0; i < n_jumps; ++i) outer_edge = vmax(outer_edge, jumps[i]);
     const double theta_min = vmax(dflt::theta_min, inner_edge);
     const double theta_max = vmin(outer_edge, theta_cut);
