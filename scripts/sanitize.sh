@@ -19,6 +19,11 @@ run("fs tophat x200 (8 lanes/model grid path needs >= 8192: 16-lane path here)",
 run("fs tophat x3 (row-split slabs)", configs.random_draw(3, seed=2))
 run("rs tophat x160", configs.random_draw(160, seed=3, rvs=True))
 run("rs series x40", configs.random_draw(40, seed=4, rvs=True), np.sort(np.tile(np.logspace(3, 6, 8), 2)), np.tile([1e9, 1e17], 8), True)
+eng.set_series_mode(2)  # banded series (k_series_bands + the (node, band) tile), forced
+run("rs series x40, banded", configs.random_draw(40, seed=4, rvs=True), np.sort(np.tile(np.logspace(3, 6, 8), 2)), np.tile([1e9, 1e17], 8), True)
+run("ssc series x6, banded", configs.random_draw(6, seed=12, ssc=True, kn=True), np.sort(np.tile(np.logspace(3, 6, 6), 3)), np.tile([1e9, 1e17, 1e24], 6), True)
+run("series of 9 frequencies (not banded)", configs.random_draw(6, seed=13), np.logspace(3, 6, 9), np.logspace(9, 18, 9), True)
+eng.set_series_mode(0)
 run("gaussian off-axis x12", configs.random_draw(12, seed=5, jet="gaussian", theta_obs_max=0.4))
 run("powerlaw wind rs x6", configs.random_draw(6, seed=6, jet="powerlaw", medium="wind", rvs=True, theta_obs_max=0.3))
 P = configs.random_draw(6, seed=7, theta_obs_max=0.3); P["spreading"] = 1
