@@ -204,9 +204,10 @@ void eats_emulate(const BatchWs& w, int mi, int which, const EatsRequest& rq0, d
                 const int nrows = std::min(rows_per_pass, erows - q0);
                 sh.rowg = rowg.data() + q0;
                 for (int tid = 0; tid < NTHR; ++tid) {
-                    if (M.mode == 0) eats_phase1<0>(M, rq, sh, nrows, l0, nl, tid, NTHR);
-                    if (M.mode == 1) eats_phase1<1>(M, rq, sh, nrows, l0, nl, tid, NTHR);
-                    if (M.mode == 2) eats_phase1<2>(M, rq, sh, nrows, l0, nl, tid, NTHR);
+                    const bool point = series && !banded;
+                    if (M.mode == 0) point ? eats_phase1<0, true>(M, rq, sh, nrows, l0, nl, tid, NTHR) : eats_phase1<0, false>(M, rq, sh, nrows, l0, nl, tid, NTHR);
+                    if (M.mode == 1) point ? eats_phase1<1, true>(M, rq, sh, nrows, l0, nl, tid, NTHR) : eats_phase1<1, false>(M, rq, sh, nrows, l0, nl, tid, NTHR);
+                    if (M.mode == 2) point ? eats_phase1<2, true>(M, rq, sh, nrows, l0, nl, tid, NTHR) : eats_phase1<2, false>(M, rq, sh, nrows, l0, nl, tid, NTHR);
                 }
                 for (int tid = 0; tid < NTHR; ++tid) {
                     if (banded) {

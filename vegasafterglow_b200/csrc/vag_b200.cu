@@ -7,7 +7,7 @@
 //                      register-resident dopri5, pair rows with the stage vectors in shared memory
 //   k_radiation      : one 64-thread CTA per unique row: finishes the shock tables from the raw node states,
 //                      EATS node geometry, photon coefficients (SoA planes, stores coalesced along k)
-//   k_eats<MODE>     : one 128-thread CTA per (model, row-split, shock), 8 CTAs / SM; staged rows, the
+//   k_eats<MODE,KIND>: one 128-thread CTA per (model, row-split, shock), 8 CTAs / SM; staged rows, the
 //                      log2_softplus table and the accumulators in dynamic shared memory
 #include <cuda_runtime.h>
 
@@ -17,6 +17,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/vag.h"
@@ -370,7 +371,9 @@ __global__ void k_band_reduce(const double* __restrict__ F, const double* __rest
 #ifndef EATS_MIN_BLOCKS
 #define EATS_MIN_BLOCKS 8
 #endif
-template <int MODE>
+// KIND: the request kind, compiled separately (see eats_phase1)
+enum { EATS_GRID = 0, EATS_POINT = 1, EATS_BANDED = 2 };
+template <int MODE, int KIND>
 __global__ void __launch_bounds__(128, EATS_MIN_BLOCKS) k_eats(BatchWs w, EatsRequest rq0, double* __restrict__ out, int n_split,
                                                  int row_chunk, int max_n_t, int nu_tile, size_t split_stride) {
     extern __shared__ __align__(16) double smem[];
@@ -393,8 +396,8 @@ __global__ void __launch_bounds__(128, EATS_MIN_BLOCKS) k_eats(BatchWs w, EatsRe
     }
     const int n_t = M.h->n_t;
     const int erows = M.h->n_theta * M.h->n_phi_eff;
-    const bool series = rq0.series != 0;
-    const bool banded = rq0.n_bands > 0;  // series points read a (node, band) tile staged as in grid mode
+    constexpr bool series = KIND != EATS_GRID;
+    constexpr bool banded = KIND == EATS_BANDED;  // series points read a (node, band) tile staged as in grid mode
     double* acc = smem + SPL_DOUBLES;     // [acc_cols][acc_stride]
     const int acc_stride = rq0.acc_stride;
     const int acc_cols = series ? 1 : nu_tile;
@@ -424,7 +427,7 @@ __global__ void __launch_bounds__(128, EATS_MIN_BLOCKS) k_eats(BatchWs w, EatsRe
                 const int nrows = imin(rpp, erows - q0);
                 sh.rowg = rowg + q0;
                 __syncthreads();  // previous pass finished reading the staged rows (and the table is loaded)
-                eats_phase1<MODE>(M, rq, sh, nrows, l0, nl, tid, nthr);
+                eats_phase1<MODE, KIND == EATS_POINT>(M, rq, sh, nrows, l0, nl, tid, nthr);
                 __syncthreads();
                 if (banded)
                     eats_phase2_banded(M, rq, sh, nrows, acc, tid, nthr);
@@ -813,6 +816,17 @@ int run_front(vag_context* ctx, BatchWs& w, const vag_params* d_params, size_t n
     return VAG_OK;
 }
 
+template <int MODE>
+void launch_eats(int kind, dim3 eg, size_t sb, cudaStream_t s, const BatchWs& w, const EatsRequest& rq, double* out,
+                 int n_split, int row_chunk, int max_n_t, int nu_tile, size_t elems) {
+    if (kind == EATS_GRID)
+        k_eats<MODE, EATS_GRID><<<eg, 128, sb, s>>>(w, rq, out, n_split, row_chunk, max_n_t, nu_tile, elems);
+    else if (kind == EATS_POINT)
+        k_eats<MODE, EATS_POINT><<<eg, 128, sb, s>>>(w, rq, out, n_split, row_chunk, max_n_t, nu_tile, elems);
+    else
+        k_eats<MODE, EATS_BANDED><<<eg, 128, sb, s>>>(w, rq, out, n_split, row_chunk, max_n_t, nu_tile, elems);
+}
+
 int run_flux_pass(vag_context* ctx, const vag_params* d_params, size_t n, const Request& rq_in, double* d_out,
                   int32_t* d_status, const double* d_lnF, const double* d_sig, const double* d_w, double* d_chi2,
                   cudaStream_t s) {
@@ -920,11 +934,12 @@ int run_flux_pass(vag_context* ctx, const vag_params* d_params, size_t n, const 
             eats_out = static_cast<double*>(ctx->split_buf.p);
             CK(cudaMemsetAsync(eats_out, 0, sizeof(double) * elems * n_split, s));
         }
-        k_eats<0><<<eg, 128, sb, s>>>(w, rq, eats_out, n_split, row_chunk, max_n_t, nu_tile, elems);
+        const int kind = !rq_in.series ? EATS_GRID : banded ? EATS_BANDED : EATS_POINT;
+        launch_eats<0>(kind, eg, sb, s, w, rq, eats_out, n_split, row_chunk, max_n_t, nu_tile, elems);
         ctx->launches++;
         if (w.any_ssc) {
-            k_eats<1><<<eg, 128, sb, s>>>(w, rq, eats_out, n_split, row_chunk, max_n_t, nu_tile, elems);
-            k_eats<2><<<eg, 128, sb, s>>>(w, rq, eats_out, n_split, row_chunk, max_n_t, nu_tile, elems);
+            launch_eats<1>(kind, eg, sb, s, w, rq, eats_out, n_split, row_chunk, max_n_t, nu_tile, elems);
+            launch_eats<2>(kind, eg, sb, s, w, rq, eats_out, n_split, row_chunk, max_n_t, nu_tile, elems);
             ctx->launches += 2;
         }
         if (n_split > 1) {
@@ -1123,9 +1138,18 @@ int vag_create(int device, vag_context** out) {
     cudaFuncSetAttribute(k_dynamics<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     // per-function process state: set once, to the largest request run_flux can make (not per call, where two contexts
     // with different request shapes would race on it)
-    CK(cudaFuncSetAttribute(k_eats<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EATS_SMEM_BUDGET));
-    CK(cudaFuncSetAttribute(k_eats<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EATS_SMEM_BUDGET));
-    CK(cudaFuncSetAttribute(k_eats<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EATS_SMEM_BUDGET));
+#define VAG_EATS_ATTR(M_, K_) \
+    CK(cudaFuncSetAttribute(k_eats<M_, K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EATS_SMEM_BUDGET))
+    VAG_EATS_ATTR(0, EATS_GRID);
+    VAG_EATS_ATTR(0, EATS_POINT);
+    VAG_EATS_ATTR(0, EATS_BANDED);
+    VAG_EATS_ATTR(1, EATS_GRID);
+    VAG_EATS_ATTR(1, EATS_POINT);
+    VAG_EATS_ATTR(1, EATS_BANDED);
+    VAG_EATS_ATTR(2, EATS_GRID);
+    VAG_EATS_ATTR(2, EATS_POINT);
+    VAG_EATS_ATTR(2, EATS_BANDED);
+#undef VAG_EATS_ATTR
     *out = c;
     return VAG_OK;
 }

@@ -283,7 +283,11 @@ VAG_HD int eats_rows_per_pass(int n_t, int row_chunk, int nthr) {
 }
 
 // phase 1: node logs (+ boundary luminosities for the frequency tile [l0, l0+nl) in grid mode)
-template <int MODE>
+// POINT: per-point series layout (node logs only, the spectra are evaluated per point in phase 2); otherwise the
+// (node, frequency) tile of grid mode / banded series.  A compile-time switch: the kernel instantiations of the
+// three request kinds then carry only their own code (k_eats runs under a 64-register cap, and every path it does
+// not take still costs it registers).
+template <int MODE, bool POINT>
 VAG_HD void eats_phase1(const EatsModel& M, const EatsRequest& rq, const EatsShared& sh, int nrows, int l0, int nl,
                         int tid, int nthr) {
     const int n_t = M.h->n_t;
@@ -295,7 +299,7 @@ VAG_HD void eats_phase1(const EatsModel& M, const EatsRequest& rq, const EatsSha
         double lt, ld, lg, dop_lin;
         node_logs(M, g, n_t, k, lt, ld, lg, dop_lin);
         sh.lg2t[it] = lt;
-        if (rq.series && rq.n_bands == 0) {
+        if (POINT) {
             sh.lg2dop[it] = ld;
             sh.lg2geo[it] = lg;
         } else {
