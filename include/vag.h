@@ -233,8 +233,14 @@ int vag_details(vag_context* ctx, const vag_params* p, double t_min, double t_ma
 /* Photon tables of one model (same front end as vag_details): for each shock [6][n_reps][n_t] in the order
  * log2 nu_m, log2 nu_c, log2 nu_a, log2 nu_M, log2 I_nu_max (code units) and 1/nu_M -- what
  * save_photon_details exports (pybind/pymodel.cpp:263-291).  rvs may be NULL; it is untouched without a
- * reverse shock.  Shocks with ssc=True are not covered (VAG_ERR_UNSUPPORTED). */
+ * reverse shock.  For a shock with ssc=True these are the photons after inverse-Compton cooling. */
 int vag_details_photons(vag_context* ctx, const vag_params* p, double t_min, double t_max, double* fwd, double* rvs);
+
+/* Electron and inverse-Compton bookkeeping of the shocks with ssc=True, after KN_cooling / Thomson_cooling
+ * (pybind/pymodel.cpp:234-291, 303): for each shock [VAG_IC_DETAIL_PLANES][n_reps][n_t] in the order gamma_m, gamma_c,
+ * gamma_a, gamma_M, gamma_m_hat, gamma_c_hat, Y_T.  Planes of a shock without ssc are zero; rvs may be NULL. */
+#define VAG_IC_DETAIL_PLANES 7
+int vag_details_ic(vag_context* ctx, const vag_params* p, double t_min, double t_max, double* fwd, double* rvs);
 
 /* Output transfer policy of the HOST-buffer flux entry points.
  * VAG_OUT_DENSE (default): every one of the VAG_NCOMP planes of `out` is written (absent components 0).

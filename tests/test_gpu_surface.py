@@ -195,7 +195,7 @@ def test_spreading_side_by_side():
 
 def test_details_side_by_side():
     """Model.details(t_min, t_max): SimulationDetails of both modules (pybind/pymodel.cpp:315-348) for a tophat,
-    an off-axis Gaussian with a reverse shock and a spreading jet."""
+    an off-axis Gaussian with a reverse shock, a spreading jet and two inverse-Compton-cooled models."""
     ours, theirs = _both()
 
     def models(va):
@@ -206,6 +206,11 @@ def test_details_side_by_side():
             va.Model(jet=va.GaussianJet(0.1, 1e52, 300, duration=100), medium=va.Wind(0.1), observer=obs_off, fwd_rad=rad,
                      rvs_rad=va.Radiation(0.1, 1e-2, 2.5)),
             va.Model(jet=va.TophatJet(0.15, 1e52, 200, spreading=True), medium=va.ISM(0.1), observer=obs_off, fwd_rad=rad),
+            # inverse-Compton cooling (Thomson and Klein-Nishina): electrons after cooling + the InverseComptonY record
+            va.Model(jet=va.TophatJet(0.1, 1e53, 300), medium=va.ISM(1), observer=obs_on,
+                     fwd_rad=va.Radiation(0.1, 1e-4, 2.3, ssc=True)),
+            va.Model(jet=va.TophatJet(0.1, 1e53, 300, duration=50), medium=va.ISM(1), observer=obs_on,
+                     fwd_rad=va.Radiation(0.1, 1e-4, 2.3, ssc=True, kn=True), rvs_rad=va.Radiation(0.1, 1e-3, 2.4, ssc=True, kn=True)),
         ]
 
     for mo, mr in zip(models(ours), models(theirs)):
@@ -217,10 +222,14 @@ def test_details_side_by_side():
         assert np.asarray(do.rvs.Gamma).ndim == np.asarray(dr.rvs.Gamma).ndim
         for so, sr in shocks:
             for name in ("t_comv", "r", "theta", "Gamma", "Gamma_th", "B_comv", "N_p", "t_obs", "Doppler", "nu_m", "nu_c",
-                         "nu_a", "nu_M", "I_nu_max", "gamma_m", "gamma_c", "gamma_a", "gamma_M", "N_e"):
+                         "nu_a", "nu_M", "I_nu_max", "gamma_m", "gamma_c", "gamma_a", "gamma_M", "N_e", "gamma_m_hat",
+                         "gamma_c_hat", "nu_m_hat", "nu_c_hat", "Y_T"):
                 a, b = np.asarray(getattr(so, name)), np.asarray(getattr(sr, name))
                 assert a.shape == b.shape, (name, a.shape, b.shape)
                 ok = np.isfinite(b) & (np.abs(b) > 0) & np.isfinite(a)
+                if not ok.any():  # e.g. Y_T without inverse-Compton cooling: identically zero in both
+                    assert np.all(a[np.isfinite(b)] == b[np.isfinite(b)]), name
+                    continue
                 # stage tables follow the theta grid / time lattice, which carry the quadrature noise of the
                 # grid builder: 1e-2 covers the noisiest early-time nodes
                 med = np.median(np.abs(a[ok] - b[ok]) / np.abs(b[ok]))

@@ -58,6 +58,7 @@ def load():
     lib.vag_last_work.argtypes = [vp, C.POINTER(C.c_double)]
     lib.vag_details.argtypes = [vp, vp, C.c_double, C.c_double, vp, dp, dp, ip, dp, dp, dp, ip]
     lib.vag_details_photons.argtypes = [vp, vp, C.c_double, C.c_double, dp, dp]
+    lib.vag_details_ic.argtypes = [vp, vp, C.c_double, C.c_double, dp, dp]
     _lib = lib
     return lib
 
@@ -66,7 +67,7 @@ EXPORTS = [
     "vag_params_default", "vag_params_validate", "vag_create", "vag_destroy", "vag_last_error", "vag_version",
     "vag_flux_density_grid", "vag_flux_density_series", "vag_flux_band", "vag_chi2_series", "vag_flux_density_grid_dev",
     "vag_flux_density_series_dev", "vag_chi2_series_dev", "vag_synchronize", "vag_set_capacity", "vag_details", "vag_details_photons",
-    "vag_set_profiling", "vag_set_output_mode", "vag_last_stage_ms", "vag_last_launch_count", "vag_measure_fp64_peak", "vag_selftest_libm", "vag_chi2", "vag_params_validate_batch", "vag_debug_set_ode_limits", "vag_last_total_alias", "vag_last_work", "vag_set_series_mode",
+    "vag_set_profiling", "vag_set_output_mode", "vag_last_stage_ms", "vag_last_launch_count", "vag_measure_fp64_peak", "vag_selftest_libm", "vag_chi2", "vag_params_validate_batch", "vag_debug_set_ode_limits", "vag_last_total_alias", "vag_last_work", "vag_set_series_mode", "vag_details_ic",
 ]
 
 

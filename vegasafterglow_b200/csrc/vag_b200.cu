@@ -490,6 +490,16 @@ __global__ void k_chi2(const double* __restrict__ flux, size_t n_models, int n, 
     }
 }
 
+// vag_details_ic: [VAG_IC_DETAIL_PLANES][n_cells] <- IcCell records
+__global__ void k_ic_export(const IcCell* __restrict__ ic, size_t n_cells, double* __restrict__ out) {
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    const IcCell& e = ic[c];
+    const double v[VAG_IC_DETAIL_PLANES] = {e.gamma_m, e.gamma_c, e.gamma_a, e.gamma_M, e.ys.gamma_m_hat, e.ys.gamma_c_hat, e.ys.Y_T};
+#pragma unroll
+    for (int a = 0; a < VAG_IC_DETAIL_PLANES; ++a) out[(size_t)a * n_cells + c] = v[a];
+}
+
 // Work counters of a batch (profiling only): [0] forward-only ODE rows, [1] pair ODE rows, [2] shock-table cells x shocks,
 // [3] EATS cells = sum_models shocks n_phi_eff n_theta n_t, [4] EATS rows = sum shocks n_phi_eff n_theta,
 // [5] theta-quadrature attempts, [6] phi-quadrature attempts x n_theta, [7] sum n_theta
@@ -1688,8 +1698,6 @@ int vag_details(vag_context* ctx, const vag_params* p, double t_min, double t_ma
 int vag_details_photons(vag_context* ctx, const vag_params* p, double t_min, double t_max, double* fwd, double* rvs) {
     if (!ctx || !p || !fwd) return fail(VAG_ERR_INVALID, "NULL argument");
     if (int rc = vag_params_validate(p)) return rc;
-    if (p->fwd.ssc || (p->has_rvs && p->rvs.ssc))
-        return fail(VAG_ERR_UNSUPPORTED, "vag_details_photons covers shocks without inverse Compton only");
     CK(cudaSetDevice(ctx->device));
     int ct, cp;
     caps_for(p, 1, ct, cp);
@@ -1716,6 +1724,47 @@ int vag_details_photons(vag_context* ctx, const vag_params* p, double t_min, dou
             CK(cudaMemcpyAsync(rvs + a * nc, w.coef_rvs + (size_t)planes[a] * nc, sizeof(double) * nc, cudaMemcpyDeviceToHost, s));
     }
     CK(cudaStreamSynchronize(s));
+    return VAG_OK;
+}
+
+// Electron / inverse-Compton bookkeeping of the shocks with ssc=True (after KN_cooling / Thomson_cooling), per unique cell
+int vag_details_ic(vag_context* ctx, const vag_params* p, double t_min, double t_max, double* fwd, double* rvs) {
+    if (!ctx || !p || !fwd) return fail(VAG_ERR_INVALID, "NULL argument");
+    if (int rc = vag_params_validate(p)) return rc;
+    CK(cudaSetDevice(ctx->device));
+    int ct, cp;
+    caps_for(p, 1, ct, cp);
+    ctx->cap_theta = ct;
+    ctx->cap_phi = cp;
+    cudaStream_t s = ctx->stream;
+    CK(ctx->io_params.ensure(sizeof(vag_params)));
+    CK(ctx->io_t.ensure(sizeof(double) * 2));
+    const double tt[2] = {t_min, t_max};
+    CK(cudaMemcpyAsync(ctx->io_params.p, p, sizeof(vag_params), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->io_t.p, tt, sizeof(tt), cudaMemcpyHostToDevice, s));
+    BatchWs w;
+    int totals[TOT_N];
+    long long cells = 0;
+    ctx->launches = 0;
+    if (int rc = run_front(ctx, w, static_cast<vag_params*>(ctx->io_params.p), 1, static_cast<double*>(ctx->io_t.p), 2,
+                           s, totals, &cells))
+        return rc;
+    const size_t nc = (size_t)cells;
+    CK(ctx->io_out.ensure(sizeof(double) * VAG_IC_DETAIL_PLANES * std::max<size_t>(nc, 1)));
+    double* d_out = static_cast<double*>(ctx->io_out.p);
+    for (int which = 0; which < 2; ++which) {
+        double* dst = which ? rvs : fwd;
+        if (which && !(rvs && p->has_rvs)) continue;
+        const bool ssc = (which ? p->rvs.ssc : p->fwd.ssc) != 0;
+        if (ssc && w.any_ssc && nc > 0) {
+            k_ic_export<<<(unsigned)((nc + 127) / 128), 128, 0, s>>>(w.ic[which], nc, d_out);
+            CK(cudaMemcpyAsync(dst, d_out, sizeof(double) * VAG_IC_DETAIL_PLANES * nc, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+        } else {
+            std::memset(dst, 0, sizeof(double) * VAG_IC_DETAIL_PLANES * nc);
+        }
+    }
+    CK(cudaGetLastError());
     return VAG_OK;
 }
 

@@ -5,8 +5,9 @@ The device keeps only the UNIQUE shock rows (symmetry collapse) and the photon c
 broadcasts them over theta (and phi for ``axisymmetric=False``), converts to the reference's CGS / second
 units and rebuilds the observer-frame grids (``t_obs``, ``Doppler``: observer.cpp:51-205) and the electron
 break Lorentz factors from the break frequencies (gamma = sqrt(nu / (K B)), synchrotron.cpp:107-116).
-Inverse-Compton bookkeeping (``Y_T``, ``*_hat``) is not exported: those fields are zero, as they are in the
-reference for ``Radiation(ssc=False)``.
+For a shock with ``Radiation(ssc=True)`` the electron break Lorentz factors and the inverse-Compton bookkeeping
+(``gamma_*``, ``gamma_m_hat``, ``gamma_c_hat``, ``Y_T``, ``nu_*_hat``) are the device's records after IC cooling
+(``vag_details_ic``); without ssc the bookkeeping fields keep the defaults the reference leaves there.
 """
 from __future__ import annotations
 
@@ -53,6 +54,8 @@ def simulation_details(engine, param, t_min, t_max):
     theta_v, z = float(p["theta_obs"][0]), float(p["z"][0])
     n_phi_eff = int(d["info"]["n_phi_eff"])
     ph_f, ph_r = engine.details_photons(p, float(t_min), float(t_max), reps.size, n_t)
+    any_ssc = bool(p["fwd"]["ssc"][0]) or (has_rvs and bool(p["rvs"]["ssc"][0]))
+    ic_f, ic_r = engine.details_ic(p, float(t_min), float(t_max), reps.size, n_t) if any_ssc else (None, None)
 
     out = types.SimpleNamespace()
     out.phi, out.theta = d["phi"].copy(), d["theta"].copy()
@@ -69,7 +72,7 @@ def simulation_details(engine, param, t_min, t_max):
     doppler = 1.0 / (Gam[None] - u[None] * cos_v)
     t_obs = (t_code[None] + (1 - cos_v) * r[None] / C) * (1 + z) / SEC
 
-    def shock_details(tab, coef, rad):
+    def shock_details(tab, coef, rad, ic):
         s = types.SimpleNamespace(**_shock(tab, rep_of, n_ext))
         if not spreading:  # Shock::broadcast_groups gives every row its own coord.theta(j) (shock.cpp:41-88)
             s.theta = np.broadcast_to(d["theta"][None, :, None], (n_ext, n_theta, n_t)).copy()
@@ -88,13 +91,23 @@ def simulation_details(engine, param, t_min, t_max):
             if rad["p"] > 3:
                 f_syn = f_syn ** ((rad["p"] - 1) / 2)
             s.N_e = ext(tab[6][rep_of] * rad["xi_e"] * f_syn)
-        for k in ("gamma_m_hat", "gamma_c_hat", "nu_m_hat", "nu_c_hat", "Y_T"):
-            setattr(s, k, np.zeros((n_ext, n_theta, n_t)))
+        if ic is not None and bool(rad["ssc"]):
+            # electrons after IC cooling and the InverseComptonY record (save_electron_details / save_photon_details)
+            for a, k in enumerate(("gamma_m", "gamma_c", "gamma_a", "gamma_M", "gamma_m_hat", "gamma_c_hat", "Y_T")):
+                setattr(s, k, ext(ic[a][rep_of]))
+            with np.errstate(over="ignore", invalid="ignore"):
+                s.nu_m_hat = ext(_K_SYN * B * ic[4][rep_of] ** 2 / HZ)  # compute_syn_freq(gamma_hat, B)
+                s.nu_c_hat = ext(_K_SYN * B * ic[5][rep_of] ** 2 / HZ)
+        else:  # InverseComptonY defaults (inverse-compton.cpp:38-44): gamma_hat = 1, Y_T = 0
+            shape = (n_ext, n_theta, n_t)
+            s.gamma_m_hat, s.gamma_c_hat, s.Y_T = np.ones(shape), np.ones(shape), np.zeros(shape)
+            s.nu_m_hat = ext(_K_SYN * B / HZ)
+            s.nu_c_hat = ext(_K_SYN * B / HZ)
         return s
 
-    out.fwd = shock_details(fwd_tab, ph_f, p["fwd"][0])
+    out.fwd = shock_details(fwd_tab, ph_f, p["fwd"][0], ic_f)
     if has_rvs:
-        out.rvs = shock_details(d["rvs_shock"], ph_r, p["rvs"][0])
+        out.rvs = shock_details(d["rvs_shock"], ph_r, p["rvs"][0], ic_r)
     else:  # the reference leaves the absent shock's arrays default-constructed (0-d)
         out.rvs = types.SimpleNamespace(**{k: np.zeros(()) for k in vars(out.fwd)})
     return out

@@ -244,6 +244,16 @@ class Engine:
                      d["fwd_shock"].ctypes.data, d["rvs_shock"].ctypes.data, d["inj_idx"].ctypes.data))
         return d
 
+    def details_ic(self, param, t_min, t_max, n_reps, n_t):
+        """Electron / inverse-Compton records of the ssc=True shocks: (fwd, rvs) each [7, n_reps, n_t] -- gamma_m, gamma_c,
+        gamma_a, gamma_M, gamma_m_hat, gamma_c_hat, Y_T (include/vag.h vag_details_ic); zero for shocks without ssc."""
+        p = self._params(param)
+        assert p.size == 1
+        fwd = np.zeros((7, n_reps, n_t))
+        rvs = np.zeros((7, n_reps, n_t))
+        _lib.check(self._lib.vag_details_ic(self._h, p.ctypes.data, t_min, t_max, fwd.ctypes.data, rvs.ctypes.data))
+        return fwd, rvs
+
     def details_photons(self, param, t_min, t_max, n_reps, n_t):
         """Photon tables of one model: (fwd, rvs) each [6, n_reps, n_t] -- log2 nu_m, nu_c, nu_a, nu_M, I_nu_max (code
         units) and 1/nu_M (include/vag.h vag_details_photons)."""
