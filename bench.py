@@ -670,7 +670,7 @@ def main():
                     for name, cb in side.items():
                         if name in line.get("configs", {}):
                             line["configs"][name]["cpu_baseline"] = cb
-                    m = min(n, 2048)
+                    m = min(n, 16384)  # x 3 repeats: ~1.6 s on 16 threads, ~26 core-seconds
                     ref.flux_density_grid(P[:64], t, nu, n_threads=cores)
                     c0 = time.perf_counter()
                     reps = 3
