@@ -123,6 +123,26 @@ def test_banded_series_equals_per_point_series(engine):
             assert np.max(np.abs(f[:, c][m] - r[:, c][m]) / r[:, c][m]) < 1e-6
 
 
+def test_long_multiband_series_takes_the_banded_path(engine):
+    # 3 bands x 500 epochs = 1500 points (several 256-point observation blocks, k_series_bands over two chunks): the
+    # default mode picks the banded evaluation here (n_bands * n_t <= 3 n_points); it must equal the per-point one
+    t = np.logspace(2.2, 7.0, 500)
+    ts, nus = np.repeat(t, 3), np.tile([1e9, 4.84e14, 1e18], 500)
+    P = configs.random_draw(8, seed=91, rvs=True)
+    try:
+        engine.set_series_mode(1)
+        f1, st1 = engine.flux_density_series(P, ts, nus, return_status=True)
+        engine.set_series_mode(0)
+        f0, st0 = engine.flux_density_series(P, ts, nus, return_status=True)
+        engine.set_series_mode(2)
+        f2 = engine.flux_density_series(P, ts, nus)
+    finally:
+        engine.set_series_mode(0)
+    assert (st1 == 0).all() and (st0 == 0).all()
+    np.testing.assert_allclose(f0, f1, rtol=1e-11)
+    np.testing.assert_array_equal(f0, f2)  # the default took the banded path
+
+
 def test_exact_invariants(engine):
     # tests/python/test_physics_invariants.py:37-105
     p, t, nu = configs.C3()

@@ -458,19 +458,20 @@ VAG_HD int solve_fwd_row(const ModelCfg& m, double theta, double theta_s, double
     st.initialize(x, t0, 0.01 * t0, m.rtol);
     const double t_back = t[n_t - 1];
     int k = 0, status = 0, fails = 0, steps = 0;
+    const int max_fails = m.max_ode_fails, max_steps = m.max_ode_steps;  // in registers: the loop stores to global memory
     // the next two lattice nodes ride in registers (+inf behind the last one): the loop test never waits for a load
     double t_next = t[0], t_next2 = 1 < n_t ? t[1] : kInf;
     st.begin_step(eqn);
     while (st.t <= t_back) {
         if (!st.try_step(eqn)) {
-            if (++fails >= m.max_ode_fails) {
+            if (++fails >= max_fails) {
                 status |= VAG_ST_ODE_FAIL500;
                 break;
             }
             continue;
         }
         fails = 0;
-        if (++steps > m.max_ode_steps) {
+        if (++steps > max_steps) {
             status |= VAG_ST_ODE_STEP_CAP;
             break;
         }
@@ -1016,19 +1017,20 @@ VAG_HD int solve_pair_row(const ModelCfg& m, double theta, double t_dec, const d
     double t_step_start = t0;
     const double t_back = t[n_t - 1];
     int status = 0, fails = 0, steps = 0;
+    const int max_fails = m.max_ode_fails, max_steps = m.max_ode_steps;  // in registers: the loop stores to global memory
     // the next two lattice nodes ride in registers (+inf behind the last one): the loop test never waits for a load
     double t_next = k < n_t ? t[k] : kInf, t_next2 = k + 1 < n_t ? t[k + 1] : kInf;
     st.begin(eqn);
     while (st.t <= t_back) {
         if (!st.try_step(eqn)) {
-            if (++fails >= m.max_ode_fails) {
+            if (++fails >= max_fails) {
                 status |= VAG_ST_ODE_FAIL500;
                 break;
             }
             continue;
         }
         fails = 0;
-        if (++steps > m.max_ode_steps) {
+        if (++steps > max_steps) {
             status |= VAG_ST_ODE_STEP_CAP;
             break;
         }
