@@ -804,7 +804,8 @@ int run_front(vag_context* ctx, BatchWs& w, const vag_params* d_params, size_t n
             // kernels have to share the SMs with.  Measured on the config-5 batch (4096 rows; 8 / 16 / 32 rows per warp):
             // one batch alone 1.80 / 1.88 / 2.03 ms, four batches in flight 1.13 / 1.33 / 1.36 M evaluations/s --
             // so warps are thinned only while they stay below two per SM.
-            while (lanes > 4 && (rows + lanes / 2 - 1) / (lanes / 2) <= ctx->sm_count * 2) lanes >>= 1;
+            // (512 rows, the share of an 8-GPU ensemble: 1 / 2 / 4 / 8 rows per warp 1.56 / 1.59 / 1.64 / 1.71 ms)
+            while (lanes > 1 && (rows + lanes / 2 - 1) / (lanes / 2) <= ctx->sm_count * 2) lanes >>= 1;
             const unsigned nb = (unsigned)((rows + lanes - 1) / lanes);
             if (ctx->h_totals[TOT_ANY_FWD_ONLY]) {
                 k_dynamics<false><<<nb, 32, 0, s>>>(w, rows, lanes);
