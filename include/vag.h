@@ -29,9 +29,8 @@ enum {
     VAG_ERR_INVALID = 1, /* argument validation failed: mirrors AFTERGLOW_REQUIRE -> ValueError
                             (pybind/error_handling.h:31-69) */
     VAG_ERR_CUDA = 2,    /* CUDA runtime error / no device                                       */
-    VAG_ERR_UNSUPPORTED = 3, /* a switch of the reference that this path does not implement:
-                                axisymmetric=False together with spreading=True; Python-callable
-                                Ejecta / Medium profiles cannot be expressed in vag_params at all   */
+    VAG_ERR_UNSUPPORTED = 3, /* a switch of the reference that this path does not implement (Python-callable
+                                Ejecta / Medium profiles cannot be expressed in vag_params at all)  */
     VAG_ERR_CAPACITY = 4     /* a per-model grid exceeded the compiled capacity                  */
 };
 
@@ -74,7 +73,7 @@ typedef struct vag_params { /* 320 bytes, mirrored by vegasafterglow_b200/abi.py
      * duration)  pybind/pymodel.cpp:47-95; two-component / step-power-law / power-law-wing :97-146 */
     int32_t jet_type;
     int32_t spreading; /* spreading=True of the jet factories: lateral spreading (forward-shock models) and
-                          Symmetry::structured lattices; not together with axisymmetric = 0 */
+                          Symmetry::structured lattices; with axisymmetric = 0 one ODE row per (phi, theta) cell */
     double theta_c, E_iso, Gamma0, k_e, k_g, duration;
     double theta_w, E_iso_w, Gamma0_w; /* wing of the two-component / step-power-law / power-law-wing jets */
     double sigma0;                     /* ejecta magnetisation (constant; the reference expresses it through

@@ -357,7 +357,8 @@ int vagemu_details(const vag_params* p, double t_min, double t_max, vag_grid_inf
     const size_t cells = (size_t)h.n_reps * h.n_t;
     if (theta) std::memcpy(theta, w.theta, sizeof(double) * h.n_theta);
     if (phi) std::memcpy(phi, w.phi, sizeof(double) * h.n_phi);
-    if (reps) std::memcpy(reps, w.reps, sizeof(int) * h.n_reps);
+    if (reps)
+        for (int r = 0; r < h.n_reps; ++r) reps[r] = h.rows3d ? r % h.n_theta : w.reps[r];
     if (t_rows) std::memcpy(t_rows, w.t_rows, sizeof(double) * cells);
     auto dump = [&](double* const* pl, double* o) {
         // order t_comv, r, theta, Gamma, Gamma_th, B, N_p
@@ -366,7 +367,7 @@ int vagemu_details(const vag_params* p, double t_min, double t_max, vag_grid_inf
             for (int r = 0; r < h.n_reps; ++r)
                 for (int k = 0; k < h.n_t; ++k)
                     o[((size_t)a * h.n_reps + r) * h.n_t + k] =
-                        map[a] < 0 ? (w.sh_theta ? w.sh_theta[(size_t)r * h.n_t + k] : w.theta[w.reps[r]]) : pl[map[a]][(size_t)r * h.n_t + k];
+                        map[a] < 0 ? (w.sh_theta ? w.sh_theta[(size_t)r * h.n_t + k] : w.theta[h.rows3d ? r % h.n_theta : w.reps[r]]) : pl[map[a]][(size_t)r * h.n_t + k];
     };
     if (fwd_shock) dump(w.fwd, fwd_shock);
     if (rvs_shock && p->has_rvs) dump(w.rvs, rvs_shock);

@@ -28,6 +28,8 @@ run("gaussian off-axis x12", configs.random_draw(12, seed=5, jet="gaussian", the
 run("powerlaw wind rs x6", configs.random_draw(6, seed=6, jet="powerlaw", medium="wind", rvs=True, theta_obs_max=0.3))
 P = configs.random_draw(6, seed=7, theta_obs_max=0.3); P["spreading"] = 1
 run("spreading x6", P)
+P = configs.random_draw(4, seed=15, theta_obs_max=0.3); P["spreading"] = 1; P["axisymmetric"] = 0
+run("spreading, axisymmetric=False x4 (one ODE row per (phi, theta) cell)", P)
 run("ssc kn x6", configs.random_draw(6, seed=8, ssc=True, kn=True), t, np.array([1e9, 1e17, 1e24]))
 P = configs.random_draw(1100, seed=9); run("fs tophat x1100 (16 lanes / model)", P, t[:6], nu[:1])
 P = configs.random_draw(8300, seed=10); run("fs tophat x8300 (8 lanes / model)", P, t[:3], nu[:1])

@@ -127,6 +127,14 @@ def main():
                    ("batch_rs_nonaxisym_tophat", configs.random_draw(8, seed=49, rvs=True, theta_obs_max=0.2))):
         P7["axisymmetric"] = 0
         save(nm, P7, t, nu)
+    # axisymmetric=False together with spreading=True: one ODE row per (phi, theta) cell on its own time lattice
+    # (build_time_grid, grid-refinement.h:612-619)
+    for nm, P7b in (("batch_fs_spreading_nonaxisym", np.concatenate([configs.random_draw(4, seed=60, theta_obs_max=0.3),
+                                                                     configs.random_draw(3, seed=61, jet="gaussian", theta_obs_max=0.4),
+                                                                     configs.random_draw(3, seed=62, jet="powerlaw", medium="wind", theta_obs_max=0.2)])),
+                    ("batch_rs_spreading_nonaxisym", configs.random_draw(4, seed=63, rvs=True, theta_obs_max=0.2))):
+        P7b["axisymmetric"], P7b["spreading"] = 0, 1
+        save(nm, P7b, t, nu)
     # Wind(A_star, n_ism, n0, k_m != 2): the reference's generic-Medium path (pybind/pymodel.cpp:169-185)
     P8 = np.concatenate([configs.random_draw(6, seed=50, medium="wind", theta_obs_max=0.2),
                          configs.random_draw(5, seed=51, jet="gaussian", medium="wind", theta_obs_max=0.3),

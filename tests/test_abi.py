@@ -77,7 +77,7 @@ def test_validation_radiation_ranges():
     assert lib.vag_params_validate(p.ctypes.data) == abi.VAG_OK
 
 
-def test_unsupported_switches_say_so():
+def test_grid_switches_are_accepted():
     lib = _lib.load()
     p = configs.make()
     p["spreading"] = 1  # lateral spreading is implemented
@@ -85,8 +85,8 @@ def test_unsupported_switches_say_so():
     p = configs.make()
     p["axisymmetric"] = 0  # implemented ...
     assert lib.vag_params_validate(p.ctypes.data) == abi.VAG_OK
-    p["spreading"] = 1     # ... except together with spreading (per-(phi,theta) lattices)
-    assert lib.vag_params_validate(p.ctypes.data) == abi.VAG_ERR_UNSUPPORTED
+    p["spreading"] = 1     # ... also together with spreading (one ODE row per (phi, theta) cell)
+    assert lib.vag_params_validate(p.ctypes.data) == abi.VAG_OK
     p = configs.make(ssc=True, kn=True)  # inverse Compton is implemented
     assert lib.vag_params_validate(p.ctypes.data) == abi.VAG_OK
 

@@ -206,6 +206,9 @@ def test_details_side_by_side():
             va.Model(jet=va.GaussianJet(0.1, 1e52, 300, duration=100), medium=va.Wind(0.1), observer=obs_off, fwd_rad=rad,
                      rvs_rad=va.Radiation(0.1, 1e-2, 2.5)),
             va.Model(jet=va.TophatJet(0.15, 1e52, 200, spreading=True), medium=va.ISM(0.1), observer=obs_off, fwd_rad=rad),
+            # spreading with axisymmetric=False: one ODE row per (phi, theta) cell
+            va.Model(jet=va.TophatJet(0.15, 1e52, 200, spreading=True), medium=va.ISM(0.1), observer=obs_off, fwd_rad=rad,
+                     axisymmetric=False),
             # inverse-Compton cooling (Thomson and Klein-Nishina): electrons after cooling + the InverseComptonY record
             va.Model(jet=va.TophatJet(0.1, 1e53, 300), medium=va.ISM(1), observer=obs_on,
                      fwd_rad=va.Radiation(0.1, 1e-4, 2.3, ssc=True)),

@@ -1103,9 +1103,6 @@ int vag_params_validate(const vag_params* p) {
     if (!std::isfinite(p->rtol) || !std::isfinite(p->phi_resol) || !std::isfinite(p->theta_resol) ||
         !std::isfinite(p->t_resol))
         return bad("resolutions and rtol must be finite");
-    if (!p->axisymmetric && p->spreading)
-        return fail(VAG_ERR_UNSUPPORTED,
-                    "axisymmetric=False together with spreading=True (per-(phi,theta) lattices) is not implemented on the GPU path");
     return VAG_OK;
 }
 
@@ -1670,13 +1667,18 @@ int vag_details(vag_context* ctx, const vag_params* p, double t_min, double t_ma
     const size_t nc = (size_t)h.n_reps * h.n_t;
     if (theta) CK(cudaMemcpyAsync(theta, w.theta, sizeof(double) * h.n_theta, cudaMemcpyDeviceToHost, s));
     if (phi) CK(cudaMemcpyAsync(phi, w.phi, sizeof(double) * h.n_phi, cudaMemcpyDeviceToHost, s));
-    if (reps) CK(cudaMemcpyAsync(reps, w.reps, sizeof(int) * h.n_reps, cudaMemcpyDeviceToHost, s));
+    // theta index of every ODE row: the representatives of the symmetry groups, or r % n_theta for a rows3d model
+    if (reps && !h.rows3d) CK(cudaMemcpyAsync(reps, w.reps, sizeof(int) * h.n_reps, cudaMemcpyDeviceToHost, s));
+    if (reps && h.rows3d)
+        for (int r = 0; r < h.n_reps; ++r) reps[r] = r % h.n_theta;
     if (t_rows) CK(cudaMemcpyAsync(t_rows, w.t_rows, sizeof(double) * nc, cudaMemcpyDeviceToHost, s));
     if (inj_idx) CK(cudaMemcpyAsync(inj_idx, w.inj_idx, sizeof(int) * h.n_reps, cudaMemcpyDeviceToHost, s));
     std::vector<double> th_host(h.n_theta);
     std::vector<int> reps_host(h.n_reps);
     CK(cudaMemcpyAsync(th_host.data(), w.theta, sizeof(double) * h.n_theta, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(reps_host.data(), w.reps, sizeof(int) * h.n_reps, cudaMemcpyDeviceToHost, s));
+    if (!h.rows3d) CK(cudaMemcpyAsync(reps_host.data(), w.reps, sizeof(int) * h.n_reps, cudaMemcpyDeviceToHost, s));
+    if (h.rows3d)
+        for (int r = 0; r < h.n_reps; ++r) reps_host[r] = r % h.n_theta;
     auto dump = [&](double* const* pl, double* o) -> int {
         const int map[7] = {0, 1, -1, 2, 3, 4, 5};
         for (int a = 0; a < 7; ++a)

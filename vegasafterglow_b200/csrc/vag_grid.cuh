@@ -31,6 +31,10 @@ struct GridHeader {
     int t_num_tot, t_num_base, has_early, is_rvs;
     double t_end, min_t_start, min_t_early;
     int spreading, structured;
+    // rows3d: structured model with axisymmetric = False -- one ODE row per (phi_i, theta_j) on its own time lattice
+    // (build_time_grid, grid-refinement.h:612-619); row index r = i * n_theta + j, n_reps = n_phi * n_theta
+    int rows3d, pad_;
+    double t_obs_min;  // first observation time (code units): the per-row lattice bounds of a rows3d model derive from it
     double theta_s;  // jet_spreading_edge (spreading models)
     int quad_attempts_theta, quad_attempts_phi;  // dopri5 attempts of the two CDF quadratures (work counters)
 };
@@ -804,6 +808,20 @@ VAG_HD void build_row_lattice(const GridHeader& h, double t_dec, double T0, doub
     if (h.has_early && tid == 0) t_row[0] = h.structured ? row_early : h.min_t_early;
 }
 
+// scan_time_bounds (grid-refinement.h:471-514): raw lattice start of cell (phi_i, theta_j)
+VAG_HD double raw_row_start(const ModelCfg& m, double t_obs_min, double th, double G, double cos_tv, double sin_tv,
+                            double phi) {
+    const double b = gamma_to_beta(G);
+    const double cos_a = cos(th) * cos_tv + sin(th) * sin_tv * cos(phi);
+    return 0.99 * t_obs_min * (1 - b) / (1 - cos_a * b) / (1 + m.z);
+}
+// lattice guard of theta row j (same source): min(0.01 t_dec, 1e-2 s[, 0.01 T0 with a reverse shock])
+VAG_HD double row_start_cut(const ModelCfg& m, bool is_rvs, double t_dec) {
+    double cut = vmin(0.01 * t_dec, 1e-2 * unit::sec);
+    if (is_rvs) cut = vmin(cut, 0.01 * m.T0);
+    return cut;
+}
+
 // ---- auto_grid: grid-refinement.h:638-706 (axisymmetric, typed jets) --------------------------
 template <class Par>
 VAG_HD void build_grid(const Par& par, const ModelCfg& m, double t_obs_min, double t_obs_max, GridHeader& h,
@@ -939,12 +957,8 @@ VAG_HD void build_grid(const Par& par, const ModelCfg& m, double t_obs_min, doub
         e_arr[j] = jet_eps_k(m, th);
         g_arr[j] = G;
         // scan_time_bounds (grid-refinement.h:471-514): raw start time of cell (i, j)
-        const double b = gamma_to_beta(G);
         double ts_min = kInf;
-        for (int i = 0; i < n_phi_scan; ++i) {
-            const double cos_a = cos(th) * cos_tv + sin(th) * sin_tv * cos(s.phi[i]);
-            ts_min = vmin(ts_min, 0.99 * t_obs_min * (1 - b) / (1 - cos_a * b) / (1 + m.z));
-        }
+        for (int i = 0; i < n_phi_scan; ++i) ts_min = vmin(ts_min, raw_row_start(m, t_obs_min, th, G, cos_tv, sin_tv, s.phi[i]));
         ts_arr[j] = ts_min;
     });
     int n_reps = 0;
@@ -968,11 +982,8 @@ VAG_HD void build_grid(const Par& par, const ModelCfg& m, double t_obs_min, doub
         for (int j = 0; j < n_theta; ++j) {
             if (r + 1 < n_reps && s.reps[r + 1] == j) td = s.t_dec[++r];
             const double ts = ts_arr[j];
-            double cut = vmin(0.01 * td, 1e-2 * unit::sec);
-            if (h.is_rvs) {
-                cut = vmin(cut, 0.01 * m.T0);
-                max_ref = vmax(max_ref, 10.0 * vmax(td, m.T0));
-            }
+            const double cut = row_start_cut(m, h.is_rvs != 0, td);
+            if (h.is_rvs) max_ref = vmax(max_ref, 10.0 * vmax(td, m.T0));
             min_raw = vmin(min_raw, ts);
             min_guarded = vmin(min_guarded, vmax(ts, cut));
             min_cut = vmin(min_cut, cut);
@@ -996,6 +1007,12 @@ VAG_HD void build_grid(const Par& par, const ModelCfg& m, double t_obs_min, doub
     h.t_num_base = (int)t_num_base;
     h.t_num_tot = (int)(t_num_base + extra);
     h.n_t = h.t_num_tot + h.has_early;
+    // structured + axisymmetric = False: every (phi, theta) cell is its own ODE row (k1_lattice_body derives the
+    // row's lattice bounds from t_obs_min; the minima above already run over every phi)
+    h.t_obs_min = t_obs_min;
+    h.rows3d = (m.structured && !axis) ? 1 : 0;
+    h.pad_ = 0;
+    if (h.rows3d) h.n_reps = n_phi * n_theta;
 }
 
 }  // namespace vag

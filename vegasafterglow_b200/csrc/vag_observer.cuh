@@ -84,7 +84,7 @@ VAG_HD RowGeom row_geometry(const EatsModel& M, int i, int j) {
         g.cos_v = cos_phi * sin_obs;
         g.t_coeff = cos_obs;
         g.lg2_dOmega = compute_dphi(h, M.phi, i);
-        g.rep = M.rep_of[j];
+        g.rep = h.rows3d ? i * h.n_theta + j : M.rep_of[j];
         return g;
     }
     g.cos_v = st * cos_phi * sin_obs + ct * cos_obs;
@@ -94,7 +94,7 @@ VAG_HD RowGeom row_geometry(const EatsModel& M, int i, int j) {
     const double cos_th_hi = (j == last) ? ct : cos(0.5 * (th + M.theta[j + 1]));
     const double dOmega = fabs((cos_th_hi - cos_th_lo) * compute_dphi(h, M.phi, i));
     g.lg2_dOmega = rlog2(dOmega);
-    g.rep = M.rep_of[j];
+    g.rep = h.rows3d ? i * h.n_theta + j : M.rep_of[j];
     return g;
 }
 

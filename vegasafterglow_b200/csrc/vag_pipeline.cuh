@@ -143,10 +143,21 @@ VAG_HD void k0c_rowmap_body(const BatchWs& w, int mi) {
         w.row_model[ro + r] = mi;
         w.row_rep[ro + r] = r;
         w.row_cell_off[ro + r] = w.cell_off[mi] + (long long)r * h.n_t;
+        if (h.rows3d) continue;  // row r = i * n_theta + j: no representative list (eats_rep)
         const int j0 = reps[r];
         const int j1 = (r + 1 < h.n_reps) ? reps[r + 1] : h.n_theta;
         for (int j = j0; j < j1; ++j) rep_of[j] = r;
     }
+    if (h.rows3d)
+        for (int j = 0; j < h.n_theta; ++j) rep_of[j] = j;
+}
+
+// theta index of ODE row r, and the ODE row behind EATS row (phi_i, theta_j)
+VAG_HD int row_theta_index(const BatchWs& w, int mi, const GridHeader& h, int r) {
+    return h.rows3d ? r % h.n_theta : w.reps[(size_t)mi * w.cap_theta + r];
+}
+VAG_HD int eats_rep(const GridHeader& h, const int* rep_of, int i, int j) {
+    return h.rows3d ? i * h.n_theta + j : rep_of[j];
 }
 
 VAG_HD ShockRow shock_row(double* const* planes, long long off) {
@@ -180,11 +191,27 @@ VAG_HD void k1_lattice_body(const BatchWs& w, int row, int tid, int nthr) {
     const GridHeader& h = w.hdr[mi];
     const ModelCfg& cfg = w.cfg[mi];
     const long long off = w.cell_off[mi] + (long long)r * h.n_t;
-    const double t_dec = w.t_dec[(size_t)mi * w.cap_theta + r];
-    // per-row lattice bounds of a structured model: work[j] and work[cap_theta + j] (build_grid)
+    // per-row lattice bounds of a structured model: work[j] and work[cap_theta + j] (build_grid); a rows3d model
+    // derives them for its own (phi_i, theta_j) (scan_time_bounds, grid-refinement.h:485-499)
     const double* work = w.work + (size_t)mi * w.work_per_model;
-    build_row_lattice(h, t_dec, cfg.T0, h.structured ? work[r] : 0.0, h.structured ? work[w.cap_theta + r] : 0.0,
-                      w.t_rows + off, tid, nthr);
+    double t_dec, row_start = 0.0, row_early = 0.0;
+    if (h.rows3d) {
+        const int i = r / h.n_theta, j = r - i * h.n_theta;
+        const double th = w.theta[(size_t)mi * w.cap_theta + j];
+        t_dec = w.t_dec[(size_t)mi * w.cap_theta + j];
+        const double ts = raw_row_start(cfg, h.t_obs_min, th, jet_Gamma0(cfg, th), cos(cfg.theta_v), sin(cfg.theta_v),
+                                        w.phi[(size_t)mi * w.cap_phi + i]);
+        const double cut = row_start_cut(cfg, h.is_rvs != 0, t_dec);
+        row_start = vmax(ts, cut);
+        row_early = 0.99 * vmin(ts, cut);
+    } else {
+        t_dec = w.t_dec[(size_t)mi * w.cap_theta + r];
+        if (h.structured) {
+            row_start = work[r];
+            row_early = work[w.cap_theta + r];
+        }
+    }
+    build_row_lattice(h, t_dec, cfg.T0, row_start, row_early, w.t_rows + off, tid, nthr);
     // grid-refinement.h:633-635: every thread re-reads the nodes it wrote itself (and thread 0 the early point)
     bool finite = true;
     for (int k = tid + (h.has_early ? 1 : 0); k < h.n_t; k += nthr) finite = finite && isfinite(w.t_rows[off + k]);
@@ -206,8 +233,9 @@ VAG_HD void k1_dynamics_body(const BatchWs& w, int row, double* col, int col_str
     const ModelCfg& cfg = w.cfg[mi];
     const long long off = w.cell_off[mi] + (long long)r * h.n_t;
     double* t_row = w.t_rows + off;  // written by k1_lattice_body
-    const double t_dec = w.t_dec[(size_t)mi * w.cap_theta + r];
-    const double theta = w.theta[(size_t)mi * w.cap_theta + w.reps[(size_t)mi * w.cap_theta + r]];
+    const int jth = row_theta_index(w, mi, h, r);
+    const double t_dec = w.t_dec[(size_t)mi * w.cap_theta + (h.rows3d ? jth : r)];
+    const double theta = w.theta[(size_t)mi * w.cap_theta + jth];
     int st = 0;  // (a non-finite lattice node was flagged by k1_lattice_body)
     const ShockRow sf = shock_row(w.fwd, off);
     const RawRow raw = raw_row(w, off);
@@ -251,7 +279,7 @@ VAG_HD RowCtx row_ctx(const BatchWs& w, int row) {
     c.n_t = w.hdr[c.mi].n_t;
     c.has_rvs = w.cfg[c.mi].has_rvs;
     c.off = w.cell_off[c.mi] + (long long)r * c.n_t;
-    c.theta = w.theta[(size_t)c.mi * w.cap_theta + w.reps[(size_t)c.mi * w.cap_theta + r]];
+    c.theta = w.theta[(size_t)c.mi * w.cap_theta + row_theta_index(w, c.mi, w.hdr[c.mi], r)];
     return c;
 }
 VAG_HD void k1b_finish_cell(const BatchWs& w, int row, const RowCtx& c, int k) {
@@ -297,8 +325,9 @@ VAG_HD double interp_theta_nb(const double* t_nb, const double* th_nb, int n_t, 
     return th_nb[h] + wgt * (th_nb[h + 1] - th_nb[h]);
 }
 VAG_HD void k1e_spread_geo_cell(const BatchWs& w, int row, const RowCtx& c, int k) {
-    const int j = w.row_rep[row];
-    const int last = w.hdr[c.mi].n_reps - 1;
+    const GridHeader& hh = w.hdr[c.mi];
+    const int j = hh.rows3d ? w.row_rep[row] % hh.n_theta : w.row_rep[row];  // neighbours in theta, within the row's phi
+    const int last = (hh.rows3d ? hh.n_theta : hh.n_reps) - 1;
     const long long o = c.off + k;
     const double th = w.sh_theta[o];
     w.geo_cth[o] = cos(th);
@@ -379,7 +408,7 @@ VAG_HD void k_dop_extrema_body(const BatchWs& w, int mi, int k) {
     const double cos_obs = cos(w.cfg[mi].theta_v);
     double lo = kInf, hi = -kInf;
     for (int q = 0; q < erows; ++q) {
-        const size_t o = (size_t)rep_of[q % h.n_theta] * h.n_t + k;
+        const size_t o = (size_t)eats_rep(h, rep_of, q / h.n_theta, q % h.n_theta) * h.n_t + k;
         const double g = Gam[o];
         const long long cell = w.cell_off[mi] + (long long)o;
         const double cos_v = spread ? w.geo_sth[cell] * rc[q] + w.geo_cth[cell] * cos_obs : rc[q];
