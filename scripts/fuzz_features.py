@@ -33,10 +33,13 @@ for i in range(n):
         p["k_e"], p["k_g"] = rng.uniform(1, 4), rng.uniform(1, 3)
     if jet == "powerlaw":
         p["k_e"], p["k_g"] = rng.uniform(1, 4), rng.uniform(1, 3)
-    if rng.random() < 0.25:
+    u_sw = rng.random()
+    if u_sw < 0.25:
         p["spreading"] = 1
-    elif rng.random() < 0.15:
+    elif u_sw < 0.36:
         p["axisymmetric"] = 0
+    elif u_sw < 0.44:  # both: one ODE row per (phi, theta) cell
+        p["spreading"], p["axisymmetric"] = 1, 0
     if jet != "powerlaw_wing" and rng.random() < 0.25:
         p["has_magnetar"] = 1
         p["magnetar_L0"], p["magnetar_t0"], p["magnetar_q"] = 10 ** rng.uniform(45, 49.5), 10 ** rng.uniform(1.5, 4.5), rng.uniform(1, 3)
