@@ -263,6 +263,25 @@ VAG_HD double photon_log2_I_nu_ic(const Get& get, double smooth_thick, double lo
     return spec - con::log2e * get(PH_INV_NU_M_MAX) * rexp2(log2_nu);
 }
 
+// The same spectrum for a frequency tile of one cell (eats_phase1): coefficients in registers, log2_softplus through the
+// shared-memory table, the two exponentials supplied as per-cell x per-frequency products (photon_log2_I_nu_tile);
+// nu_lin = 2^log2_nu is the comoving frequency the IC correction is evaluated at.
+VAG_HD double photon_log2_I_nu_ic_tile(const SynCoefRegs& c, double log2_nu_c, const double* __restrict__ sp_lut,
+                                       double smooth_thick, double log2_x_far, const IcCell& ic, double log2_nu, double x23,
+                                       double cut, double nu_lin) {
+    const double dlo = log2_nu - c.log2_nu_lo;
+    double thin = dlo * (1.0 / 3.0) - log2_softplus_lut(sp_lut, c.diff_lo * dlo) * c.inv_smooth_lo -
+                  log2_softplus_lut(sp_lut, c.diff_hi * (log2_nu - c.log2_nu_hi)) * c.inv_smooth_hi;
+    const double log2_x = log2_nu - c.log2_nu_m;
+    double thick = 2.5 * log2_x;
+    if (!(log2_x > log2_x_far)) thick += log2_softplus_lut(sp_lut, -0.5 * log2_x - smooth_thick * x23);
+    if (log2_nu > log2_nu_c && (ic.Y_c > 0 || ic.ys.Y_T > 0)) thin += rlog2((1. + ic.Y_c) / (1 + icy_nu_spectrum(ic.ys, nu_lin)));
+    const double b = thick + c.log2_thick_norm;
+    const double smooth = thin - log2_softplus_lut(sp_lut, c.s_a * (thin - b)) * c.inv_s_a;
+    const double spec = c.log2_I_max + (c.inv_smooth_lo + smooth);
+    return (log2_nu - c.log2_nu_M < -20) ? spec : spec - cut;
+}
+
 // ---------------------------------------------------------------------------------------------
 // One row of generate_syn_electrons + IC_cooling + generate_syn_photons for a shock with ssc
 // (synchrotron.cpp:315-408, inverse-compton.h:729-764).  Sequential in k.
@@ -528,8 +547,23 @@ VAG_HD int ic_generate(const Par& par, const IcCell& c, const Seed& seed_log2_I,
         ratio_t[j] = (trap > 0) ? exact / trap : 1;
     });
     par.for_each(1, [&](int) {
+        double run = 0;  // cdf_t[j] = cdf_t[j + 1] + fv_buf[j], addends fetched eight ahead
         cdf_t[nu_last] = 0;
-        for (int j = nu_last - 1; j >= 0; --j) cdf_t[j] = cdf_t[j + 1] + fv_buf[j];
+        int j = nu_last - 1;
+        for (; j - 7 >= 0; j -= 8) {
+            double v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = fv_buf[j - q];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                run = run + v[q];
+                cdf_t[j - q] = run;
+            }
+        }
+        for (; j >= 0; --j) {
+            run = run + fv_buf[j];
+            cdf_t[j] = run;
+        }
     });
 
     // accumulate_IC (inverse-compton.h:486-527): lane <-> output node k; the gamma loop stays outside
@@ -586,9 +620,22 @@ VAG_HD int ic_generate(const Par& par, const IcCell& c, const Seed& seed_log2_I,
                 ratio_buf[j] = (trap > 0) ? exact / trap : 1;
             });
             par.for_each(1, [&](int) {
+                // the reference's running sum, in its order; eight addends are fetched ahead of the dependent chain of
+                // additions (one lane, scratch in global memory: the load latency used to sit inside the chain)
                 double run = 0;
                 cdf_buf[nu_last] = 0;
-                for (int j = nu_last - 1; j >= j_split; --j) {
+                int j = nu_last - 1;
+                for (; j - 7 >= j_split; j -= 8) {
+                    double v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q] = cdf_buf[j - q];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        run = run + v[q];
+                        cdf_buf[j - q] = run;
+                    }
+                }
+                for (; j >= j_split; --j) {
                     run = run + cdf_buf[j];
                     cdf_buf[j] = run;
                 }

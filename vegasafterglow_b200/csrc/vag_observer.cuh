@@ -324,6 +324,23 @@ VAG_HD void eats_phase1(const EatsModel& M, const EatsRequest& rq, const EatsSha
                         bv[l] = photon_log2_I_nu_tile(cr, M.sp_lut, M.smooth_thick, M.log2_x_far, lg2_nu_src - ld,
                                                       x23_cell * rq.nu23_obs[l0 + l], cut_cell * rq.nu_obs_lin[l0 + l]) + lg;
                     }
+                } else if (MODE == 1) {
+                    // synchrotron of a shock with ssc: the same tile scheme with the IC correction of the thin branch
+                    const long cell = (long)g.rep * n_t + k;
+                    const double* base = M.coef + cell;
+                    const long stride = M.coef_stride;
+                    const SynCoefRegs cr = load_syn_coefs([&](int c) { return base[c * stride]; });
+                    const double log2_nu_c = base[PH_LOG2_NU_C * stride];
+                    const double x23_cell = rexp2((-2. / 3) * (ld + cr.log2_nu_m - lg2_1pz));
+                    const double nu_cell = M.one_plus_z * dop_lin;  // comoving nu = nu_cell nu_obs
+                    const double cut_cell = con::log2e * cr.inv_nu_M * nu_cell;
+                    for (int l = 0; l < nl; ++l) {
+                        const double lg2_nu_src = rq.lg2_nu_obs[l0 + l] + lg2_1pz;
+                        const double nu_o = rq.nu_obs_lin[l0 + l];
+                        bv[l] = photon_log2_I_nu_ic_tile(cr, log2_nu_c, M.sp_lut, M.smooth_thick, M.log2_x_far, M.ic[cell],
+                                                         lg2_nu_src - ld, x23_cell * rq.nu23_obs[l0 + l], cut_cell * nu_o,
+                                                         nu_cell * nu_o) + lg;
+                    }
                 } else {
                     for (int l = 0; l < nl; ++l) {
                         const double lg2_nu_src = rq.lg2_nu_obs[l0 + l] + lg2_1pz;
