@@ -352,6 +352,44 @@ VAG_HD void eats_phase1(const EatsModel& M, const EatsRequest& rq, const EatsSha
     }
 }
 
+// Phase-2 work assignment of one warp over a block of `ni` observation points.  A warp with a full complement takes
+// one point per lane and every staged row.  The warp holding the block's remainder (100 epochs on 128 threads leave it
+// 4 points) would run the whole row loop for a handful of lanes; it instead deals the rows to S = 32 / R row slices
+// (R = its point count rounded up to a power of two <= 16), every lane sums its slice and the slices are added with a
+// fixed shuffle tree -- the row loop of that warp shrinks S-fold.  (Device only: the host emulation keeps one point per
+// thread; the two differ by the association of the row sum.)
+struct P2Lane {
+    int ii;       // point of this lane within the block, or -1
+    int slice;    // first row of this lane
+    int n_slices; // row stride
+    int r_width;  // R: lanes per slice (shuffle tree starts at this offset); 32 = no tree
+};
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ P2Lane p2_lane(int w0, int ni, int lane) {
+    const int cnt = imin(32, ni - w0);
+    P2Lane m;
+    if (cnt > 16) {
+        m.ii = lane < cnt ? w0 + lane : -1;
+        m.slice = 0;
+        m.n_slices = 1;
+        m.r_width = 32;
+    } else {
+        int R = 1;
+        while (R < cnt) R <<= 1;
+        const int q = lane & (R - 1);
+        m.ii = q < cnt ? w0 + q : -1;
+        m.slice = lane / R;
+        m.n_slices = 32 / R;
+        m.r_width = R;
+    }
+    return m;
+}
+__device__ __forceinline__ double p2_reduce(double v, int r_width) {
+    for (int off = r_width; off < 32; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+#endif
+
 // phase 2 (grid): thread <-> observation time; accumulates the chunk's rows into acc[l][idx]
 // acc layout: [nu_tile][rq.acc_stride] (thread-owned columns, no atomics).  NLC = compile-time number of
 // frequencies of the tile: their NLC interpolation exponentials are evaluated as one interleaved batch.
@@ -361,12 +399,20 @@ template <int NLC>
 VAG_HD void eats_phase2_grid_n(const EatsModel& M, const EatsRequest& rq, const EatsShared& sh, int nrows, double* acc,
                                int tid, int nthr) {
     const int n_t = M.h->n_t;
+#if defined(__CUDA_ARCH__)
+    for (int w0 = tid & ~31; w0 < rq.ni; w0 += nthr) {
+        const P2Lane pl = p2_lane(w0, rq.ni, tid & 31);
+        const int ii = pl.ii, r_first = pl.ii >= 0 ? pl.slice : nrows, r_step = pl.n_slices;  // idle lanes skip the rows
+        const double x = rq.lg2_t_obs[rq.i0 + (ii >= 0 ? ii : w0)];
+#else
     for (int ii = tid; ii < rq.ni; ii += nthr) {
+        const int r_first = 0, r_step = 1;
         const double x = rq.lg2_t_obs[rq.i0 + ii];
+#endif
         double sum[NLC];
 #pragma unroll
         for (int l = 0; l < NLC; ++l) sum[l] = 0;
-        for (int r = 0; r < nrows; ++r) {
+        for (int r = r_first; r < nrows; r += r_step) {
             const double* t_row = sh.lg2t + (size_t)r * n_t;
             const int k = find_interval(t_row, n_t, x, false);
             if (k < 0) continue;
@@ -387,6 +433,11 @@ VAG_HD void eats_phase2_grid_n(const EatsModel& M, const EatsRequest& rq, const 
 #pragma unroll
             for (int l = 0; l < NLC; ++l) sum[l] += fin[l] ? val[l] : 0.0;
         }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+        for (int l = 0; l < NLC; ++l) sum[l] = p2_reduce(sum[l], pl.r_width);
+        if (ii < 0 || r_first != 0) continue;
+#endif
 #pragma unroll
         for (int l = 0; l < NLC; ++l) acc[l * rq.acc_stride + ii] += sum[l];
     }
@@ -411,12 +462,20 @@ VAG_HD void eats_phase2_series(const EatsModel& M, const EatsRequest& rq, const 
                                int tid, int nthr) {
     const int n_t = M.h->n_t;
     const double lg2_1pz = fast_log2(M.one_plus_z);
+#if defined(__CUDA_ARCH__)
+    for (int w0 = tid & ~31; w0 < rq.ni; w0 += nthr) {
+        const P2Lane pl = p2_lane(w0, rq.ni, tid & 31);
+        const int ii = pl.ii, r_first = pl.ii >= 0 ? pl.slice : nrows, r_step = pl.n_slices;  // idle lanes skip the rows
+        const int s = rq.i0 + (ii >= 0 ? ii : w0);
+#else
     for (int ii = tid; ii < rq.ni; ii += nthr) {
+        const int r_first = 0, r_step = 1;
         const int s = rq.i0 + ii;
+#endif
         const double x = rq.lg2_t_obs[s];
         const double lg2_nu = rq.lg2_nu_obs[s] + lg2_1pz;
         double sum = 0;
-        for (int r = 0; r < nrows; ++r) {
+        for (int r = r_first; r < nrows; r += r_step) {
             const size_t ro = (size_t)r * n_t;
             const double* t_row = sh.lg2t + ro;
             const int k = find_interval(t_row, n_t, x, true);
@@ -426,6 +485,10 @@ VAG_HD void eats_phase2_series(const EatsModel& M, const EatsRequest& rq, const 
             const double hi = cell_log2_I_nu<MODE>(M, rep, n_t, k + 1, lg2_nu - sh.lg2dop[ro + k + 1]) + sh.lg2geo[ro + k + 1];
             sum += interp_contrib(lo, hi, t_row[k], t_row[k + 1], x);
         }
+#if defined(__CUDA_ARCH__)
+        sum = p2_reduce(sum, pl.r_width);
+        if (ii < 0 || r_first != 0) continue;
+#endif
         acc[ii] += sum;
     }
 }
