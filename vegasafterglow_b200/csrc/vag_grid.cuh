@@ -163,7 +163,21 @@ VAG_HD int find_jet_jumps(const Par& par, const ModelCfg& m, double gamma_cut, d
         jumps[0] = theta_hi;
         return 1;
     }
-    par.for_each(n_scan, [&](int j) { G[j] = jet_Gamma0(m, j == 0 ? theta_lo : gl::fma((double)j, dtheta, theta_lo)); });
+    auto node = [&](int j) { return j == 0 ? theta_lo : gl::fma((double)j, dtheta, theta_lo); };
+    // A plain top-hat profile (Gamma0 inside theta_c, 1 outside; Gamma0 >= gamma_cut) has exactly one candidate, the
+    // first node with !(theta_j < theta_c): it is located directly on the same node expression instead of evaluating
+    // and scanning all 512 nodes -- same j, same refinement below.
+    const bool tophat = m.jet_type == VAG_JET_TOPHAT && !m.ejecta && m.Gamma0 >= gamma_cut;
+    int j_top = n_scan;
+    if (tophat) {
+        int j = (int)((m.theta_c - theta_lo) / dtheta);
+        j = j < 0 ? 0 : (j > n_scan - 1 ? n_scan - 1 : j);
+        while (j > 0 && !(node(j - 1) < m.theta_c)) --j;
+        while (j < n_scan && node(j) < m.theta_c) ++j;
+        j_top = (j >= 1) ? j : n_scan;  // theta_c <= theta_lo: the profile is 1 everywhere, no candidate
+    } else {
+        par.for_each(n_scan, [&](int j) { G[j] = jet_Gamma0(m, node(j)); });
+    }
     // The walk's jump test at node j reads only G[j-1] and G[j]: the candidates are found with an
     // order-preserving parallel search, each hit is then refined exactly as the sequential walk does.
     int n = 0;
@@ -174,10 +188,14 @@ VAG_HD int find_jet_jumps(const Par& par, const ModelCfg& m, double gamma_cut, d
         const double scale = vmax(prev_G - 1, cur_G - 1);
         return scale > 0 && dG > 0.5 * scale;
     };
-    for (int j = par.first_true(1, n_scan, is_jump); j < n_scan; j = par.first_true(j + 1, n_scan, is_jump)) {
+    auto next_jump = [&](int from) {
+        if (tophat) return (from <= j_top) ? j_top : n_scan;
+        return par.first_true(from, n_scan, is_jump);
+    };
+    for (int j = next_jump(1); j < n_scan; j = next_jump(j + 1)) {
         const double prev_th = (j - 1 == 0) ? theta_lo : gl::fma((double)(j - 1), dtheta, theta_lo);
         const double cur_th = gl::fma((double)j, dtheta, theta_lo);
-        const double prev_G = G[j - 1], cur_G = G[j];
+        const double prev_G = tophat ? m.Gamma0 : G[j - 1], cur_G = tophat ? 1.0 : G[j];
         double lo = prev_th, hi = cur_th;
         while (hi - lo > eps) {
             const double mid = 0.5 * (lo + hi);
@@ -241,7 +259,21 @@ VAG_HD void find_theta_range(const Par& par, const ModelCfg& m, double gamma_cut
     theta_min = dflt::theta_min;
     {
         const int n = tw.n_down;
-        const int j = par.first_true(0, n, [&](int q) { return jet_Gamma0(m, tw.down[q]) >= gamma_cut; });
+        int j;
+        if (m.jet_type == VAG_JET_TOPHAT && !m.ejecta && m.Gamma0 >= gamma_cut) {
+            // top-hat: the hit test is theta < theta_c on a strictly descending sequence -- bisection finds the same first hit
+            int lo = 0, hi = n;  // first q with down[q] < theta_c
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (tw.down[mid] < m.theta_c)
+                    hi = mid;
+                else
+                    lo = mid + 1;
+            }
+            j = lo;
+        } else {
+            j = par.first_true(0, n, [&](int q) { return jet_Gamma0(m, tw.down[q]) >= gamma_cut; });
+        }
         if (j < n) theta_max = tw.down[j];
     }
     {
