@@ -44,7 +44,10 @@ inline StepStats g_step_stats;
 template <bool EXACT>
 VAG_HD double ctrl_pow(double err, double p) {
     if (EXACT) return pow(err, p);
-    return dexp2(p * dlog2(err));
+    // both call sites pass a positive err (> 1 when a step is rejected, in [5^-5, 1/2) when the next step grows) and a
+    // negative exponent: clamped to the range of the guard-free polynomials, an infinite error gives the same 0 the
+    // library call would (the caller's max(., 0.2) then applies) -- no range checks, no fallback call in the step loop
+    return dexp2_nc(vmax(p * dlog2_nc(vmin(err, 1e300)), -1000.0));
 }
 template <bool EXACT>
 VAG_HD double ctrl_div(double a, double b) {
