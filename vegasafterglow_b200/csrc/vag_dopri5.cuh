@@ -373,13 +373,13 @@ struct Dopri5S {
 
     // Dense-output weights (runge_kutta_dopri5.hpp:229-275).  The rational constants of the published
     // formula are folded into reciprocal multipliers (<= 1 ulp per weight against the divisions).
-    VAG_HD double dense_theta(double tq) const { return (tq - t_old) / (t - t_old); }
+    VAG_HD double dense_theta(double tq) const { return vdiv(tq - t_old, t - t_old); }  // t > t_old: an accepted step
     VAG_HD void dense_weights(double tq, double* w) const {
         constexpr double b1 = 35.0 / 384, b3 = 500.0 / 1113, b4 = 125.0 / 192, b5 = -2187.0 / 6784, b6 = 11.0 / 84;
         constexpr double r1 = 5.0 / 11282082432.0, r3 = 100.0 / 32700410799.0, r4 = 25.0 / 1880347072.0,
                          r5 = 32805.0 / 199316789632.0, r6 = 55.0 / 822651844.0, r7 = 10.0 / 29380423.0;
         const double h = t - t_old;
-        const double th = (tq - t_old) / h;
+        const double th = vdiv(tq - t_old, h);
         const double X1 = r1 * (2558722523.0 - 31403016.0 * th);
         const double X3 = r3 * (882725551.0 - 15701508.0 * th);
         const double X4 = r4 * (443332067.0 - 31403016.0 * th);
