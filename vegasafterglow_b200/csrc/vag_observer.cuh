@@ -196,7 +196,7 @@ VAG_HD double interp_contrib2(double lo, double hi, double inv_dt, double dx) {
     return rexp2(lo + dx * s);
 }
 VAG_HD double interp_contrib(double lo, double hi, double t_lo, double t_hi, double x) {
-    return interp_contrib2(lo, hi, 1.0 / (t_hi - t_lo), x - t_lo);
+    return interp_contrib2(lo, hi, vdiv(1.0, t_hi - t_lo), x - t_lo);  // a zero interval gives a non-finite slope: no contribution
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -418,7 +418,7 @@ VAG_HD void eats_phase2_grid_n(const EatsModel& M, const EatsRequest& rq, const 
             if (k < 0) continue;
             const double* b_lo = sh.bv + ((size_t)r * n_t + k) * sh.nu_tile;
             const double* b_hi = b_lo + sh.nu_tile;
-            const double inv_dt = 1.0 / (t_row[k + 1] - t_row[k]), dx = x - t_row[k];
+            const double inv_dt = vdiv(1.0, t_row[k + 1] - t_row[k]), dx = x - t_row[k];  // zero interval -> non-finite slope -> skipped
             double arg[NLC], val[NLC];
             bool fin[NLC];
 #pragma unroll
