@@ -313,7 +313,7 @@ VAG_HD void eats_phase1(const EatsModel& M, const EatsRequest& rq, const EatsSha
                     // the cell's coefficients are read once and serve every frequency of the tile
                     const double* base = M.coef + ((long)g.rep * n_t + k);
                     const long stride = M.coef_stride;
-                    const SynCoefRegs cr = load_syn_coefs([&](int c) { return base[c * stride]; });
+                    const SynCoefRegs cr = load_syn_coefs<true>([&](int c) { return base[c * stride]; });
                     // The two exponentials of a spectrum point factor into a cell part and a frequency part (comoving
                     // nu' = nu_obs (1 + z) dop_lin):  (nu' / nu_m)^(2/3) = x23_cell nu_obs^(2/3),  nu' / nu_M = cut_cell nu_obs.
                     // One exp2 per cell serves the whole tile instead of two per frequency.
@@ -329,7 +329,7 @@ VAG_HD void eats_phase1(const EatsModel& M, const EatsRequest& rq, const EatsSha
                     const long cell = (long)g.rep * n_t + k;
                     const double* base = M.coef + cell;
                     const long stride = M.coef_stride;
-                    const SynCoefRegs cr = load_syn_coefs([&](int c) { return base[c * stride]; });
+                    const SynCoefRegs cr = load_syn_coefs<true>([&](int c) { return base[c * stride]; });
                     const double log2_nu_c = base[PH_LOG2_NU_C * stride];
                     const double x23_cell = rexp2((-2. / 3) * (ld + cr.log2_nu_m - lg2_1pz));
                     const double nu_cell = M.one_plus_z * dop_lin;  // comoving nu = nu_cell nu_obs
