@@ -374,8 +374,10 @@ __global__ void k_band_reduce(const double* __restrict__ F, const double* __rest
 #endif
 // KIND: the request kind, compiled separately (see eats_phase1)
 enum { EATS_GRID = 0, EATS_POINT = 1, EATS_BANDED = 2 };
+// MODE 1 (synchrotron with the inverse-Compton correction) carries the IC record of the cell next to the tile state: at
+// 64 registers it spilled 120 M local loads per config-4 batch; 5 CTAs / SM (90 registers) hold it without spills.
 template <int MODE, int KIND>
-__global__ void __launch_bounds__(128, EATS_MIN_BLOCKS) k_eats(BatchWs w, EatsRequest rq0, double* __restrict__ out, int n_split,
+__global__ void __launch_bounds__(128, MODE == 1 ? 5 : EATS_MIN_BLOCKS) k_eats(BatchWs w, EatsRequest rq0, double* __restrict__ out, int n_split,
                                                  int row_chunk, int max_n_t, int nu_tile, size_t split_stride) {
     extern __shared__ __align__(16) double smem[];
     const int mi = blockIdx.x;
