@@ -626,6 +626,9 @@ struct vag_context {
     DevBuf work_buf;
     int launches = 0;
     int sm_count = 148;
+    // warps of k_ic_spectrum per SM (one warp per cell in flight, 30 KB of scratch each): as many as are resident.  Measured
+    // on config 4: 12 / 16 / 20 / 24 / 28 warps per SM -> 75.1 / 68.6 / 65.0 / 61.1 / 58.5 ms per batch (latency-bound, IPC 1.3)
+    int ic_warps_per_sm = 16;
 };
 
 namespace {
@@ -789,7 +792,7 @@ int run_front(vag_context* ctx, BatchWs& w, const vag_params* d_params, size_t n
     w.rowgeom = static_cast<RowGeom*>(ctx->geom_buf.p);
     w.any_ssc = ctx->h_totals[TOT_ANY_SSC];
     if (w.any_ssc) {
-        const int n_ic_warps = (int)std::min<long long>(std::max<long long>(cells, 1), (long long)ctx->sm_count * 16);
+        const int n_ic_warps = (int)std::min<long long>(std::max<long long>(cells, 1), (long long)ctx->sm_count * ctx->ic_warps_per_sm);
         rc = setup_ic(ctx, w, n, std::max<long long>(cells, 1), n_ic_warps, s);
         if (rc) return rc;
     }
@@ -887,7 +890,7 @@ int run_flux_pass(vag_context* ctx, const vag_params* d_params, size_t n, const 
         k_nu_range<<<1, 256, 0, s>>>(lg2_nu, (int)n_nu, nu_range);
         k_rowcos<<<dim3((unsigned)((w.max_erows + 127) / 128), (unsigned)n), 128, 0, s>>>(w);
         k_dop_extrema<<<dim3((unsigned)((w.max_n_t + 63) / 64), (unsigned)n), 64, 0, s>>>(w);
-        const int n_ic_warps = (int)std::min<long long>(std::max<long long>(cells, 1), (long long)ctx->sm_count * 16);
+        const int n_ic_warps = (int)std::min<long long>(std::max<long long>(cells, 1), (long long)ctx->sm_count * ctx->ic_warps_per_sm);
         k_ic_spectrum<<<(unsigned)((n_ic_warps * 32 + 127) / 128), 128, 0, s>>>(w, totals[TOT_ROWS], n_ic_warps);
         ctx->launches += 4;
     }
@@ -1165,6 +1168,11 @@ int vag_create(int device, vag_context** out) {
     VAG_EATS_ATTR(2, EATS_POINT);
     VAG_EATS_ATTR(2, EATS_BANDED);
 #undef VAG_EATS_ATTR
+    {
+        int blocks = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_ic_spectrum, 128, 0) == cudaSuccess && blocks > 0)
+            c->ic_warps_per_sm = std::min(blocks, 8) * 4;
+    }
     *out = c;
     return VAG_OK;
 }
