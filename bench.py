@@ -31,6 +31,8 @@ sys.path.insert(0, ROOT)
 from vegasafterglow_b200 import abi, configs  # noqa: E402
 
 METRIC = "model evals/sec (flux_density_grid 100t x 3nu)"
+REF_BUILD = ("oracle/Makefile: g++ -O3 -march=x86-64-v3 -ffp-contract=fast -freciprocal-math, no LTO "
+             "(the reference's CMake uses -march=native and LTO where available)")
 UNIT = "evals/s"
 
 
@@ -216,8 +218,7 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference",
-                         "build": "oracle/Makefile: g++ -O3 -march=x86-64-v3 -ffp-contract=fast -freciprocal-math, no LTO "
-                                  "(the reference's CMake uses -march=native and LTO where available)",
+                         "build": REF_BUILD,
                          "sample": f"first {n} parameter sets of the {args.batch}-set batch per step x {args.steps} steps, "
                                    f"std::thread over the unmodified reference (oracle/ref_driver.cpp), {cores} threads"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -678,6 +679,7 @@ def main():
                         ref.flux_density_grid(P[:m], t, nu, n_threads=cores)
                     cdt = (time.perf_counter() - c0) / reps
                     line["cpu_baseline"] = {"value": m / cdt, "unit": UNIT, "cores": cores, "kind": "reference",
+                                            "build": REF_BUILD,
                                             "sample": f"first {m} parameter sets of the same batch x {reps} repeats, unmodified "
                                                       f"reference via oracle/_ref/libvagref.so with {cores} std::threads"}
             except Exception as exc:  # noqa: BLE001
